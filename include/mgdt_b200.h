@@ -1,0 +1,178 @@
+/*
+ * mgdt_b200.h -- C ABI of libmgdt_b200.so, the B200 (sm_100a) kernels behind the
+ * MGDT-YOLO detection forward path.
+ *
+ * The reference (zzuiekongning/MGDT-YOLO, an Ultralytics 8.0.120 fork) is pure
+ * Python and has no FFI of its own; its "operator
+ * interface" for this path is the nn.Module class surface of nn/modules/ plus
+ * yolo/utils/ops.py:non_max_suppression.  Each entry point below names the
+ * reference op(s) it replaces (paths relative to the reference root).  The
+ * Python modules in mgdt-yolo_b200/modules/ keep the reference's class names,
+ * constructor/forward signatures and state_dict keys and call ONLY these
+ * functions for arithmetic (ctypes).
+ *
+ * Conventions
+ *   - caller owns all memory; the library never allocates device memory and
+ *     keeps no pointer after return;
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*),
+ *     nothing synchronises; every function is CUDA-graph capturable;
+ *   - activations are NHWC ("channels_last") with an explicit channel stride
+ *     `*_cs` (elements between consecutive pixels), so a channel slice of a
+ *     concat buffer is addressed without a copy;
+ *   - dtype: MGDT_F32 (validation mode) or MGDT_BF16 (bf16 storage, fp32 accumulate);
+ *   - return 0 on success, negative errno-style code on failure; the message is
+ *     available (thread-local) from mgdt_last_error().
+ */
+#ifndef MGDT_B200_H
+#define MGDT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGDT_ABI_VERSION 1
+
+enum { MGDT_F32 = 0, MGDT_BF16 = 1 };
+enum { MGDT_ACT_NONE = 0, MGDT_ACT_SILU = 1, MGDT_ACT_RELU = 2, MGDT_ACT_SIGMOID = 3, MGDT_ACT_HSIGMOID = 4,
+       MGDT_ACT_GELU = 5 };
+enum { MGDT_RS_COPY = 0, MGDT_RS_AVGPOOL = 1, MGDT_RS_BILINEAR = 2, MGDT_RS_NEAREST = 3 };
+
+int mgdt_abi_version(void);
+const char* mgdt_last_error(void);
+/* Compiled-in facts for tests: returns 1 if the tcgen05/TMA conv path was built. */
+int mgdt_has_umma(void);
+
+/* ---------------------------------------------------------------- convolution
+ * Replaces Conv.forward/forward_fuse (nn/modules/conv.py:36-42) with BatchNorm folded
+ * (yolo/utils/torch_utils.py:114-135), Bottleneck's residual add (nn/modules/block.py:524-526),
+ * the raw nn.Conv2d leaves of Detect/TOODHead (nn/modules/head.py:150-151,484-493), the
+ * nn.Linear layers of ConvNeXtV2_Block (nn/modules/convnextv2.py:27,30), MSPA_C2f's
+ * `sp + spx[i]` (block.py:253), TaskDecomposition's per-sample reweighted 1x1 (head.py:122-126),
+ * GRN folded into pwconv2 (nn/modules/utils.py:179-182) and `cls_feat * cls_prob` /
+ * `F.relu(reg_feat)` in front of cv3/cv2 (head.py:528).
+ *
+ *   a(n,h,w,c) = relu?( (x + pre_add) * in_scale[n,c] * pix_scale[n,h,w] )
+ *   y = act( conv(a, w) + bias ) + residual
+ *
+ * w is OHWI [Cout][kh][kw][Cin] in `dtype`; bias fp32 [Cout] or NULL; in_scale fp32 [N][Cin].
+ */
+typedef struct mgdt_conv_args {
+    const void* x;         /* (N,H,W,Cin) channel stride x_cs */
+    const void* w;
+    const float* bias;
+    void* y;               /* (N,Ho,Wo,Cout) channel stride y_cs */
+    const void* pre_add;   /* NULL or same shape as x, stride add_cs */
+    const float* in_scale; /* NULL or [N][Cin] */
+    const void* pix_scale; /* NULL or (N,H,W,1) stride ps_cs */
+    const void* residual;  /* NULL or same shape as y, stride res_cs */
+    int32_t N, H, W, Cin, Cout;
+    int32_t kh, kw, stride, pad;
+    int32_t x_cs, y_cs, add_cs, ps_cs, res_cs;
+    int32_t act, in_relu, dtype;
+    int32_t impl;          /* 0 auto, 1 force CUDA-core path, 2 force tcgen05 path */
+} mgdt_conv_args;
+int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
+
+/* Depthwise 7x7 (pad 3, bias) + channels-last LayerNorm(eps), ConvNeXtV2_Block.forward
+ * (nn/modules/convnextv2.py:35-37, nn/modules/utils.py:162-163).  w is [49][C] in dtype,
+ * bias/ln_w/ln_b fp32 [C]. */
+int mgdt_dwconv7_ln(const void* x, int x_cs, const void* w, const float* bias, const float* ln_w, const float* ln_b,
+                    float eps, void* y, int y_cs, int N, int H, int W, int C, int dtype, void* stream);
+
+/* Modulated deformable 3x3 conv, stride 1, pad 1 (DyDCNv2.forward, nn/modules/block.py:427-429;
+ * arithmetic of mmcv ModulatedDeformConv2d / torchvision.ops.deform_conv2d).  offset: 18 channels
+ * ((dy,dx) per tap), mask: 9 channels; with mask_is_logit the sigmoid of head.py:517 is applied
+ * here, so both may be channel slices of the raw spatial_conv_offset output (head.py:515-517).
+ * w is [Cout][9][Cin] in dtype. */
+int mgdt_dcn3x3(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs,
+                int mask_is_logit, const void* w, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, int dtype,
+                void* stream);
+
+/* ---------------------------------------------------------------- reductions
+ * Per-(n,c) sums over the image, optionally per adaptive 2x2 window as well.
+ * quads=0: out_sum[N][1][C];  quads=1: out_sum[N][5][C] = {total, q00, q01, q10, q11} with
+ * adaptive_avg_pool2d(2) windows [floor(i*H/2), ceil((i+1)*H/2)).  out_sumsq (same layout, total
+ * only -> [N][C]) may be NULL.  Feeds SPRModule (spr_module.py:22-24), GRN (utils.py:180),
+ * GroupNorm (head.py:76, block.py:425) and TaskDecomposition's GAP (head.py:507).
+ * Deterministic two-stage reduction; `ws` needs mgdt_chan_stats_ws_bytes(). */
+size_t mgdt_chan_stats_ws_bytes(int N, int H, int W, int C, int quads);
+int mgdt_chan_stats(const void* x, int x_cs, int N, int H, int W, int C, int quads, float* out_sum, float* out_sumsq,
+                    void* ws, size_t ws_bytes, int dtype, void* stream);
+
+/* SPR gate of MSPA_C2f (block.py:270-279 + spr_module.py:20-31): stats[N][5][C] (sums) ->
+ * scale[N][C] = softmax over the `groups` (4) channel groups of sigmoid(fc2(relu(fc1([mean | 2x2 means])))).
+ * fc1_w [hidden][5*ow], fc2_w [ow][hidden] fp32, ow = C/groups.  groups=1, softmax=0 gives
+ * SPRModule.forward alone. */
+int mgdt_mspa_gate(const float* stats, int N, int H, int W, int C, int groups, int softmax, const float* fc1_w,
+                   const float* fc1_b, const float* fc2_w, const float* fc2_b, int hidden, float* scale, void* stream);
+
+/* GRN (utils.py:179-182) as a per-(n,c) input scale for pwconv2: s = 1 + gamma*Gx/(mean_c Gx + 1e-6),
+ * Gx = sqrt(sumsq).  (The beta term is folded into pwconv2's bias by the host.) */
+int mgdt_grn_scale(const float* sumsq, const float* gamma, int N, int C, float* scale, void* stream);
+
+/* GroupNorm finalize: per-(n,c) affine a,b with y = x*a + b  (nn.GroupNorm(groups, C), eps). */
+int mgdt_gn_affine(const float* sum, const float* sumsq, int N, int C, int groups, int hw, float eps,
+                   const float* gamma, const float* beta, float* a, float* b, void* stream);
+
+/* TaskDecomposition layer attention (head.py:116-117): sum[N][C] -> in_scale[which][N][C] for both
+ * `ndec` decompositions at once (weights stacked): sigmoid(la2(relu(la1(mean))))[c / (C/stacked)]. */
+int mgdt_td_attn(const float* sum, int N, int C, int hw, int hidden, int stacked, int ndec, const float* la1_w,
+                 const float* la1_b, const float* la2_w, const float* la2_b, float* in_scale, void* stream);
+
+/* ---------------------------------------------------------------- elementwise / gather
+ * y = act(x * a[n,c] + b[n,c]) (+ other);  a/b may be NULL (1 / 0).  Used for GroupNorm apply
+ * (+SiLU / +ReLU), the MSPA attention scale (block.py:279) and MSPA's sp + spx[3]. */
+int mgdt_affine_act(const void* x, int x_cs, const float* a, const float* b, const void* other, int o_cs, int act,
+                    void* y, int y_cs, int N, int H, int W, int C, int dtype, void* stream);
+
+/* Resample x (N,Hi,Wi,C) into y (N,Ho,Wo,C): copy / adaptive average pool / bilinear
+ * (align_corners=False) / nearest.  SimFusion_4in/3in (block.py:294-329), nn.Upsample + Concat of
+ * the PAN neck (models/v8/yolov8.yaml:30-46), Concat (conv.py:287-297). */
+int mgdt_resample(const void* x, int x_cs, int Hi, int Wi, void* y, int y_cs, int Ho, int Wo, int N, int C, int mode,
+                  int dtype, void* stream);
+
+/* SPPF pooling chain (block.py:151-153): y1 = maxpool5(x), y2 = maxpool5(y1), y3 = maxpool5(y2),
+ * i.e. 5x5 / 9x9 / 13x13 windows (k=5).  x and y1..y3 are slices with the given strides. */
+int mgdt_sppf_pool(const void* x, int x_cs, void* y1, void* y2, void* y3, int y_cs, int N, int H, int W, int C, int k,
+                   int dtype, void* stream);
+
+/* InjectionMultiSum_Auto_pool tail (block.py:385-396): out = local * G(act) + G(feat) where
+ * G = bilinear(align_corners=False) of (h_sigmoid(act), feat) when Hg <= H, else adaptive avg pool
+ * of (act, feat) without h_sigmoid. */
+int mgdt_inject(const void* local, int l_cs, const void* gact, int a_cs, const void* gfeat, int f_cs, void* y, int y_cs,
+                int N, int H, int W, int Hg, int Wg, int C, int dtype, void* stream);
+
+/* uint8 NCHW -> NHWC float/bf16, scaled by 1/255 (BasePredictor.preprocess,
+ * yolo/engine/predictor.py:115-130).  Also float NCHW -> NHWC (scale 1). */
+int mgdt_preprocess(const void* src, int src_is_u8, void* y, int y_cs, int N, int C, int H, int W, int dtype,
+                    void* stream);
+
+/* ---------------------------------------------------------------- decode
+ * Detect/TOODHead inference tail (head.py:165-177,536-559) = DFL (block.py:50-53) + make_anchors /
+ * dist2bbox(xywh) (yolo/utils/tal.py:476-500) + sigmoid + cat.  y is fp32 (N, 4+nc, A).
+ * dist_only=1: DFL.forward alone, y is (N, 4, A) ltrb expectations. */
+typedef struct mgdt_decode_level {
+    const void* raw; /* (N,H,W,4*reg_max+nc) */
+    int32_t H, W, cs;
+    float stride;
+} mgdt_decode_level;
+int mgdt_decode(const mgdt_decode_level* levels, int nl, int N, int reg_max, int nc, int dist_only, float* y, int dtype,
+                void* stream);
+
+/* ---------------------------------------------------------------- NMS
+ * non_max_suppression (yolo/utils/ops.py:136-266) + torchvision.ops.nms, whole batch, no host
+ * sync.  pred fp32 (N, 4+nc, A).  out fp32 (N, max_det, 6) rows (x1,y1,x2,y2,conf,cls); counts
+ * int32 [N].  classes: NULL or int32 list of allowed class ids.  Score ties are broken by
+ * candidate index (anchor-major, then class), i.e. a stable sort. */
+size_t mgdt_nms_ws_bytes(int N, int nc, int A, int multi_label, int max_nms);
+int mgdt_nms(const float* pred, int N, int nc, int A, float conf_thres, float iou_thres, int multi_label, int agnostic,
+             int max_det, int max_nms, float max_wh, const int32_t* classes, int n_classes, float* out,
+             int32_t* counts, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGDT_B200_H */

@@ -1,0 +1,84 @@
+"""ctypes binding of libmgdt_b200.so (include/mgdt_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised with the library's own message.  `python -m
+mgdt_yolo_b200.build` (or `__graft_entry__.build()`) compiles it with nvcc for
+sm_100a; the file travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmgdt_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_SILU, ACT_RELU, ACT_SIGMOID, ACT_HSIGMOID, ACT_GELU = range(6)
+RS_COPY, RS_AVGPOOL, RS_BILINEAR, RS_NEAREST = range(4)
+
+vp, i32, f32, sz = C.c_void_p, C.c_int32, C.c_float, C.c_size_t
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("x", vp), ("w", vp), ("bias", vp), ("y", vp), ("pre_add", vp), ("in_scale", vp), ("pix_scale", vp),
+                ("residual", vp),
+                ("N", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32),
+                ("kh", i32), ("kw", i32), ("stride", i32), ("pad", i32),
+                ("x_cs", i32), ("y_cs", i32), ("add_cs", i32), ("ps_cs", i32), ("res_cs", i32),
+                ("act", i32), ("in_relu", i32), ("dtype", i32), ("impl", i32)]
+
+
+class DecodeLevel(C.Structure):
+    _fields_ = [("raw", vp), ("H", i32), ("W", i32), ("cs", i32), ("stride", f32)]
+
+
+# name -> (restype, argtypes); every symbol include/mgdt_b200.h declares
+SIGNATURES = {
+    "mgdt_abi_version": (C.c_int, []),
+    "mgdt_last_error": (C.c_char_p, []),
+    "mgdt_has_umma": (C.c_int, []),
+    "mgdt_conv2d": (C.c_int, [C.POINTER(ConvArgs), vp]),
+    "mgdt_dwconv7_ln": (C.c_int, [vp, i32, vp, vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_dcn3x3": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_chan_stats_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
+    "mgdt_chan_stats": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, i32, vp]),
+    "mgdt_mspa_gate": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
+    "mgdt_grn_scale": (C.c_int, [vp, vp, i32, i32, vp, vp]),
+    "mgdt_gn_affine": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
+    "mgdt_td_attn": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "mgdt_affine_act": (C.c_int, [vp, i32, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_resample": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_sppf_pool": (C.c_int, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_inject": (C.c_int, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_preprocess": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_decode": (C.c_int, [C.POINTER(DecodeLevel), i32, i32, i32, i32, i32, vp, i32, vp]),
+    "mgdt_nms_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
+    "mgdt_nms": (C.c_int, [vp, i32, i32, i32, f32, f32, i32, i32, i32, i32, f32, vp, i32, vp, vp, vp, sz, vp]),
+}
+
+_LIB = None
+
+
+def lib():
+    """Load (once) and return the CDLL; raises if the library was not built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"mgdt_yolo_b200: {LIB_PATH} is missing -- build it with `python -m mgdt_yolo_b200.build` "
+                "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is missing
+            fn.restype, fn.argtypes = res, args
+        if L.mgdt_abi_version() != 1:
+            raise RuntimeError("mgdt_yolo_b200: ABI version mismatch, rebuild the library")
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().mgdt_last_error().decode(errors="replace")
+        raise RuntimeError(f"mgdt_b200 {what} failed ({rc}): {msg}")

@@ -1,0 +1,255 @@
+// Block-specific kernels: ConvNeXtV2 depthwise 7x7 + LayerNorm, modulated deformable conv
+// (DCNv2), and the DFL / dist2bbox decode.
+#include "common.cuh"
+
+namespace mgdt {
+
+// ------------------------------------------------------------------ dwconv7 + LN
+// One warp per output pixel; lanes stride over channels (NHWC: contiguous), so every tap is a
+// coalesced row read and the LayerNorm reduction is a warp shuffle.  Up to 8 channels per lane
+// (C <= 256) are kept in registers.
+constexpr int DW_WARPS = 8;
+constexpr int DW_MAXPL = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(DW_WARPS * 32) dwconv7_ln_kernel(const T* __restrict__ x, int x_cs,
+                                                                   const T* __restrict__ w, const float* __restrict__ bias,
+                                                                   const float* __restrict__ ln_w,
+                                                                   const float* __restrict__ ln_b, float eps,
+                                                                   T* __restrict__ y, int y_cs, int H, int W, int C,
+                                                                   long long npix) {
+    const int lane = threadIdx.x & 31;
+    const long long pix = (long long)blockIdx.x * DW_WARPS + (threadIdx.x >> 5);
+    if (pix >= npix) return;
+    const int wq = (int)(pix % W);
+    const int hq = (int)((pix / W) % H);
+    const long long n = pix / ((long long)W * H);
+    const T* xn = x + n * (long long)H * W * x_cs;
+    float acc[DW_MAXPL];
+#pragma unroll
+    for (int j = 0; j < DW_MAXPL; ++j) {
+        const int c = lane + 32 * j;
+        acc[j] = (c < C) ? bias[c] : 0.f;
+    }
+    for (int dy = 0; dy < 7; ++dy) {
+        const int hh = hq + dy - 3;
+        if (hh < 0 || hh >= H) continue;
+        for (int dx = 0; dx < 7; ++dx) {
+            const int ww = wq + dx - 3;
+            if (ww < 0 || ww >= W) continue;
+            const T* xp = xn + ((long long)hh * W + ww) * x_cs;
+            const T* wp = w + (dy * 7 + dx) * C;
+#pragma unroll
+            for (int j = 0; j < DW_MAXPL; ++j) {
+                const int c = lane + 32 * j;
+                if (c < C) acc[j] = fmaf(ldf(xp + c), ldf(wp + c), acc[j]);
+            }
+        }
+    }
+    // LayerNorm over C (biased variance, two-pass in registers)
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < DW_MAXPL; ++j)
+        if (lane + 32 * j < C) s += acc[j];
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < DW_MAXPL; ++j)
+        if (lane + 32 * j < C) {
+            const float d = acc[j] - mean;
+            q += d * d;
+        }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    T* yp = y + pix * y_cs;
+#pragma unroll
+    for (int j = 0; j < DW_MAXPL; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) stf(yp + c, (acc[j] - mean) * rstd * ln_w[c] + ln_b[c]);
+    }
+}
+
+// ------------------------------------------------------------------ DCNv2 3x3
+// CTA = DCN_PIX output pixels.  Phase 1 builds the modulated bilinear im2col tile
+// cols[pixel][tap*Cin + ci] in shared memory; phase 2 is a small GEMM against w[Cout][9*Cin].
+constexpr int DCN_PIX = 32;
+constexpr int DCN_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(DCN_THREADS) dcn3x3_kernel(const T* __restrict__ x, int x_cs,
+                                                             const T* __restrict__ off, int off_cs,
+                                                             const T* __restrict__ msk, int msk_cs, int mask_is_logit,
+                                                             const T* __restrict__ w, T* __restrict__ y, int y_cs,
+                                                             int H, int W, int Cin, int Cout, long long npix) {
+    extern __shared__ float cols[];  // [DCN_PIX][K + 1]
+    const int K = 9 * Cin;
+    const int ld = K + 1;
+    const long long p0 = (long long)blockIdx.x * DCN_PIX;
+    // phase 1: thread <-> (pixel, tap, ci) with ci fastest
+    for (int e = threadIdx.x; e < DCN_PIX * K; e += DCN_THREADS) {
+        const int ci = e % Cin;
+        const int tap = (e / Cin) % 9;
+        const int pl = e / K;
+        const long long pix = p0 + pl;
+        float v = 0.f;
+        if (pix < npix) {
+            const int wq = (int)(pix % W);
+            const int hq = (int)((pix / W) % H);
+            const long long n = pix / ((long long)W * H);
+            const T* ofp = off + pix * off_cs;
+            const float dy = ldf(ofp + 2 * tap), dx = ldf(ofp + 2 * tap + 1);
+            float m = ldf(msk + pix * msk_cs + tap);
+            if (mask_is_logit) m = sigmoidf_(m);
+            const float py = (float)(hq + tap / 3 - 1) + dy;
+            const float px = (float)(wq + tap % 3 - 1) + dx;
+            if (py > -1.f && py < (float)H && px > -1.f && px < (float)W) {
+                const int y0 = (int)floorf(py), x0 = (int)floorf(px);
+                const float ly = py - (float)y0, lx = px - (float)x0;
+                const float hy = 1.f - ly, hx = 1.f - lx;
+                const T* xn = x + n * (long long)H * W * x_cs + ci;
+                float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
+                if (y0 >= 0 && x0 >= 0) v00 = ldf(xn + ((long long)y0 * W + x0) * x_cs);
+                if (y0 >= 0 && x0 + 1 <= W - 1) v01 = ldf(xn + ((long long)y0 * W + x0 + 1) * x_cs);
+                if (y0 + 1 <= H - 1 && x0 >= 0) v10 = ldf(xn + ((long long)(y0 + 1) * W + x0) * x_cs);
+                if (y0 + 1 <= H - 1 && x0 + 1 <= W - 1) v11 = ldf(xn + ((long long)(y0 + 1) * W + x0 + 1) * x_cs);
+                v = (hy * hx * v00 + hy * lx * v01 + ly * hx * v10 + ly * lx * v11) * m;
+            }
+        }
+        cols[pl * ld + tap * Cin + ci] = v;
+    }
+    __syncthreads();
+    // phase 2: thread <-> (pixel, cout) pairs, cout fastest
+    for (int e = threadIdx.x; e < DCN_PIX * Cout; e += DCN_THREADS) {
+        const int co = e % Cout, pl = e / Cout;
+        const long long pix = p0 + pl;
+        if (pix >= npix) continue;
+        const T* wr = w + (long long)co * K;
+        const float* cr = cols + pl * ld;
+        float a = 0.f;
+        for (int k = 0; k < K; ++k) a = fmaf(cr[k], ldf(wr + k), a);
+        stf(y + pix * y_cs + co, a);
+    }
+}
+
+// ------------------------------------------------------------------ decode
+struct DecodeLevels {
+    const void* raw[4];
+    int H[4], W[4], cs[4], a0[4];
+    float stride[4];
+    int nl, A;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) decode_kernel(DecodeLevels L, int reg_max, int nc, int dist_only,
+                                                     float* __restrict__ y) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (a >= L.A) return;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (i < L.nl && a >= L.a0[i]) l = i;
+    const int la = a - L.a0[l];
+    const int Wl = L.W[l], Hl = L.H[l];
+    const int hq = la / Wl, wq = la - hq * Wl;
+    const T* p = (const T*)L.raw[l] + ((long long)n * Hl * Wl + la) * L.cs[l];
+    float d[4];
+    for (int side = 0; side < 4; ++side) {
+        if (reg_max > 1) {
+            // softmax over reg_max bins, expectation with weights 0..reg_max-1 (DFL)
+            float mx = -INFINITY;
+            for (int k = 0; k < reg_max; ++k) mx = fmaxf(mx, ldf(p + side * reg_max + k));
+            float den = 0.f, num = 0.f;
+            for (int k = 0; k < reg_max; ++k) {
+                const float e = expf(ldf(p + side * reg_max + k) - mx);
+                den += e;
+                num += e * (float)k;
+            }
+            d[side] = num / den;
+        } else {
+            d[side] = ldf(p + side);
+        }
+    }
+    if (dist_only) {  // DFL.forward alone (block.py:50-53): (N, 4, A) expectations
+        float* yd = y + (long long)n * 4 * L.A + a;
+        for (int side = 0; side < 4; ++side) yd[(long long)side * L.A] = d[side];
+        return;
+    }
+    const float ax = (float)wq + 0.5f, ay = (float)hq + 0.5f, st = L.stride[l];
+    const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+    float* yo = y + (long long)n * (4 + nc) * L.A + a;
+    yo[0] = (x1 + x2) / 2.f * st;
+    yo[(long long)L.A] = (y1 + y2) / 2.f * st;
+    yo[2LL * L.A] = (x2 - x1) * st;
+    yo[3LL * L.A] = (y2 - y1) * st;
+    const T* pc = p + 4 * reg_max;
+    for (int j = 0; j < nc; ++j) yo[(4LL + j) * L.A] = sigmoidf_(ldf(pc + j));
+}
+
+}  // namespace mgdt
+
+using namespace mgdt;
+
+extern "C" int mgdt_dwconv7_ln(const void* x, int x_cs, const void* w, const float* bias, const float* ln_w,
+                               const float* ln_b, float eps, void* y, int y_cs, int N, int H, int W, int C, int dtype,
+                               void* stream) {
+    MGDT_CHECK(x && w && bias && ln_w && ln_b && y, "dwconv7_ln: null pointer");
+    MGDT_CHECK(N > 0 && H > 0 && W > 0 && C > 0 && C <= 32 * DW_MAXPL, "dwconv7_ln: C=%d unsupported (max %d)", C,
+               32 * DW_MAXPL);
+    MGDT_CHECK(x_cs >= C && y_cs >= C, "dwconv7_ln: bad strides");
+    const long long npix = (long long)N * H * W;
+    MGDT_DTYPE_SWITCH(dtype, T, {
+        dwconv7_ln_kernel<T><<<cdiv(npix, DW_WARPS), DW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            (const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps, (T*)y, y_cs, H, W, C, npix);
+    });
+    MGDT_LAUNCH_CHECK("dwconv7_ln");
+    return 0;
+}
+
+extern "C" int mgdt_dcn3x3(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs,
+                           int mask_is_logit, const void* w, void* y, int y_cs, int N, int H, int W, int Cin, int Cout,
+                           int dtype, void* stream) {
+    MGDT_CHECK(x && offset && mask && w && y, "dcn3x3: null pointer");
+    MGDT_CHECK(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && off_cs >= 18 && mask_cs >= 9, "dcn3x3: bad shape");
+    const size_t smem = sizeof(float) * DCN_PIX * (9 * Cin + 1);
+    MGDT_CHECK(smem <= 200 * 1024, "dcn3x3: Cin=%d too large", Cin);
+    const long long npix = (long long)N * H * W;
+    cudaStream_t s = (cudaStream_t)stream;
+    MGDT_DTYPE_SWITCH(dtype, T, {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(dcn3x3_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return set_error(-EIO, "dcn3x3: smem attr: %s", cudaGetErrorString(e));
+        }
+        dcn3x3_kernel<T><<<cdiv(npix, DCN_PIX), DCN_THREADS, smem, s>>>((const T*)x, x_cs, (const T*)offset, off_cs,
+                                                                        (const T*)mask, mask_cs, mask_is_logit,
+                                                                        (const T*)w, (T*)y, y_cs, H, W, Cin, Cout, npix);
+    });
+    MGDT_LAUNCH_CHECK("dcn3x3");
+    return 0;
+}
+
+extern "C" int mgdt_decode(const mgdt_decode_level* levels, int nl, int N, int reg_max, int nc, int dist_only, float* y,
+                           int dtype, void* stream) {
+    MGDT_CHECK(levels && y, "decode: null pointer");
+    MGDT_CHECK(nl >= 1 && nl <= 4, "decode: 1..4 levels supported, got %d", nl);
+    MGDT_CHECK(N > 0 && reg_max >= 1 && reg_max <= 64 && nc >= 0, "decode: bad shape");
+    DecodeLevels L;
+    L.nl = nl;
+    int a0 = 0;
+    for (int i = 0; i < 4; ++i) {
+        if (i < nl) {
+            MGDT_CHECK(levels[i].raw && levels[i].H > 0 && levels[i].W > 0 && levels[i].cs >= 4 * reg_max + nc,
+                       "decode: bad level %d", i);
+            L.raw[i] = levels[i].raw; L.H[i] = levels[i].H; L.W[i] = levels[i].W; L.cs[i] = levels[i].cs;
+            L.stride[i] = levels[i].stride; L.a0[i] = a0;
+            a0 += levels[i].H * levels[i].W;
+        } else {
+            L.raw[i] = nullptr; L.H[i] = L.W[i] = L.cs[i] = 0; L.stride[i] = 0.f; L.a0[i] = 0x7fffffff;
+        }
+    }
+    L.A = a0;
+    MGDT_DTYPE_SWITCH(dtype, T, {
+        decode_kernel<T><<<dim3(cdiv(L.A, 128), N), 128, 0, (cudaStream_t)stream>>>(L, reg_max, nc, dist_only, y);
+    });
+    MGDT_LAUNCH_CHECK("decode");
+    return 0;
+}

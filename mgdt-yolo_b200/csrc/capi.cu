@@ -1,0 +1,55 @@
+// C-ABI glue: error strings, version, conv dispatch between the CUDA-core and tcgen05 paths.
+#include "common.cuh"
+
+namespace mgdt {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int conv2d_direct(const mgdt_conv_args* a, cudaStream_t s);
+#ifdef MGDT_WITH_UMMA
+bool conv2d_umma_supported(const mgdt_conv_args* a);
+int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s);
+#endif
+
+}  // namespace mgdt
+
+using namespace mgdt;
+
+extern "C" int mgdt_abi_version(void) { return MGDT_ABI_VERSION; }
+extern "C" const char* mgdt_last_error(void) { return g_err; }
+extern "C" int mgdt_has_umma(void) {
+#ifdef MGDT_WITH_UMMA
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+extern "C" int mgdt_conv2d(const mgdt_conv_args* a, void* stream) {
+    MGDT_CHECK(a, "conv2d: null args");
+    MGDT_CHECK(a->x && a->w && a->y, "conv2d: null tensor pointer");
+    MGDT_CHECK(a->N > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "conv2d: bad shape");
+    MGDT_CHECK(a->kh > 0 && a->kw > 0 && a->stride > 0 && a->pad >= 0, "conv2d: bad kernel/stride/pad");
+    MGDT_CHECK(a->H + 2 * a->pad >= a->kh && a->W + 2 * a->pad >= a->kw, "conv2d: kernel larger than padded input");
+    MGDT_CHECK(a->x_cs >= a->Cin && a->y_cs >= a->Cout, "conv2d: channel stride smaller than channel count");
+    MGDT_CHECK(!a->pre_add || a->add_cs >= a->Cin, "conv2d: bad pre_add stride");
+    MGDT_CHECK(!a->residual || a->res_cs >= a->Cout, "conv2d: bad residual stride");
+    MGDT_CHECK(!a->pix_scale || a->ps_cs >= 1, "conv2d: bad pix_scale stride");
+    MGDT_CHECK(a->act >= MGDT_ACT_NONE && a->act <= MGDT_ACT_GELU, "conv2d: bad act %d", a->act);
+    cudaStream_t s = (cudaStream_t)stream;
+#ifdef MGDT_WITH_UMMA
+    if (a->impl != 1 && conv2d_umma_supported(a)) return conv2d_umma(a, s);
+    MGDT_CHECK(a->impl != 2, "conv2d: tcgen05 path does not support this shape");
+#else
+    MGDT_CHECK(a->impl != 2, "conv2d: library built without the tcgen05 path");
+#endif
+    return conv2d_direct(a, s);
+}

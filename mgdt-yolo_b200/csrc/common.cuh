@@ -1,0 +1,73 @@
+// Shared device/host helpers for libmgdt_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mgdt_b200.h"
+
+namespace mgdt {
+
+// ---- error plumbing (thread-local message, errno-style negative return codes)
+int set_error(int code, const char* fmt, ...);
+
+#define MGDT_CHECK(cond, ...)                                   \
+    do {                                                        \
+        if (!(cond)) return ::mgdt::set_error(-EINVAL, __VA_ARGS__); \
+    } while (0)
+
+#define MGDT_LAUNCH_CHECK(name)                                                              \
+    do {                                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                                 \
+        if (e_ != cudaSuccess) return ::mgdt::set_error(-EIO, "%s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- storage-type helpers: T is float or __nv_bfloat16, arithmetic is always fp32
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case MGDT_ACT_SILU: return v / (1.0f + expf(-v));
+        case MGDT_ACT_RELU: return fmaxf(v, 0.0f);
+        case MGDT_ACT_SIGMOID: return sigmoidf_(v);
+        case MGDT_ACT_HSIGMOID: return fminf(fmaxf(v + 3.0f, 0.0f), 6.0f) / 6.0f;
+        case MGDT_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Dispatch a templated launch on the runtime dtype.
+#define MGDT_DTYPE_SWITCH(dtype, T, ...)                                      \
+    do {                                                                      \
+        if ((dtype) == MGDT_F32) {                                            \
+            using T = float;                                                  \
+            __VA_ARGS__;                                                      \
+        } else if ((dtype) == MGDT_BF16) {                                    \
+            using T = __nv_bfloat16;                                          \
+            __VA_ARGS__;                                                      \
+        } else {                                                              \
+            return ::mgdt::set_error(-EINVAL, "unsupported dtype %d", (int)(dtype)); \
+        }                                                                     \
+    } while (0)
+
+}  // namespace mgdt

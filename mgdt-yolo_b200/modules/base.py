@@ -1,0 +1,64 @@
+"""Common machinery of the drop-in modules.
+
+Every class keeps the reference's name, constructor signature, attribute names and state_dict
+keys; its parameters live in ordinary torch containers (nn.Conv2d,
+nn.BatchNorm2d, ...) that are never *called* -- `forward` packs them once per (dtype, device,
+parameter version) into the kernels' layouts and dispatches through the C ABI.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class KernelModule(nn.Module):
+    """nn.Module whose forward runs sm_100a kernels (eval mode, CUDA tensors only)."""
+
+    def _packed(self, name, dtype, device, tensors, builder):
+        cache = self.__dict__.setdefault("_pk", {})
+        key = (dtype, device, tuple((t.data_ptr(), t._version) for t in tensors))
+        hit = cache.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        with torch.no_grad():
+            val = builder()
+        cache[name] = (key, val)
+        return val
+
+    def _check_mode(self, x):
+        t = x[0] if isinstance(x, (list, tuple)) else x
+        ops.require_cuda(t, f"{type(self).__name__} input")
+        if self.training:
+            raise NotImplementedError(
+                f"{type(self).__name__}: the B200 path implements the inference forward (call .eval()); the "
+                "training step is outside the accelerated hot path (DESIGN.md, out of scope).")
+
+    def __getstate__(self):  # packed caches hold device pointers; never pickle them
+        d = dict(self.__dict__)
+        d.pop("_pk", None)
+        return d
+
+
+def act_name(m) -> str | None:
+    if m is None or isinstance(m, nn.Identity):
+        return None
+    if isinstance(m, nn.SiLU):
+        return "silu"
+    if isinstance(m, nn.ReLU):
+        return "relu"
+    if isinstance(m, nn.Sigmoid):
+        return "sigmoid"
+    if isinstance(m, nn.GELU):
+        return "gelu"
+    raise NotImplementedError(f"activation {type(m).__name__} has no fused epilogue in mgdt_b200")
+
+
+def ohwi(w: torch.Tensor, dtype, device) -> torch.Tensor:
+    """(Cout, Cin, kh, kw) -> contiguous (Cout, kh, kw, Cin) in the compute dtype."""
+    return w.detach().to(device=device, dtype=torch.float32).permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()

@@ -1,0 +1,320 @@
+"""Tensor-level wrappers over the C ABI (torch is used for device memory and streams only).
+
+Activations are torch CUDA tensors with logical shape (N, C, H, W) and NHWC physical layout
+("channels_last", possibly a channel slice of a wider buffer).  `view(t)` validates that layout
+and yields the raw pointer + channel stride the kernels take.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_HSIGMOID, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, BF16, F32, RS_AVGPOOL,  # noqa: F401
+                   RS_BILINEAR, RS_COPY, RS_NEAREST, ConvArgs, DecodeLevel, check, lib)
+
+ACTS = {None: ACT_NONE, "none": ACT_NONE, "silu": ACT_SILU, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID,
+        "hsigmoid": ACT_HSIGMOID, "gelu": ACT_GELU}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise TypeError(f"mgdt_b200 computes in float32 (validation) or bfloat16; got {dt}")
+
+
+def require_cuda(t: torch.Tensor, what: str = "input"):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"mgdt_b200: {what} is on {t.device}; this path runs only as sm_100a CUDA kernels -- there is no CPU "
+            "fallback (move the model and tensors to a B200 device).")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def new_act(n, c, h, w, dtype, device) -> torch.Tensor:
+    """(N,C,H,W)-shaped tensor with dense NHWC storage."""
+    return torch.empty((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def _cs(t: torch.Tensor):
+    """Channel stride of an NHWC-laid-out (N,C,H,W) tensor, or None if it is not one."""
+    n, c, h, w = t.shape
+    s0, s1, s2, s3 = t.stride()
+    if w > 1:
+        cs = s3
+    elif h > 1:
+        cs = s2
+    elif n > 1:
+        cs = s0
+    else:
+        cs = c
+    ok = (cs >= c and (c == 1 or s1 == 1) and (w == 1 or s3 == cs) and (h == 1 or s2 == w * cs)
+          and (n == 1 or s0 == h * w * cs))
+    return cs if ok else None
+
+
+def as_act(t: torch.Tensor, dtype: torch.dtype | None = None) -> torch.Tensor:
+    """Bring any (N,C,H,W) tensor into NHWC storage (no copy if it already is)."""
+    require_cuda(t)
+    if t.dim() != 4:
+        raise ValueError(f"expected a 4-D (N,C,H,W) tensor, got shape {tuple(t.shape)}")
+    if dtype is None:
+        dtype = torch.bfloat16 if t.dtype in (torch.bfloat16, torch.float16) else torch.float32
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if _cs(t) is None:
+        t = t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    return t
+
+
+def view(t: torch.Tensor):
+    """-> (ptr, N, C, H, W, channel_stride) of a conforming tensor."""
+    cs = _cs(t)
+    if cs is None:
+        raise ValueError(f"tensor with shape {tuple(t.shape)} strides {t.stride()} is not NHWC-laid-out")
+    n, c, h, w = t.shape
+    return t.data_ptr(), n, c, h, w, cs
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------- conv
+def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scale=None, pix_scale=None,
+           residual=None, in_relu=False, cout=None, impl=0):
+    """y = act(conv((x + pre_add) * in_scale[n,c] * pix_scale[n,h,w] |> relu?, w) + bias) + residual.
+    `w` is OHWI (Cout, k, k, Cin) in x's dtype; `out` may be a channel slice of a concat buffer."""
+    xp, n, cin, h, wd, xcs = view(x)
+    cout = cout if cout is not None else w.shape[0]
+    p = k // 2 if p is None else p
+    ho, wo = (h + 2 * p - k) // s + 1, (wd + 2 * p - k) // s + 1
+    if out is None:
+        out = new_act(n, cout, ho, wo, x.dtype, x.device)
+    yp, yn, yc, yh, yw, ycs = view(out)
+    if (yn, yc, yh, yw) != (n, cout, ho, wo):
+        raise ValueError(f"conv2d: out shape {tuple(out.shape)} != {(n, cout, ho, wo)}")
+    if w.dtype != x.dtype or out.dtype != x.dtype:
+        raise TypeError("conv2d: x, w and out must share one dtype")
+    a = ConvArgs()
+    a.x, a.w, a.bias, a.y = xp, w.data_ptr(), _p(bias), yp
+    a.N, a.H, a.W, a.Cin, a.Cout = n, h, wd, cin, cout
+    a.kh = a.kw = k
+    a.stride, a.pad = s, p
+    a.x_cs, a.y_cs = xcs, ycs
+    if pre_add is not None:
+        ap, an, ac, ah, aw, acs = view(pre_add)
+        if (an, ac, ah, aw) != (n, cin, h, wd) or pre_add.dtype != x.dtype:
+            raise ValueError("conv2d: pre_add must match x")
+        a.pre_add, a.add_cs = ap, acs
+    if in_scale is not None:
+        if in_scale.dtype != torch.float32 or in_scale.numel() != n * cin or not in_scale.is_contiguous():
+            raise ValueError("conv2d: in_scale must be contiguous fp32 [N, Cin]")
+        a.in_scale = in_scale.data_ptr()
+    if pix_scale is not None:
+        pp, pn, pc, ph, pw, pcs = view(pix_scale)
+        if (pn, pc, ph, pw) != (n, 1, h, wd) or pix_scale.dtype != x.dtype:
+            raise ValueError("conv2d: pix_scale must be (N,1,H,W) in x's dtype")
+        a.pix_scale, a.ps_cs = pp, pcs
+    if residual is not None:
+        rp, rn, rc, rh, rw, rcs = view(residual)
+        if (rn, rc, rh, rw) != (n, cout, ho, wo) or residual.dtype != x.dtype:
+            raise ValueError("conv2d: residual must match the output")
+        a.residual, a.res_cs = rp, rcs
+    a.act = ACTS[act] if not isinstance(act, int) else act
+    a.in_relu = 1 if in_relu else 0
+    a.dtype = dtype_code(x.dtype)
+    a.impl = impl
+    check(lib().mgdt_conv2d(C.byref(a), stream_ptr()), "conv2d")
+    return out
+
+
+def dwconv7_ln(x, w49c, bias, ln_w, ln_b, eps=1e-6, out=None):
+    xp, n, c, h, w, xcs = view(x)
+    if out is None:
+        out = new_act(n, c, h, w, x.dtype, x.device)
+    yp, *_, ycs = view(out)
+    check(lib().mgdt_dwconv7_ln(xp, xcs, w49c.data_ptr(), bias.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), eps, yp,
+                                ycs, n, h, w, c, dtype_code(x.dtype), stream_ptr()), "dwconv7_ln")
+    return out
+
+
+def dcn3x3(x, offset, mask, w, cout, mask_is_logit, out=None):
+    xp, n, cin, h, wd, xcs = view(x)
+    op, on, oc, oh, ow, ocs = view(offset)
+    mp, mn, mc, mh, mw, mcs = view(mask)
+    if (on, oc, oh, ow) != (n, 18, h, wd) or (mn, mc, mh, mw) != (n, 9, h, wd):
+        raise ValueError("dcn3x3: offset must be (N,18,H,W) and mask (N,9,H,W)")
+    if offset.dtype != x.dtype or mask.dtype != x.dtype:
+        raise TypeError("dcn3x3: x, offset and mask must share one dtype")
+    if out is None:
+        out = new_act(n, cout, h, wd, x.dtype, x.device)
+    yp, *_, ycs = view(out)
+    check(lib().mgdt_dcn3x3(xp, xcs, op, ocs, mp, mcs, 1 if mask_is_logit else 0, w.data_ptr(), yp, ycs, n, h, wd,
+                            cin, cout, dtype_code(x.dtype), stream_ptr()), "dcn3x3")
+    return out
+
+
+# ------------------------------------------------------------------------------------- reductions
+def chan_stats(x, quads=False, sumsq=False):
+    """-> (sum [N, 5|1, C] fp32, sumsq [N, C] fp32 | None)."""
+    xp, n, c, h, w, xcs = view(x)
+    q = 5 if quads else 1
+    s = torch.empty((n, q, c), dtype=torch.float32, device=x.device)
+    ss = torch.empty((n, c), dtype=torch.float32, device=x.device) if sumsq else None
+    nbytes = lib().mgdt_chan_stats_ws_bytes(n, h, w, c, 1 if quads else 0)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    check(lib().mgdt_chan_stats(xp, xcs, n, h, w, c, 1 if quads else 0, s.data_ptr(), _p(ss), ws.data_ptr(), nbytes,
+                                dtype_code(x.dtype), stream_ptr()), "chan_stats")
+    return s, ss
+
+
+def mspa_gate(stats, h, w, c, fc1_w, fc1_b, fc2_w, fc2_b, groups=4, softmax=True):
+    n = stats.shape[0]
+    scale = torch.empty((n, c), dtype=torch.float32, device=stats.device)
+    check(lib().mgdt_mspa_gate(stats.data_ptr(), n, h, w, c, groups, 1 if softmax else 0, fc1_w.data_ptr(),
+                               fc1_b.data_ptr(), fc2_w.data_ptr(), fc2_b.data_ptr(), fc1_w.shape[0], scale.data_ptr(),
+                               stream_ptr()), "mspa_gate")
+    return scale
+
+
+def grn_scale(sumsq, gamma):
+    n, c = sumsq.shape
+    scale = torch.empty((n, c), dtype=torch.float32, device=sumsq.device)
+    check(lib().mgdt_grn_scale(sumsq.data_ptr(), gamma.data_ptr(), n, c, scale.data_ptr(), stream_ptr()), "grn_scale")
+    return scale
+
+
+def gn_affine(s, ss, groups, hw, eps, gamma, beta):
+    n, c = ss.shape
+    a = torch.empty((n, c), dtype=torch.float32, device=ss.device)
+    b = torch.empty((n, c), dtype=torch.float32, device=ss.device)
+    check(lib().mgdt_gn_affine(s.data_ptr(), ss.data_ptr(), n, c, groups, hw, eps, gamma.data_ptr(), beta.data_ptr(),
+                               a.data_ptr(), b.data_ptr(), stream_ptr()), "gn_affine")
+    return a, b
+
+
+def td_attn(s, hw, la1_w, la1_b, la2_w, la2_b, stacked):
+    """s [N,1,C] sums -> in_scale [ndec, N, C]; weights are stacked over the decompositions:
+    la1_w [ndec, hidden, C], la1_b [ndec, hidden], la2_w [ndec, stacked, hidden], la2_b [ndec, stacked]."""
+    n, c = s.shape[0], s.shape[-1]
+    ndec, hidden = la1_w.shape[0], la1_w.shape[1]
+    out = torch.empty((ndec, n, c), dtype=torch.float32, device=s.device)
+    check(lib().mgdt_td_attn(s.data_ptr(), n, c, hw, hidden, stacked, ndec, la1_w.data_ptr(), la1_b.data_ptr(),
+                             la2_w.data_ptr(), la2_b.data_ptr(), out.data_ptr(), stream_ptr()), "td_attn")
+    return out
+
+
+# ------------------------------------------------------------------------------------- elementwise
+def affine_act(x, a=None, b=None, act=None, other=None, out=None):
+    xp, n, c, h, w, xcs = view(x)
+    if out is None:
+        out = new_act(n, c, h, w, x.dtype, x.device)
+    yp, *_, ycs = view(out)
+    op, ocs = None, 0
+    if other is not None:
+        op, on, oc, oh, ow, ocs = view(other)
+        if (on, oc, oh, ow) != (n, c, h, w):
+            raise ValueError("affine_act: other must match x")
+    check(lib().mgdt_affine_act(xp, xcs, _p(a), _p(b), op, ocs, ACTS[act], yp, ycs, n, h, w, c, dtype_code(x.dtype),
+                                stream_ptr()), "affine_act")
+    return out
+
+
+def resample(x, ho, wo, mode, out=None):
+    xp, n, c, h, w, xcs = view(x)
+    if out is None:
+        out = new_act(n, c, ho, wo, x.dtype, x.device)
+    yp, yn, yc, yh, yw, ycs = view(out)
+    if (yn, yc, yh, yw) != (n, c, ho, wo):
+        raise ValueError(f"resample: out shape {tuple(out.shape)} != {(n, c, ho, wo)}")
+    check(lib().mgdt_resample(xp, xcs, h, w, yp, ycs, ho, wo, n, c, mode, dtype_code(x.dtype), stream_ptr()),
+          "resample")
+    return out
+
+
+def sppf_pool(x, y1, y2, y3, k=5):
+    xp, n, c, h, w, xcs = view(x)
+    p1, *_, ycs = view(y1)
+    p2, *_, ycs2 = view(y2)
+    p3, *_, ycs3 = view(y3)
+    assert ycs == ycs2 == ycs3
+    check(lib().mgdt_sppf_pool(xp, xcs, p1, p2, p3, ycs, n, h, w, c, k, dtype_code(x.dtype), stream_ptr()), "sppf_pool")
+
+
+def inject(local, gact, gfeat, out=None):
+    lp, n, c, h, w, lcs = view(local)
+    ap, an, ac, hg, wg, acs = view(gact)
+    fp, fn, fc, fh, fw, fcs = view(gfeat)
+    if (an, ac) != (n, c) or (fn, fc, fh, fw) != (an, ac, hg, wg):
+        raise ValueError("inject: shape mismatch")
+    if out is None:
+        out = new_act(n, c, h, w, local.dtype, local.device)
+    yp, *_, ycs = view(out)
+    check(lib().mgdt_inject(lp, lcs, ap, acs, fp, fcs, yp, ycs, n, h, w, hg, wg, c, dtype_code(local.dtype),
+                            stream_ptr()), "inject")
+    return out
+
+
+def preprocess(src: torch.Tensor, dtype: torch.dtype, out=None):
+    """uint8 or float32 NCHW-contiguous (N,C,H,W) -> NHWC `dtype`; uint8 is divided by 255."""
+    require_cuda(src)
+    if not src.is_contiguous() or src.dtype not in (torch.uint8, torch.float32):
+        raise ValueError("preprocess: source must be a contiguous uint8/float32 NCHW tensor")
+    n, c, h, w = src.shape
+    if out is None:
+        out = new_act(n, c, h, w, dtype, src.device)
+    yp, *_, ycs = view(out)
+    check(lib().mgdt_preprocess(src.data_ptr(), 1 if src.dtype == torch.uint8 else 0, yp, ycs, n, c, h, w,
+                                dtype_code(dtype), stream_ptr()), "preprocess")
+    return out
+
+
+# ------------------------------------------------------------------------------------- decode / NMS
+def decode(raws, strides, reg_max, nc, out=None, dist_only=False):
+    n = raws[0].shape[0]
+    levels = (DecodeLevel * len(raws))()
+    total = 0
+    for i, (r, s) in enumerate(zip(raws, strides)):
+        rp, rn, rc, rh, rw, rcs = view(r)
+        if rc != 4 * reg_max + nc:
+            raise ValueError("decode: raw map has the wrong channel count")
+        levels[i].raw, levels[i].H, levels[i].W, levels[i].cs, levels[i].stride = rp, rh, rw, rcs, float(s)
+        total += rh * rw
+    if out is None:
+        out = torch.empty((n, 4 if dist_only else 4 + nc, total), dtype=torch.float32, device=raws[0].device)
+    check(lib().mgdt_decode(levels, len(raws), n, reg_max, nc, 1 if dist_only else 0, out.data_ptr(),
+                            dtype_code(raws[0].dtype),
+                            stream_ptr()), "decode")
+    return out
+
+
+def nms_packed(pred, conf_thres, iou_thres, multi_label=False, agnostic=False, max_det=300, max_nms=30000,
+               max_wh=7680.0, classes=None, out=None, counts=None, ws=None):
+    """-> (out [N, max_det, 6] fp32, counts [N] int32), all on device, no synchronisation."""
+    require_cuda(pred, "prediction")
+    if pred.dtype != torch.float32 or not pred.is_contiguous():
+        pred = pred.float().contiguous()
+    n, ch, a = pred.shape
+    nc = ch - 4
+    nbytes = lib().mgdt_nms_ws_bytes(n, nc, a, 1 if multi_label else 0, max_nms)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=pred.device)
+    if out is None:
+        out = torch.empty((n, max_det, 6), dtype=torch.float32, device=pred.device)
+    if counts is None:
+        counts = torch.empty((n,), dtype=torch.int32, device=pred.device)
+    cls_t = None
+    if classes is not None:
+        cls_t = torch.as_tensor(list(classes), dtype=torch.int32, device=pred.device)
+    check(lib().mgdt_nms(pred.data_ptr(), n, nc, a, float(conf_thres), float(iou_thres), 1 if multi_label else 0,
+                         1 if agnostic else 0, max_det, max_nms, float(max_wh), _p(cls_t),
+                         0 if cls_t is None else cls_t.numel(), out.data_ptr(), counts.data_ptr(), ws.data_ptr(),
+                         ws.numel(), stream_ptr()), "nms")
+    return out, counts

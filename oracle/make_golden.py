@@ -1,0 +1,116 @@
+"""TEST INFRASTRUCTURE -- golden-vector generator (runs ONLY in the build container).
+
+Runs the LIVE, unmodified reference (/root/reference through oracle/ref_live.py)
+on synthetic weights/inputs from mgdt_yolo_b200.synth and writes small fixtures
+to tests/golden/.  The fixtures hold OUTPUTS only; weights and inputs are
+regenerated from the (seed, key-name) recipe on the consumer side, so the same
+file pins the oracle on CPU and the CUDA path on the GPU box.
+
+    python oracle/make_golden.py            # regenerate everything
+
+Fixture index (tests/golden/):
+  model_<cfg>.npz    y, raw maps (B=2, 64x96) + every layer output (B=1, 64x64), un-fused eval
+  modules.npz        one entry per module class on odd/ragged shapes
+  nms.npz            reference non_max_suppression outputs for a parameter grid
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from mgdt_yolo_b200.synth import synth_images, synth_predictions, synth_state_dict  # noqa: E402
+from oracle import ref_live  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+from oracle.cases import LAYER_CFGS, MODEL_CFGS, MODULE_CASES, NMS_CASES, module_inputs  # noqa: E402
+
+
+def gen_models():
+    for cfg in MODEL_CFGS:
+        m = ref_live.build_model(cfg)
+        m.load_state_dict(synth_state_dict(m.state_dict(), seed=1))
+        m.eval()
+        blob = {}
+        with torch.inference_mode():
+            y, raw = m(synth_images(2, h=64, w=96, seed=0))
+            blob["y"] = y.numpy()
+            for i, r in enumerate(raw):
+                blob[f"raw{i}"] = r.numpy()
+            if cfg in LAYER_CFGS:
+                x = synth_images(1, h=64, w=64, seed=5)
+                ys, cur = [], x
+                for layer in m.model:  # BaseModel._predict_once (nn/tasks.py:78-84), keeping every output
+                    if layer.f != -1:
+                        cur = ys[layer.f] if isinstance(layer.f, int) else [cur if j == -1 else ys[j] for j in layer.f]
+                    cur = layer(cur)
+                    ys.append(cur)
+                    if isinstance(cur, torch.Tensor):
+                        blob[f"layer{layer.i}"] = cur.numpy()
+                blob["y1"] = cur[0].numpy()
+        blob["n_params"] = np.int64(sum(p.numel() for p in m.parameters()))
+        blob["keys"] = np.array(list(m.state_dict().keys()))
+        blob["shapes"] = np.array([",".join(map(str, v.shape)) for v in m.state_dict().values()])
+        path = os.path.join(OUT, f"model_{cfg[:-5]}.npz")
+        np.savez_compressed(path, **blob)
+        print(path, os.path.getsize(path) // 1024, "KiB")
+
+
+def gen_modules():
+    ref_live.load()
+    import ultralytics.nn.modules as M
+    import ultralytics.nn.modules.head as H
+    ns = {k: getattr(M, k) for k in dir(M)}
+    ns.update(Conv_GN=H.Conv_GN, TaskDecomposition=H.TaskDecomposition)
+    blob = {}
+    from ultralytics.yolo.utils.torch_utils import initialize_weights
+    for name, ctor, shapes, is_list in MODULE_CASES:
+        torch.manual_seed(0)
+        mod = eval(ctor, ns)
+        initialize_weights(mod)  # BN eps = 1e-3 (torch_utils.py:254-256)
+        if hasattr(mod, "stride") and isinstance(mod.stride, torch.Tensor):
+            mod.stride = torch.tensor([8.0 * 2 ** i for i in range(len(shapes))])
+        mod.load_state_dict(synth_state_dict(mod.state_dict(), seed=7))
+        mod.eval()
+        xs = module_inputs(name, shapes)
+        with torch.inference_mode():
+            out = mod([t.clone() for t in xs]) if is_list else mod(xs[0])
+        if isinstance(out, tuple):  # heads: (y, raw)
+            blob[f"{name}.y"] = out[0].numpy()
+            for i, r in enumerate(out[1]):
+                blob[f"{name}.raw{i}"] = r.numpy()
+        else:
+            blob[f"{name}.y"] = out.numpy()
+        blob[f"{name}.keys"] = np.array(list(mod.state_dict().keys()))
+    path = os.path.join(OUT, "modules.npz")
+    np.savez_compressed(path, **blob)
+    print(path, os.path.getsize(path) // 1024, "KiB")
+
+
+def gen_nms():
+    ref_live.load()
+    from ultralytics.yolo.utils import ops
+    blob = {}
+    for ci, (name, nc, anchors, batch, kw) in enumerate(NMS_CASES):
+        pred = synth_predictions(batch, nc, anchors, seed=20 + ci)
+        out = ops.non_max_suppression(pred.clone(), max_time_img=1000.0, **kw)
+        for b, t in enumerate(out):
+            blob[f"{name}.{b}"] = t.numpy()
+        print(name, [tuple(t.shape) for t in out])
+    path = os.path.join(OUT, "nms.npz")
+    np.savez_compressed(path, **blob)
+    print(path, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    gen_models()
+    gen_modules()
+    gen_nms()
