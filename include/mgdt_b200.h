@@ -42,6 +42,9 @@ enum { MGDT_RS_COPY = 0, MGDT_RS_AVGPOOL = 1, MGDT_RS_BILINEAR = 2, MGDT_RS_NEAR
 
 int mgdt_abi_version(void);
 const char* mgdt_last_error(void);
+/* Number of kernels this library has enqueued so far in this process (every launch counts once;
+ * a launch recorded into a CUDA graph counts when recorded, not per replay). */
+unsigned long long mgdt_launch_count(void);
 /* Compiled-in facts for tests: returns 1 if the tcgen05/TMA conv path was built. */
 int mgdt_has_umma(void);
 

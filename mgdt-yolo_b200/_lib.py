@@ -37,6 +37,7 @@ class DecodeLevel(C.Structure):
 SIGNATURES = {
     "mgdt_abi_version": (C.c_int, []),
     "mgdt_last_error": (C.c_char_p, []),
+    "mgdt_launch_count": (C.c_ulonglong, []),
     "mgdt_has_umma": (C.c_int, []),
     "mgdt_conv2d": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "mgdt_dwconv7_ln": (C.c_int, [vp, i32, vp, vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]),

@@ -215,7 +215,7 @@ extern "C" int mgdt_dcn3x3(const void* x, int x_cs, const void* offset, int off_
     const long long npix = (long long)N * H * W;
     cudaStream_t s = (cudaStream_t)stream;
     MGDT_DTYPE_SWITCH(dtype, T, {
-        if (smem > 48 * 1024) {
+        if (smem + 1024 > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(dcn3x3_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return set_error(-EIO, "dcn3x3: smem attr: %s", cudaGetErrorString(e));
         }

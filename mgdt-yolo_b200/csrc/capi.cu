@@ -4,6 +4,7 @@
 namespace mgdt {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -25,6 +26,7 @@ using namespace mgdt;
 
 extern "C" int mgdt_abi_version(void) { return MGDT_ABI_VERSION; }
 extern "C" const char* mgdt_last_error(void) { return g_err; }
+extern "C" unsigned long long mgdt_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" int mgdt_has_umma(void) {
 #ifdef MGDT_WITH_UMMA
     return 1;

@@ -20,8 +20,11 @@ int set_error(int code, const char* fmt, ...);
         if (!(cond)) return ::mgdt::set_error(-EINVAL, __VA_ARGS__); \
     } while (0)
 
+extern unsigned long long g_launches;  // kernels enqueued by this library (see mgdt_launch_count)
+
 #define MGDT_LAUNCH_CHECK(name)                                                              \
     do {                                                                                     \
+        __atomic_fetch_add(&::mgdt::g_launches, 1ULL, __ATOMIC_RELAXED);                     \
         cudaError_t e_ = cudaGetLastError();                                                 \
         if (e_ != cudaSuccess) return ::mgdt::set_error(-EIO, "%s: %s", name, cudaGetErrorString(e_)); \
     } while (0)

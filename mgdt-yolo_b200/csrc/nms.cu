@@ -300,7 +300,7 @@ extern "C" int mgdt_nms(const float* pred, int N, int nc, int A, float conf_thre
     MGDT_LAUNCH_CHECK("nms_rank");
     const size_t smem = (sizeof(Box) + sizeof(float)) * (size_t)(max_det + NMS_CHUNK) +
                         sizeof(unsigned) * (size_t)(NMS_CHUNK * NMS_WORDS + NMS_WORDS);
-    if (smem > 48 * 1024) {
+    if (smem + 4096 > 48 * 1024) {  // the 48 KB default covers static + dynamic shared memory together
         cudaError_t e = cudaFuncSetAttribute(nms_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(-EIO, "nms: smem attr: %s", cudaGetErrorString(e));
     }

@@ -1,0 +1,148 @@
+"""Whole-pipeline executor: preprocess -> DetectionModel forward -> decode -> batched NMS.
+
+The reference runs this path as a Python loop over layers plus a Python loop over images with a
+host sync per image.  Here the model forward, decode and NMS of one batch are
+recorded ONCE into a CUDA graph over a private memory pool (all shapes are static for a given
+batch size), so a step is: one preprocess launch + one graph replay, no host work in between and
+no device->host traffic except the packed detections.
+
+One Engine drives one GPU.  Multi-GPU inference shards the batch over one process per GPU with no
+collective (images are independent).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import lib
+
+__all__ = ("Engine",)
+
+
+class _Slot:
+    """One in-flight batch: device input, graph, outputs, pinned host mirrors, stream."""
+    pass
+
+
+class Engine:
+    def __init__(self, model, batch: int, imgsz=640, dtype=torch.bfloat16, device=None, conf=0.25, iou=0.7,
+                 max_det=300, multi_label=False, agnostic=False, classes=None, max_nms=30000, max_wh=7680.0,
+                 input_dtype=torch.uint8, slots: int = 2, use_graph: bool = True):
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise RuntimeError("Engine: a CUDA (B200) device is required; there is no CPU fallback")
+        h, w = (imgsz, imgsz) if isinstance(imgsz, int) else imgsz
+        self.model = model.to(self.device).eval()
+        self.batch, self.h, self.w, self.dtype = batch, h, w, dtype
+        self.nms_args = dict(conf_thres=conf, iou_thres=iou, multi_label=multi_label, agnostic=agnostic,
+                             max_det=max_det, max_nms=max_nms, max_wh=max_wh)
+        self.max_det = max_det
+        self.input_dtype = input_dtype
+        self.ch = self.model.yaml.get("ch", 3)
+        self.use_graph = use_graph
+        self.launches_per_step = 0
+        with torch.cuda.device(self.device):
+            self._classes = None if classes is None else torch.as_tensor(list(classes), dtype=torch.int32,
+                                                                         device=self.device)
+            self.slots = [self._make_slot() for _ in range(max(1, slots))]
+        self._next = 0
+
+    # ------------------------------------------------------------------ construction
+    def _body(self, s):
+        """Everything after preprocess, on the current stream, into the slot's static outputs."""
+        y, _ = self.model(s.x)
+        s.pred = y
+        nb = lib().mgdt_nms_ws_bytes(self.batch, y.shape[1] - 4, y.shape[2], 1 if self.nms_args["multi_label"] else 0,
+                                     self.nms_args["max_nms"])
+        if s.ws is None:
+            s.ws = torch.empty((nb,), dtype=torch.uint8, device=self.device)
+        a = self.nms_args
+        ops.nms_packed(y, a["conf_thres"], a["iou_thres"], a["multi_label"], a["agnostic"], a["max_det"], a["max_nms"],
+                       a["max_wh"], classes=self._classes, out=s.out, counts=s.counts, ws=s.ws)
+
+    def _make_slot(self):
+        s = _Slot()
+        B, C, H, W = self.batch, self.ch, self.h, self.w
+        s.stream = torch.cuda.Stream(device=self.device)
+        s.src = torch.zeros((B, C, H, W), dtype=self.input_dtype, device=self.device)
+        s.x = ops.new_act(B, C, H, W, self.dtype, self.device)
+        s.out = torch.zeros((B, self.max_det, 6), dtype=torch.float32, device=self.device)
+        s.counts = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        s.ws = None
+        s.host_out = torch.empty((B, self.max_det, 6), dtype=torch.float32).pin_memory()
+        s.host_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
+        s.done = torch.cuda.Event()
+        s.graph = None
+        with torch.no_grad():
+            # warm-up (packs weights, sizes the NMS workspace) on the slot's stream, then capture
+            s.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s.stream):
+                ops.preprocess(s.src, self.dtype, out=s.x)
+                for _ in range(2):
+                    self._body(s)
+            s.stream.synchronize()
+            if self.use_graph:
+                c0 = lib().mgdt_launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s.stream):
+                    self._body(s)
+                s.graph = g
+                self.launches_per_step = int(lib().mgdt_launch_count() - c0) + 1  # + preprocess
+            else:
+                c0 = lib().mgdt_launch_count()
+                with torch.cuda.stream(s.stream):
+                    self._body(s)
+                self.launches_per_step = int(lib().mgdt_launch_count() - c0) + 1
+                s.stream.synchronize()
+        return s
+
+    # ------------------------------------------------------------------ execution
+    def _run(self, s, src):
+        """Enqueue preprocess(src) + forward + decode + NMS on the slot's stream (no sync)."""
+        with torch.cuda.stream(s.stream), torch.no_grad():
+            ops.preprocess(src, self.dtype, out=s.x)
+            if s.graph is not None:
+                s.graph.replay()
+            else:
+                self._body(s)
+
+    def step_device(self, src: torch.Tensor, slot: int = 0):
+        """Inputs already resident in HBM: `src` is a (B,C,H,W) uint8/float32 device tensor.
+        Returns the slot (outputs in slot.out / slot.counts, on the device, not synchronised)."""
+        s = self.slots[slot]
+        self._run(s, src)
+        return s
+
+    def submit(self, host_src: torch.Tensor):
+        """End-to-end: pinned host batch -> H2D -> pipeline -> D2H of the packed detections.
+        Asynchronous; returns the slot, call `collect(slot)` for the result.  Consecutive submits
+        alternate slots so the copies of one batch overlap the kernels of the other."""
+        s = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        with torch.cuda.stream(s.stream):
+            s.src.copy_(host_src, non_blocking=True)
+        self._run(s, s.src)
+        with torch.cuda.stream(s.stream):
+            s.host_out.copy_(s.out, non_blocking=True)
+            s.host_counts.copy_(s.counts, non_blocking=True)
+            s.done.record(s.stream)
+        return s
+
+    def collect(self, s):
+        """Wait for a submitted batch; returns the reference's format: list of (n_i, 6) CPU tensors."""
+        s.done.synchronize()
+        cnt = s.host_counts.tolist()
+        return [s.host_out[i, :cnt[i]].clone() for i in range(self.batch)]
+
+    def __call__(self, images: torch.Tensor):
+        """Convenience: images (B,C,H,W) uint8 or float on host or device -> list of (n_i,6) tensors."""
+        if images.shape != self.slots[0].src.shape:
+            raise ValueError(f"Engine was built for input {tuple(self.slots[0].src.shape)}, got {tuple(images.shape)}")
+        if images.dtype != self.input_dtype:
+            raise TypeError(f"Engine was built for {self.input_dtype} input")
+        if images.is_cuda:
+            s = self.step_device(images.contiguous())
+            s.stream.synchronize()
+            cnt = s.counts.tolist()
+            return [s.out[i, :cnt[i]].clone() for i in range(self.batch)]
+        return self.collect(self.submit(images))

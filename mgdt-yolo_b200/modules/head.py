@@ -118,12 +118,23 @@ class _HeadBase(KernelModule):
     anchors = torch.empty(0)
     strides = torch.empty(0)
 
+    def _strides(self):
+        """self.stride as python floats, read back once per tensor (a .tolist() on a CUDA tensor is a
+        sync and would invalidate a CUDA-graph capture)."""
+        st = self.stride
+        key = (st.data_ptr(), st._version, str(st.device))
+        c = self.__dict__.get("_stride_cache")
+        if c is None or c[0] != key:
+            c = (key, [float(v) for v in st.tolist()])
+            self.__dict__["_stride_cache"] = c
+        return c[1]
+
     def _finish(self, x):
         """Inference tail shared by both heads (head.py:165-177,536-559): DFL + dist2bbox + sigmoid."""
         if self.training:
             return x
         self.shape = x[0].shape
-        y = ops.decode(x, [float(s) for s in self.stride], self.reg_max, self.nc)
+        y = ops.decode(x, self._strides(), self.reg_max, self.nc)
         return y if self.export else (y, x)
 
 

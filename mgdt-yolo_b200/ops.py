@@ -86,6 +86,28 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+# Per-launch profiling (bench.py roofline): when PROFILE is a list every C-ABI call is bracketed by
+# CUDA events on the current stream and appended as (name, meta, start, stop).  meta carries the
+# ALGORITHMIC bytes / flops of the call (unique input elements + outputs + weights), not measured traffic.
+PROFILE = None
+
+
+def _nb(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
+def _invoke(name, meta, *args):
+    fn = getattr(lib(), name)
+    if PROFILE is None:
+        check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(*args), name)
+    e1.record()
+    PROFILE.append((name, meta, e0, e1))
+
+
 # ------------------------------------------------------------------------------------- conv
 def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scale=None, pix_scale=None,
            residual=None, in_relu=False, cout=None, impl=0):
@@ -131,7 +153,12 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
     a.in_relu = 1 if in_relu else 0
     a.dtype = dtype_code(x.dtype)
     a.impl = impl
-    check(lib().mgdt_conv2d(C.byref(a), stream_ptr()), "conv2d")
+    es = x.element_size()
+    meta = dict(shape=f"{cin}->{cout} k{k}s{s} {n}x{h}x{wd}", flops=2.0 * n * ho * wo * cout * cin * k * k,
+                bytes=es * (n * h * wd * cin * (2 if pre_add is not None else 1)
+                            + n * ho * wo * cout * (2 if residual is not None else 1) + cout * cin * k * k)
+                + (n * h * wd * es if pix_scale is not None else 0))
+    _invoke("mgdt_conv2d", meta, C.byref(a), stream_ptr())
     return out
 
 
@@ -140,8 +167,8 @@ def dwconv7_ln(x, w49c, bias, ln_w, ln_b, eps=1e-6, out=None):
     if out is None:
         out = new_act(n, c, h, w, x.dtype, x.device)
     yp, *_, ycs = view(out)
-    check(lib().mgdt_dwconv7_ln(xp, xcs, w49c.data_ptr(), bias.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), eps, yp,
-                                ycs, n, h, w, c, dtype_code(x.dtype), stream_ptr()), "dwconv7_ln")
+    _invoke("mgdt_dwconv7_ln", dict(shape=f"dw7+ln C{c} {n}x{h}x{w}", bytes=_nb(x, out), flops=2.0 * 49 * x.numel()), xp, xcs, w49c.data_ptr(), bias.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), eps, yp,
+                                ycs, n, h, w, c, dtype_code(x.dtype), stream_ptr())
     return out
 
 
@@ -156,8 +183,8 @@ def dcn3x3(x, offset, mask, w, cout, mask_is_logit, out=None):
     if out is None:
         out = new_act(n, cout, h, wd, x.dtype, x.device)
     yp, *_, ycs = view(out)
-    check(lib().mgdt_dcn3x3(xp, xcs, op, ocs, mp, mcs, 1 if mask_is_logit else 0, w.data_ptr(), yp, ycs, n, h, wd,
-                            cin, cout, dtype_code(x.dtype), stream_ptr()), "dcn3x3")
+    _invoke("mgdt_dcn3x3", dict(shape=f"dcn {cin}->{cout} {n}x{h}x{wd}", bytes=_nb(x, offset, mask, out), flops=2.0 * 9 * cin * cout * n * h * wd), xp, xcs, op, ocs, mp, mcs, 1 if mask_is_logit else 0, w.data_ptr(), yp, ycs, n, h, wd,
+                            cin, cout, dtype_code(x.dtype), stream_ptr())
     return out
 
 
@@ -170,24 +197,24 @@ def chan_stats(x, quads=False, sumsq=False):
     ss = torch.empty((n, c), dtype=torch.float32, device=x.device) if sumsq else None
     nbytes = lib().mgdt_chan_stats_ws_bytes(n, h, w, c, 1 if quads else 0)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
-    check(lib().mgdt_chan_stats(xp, xcs, n, h, w, c, 1 if quads else 0, s.data_ptr(), _p(ss), ws.data_ptr(), nbytes,
-                                dtype_code(x.dtype), stream_ptr()), "chan_stats")
+    _invoke("mgdt_chan_stats", dict(shape=f"stats C{c} {n}x{h}x{w} q{q}", bytes=_nb(x), flops=0.0), xp, xcs, n, h, w, c, 1 if quads else 0, s.data_ptr(), _p(ss), ws.data_ptr(), nbytes,
+                                dtype_code(x.dtype), stream_ptr())
     return s, ss
 
 
 def mspa_gate(stats, h, w, c, fc1_w, fc1_b, fc2_w, fc2_b, groups=4, softmax=True):
     n = stats.shape[0]
     scale = torch.empty((n, c), dtype=torch.float32, device=stats.device)
-    check(lib().mgdt_mspa_gate(stats.data_ptr(), n, h, w, c, groups, 1 if softmax else 0, fc1_w.data_ptr(),
+    _invoke("mgdt_mspa_gate", dict(shape="gate", bytes=_nb(stats, scale), flops=0.0), stats.data_ptr(), n, h, w, c, groups, 1 if softmax else 0, fc1_w.data_ptr(),
                                fc1_b.data_ptr(), fc2_w.data_ptr(), fc2_b.data_ptr(), fc1_w.shape[0], scale.data_ptr(),
-                               stream_ptr()), "mspa_gate")
+                               stream_ptr())
     return scale
 
 
 def grn_scale(sumsq, gamma):
     n, c = sumsq.shape
     scale = torch.empty((n, c), dtype=torch.float32, device=sumsq.device)
-    check(lib().mgdt_grn_scale(sumsq.data_ptr(), gamma.data_ptr(), n, c, scale.data_ptr(), stream_ptr()), "grn_scale")
+    _invoke("mgdt_grn_scale", dict(shape="grn", bytes=_nb(sumsq, scale), flops=0.0), sumsq.data_ptr(), gamma.data_ptr(), n, c, scale.data_ptr(), stream_ptr())
     return scale
 
 
@@ -195,8 +222,8 @@ def gn_affine(s, ss, groups, hw, eps, gamma, beta):
     n, c = ss.shape
     a = torch.empty((n, c), dtype=torch.float32, device=ss.device)
     b = torch.empty((n, c), dtype=torch.float32, device=ss.device)
-    check(lib().mgdt_gn_affine(s.data_ptr(), ss.data_ptr(), n, c, groups, hw, eps, gamma.data_ptr(), beta.data_ptr(),
-                               a.data_ptr(), b.data_ptr(), stream_ptr()), "gn_affine")
+    _invoke("mgdt_gn_affine", dict(shape="gn", bytes=_nb(s, ss, a, b), flops=0.0), s.data_ptr(), ss.data_ptr(), n, c, groups, hw, eps, gamma.data_ptr(), beta.data_ptr(),
+                               a.data_ptr(), b.data_ptr(), stream_ptr())
     return a, b
 
 
@@ -206,8 +233,8 @@ def td_attn(s, hw, la1_w, la1_b, la2_w, la2_b, stacked):
     n, c = s.shape[0], s.shape[-1]
     ndec, hidden = la1_w.shape[0], la1_w.shape[1]
     out = torch.empty((ndec, n, c), dtype=torch.float32, device=s.device)
-    check(lib().mgdt_td_attn(s.data_ptr(), n, c, hw, hidden, stacked, ndec, la1_w.data_ptr(), la1_b.data_ptr(),
-                             la2_w.data_ptr(), la2_b.data_ptr(), out.data_ptr(), stream_ptr()), "td_attn")
+    _invoke("mgdt_td_attn", dict(shape="td_attn", bytes=_nb(s, out), flops=0.0), s.data_ptr(), n, c, hw, hidden, stacked, ndec, la1_w.data_ptr(), la1_b.data_ptr(),
+                             la2_w.data_ptr(), la2_b.data_ptr(), out.data_ptr(), stream_ptr())
     return out
 
 
@@ -222,8 +249,8 @@ def affine_act(x, a=None, b=None, act=None, other=None, out=None):
         op, on, oc, oh, ow, ocs = view(other)
         if (on, oc, oh, ow) != (n, c, h, w):
             raise ValueError("affine_act: other must match x")
-    check(lib().mgdt_affine_act(xp, xcs, _p(a), _p(b), op, ocs, ACTS[act], yp, ycs, n, h, w, c, dtype_code(x.dtype),
-                                stream_ptr()), "affine_act")
+    _invoke("mgdt_affine_act", dict(shape=f"affine C{c} {n}x{h}x{w}", bytes=_nb(x, out, other), flops=0.0), xp, xcs, _p(a), _p(b), op, ocs, ACTS[act], yp, ycs, n, h, w, c, dtype_code(x.dtype),
+                                stream_ptr())
     return out
 
 
@@ -234,8 +261,7 @@ def resample(x, ho, wo, mode, out=None):
     yp, yn, yc, yh, yw, ycs = view(out)
     if (yn, yc, yh, yw) != (n, c, ho, wo):
         raise ValueError(f"resample: out shape {tuple(out.shape)} != {(n, c, ho, wo)}")
-    check(lib().mgdt_resample(xp, xcs, h, w, yp, ycs, ho, wo, n, c, mode, dtype_code(x.dtype), stream_ptr()),
-          "resample")
+    _invoke("mgdt_resample", dict(shape=f"resample m{mode} C{c} {h}x{w}->{ho}x{wo}", bytes=_nb(x, out), flops=0.0), xp, xcs, h, w, yp, ycs, ho, wo, n, c, mode, dtype_code(x.dtype), stream_ptr())
     return out
 
 
@@ -245,7 +271,7 @@ def sppf_pool(x, y1, y2, y3, k=5):
     p2, *_, ycs2 = view(y2)
     p3, *_, ycs3 = view(y3)
     assert ycs == ycs2 == ycs3
-    check(lib().mgdt_sppf_pool(xp, xcs, p1, p2, p3, ycs, n, h, w, c, k, dtype_code(x.dtype), stream_ptr()), "sppf_pool")
+    _invoke("mgdt_sppf_pool", dict(shape=f"sppf C{c} {n}x{h}x{w}", bytes=_nb(x) * 4, flops=0.0), xp, xcs, p1, p2, p3, ycs, n, h, w, c, k, dtype_code(x.dtype), stream_ptr())
 
 
 def inject(local, gact, gfeat, out=None):
@@ -257,8 +283,8 @@ def inject(local, gact, gfeat, out=None):
     if out is None:
         out = new_act(n, c, h, w, local.dtype, local.device)
     yp, *_, ycs = view(out)
-    check(lib().mgdt_inject(lp, lcs, ap, acs, fp, fcs, yp, ycs, n, h, w, hg, wg, c, dtype_code(local.dtype),
-                            stream_ptr()), "inject")
+    _invoke("mgdt_inject", dict(shape=f"inject C{c} {n}x{h}x{w}", bytes=_nb(local, gact, gfeat, out), flops=0.0), lp, lcs, ap, acs, fp, fcs, yp, ycs, n, h, w, hg, wg, c, dtype_code(local.dtype),
+                            stream_ptr())
     return out
 
 
@@ -271,8 +297,8 @@ def preprocess(src: torch.Tensor, dtype: torch.dtype, out=None):
     if out is None:
         out = new_act(n, c, h, w, dtype, src.device)
     yp, *_, ycs = view(out)
-    check(lib().mgdt_preprocess(src.data_ptr(), 1 if src.dtype == torch.uint8 else 0, yp, ycs, n, c, h, w,
-                                dtype_code(dtype), stream_ptr()), "preprocess")
+    _invoke("mgdt_preprocess", dict(shape=f"preprocess {n}x{c}x{h}x{w}", bytes=_nb(src, out), flops=0.0), src.data_ptr(), 1 if src.dtype == torch.uint8 else 0, yp, ycs, n, c, h, w,
+                                dtype_code(dtype), stream_ptr())
     return out
 
 
@@ -289,9 +315,9 @@ def decode(raws, strides, reg_max, nc, out=None, dist_only=False):
         total += rh * rw
     if out is None:
         out = torch.empty((n, 4 if dist_only else 4 + nc, total), dtype=torch.float32, device=raws[0].device)
-    check(lib().mgdt_decode(levels, len(raws), n, reg_max, nc, 1 if dist_only else 0, out.data_ptr(),
+    _invoke("mgdt_decode", dict(shape=f"decode A{total} nc{nc}", bytes=_nb(*raws) + _nb(out), flops=0.0), levels, len(raws), n, reg_max, nc, 1 if dist_only else 0, out.data_ptr(),
                             dtype_code(raws[0].dtype),
-                            stream_ptr()), "decode")
+                            stream_ptr())
     return out
 
 
@@ -311,10 +337,12 @@ def nms_packed(pred, conf_thres, iou_thres, multi_label=False, agnostic=False, m
     if counts is None:
         counts = torch.empty((n,), dtype=torch.int32, device=pred.device)
     cls_t = None
-    if classes is not None:
+    if isinstance(classes, torch.Tensor):
+        cls_t = classes  # int32, on the device already (graph-capturable)
+    elif classes is not None:
         cls_t = torch.as_tensor(list(classes), dtype=torch.int32, device=pred.device)
-    check(lib().mgdt_nms(pred.data_ptr(), n, nc, a, float(conf_thres), float(iou_thres), 1 if multi_label else 0,
+    _invoke("mgdt_nms", dict(shape=f"nms N{n} nc{nc} A{a}", bytes=_nb(pred, out), flops=0.0), pred.data_ptr(), n, nc, a, float(conf_thres), float(iou_thres), 1 if multi_label else 0,
                          1 if agnostic else 0, max_det, max_nms, float(max_wh), _p(cls_t),
                          0 if cls_t is None else cls_t.numel(), out.data_ptr(), counts.data_ptr(), ws.data_ptr(),
-                         ws.numel(), stream_ptr()), "nms")
+                         ws.numel(), stream_ptr())
     return out, counts
