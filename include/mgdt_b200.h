@@ -76,8 +76,15 @@ typedef struct mgdt_conv_args {
     int32_t x_cs, y_cs, add_cs, ps_cs, res_cs;
     int32_t act, in_relu, dtype;
     int32_t impl;          /* 0 auto, 1 force CUDA-core path, 2 force tcgen05 path */
+    const void* w_umma;    /* NULL, or the weights packed by mgdt_conv_umma_pack (bf16 tcgen05 path) */
 } mgdt_conv_args;
 int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
+
+/* tcgen05 path: K-major shared-memory image of the weights, [col split][16-byte K chunk][Nc][8].
+ * mgdt_conv_umma_packed_bytes returns 0 when (Cin, Cout, k, stride) is not taken by that path
+ * (needs bf16, Cin % 8 == 0, k in {1,3} with pad k/2, stride 1 or (k=3) 2). */
+size_t mgdt_conv_umma_packed_bytes(int Cin, int Cout, int k, int stride);
+int mgdt_conv_umma_pack(const void* w_ohwi, int Cin, int Cout, int k, int stride, void* packed, void* stream);
 
 /* Depthwise 7x7 (pad 3, bias) + channels-last LayerNorm(eps), ConvNeXtV2_Block.forward
  * (nn/modules/convnextv2.py:35-37, nn/modules/utils.py:162-163).  w is [49][C] in dtype,

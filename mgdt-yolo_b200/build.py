@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libmgdt_b200.so")
 OBJ = os.path.join(HERE, "build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", ]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-DMGDT_WITH_UMMA"]
 PER_FILE = {"nms.cu": ["-fmad=false"]}  # bit-exact IoU arithmetic
 
 

@@ -55,9 +55,11 @@ def act_name(m) -> str | None:
     raise NotImplementedError(f"activation {type(m).__name__} has no fused epilogue in mgdt_b200")
 
 
-def ohwi(w: torch.Tensor, dtype, device) -> torch.Tensor:
-    """(Cout, Cin, kh, kw) -> contiguous (Cout, kh, kw, Cin) in the compute dtype."""
-    return w.detach().to(device=device, dtype=torch.float32).permute(0, 2, 3, 1).contiguous().to(dtype)
+def ohwi(w: torch.Tensor, dtype, device, stride: int = 1) -> "ops.PackedConv":
+    """(Cout, Cin, kh, kw) -> kernel weight pack: contiguous OHWI (Cout, kh, kw, Cin) in the compute dtype
+    for the CUDA-core path plus, for bf16 shapes the tcgen05 path takes, its K-major shared-memory image."""
+    t = w.detach().to(device=device, dtype=torch.float32).permute(0, 2, 3, 1).contiguous().to(dtype)
+    return ops.PackedConv(t, stride)
 
 
 def f32(t: torch.Tensor, device) -> torch.Tensor:

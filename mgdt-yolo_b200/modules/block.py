@@ -271,9 +271,9 @@ class ConvNeXtV2_Block(KernelModule):
             return dict(
                 dw=self.dwconv.weight.detach().float().reshape(c, 49).t().contiguous().to(device=device, dtype=dtype),
                 dwb=f32(self.dwconv.bias, device), lnw=f32(self.norm.weight, device), lnb=f32(self.norm.bias, device),
-                w1=self.pwconv1.weight.detach().float().reshape(4 * c, 1, 1, c).contiguous().to(device=device, dtype=dtype),
+                w1=ops.PackedConv(self.pwconv1.weight.detach().float().reshape(4 * c, 1, 1, c).contiguous().to(device=device, dtype=dtype)),
                 b1=f32(self.pwconv1.bias, device), gamma=f32(self.grn.gamma.reshape(-1), device),
-                w2=w2.reshape(c, 1, 1, 4 * c).contiguous().to(device=device, dtype=dtype), b2=f32(b2, device))
+                w2=ops.PackedConv(w2.reshape(c, 1, 1, 4 * c).contiguous().to(device=device, dtype=dtype)), b2=f32(b2, device))
 
         return self._packed("blk", dtype, device, t, build)
 

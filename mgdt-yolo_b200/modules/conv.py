@@ -50,7 +50,7 @@ class Conv(KernelModule):
 
         def build():
             w, b = fold_conv_bn(self.conv, bn)
-            return ohwi(w, dtype, device), f32(b, device)
+            return ohwi(w, dtype, device, self.conv.stride[0]), f32(b, device)
 
         return self._packed("conv", dtype, device, tensors, build)
 

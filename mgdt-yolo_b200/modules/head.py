@@ -48,7 +48,7 @@ class Conv_GN(KernelModule):
 
     def _pack(self, dtype, device):
         t = [self.conv.weight, self.gn.weight, self.gn.bias]
-        return self._packed("cgn", dtype, device, t, lambda: (ohwi(self.conv.weight, dtype, device),
+        return self._packed("cgn", dtype, device, t, lambda: (ohwi(self.conv.weight, dtype, device, self.conv.stride[0]),
                                                               f32(self.gn.weight, device), f32(self.gn.bias, device)))
 
     def forward(self, x, out=None):

@@ -109,11 +109,44 @@ def _invoke(name, meta, *args):
 
 
 # ------------------------------------------------------------------------------------- conv
+class PackedConv:
+    """Weights of one convolution in the kernels' layouts: `.ohwi` (Cout,k,k,Cin) for the CUDA-core
+    path and, when the tcgen05 path takes the shape (bf16 on a CUDA device), `.umma`, the K-major
+    shared-memory image built by mgdt_conv_umma_pack for the stride it will be used with."""
+
+    def __init__(self, ohwi: torch.Tensor, stride: int = 1):
+        self.ohwi = ohwi
+        self.umma = None
+        self.shape = ohwi.shape
+        self.dtype = ohwi.dtype
+        cout, k, k2, cin = ohwi.shape
+        if ohwi.is_cuda and ohwi.dtype == torch.bfloat16 and k == k2 and USE_UMMA and lib().mgdt_has_umma():
+            nbytes = lib().mgdt_conv_umma_packed_bytes(cin, cout, k, stride)
+            if nbytes:
+                self.umma = torch.empty((nbytes,), dtype=torch.uint8, device=ohwi.device)
+                with torch.cuda.device(ohwi.device):
+                    check(lib().mgdt_conv_umma_pack(ohwi.data_ptr(), cin, cout, k, stride, self.umma.data_ptr(),
+                                                    stream_ptr()), "conv_umma_pack")
+                self.stride = stride
+
+    def data_ptr(self):
+        return self.ohwi.data_ptr()
+
+
+USE_UMMA = True  # tests flip this to compare the tcgen05 path with the CUDA-core path
+
+
 def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scale=None, pix_scale=None,
            residual=None, in_relu=False, cout=None, impl=0):
     """y = act(conv((x + pre_add) * in_scale[n,c] * pix_scale[n,h,w] |> relu?, w) + bias) + residual.
-    `w` is OHWI (Cout, k, k, Cin) in x's dtype; `out` may be a channel slice of a concat buffer."""
+    `w` is a PackedConv (or a plain OHWI (Cout, k, k, Cin) tensor) in x's dtype; `out` may be a channel
+    slice of a concat buffer."""
     xp, n, cin, h, wd, xcs = view(x)
+    w_umma = None
+    if isinstance(w, PackedConv):
+        if w.umma is not None and w.stride == s:
+            w_umma = w.umma
+        w = w.ohwi
     cout = cout if cout is not None else w.shape[0]
     p = k // 2 if p is None else p
     ho, wo = (h + 2 * p - k) // s + 1, (wd + 2 * p - k) // s + 1
@@ -153,6 +186,7 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
     a.in_relu = 1 if in_relu else 0
     a.dtype = dtype_code(x.dtype)
     a.impl = impl
+    a.w_umma = None if (w_umma is None or impl == 1) else w_umma.data_ptr()
     es = x.element_size()
     meta = dict(shape=f"{cin}->{cout} k{k}s{s} {n}x{h}x{wd}", flops=2.0 * n * ho * wo * cout * cin * k * k,
                 bytes=es * (n * h * wd * cin * (2 if pre_add is not None else 1)

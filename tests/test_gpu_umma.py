@@ -1,0 +1,93 @@
+"""GPU: the tcgen05/TMEM convolution path against the CUDA-core path and the oracle.
+
+Both paths see identical bf16 inputs/weights and accumulate in fp32, so they must agree to bf16
+output rounding (1 ulp = 2^-8 relative) -- far tighter than the 1e-2 budget against the fp32 oracle.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (Cin, Cout, k, s, N, H, W)
+SHAPES = [
+    (32, 32, 1, 1, 2, 20, 24), (8, 8, 1, 1, 3, 17, 19), (16, 16, 1, 1, 2, 40, 40), (96, 384, 1, 1, 2, 12, 10),
+    (384, 96, 1, 1, 2, 12, 10), (480, 96, 1, 1, 1, 9, 11), (64, 256, 1, 1, 2, 16, 16), (256, 64, 1, 1, 2, 16, 16),
+    (192, 64, 1, 1, 1, 8, 9), (32, 2, 1, 1, 2, 10, 10), (32, 64, 1, 1, 1, 80, 80), (512, 256, 1, 1, 2, 6, 7),
+    (8, 8, 3, 1, 2, 21, 19), (16, 16, 3, 1, 2, 16, 24), (32, 32, 3, 1, 2, 20, 20), (64, 64, 3, 1, 2, 9, 11),
+    (64, 32, 3, 1, 1, 24, 20), (64, 27, 3, 1, 2, 12, 16), (16, 1, 3, 1, 2, 14, 10), (32, 32, 3, 1, 1, 80, 80),
+    (16, 32, 3, 2, 2, 32, 40), (32, 64, 3, 2, 2, 20, 24), (64, 128, 3, 2, 2, 16, 12), (16, 32, 3, 2, 1, 21, 23),
+    (8, 16, 3, 2, 2, 18, 14), (128, 256, 3, 2, 1, 8, 8),
+]
+
+
+def _mk(cin, cout, k, n, h, w, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    return x, wt, b
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"{s[0]}to{s[1]}k{s[2]}s{s[3]}_{s[4]}x{s[5]}x{s[6]}" for s in SHAPES])
+def test_umma_vs_direct_and_oracle(shape):
+    from mgdt_yolo_b200 import ops
+    from mgdt_yolo_b200._lib import lib
+    if not lib().mgdt_has_umma():
+        pytest.skip("library built without the tcgen05 path")
+    cin, cout, k, s, n, h, w = shape
+    x, wt, b = _mk(cin, cout, k, n, h, w)
+    xb = ops.as_act(x.cuda().to(torch.bfloat16))
+    pw = ops.PackedConv(wt.cuda().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), s)
+    if pw.umma is None:
+        pytest.skip("shape not taken by the tcgen05 path")
+    bias = b.cuda()
+    try:
+        y_umma = ops.conv2d(xb, pw, bias, k, s, act="silu", impl=2)
+    except RuntimeError as e:
+        if "does not support this shape" in str(e):
+            pytest.skip("operands do not fit the whole-K-resident tile (falls back to the CUDA-core path)")
+        raise
+    y_dir = ops.conv2d(xb, pw, bias, k, s, act="silu", impl=1)
+    torch.cuda.synchronize()
+    ref = F.silu(F.conv2d(xb.float(), pw.ohwi.float().permute(0, 3, 1, 2), bias, stride=s, padding=k // 2))
+    scale = float(ref.abs().max())
+    e_ud = float((y_umma.float() - y_dir.float()).abs().max()) / scale
+    e_uo = float((y_umma.float() - ref).abs().max()) / scale
+    assert y_umma.shape == ref.shape
+    assert e_ud <= 2 ** -7, f"tcgen05 vs CUDA-core: {e_ud:.3e}"
+    assert e_uo <= 2 ** -7, f"tcgen05 vs fp32 reference on identical bf16 operands: {e_uo:.3e}"
+
+
+def test_umma_fused_options():
+    """pre_add, in_scale, pix_scale, in_relu, residual, channel-slice input/output."""
+    from mgdt_yolo_b200 import ops
+    from mgdt_yolo_b200._lib import lib
+    if not lib().mgdt_has_umma():
+        pytest.skip("library built without the tcgen05 path")
+    g = torch.Generator().manual_seed(5)
+    n, h, w, cin, cout = 2, 18, 22, 32, 48
+    xbuf = ops.as_act(torch.randn(n, 80, h, w, generator=g).cuda().to(torch.bfloat16))
+    x = xbuf[:, 16:48]
+    add = ops.as_act(torch.randn(n, cin, h, w, generator=g).cuda().to(torch.bfloat16))
+    res = ops.as_act(torch.randn(n, cout, h, w, generator=g).cuda().to(torch.bfloat16))
+    pix = ops.as_act(torch.rand(n, 1, h, w, generator=g).cuda().to(torch.bfloat16))
+    insc = (torch.rand(n, cin, generator=g) + 0.5).cuda().contiguous()
+    bias = torch.randn(cout, generator=g).cuda()
+    for k in (1, 3):
+        wt = (torch.randn(cout, k, k, cin, generator=g) * (2.0 / (cin * k * k)) ** 0.5).cuda().to(torch.bfloat16)
+        pw = ops.PackedConv(wt, 1)
+        outs = []
+        for impl in (2, 1):
+            obuf = ops.new_act(n, 96, h, w, torch.bfloat16, "cuda")
+            obuf.zero_()
+            ops.conv2d(x, pw, bias, k, 1, act="relu", out=obuf[:, 32:80], pre_add=add, in_scale=insc, pix_scale=pix,
+                       residual=res, in_relu=True, impl=impl)
+            outs.append(obuf.float())
+        torch.cuda.synchronize()
+        assert float(outs[0][:, :32].abs().max()) == 0 and float(outs[0][:, 80:].abs().max()) == 0
+        a = torch.relu((x.float() + add.float()) * insc.view(n, cin, 1, 1) * pix.float()).to(torch.bfloat16).float()
+        ref = F.relu(F.conv2d(a, wt.float().permute(0, 3, 1, 2), bias, padding=k // 2)) + res.float()
+        scale = float(ref.abs().max())
+        assert float((outs[0] - outs[1]).abs().max()) / scale <= 2 ** -6
+        assert float((outs[0][:, 32:80] - ref).abs().max()) / scale <= 2 ** -6
