@@ -96,10 +96,12 @@ int mgdt_dwconv7_ln(const void* x, int x_cs, const void* w, const float* bias, c
  * arithmetic of mmcv ModulatedDeformConv2d / torchvision.ops.deform_conv2d).  offset: 18 channels
  * ((dy,dx) per tap), mask: 9 channels; with mask_is_logit the sigmoid of head.py:517 is applied
  * here, so both may be channel slices of the raw spatial_conv_offset output (head.py:515-517).
- * w is [Cout][9][Cin] in dtype. */
+ * w is [Cout][9][Cin] in dtype; w_umma (optional, bf16) is that matrix packed by mgdt_conv_umma_pack as
+ * a 1x1 conv over 9*Cin channels: the tensor-core path builds the modulated bilinear im2col tile in
+ * shared memory and runs it through tcgen05. */
 int mgdt_dcn3x3(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs,
-                int mask_is_logit, const void* w, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, int dtype,
-                void* stream);
+                int mask_is_logit, const void* w, const void* w_umma, void* y, int y_cs, int N, int H, int W, int Cin,
+                int Cout, int dtype, void* stream);
 
 /* ---------------------------------------------------------------- reductions
  * Per-(n,c) sums over the image, optionally per adaptive 2x2 window as well.

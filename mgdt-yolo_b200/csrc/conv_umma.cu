@@ -186,6 +186,9 @@ struct UmmaP {
     UmmaPlan pl;
     UmmaRun rn;
     long long M_total;   // mode 0: N*H*W
+    // DCNv2 staging (mode 0 over a virtual 9*dcn_cin-channel input built by modulated bilinear sampling)
+    const __nv_bfloat16 *dcn_off, *dcn_mask;
+    int off_cs, mask_cs, mask_logit, dcn_cin;
 };
 
 // position (tile-relative index m in [0, 128*MB)) -> output pixel index (n*Ho*Wo + ho*Wo + wo) or -1
@@ -256,6 +259,58 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const UmmaP p)
             n_img = (int)(tile / rn.tiles_per_img);
             tt = (int)(tile - (long long)n_img * rn.tiles_per_img);
         }
+        if (p.dcn_off) {
+            // DCNv2 (DyDCNv2.forward, block.py:427-429): chunk (pos, plane) = 8 channels of tap = plane / (Cin/8),
+            // value = mask * bilinear(x, (h + ky - 1 + dy, w + kx - 1 + dx)), zero outside (-1,H)x(-1,W).
+            const int cgs = p.dcn_cin / 8;
+            for (int e = tid; e < total; e += UM_THREADS) {
+                const int plane = e % planes;
+                const int pos = e / planes;
+                const long long g = pix0 + pos;
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = 0.f;
+                if (g < p.M_total) {
+                    const int tap = plane / cgs, cg = plane - tap * cgs;
+                    const int n = (int)(g / ((long long)p.H * p.W));
+                    const int rem = (int)(g - (long long)n * p.H * p.W);
+                    const int hq = rem / p.W, wq = rem - hq * p.W;
+                    const __nv_bfloat16* ofp = p.dcn_off + g * p.off_cs + 2 * tap;
+                    const float dy = __bfloat162float(ofp[0]), dx = __bfloat162float(ofp[1]);
+                    float m = __bfloat162float(p.dcn_mask[g * p.mask_cs + tap]);
+                    if (p.mask_logit) m = sigmoidf_(m);
+                    const float py = (float)(hq + tap / 3 - 1) + dy, px = (float)(wq + tap % 3 - 1) + dx;
+                    if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
+                        const int y0 = (int)floorf(py), x0 = (int)floorf(px);
+                        const float ly = py - (float)y0, lx = px - (float)x0;
+                        const float hy = 1.f - ly, hx = 1.f - lx;
+                        const __nv_bfloat16* xn = p.x + (long long)n * p.H * p.W * p.x_cs + cg * 8;
+                        const float wgt[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+                        const int yy[4] = {y0, y0, y0 + 1, y0 + 1}, xx[4] = {x0, x0 + 1, x0, x0 + 1};
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            if (yy[c4] >= 0 && yy[c4] <= p.H - 1 && xx[c4] >= 0 && xx[c4] <= p.W - 1) {
+                                const uint4 v = __ldg(reinterpret_cast<const uint4*>(xn + ((long long)yy[c4] * p.W + xx[c4]) * p.x_cs));
+                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 t = __bfloat1622float2(h[j]);
+                                    f[2 * j] = fmaf(wgt[c4], t.x, f[2 * j]);
+                                    f[2 * j + 1] = fmaf(wgt[c4], t.y, f[2 * j + 1]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] *= m;
+                    }
+                }
+                uint4 o;
+                __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                *reinterpret_cast<uint4*>(sA + ((size_t)plane * rn.pstride16 + pos) * 16) = o;
+            }
+        } else
         for (int e = tid; e < total; e += UM_THREADS) {
             const int plane = e % planes;
             const int rest = e / planes;
@@ -470,6 +525,7 @@ int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
     p.res_vec = (a->residual && ((uintptr_t)a->residual & 15) == 0 && (a->res_cs & 7) == 0) ? 1 : 0;
     p.pl = pl; p.rn = rn;
     p.M_total = (long long)a->N * a->H * a->W;
+    p.dcn_off = nullptr; p.dcn_mask = nullptr; p.off_cs = p.mask_cs = p.mask_logit = p.dcn_cin = 0;
     {
         cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_MAX_SMEM);
         if (e != cudaSuccess) return set_error(-EIO, "conv2d_umma: smem attr: %s", cudaGetErrorString(e));
@@ -477,6 +533,37 @@ int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
     dim3 grid((unsigned)rn.tiles, (unsigned)pl.nsplit);
     conv_umma_kernel<<<grid, UM_THREADS, rn.smem_total, s>>>(p);
     MGDT_LAUNCH_CHECK("conv_umma");
+    return 0;
+}
+
+// DCNv2 3x3 on the tensor cores: a 1x1 GEMM over the virtual (9*Cin)-channel im2col built while staging.
+bool dcn_umma_supported(const void* x, int x_cs, const void* w_umma, int N, int H, int W, int Cin, int Cout) {
+    if (!w_umma || Cin % 8 != 0 || ((uintptr_t)x & 15) || (x_cs & 7) || ((uintptr_t)w_umma & 15)) return false;
+    UmmaPlan pl = make_plan(9 * Cin, Cout, 1, 1);
+    UmmaRun rn;
+    return pl.ok && make_run(pl, N, H, W, H, W, rn) && rn.tiles <= 0x7fffffffLL;
+}
+
+int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs, int mask_is_logit,
+             const void* w_umma, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, cudaStream_t s) {
+    UmmaPlan pl = make_plan(9 * Cin, Cout, 1, 1);
+    UmmaRun rn;
+    if (!pl.ok || !make_run(pl, N, H, W, H, W, rn)) return set_error(-EINVAL, "dcn_umma: unsupported shape");
+    UmmaP p;
+    p.x = (const __nv_bfloat16*)x; p.w = (const __nv_bfloat16*)w_umma; p.pre_add = nullptr; p.pix_scale = nullptr;
+    p.residual = nullptr; p.bias = nullptr; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y;
+    p.N = N; p.H = H; p.W = W; p.Cin = 9 * Cin; p.Cout = Cout; p.Ho = H; p.Wo = W;
+    p.x_cs = x_cs; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = MGDT_ACT_NONE; p.in_relu = 0;
+    p.y_vec = (((uintptr_t)y & 15) == 0 && (y_cs & 7) == 0) ? 1 : 0;
+    p.res_vec = 0;
+    p.pl = pl; p.rn = rn;
+    p.M_total = (long long)N * H * W;
+    p.dcn_off = (const __nv_bfloat16*)offset; p.dcn_mask = (const __nv_bfloat16*)mask;
+    p.off_cs = off_cs; p.mask_cs = mask_cs; p.mask_logit = mask_is_logit; p.dcn_cin = Cin;
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_MAX_SMEM);
+    if (e != cudaSuccess) return set_error(-EIO, "dcn_umma: smem attr: %s", cudaGetErrorString(e));
+    conv_umma_kernel<<<dim3((unsigned)rn.tiles, (unsigned)pl.nsplit), UM_THREADS, rn.smem_total, s>>>(p);
+    MGDT_LAUNCH_CHECK("dcn_umma");
     return 0;
 }
 

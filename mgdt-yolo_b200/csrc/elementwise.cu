@@ -1,6 +1,10 @@
 // Memory-bound NHWC kernels: per-(n,c) affine + activation, resampling into concat slices, the
-// SPPF pooling chain, the injection gate and input preprocessing.  Thread <-> (pixel, channel)
-// with the channel fastest so that every warp touches contiguous bytes.
+// SPPF pooling chain, the injection gate and input preprocessing.
+//
+// Mapping: one thread owns VEC = 8 consecutive channels of one pixel (a 16-byte bf16 / 32-byte fp32
+// access), the channel-vector index is the fastest-varying thread index, so a warp touches
+// contiguous bytes; all index arithmetic is 32-bit.  A scalar (VEC = 1) instantiation covers
+// channel counts / strides / pointers that are not 8-aligned.
 #include "common.cuh"
 
 namespace mgdt {
@@ -9,29 +13,77 @@ constexpr int EW_THREADS = 256;
 
 static inline int ew_grid(long long total) {
     long long b = (total + EW_THREADS - 1) / EW_THREADS;
-    const long long cap = 148LL * 16;  // grid-stride beyond 16 resident CTAs per SM
+    const long long cap = 148LL * 32;
     return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
+// ---- vector load/store of V channels as floats
+template <typename T, int V> struct VecIO;
+template <typename T> struct VecIO<T, 1> {
+    static __device__ __forceinline__ void ld(const T* p, float* f) { f[0] = ldf(p); }
+    static __device__ __forceinline__ void st(T* p, const float* f) { stf(p, f[0]); }
+};
+template <> struct VecIO<__nv_bfloat16, 8> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* f) {
+        uint4 v;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        *reinterpret_cast<uint4*>(p) = v;
+    }
+};
+template <> struct VecIO<float, 8> {
+    static __device__ __forceinline__ void ld(const float* p, float* f) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* f) {
+        reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+};
+
+static inline bool aligned8(const void* p, int cs, size_t esize) {
+    return p == nullptr || ((((uintptr_t)p) % (8 * esize)) == 0 && (cs % 8) == 0);
+}
+
 // ------------------------------------------------------------------ affine + act (+ other)
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(EW_THREADS) affine_act_kernel(const T* __restrict__ x, int x_cs,
                                                                 const float* __restrict__ a,
                                                                 const float* __restrict__ b,
                                                                 const T* __restrict__ other, int o_cs, int act,
-                                                                T* __restrict__ y, int y_cs, long long HW, int C,
-                                                                long long total) {
-    for (long long i = blockIdx.x * (long long)EW_THREADS + threadIdx.x; i < total;
-         i += (long long)gridDim.x * EW_THREADS) {
-        const int c = (int)(i % C);
-        const long long pix = i / C;
-        const long long n = pix / HW;
-        float v = ldf(x + pix * x_cs + c);
-        if (a) v *= a[n * C + c];
-        if (b) v += b[n * C + c];
-        v = apply_act(v, act);
-        if (other) v += ldf(other + pix * o_cs + c);
-        stf(y + pix * y_cs + c, v);
+                                                                T* __restrict__ y, int y_cs, unsigned HW, unsigned C,
+                                                                unsigned total) {
+    const unsigned CV = C / V;
+    for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
+        const unsigned cv = i % CV, pix = i / CV;
+        const unsigned c = cv * V;
+        float f[V];
+        VecIO<T, V>::ld(x + (size_t)pix * x_cs + c, f);
+        if (a || b) {
+            const unsigned n = pix / HW;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if (a) f[j] *= a[n * C + c + j];
+                if (b) f[j] += b[n * C + c + j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) f[j] = apply_act(f[j], act);
+        if (other) {
+            float g[V];
+            VecIO<T, V>::ld(other + (size_t)pix * o_cs + c, g);
+#pragma unroll
+            for (int j = 0; j < V; ++j) f[j] += g[j];
+        }
+        VecIO<T, V>::st(y + (size_t)pix * y_cs + c, f);
     }
 }
 
@@ -47,62 +99,79 @@ __device__ __forceinline__ void bilinear_src(int o, int in, int out, int& i0, in
     l = src - (float)i0;
 }
 
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(EW_THREADS) resample_kernel(const T* __restrict__ x, int x_cs, int Hi, int Wi,
-                                                              T* __restrict__ y, int y_cs, int Ho, int Wo, int C,
-                                                              int mode, long long total) {
-    for (long long i = blockIdx.x * (long long)EW_THREADS + threadIdx.x; i < total;
-         i += (long long)gridDim.x * EW_THREADS) {
-        const int c = (int)(i % C);
-        long long pix = i / C;
-        const int wo = (int)(pix % Wo);
-        const int ho = (int)((pix / Wo) % Ho);
-        const long long n = pix / ((long long)Wo * Ho);
-        const T* xn = x + n * (long long)Hi * Wi * x_cs + c;
-        float v;
+                                                              T* __restrict__ y, int y_cs, int Ho, int Wo, unsigned C,
+                                                              int mode, unsigned total) {
+    const unsigned CV = C / V;
+    for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
+        const unsigned cv = i % CV, pix = i / CV;
+        const unsigned c = cv * V;
+        const int wo = (int)(pix % (unsigned)Wo);
+        const unsigned t = pix / (unsigned)Wo;
+        const int ho = (int)(t % (unsigned)Ho);
+        const unsigned n = t / (unsigned)Ho;
+        const T* xn = x + (size_t)n * Hi * Wi * x_cs + c;
+        float f[V];
         if (mode == MGDT_RS_COPY) {
-            v = ldf(xn + ((long long)ho * Wi + wo) * x_cs);
+            VecIO<T, V>::ld(xn + (size_t)(ho * Wi + wo) * x_cs, f);
         } else if (mode == MGDT_RS_NEAREST) {
             // nn.Upsample(mode='nearest'): src = floor(dst * in/out)
             const int hi = min((int)floorf((float)ho * ((float)Hi / (float)Ho)), Hi - 1);
             const int wi = min((int)floorf((float)wo * ((float)Wi / (float)Wo)), Wi - 1);
-            v = ldf(xn + ((long long)hi * Wi + wi) * x_cs);
+            VecIO<T, V>::ld(xn + (size_t)(hi * Wi + wi) * x_cs, f);
         } else if (mode == MGDT_RS_AVGPOOL) {
             // adaptive_avg_pool2d: window [floor(o*in/out), ceil((o+1)*in/out))
-            const int h0 = (int)(((long long)ho * Hi) / Ho), h1 = (int)((((long long)ho + 1) * Hi + Ho - 1) / Ho);
-            const int w0 = (int)(((long long)wo * Wi) / Wo), w1 = (int)((((long long)wo + 1) * Wi + Wo - 1) / Wo);
-            float s = 0.f;
+            const int h0 = (ho * Hi) / Ho, h1 = ((ho + 1) * Hi + Ho - 1) / Ho;
+            const int w0 = (wo * Wi) / Wo, w1 = ((wo + 1) * Wi + Wo - 1) / Wo;
+#pragma unroll
+            for (int j = 0; j < V; ++j) f[j] = 0.f;
             for (int h = h0; h < h1; ++h)
-                for (int w = w0; w < w1; ++w) s += ldf(xn + ((long long)h * Wi + w) * x_cs);
-            v = s / (float)((h1 - h0) * (w1 - w0));
+                for (int w = w0; w < w1; ++w) {
+                    float g[V];
+                    VecIO<T, V>::ld(xn + (size_t)(h * Wi + w) * x_cs, g);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) f[j] += g[j];
+                }
+            const float cnt = (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+            for (int j = 0; j < V; ++j) f[j] = f[j] / cnt;
         } else {
             int h0, h1, w0, w1;
             float lh, lw;
             bilinear_src(ho, Hi, Ho, h0, h1, lh);
             bilinear_src(wo, Wi, Wo, w0, w1, lw);
-            const float v00 = ldf(xn + ((long long)h0 * Wi + w0) * x_cs), v01 = ldf(xn + ((long long)h0 * Wi + w1) * x_cs);
-            const float v10 = ldf(xn + ((long long)h1 * Wi + w0) * x_cs), v11 = ldf(xn + ((long long)h1 * Wi + w1) * x_cs);
-            v = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
+            float v00[V], v01[V], v10[V], v11[V];
+            VecIO<T, V>::ld(xn + (size_t)(h0 * Wi + w0) * x_cs, v00);
+            VecIO<T, V>::ld(xn + (size_t)(h0 * Wi + w1) * x_cs, v01);
+            VecIO<T, V>::ld(xn + (size_t)(h1 * Wi + w0) * x_cs, v10);
+            VecIO<T, V>::ld(xn + (size_t)(h1 * Wi + w1) * x_cs, v11);
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                f[j] = (1.f - lh) * ((1.f - lw) * v00[j] + lw * v01[j]) + lh * ((1.f - lw) * v10[j] + lw * v11[j]);
         }
-        stf(y + pix * y_cs + c, v);
+        VecIO<T, V>::st(y + (size_t)pix * y_cs + c, f);
     }
 }
 
 // ------------------------------------------------------------------ SPPF pooling chain
 // maxpool(k,1,k/2) applied 1x/2x/3x == max over (k-1)*j+1 windows, j = 1..3 (padding is -inf).
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(EW_THREADS) sppf_pool_kernel(const T* __restrict__ x, int x_cs, T* __restrict__ y1,
                                                                T* __restrict__ y2, T* __restrict__ y3, int y_cs, int H,
-                                                               int W, int C, int r, long long total) {
-    for (long long i = blockIdx.x * (long long)EW_THREADS + threadIdx.x; i < total;
-         i += (long long)gridDim.x * EW_THREADS) {
-        const int c = (int)(i % C);
-        long long pix = i / C;
-        const int w = (int)(pix % W);
-        const int h = (int)((pix / W) % H);
-        const long long n = pix / ((long long)W * H);
-        const T* xn = x + n * (long long)H * W * x_cs + c;
-        float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                                                               int W, unsigned C, int r, unsigned total) {
+    const unsigned CV = C / V;
+    for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
+        const unsigned cv = i % CV, pix = i / CV;
+        const unsigned c = cv * V;
+        const int w = (int)(pix % (unsigned)W);
+        const unsigned t = pix / (unsigned)W;
+        const int h = (int)(t % (unsigned)H);
+        const unsigned n = t / (unsigned)H;
+        const T* xn = x + (size_t)n * H * W * x_cs + c;
+        float m1[V], m2[V], m3[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) m1[j] = m2[j] = m3[j] = -INFINITY;
         for (int dy = -3 * r; dy <= 3 * r; ++dy) {
             const int hh = h + dy;
             if (hh < 0 || hh >= H) continue;
@@ -111,81 +180,98 @@ __global__ void __launch_bounds__(EW_THREADS) sppf_pool_kernel(const T* __restri
                 const int ww = w + dx;
                 if (ww < 0 || ww >= W) continue;
                 const int adx = dx < 0 ? -dx : dx;
-                const float v = ldf(xn + ((long long)hh * W + ww) * x_cs);
                 const int d = ady > adx ? ady : adx;
-                m3 = fmaxf(m3, v);
-                if (d <= 2 * r) m2 = fmaxf(m2, v);
-                if (d <= r) m1 = fmaxf(m1, v);
+                float g[V];
+                VecIO<T, V>::ld(xn + (size_t)(hh * W + ww) * x_cs, g);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    m3[j] = fmaxf(m3[j], g[j]);
+                    if (d <= 2 * r) m2[j] = fmaxf(m2[j], g[j]);
+                    if (d <= r) m1[j] = fmaxf(m1[j], g[j]);
+                }
             }
         }
-        stf(y1 + pix * y_cs + c, m1);
-        stf(y2 + pix * y_cs + c, m2);
-        stf(y3 + pix * y_cs + c, m3);
+        VecIO<T, V>::st(y1 + (size_t)pix * y_cs + c, m1);
+        VecIO<T, V>::st(y2 + (size_t)pix * y_cs + c, m2);
+        VecIO<T, V>::st(y3 + (size_t)pix * y_cs + c, m3);
     }
 }
 
 // ------------------------------------------------------------------ injection gate
-template <typename T>
+__device__ __forceinline__ float hsig(float v) { return fminf(fmaxf(v + 3.0f, 0.0f), 6.0f) / 6.0f; }
+
+template <typename T, int V>
 __global__ void __launch_bounds__(EW_THREADS) inject_kernel(const T* __restrict__ local, int l_cs,
                                                             const T* __restrict__ gact, int a_cs,
                                                             const T* __restrict__ gfeat, int f_cs, T* __restrict__ y,
-                                                            int y_cs, int H, int W, int Hg, int Wg, int C,
-                                                            long long total) {
+                                                            int y_cs, int H, int W, int Hg, int Wg, unsigned C,
+                                                            unsigned total) {
     const bool pool = H < Hg;
-    for (long long i = blockIdx.x * (long long)EW_THREADS + threadIdx.x; i < total;
-         i += (long long)gridDim.x * EW_THREADS) {
-        const int c = (int)(i % C);
-        long long pix = i / C;
-        const int w = (int)(pix % W);
-        const int h = (int)((pix / W) % H);
-        const long long n = pix / ((long long)W * H);
-        const T* an = gact + n * (long long)Hg * Wg * a_cs + c;
-        const T* fn = gfeat + n * (long long)Hg * Wg * f_cs + c;
-        float sig, gf;
+    const unsigned CV = C / V;
+    for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
+        const unsigned cv = i % CV, pix = i / CV;
+        const unsigned c = cv * V;
+        const int w = (int)(pix % (unsigned)W);
+        const unsigned t = pix / (unsigned)W;
+        const int h = (int)(t % (unsigned)H);
+        const unsigned n = t / (unsigned)H;
+        const T* an = gact + (size_t)n * Hg * Wg * a_cs + c;
+        const T* fn = gfeat + (size_t)n * Hg * Wg * f_cs + c;
+        float sig[V], gf[V];
         if (pool) {
-            const int h0 = (int)(((long long)h * Hg) / H), h1 = (int)((((long long)h + 1) * Hg + H - 1) / H);
-            const int w0 = (int)(((long long)w * Wg) / W), w1 = (int)((((long long)w + 1) * Wg + W - 1) / W);
-            float sa = 0.f, sf = 0.f;
+            const int h0 = (h * Hg) / H, h1 = ((h + 1) * Hg + H - 1) / H;
+            const int w0 = (w * Wg) / W, w1 = ((w + 1) * Wg + W - 1) / W;
+#pragma unroll
+            for (int j = 0; j < V; ++j) sig[j] = gf[j] = 0.f;
             for (int hh = h0; hh < h1; ++hh)
                 for (int ww = w0; ww < w1; ++ww) {
-                    sa += ldf(an + ((long long)hh * Wg + ww) * a_cs);
-                    sf += ldf(fn + ((long long)hh * Wg + ww) * f_cs);
+                    float a[V], f[V];
+                    VecIO<T, V>::ld(an + (size_t)(hh * Wg + ww) * a_cs, a);
+                    VecIO<T, V>::ld(fn + (size_t)(hh * Wg + ww) * f_cs, f);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) { sig[j] += a[j]; gf[j] += f[j]; }
                 }
-            const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
-            sig = sa * inv;
-            gf = sf * inv;
+            const float cnt = (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+            for (int j = 0; j < V; ++j) { sig[j] = sig[j] / cnt; gf[j] = gf[j] / cnt; }
         } else {
             int h0, h1, w0, w1;
             float lh, lw;
             bilinear_src(h, Hg, H, h0, h1, lh);
             bilinear_src(w, Wg, W, w0, w1, lw);
-            const long long o00 = (long long)h0 * Wg + w0, o01 = (long long)h0 * Wg + w1;
-            const long long o10 = (long long)h1 * Wg + w0, o11 = (long long)h1 * Wg + w1;
-            const float a00 = apply_act(ldf(an + o00 * a_cs), MGDT_ACT_HSIGMOID), a01 = apply_act(ldf(an + o01 * a_cs), MGDT_ACT_HSIGMOID);
-            const float a10 = apply_act(ldf(an + o10 * a_cs), MGDT_ACT_HSIGMOID), a11 = apply_act(ldf(an + o11 * a_cs), MGDT_ACT_HSIGMOID);
-            sig = (1.f - lh) * ((1.f - lw) * a00 + lw * a01) + lh * ((1.f - lw) * a10 + lw * a11);
-            const float f00 = ldf(fn + o00 * f_cs), f01 = ldf(fn + o01 * f_cs);
-            const float f10 = ldf(fn + o10 * f_cs), f11 = ldf(fn + o11 * f_cs);
-            gf = (1.f - lh) * ((1.f - lw) * f00 + lw * f01) + lh * ((1.f - lw) * f10 + lw * f11);
+            const size_t o00 = (size_t)(h0 * Wg + w0), o01 = (size_t)(h0 * Wg + w1);
+            const size_t o10 = (size_t)(h1 * Wg + w0), o11 = (size_t)(h1 * Wg + w1);
+            float a00[V], a01[V], a10[V], a11[V], f00[V], f01[V], f10[V], f11[V];
+            VecIO<T, V>::ld(an + o00 * a_cs, a00); VecIO<T, V>::ld(an + o01 * a_cs, a01);
+            VecIO<T, V>::ld(an + o10 * a_cs, a10); VecIO<T, V>::ld(an + o11 * a_cs, a11);
+            VecIO<T, V>::ld(fn + o00 * f_cs, f00); VecIO<T, V>::ld(fn + o01 * f_cs, f01);
+            VecIO<T, V>::ld(fn + o10 * f_cs, f10); VecIO<T, V>::ld(fn + o11 * f_cs, f11);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                sig[j] = (1.f - lh) * ((1.f - lw) * hsig(a00[j]) + lw * hsig(a01[j])) +
+                         lh * ((1.f - lw) * hsig(a10[j]) + lw * hsig(a11[j]));
+                gf[j] = (1.f - lh) * ((1.f - lw) * f00[j] + lw * f01[j]) + lh * ((1.f - lw) * f10[j] + lw * f11[j]);
+            }
         }
-        const float l = ldf(local + pix * l_cs + c);
-        stf(y + pix * y_cs + c, l * sig + gf);
+        float l[V];
+        VecIO<T, V>::ld(local + (size_t)pix * l_cs + c, l);
+#pragma unroll
+        for (int j = 0; j < V; ++j) l[j] = l[j] * sig[j] + gf[j];
+        VecIO<T, V>::st(y + (size_t)pix * y_cs + c, l);
     }
 }
 
 // ------------------------------------------------------------------ preprocess
 template <typename S, typename T>
 __global__ void __launch_bounds__(EW_THREADS) preprocess_kernel(const S* __restrict__ src, T* __restrict__ y, int y_cs,
-                                                                int C, long long HW, float div, long long total) {
-    // output-major mapping (channel fastest) -> coalesced NHWC stores; the NCHW reads of one warp hit
-    // C planes at consecutive pixels, which L1/L2 merge.
-    for (long long i = blockIdx.x * (long long)EW_THREADS + threadIdx.x; i < total;
-         i += (long long)gridDim.x * EW_THREADS) {
-        const int c = (int)(i % C);
-        const long long pix = i / C;
-        const long long n = pix / HW, p = pix - n * HW;
-        const float v = (float)src[(n * C + c) * HW + p] / div;  // `im /= 255` (predictor.py:129)
-        stf(y + pix * y_cs + c, v);
+                                                                int C, unsigned HW, float div, unsigned npix) {
+    // thread <-> pixel: per-plane reads are contiguous across the warp; the C outputs of a pixel are
+    // adjacent, so the warp's stores cover one contiguous span.
+    for (unsigned pix = blockIdx.x * EW_THREADS + threadIdx.x; pix < npix; pix += gridDim.x * EW_THREADS) {
+        const unsigned n = pix / HW, p = pix - n * HW;
+        const S* s = src + (size_t)n * C * HW + p;
+        T* o = y + (size_t)pix * y_cs;
+        for (int c = 0; c < C; ++c) stf(o + c, (float)s[(size_t)c * HW] / div);  // `im /= 255` (predictor.py:129)
     }
 }
 
@@ -193,14 +279,30 @@ __global__ void __launch_bounds__(EW_THREADS) preprocess_kernel(const S* __restr
 
 using namespace mgdt;
 
+#define MGDT_VEC_SWITCH(vec_ok, V, ...) \
+    do {                                \
+        if (vec_ok) {                   \
+            constexpr int V = 8;        \
+            __VA_ARGS__;                \
+        } else {                        \
+            constexpr int V = 1;        \
+            __VA_ARGS__;                \
+        }                               \
+    } while (0)
+
 extern "C" int mgdt_affine_act(const void* x, int x_cs, const float* a, const float* b, const void* other, int o_cs,
                                int act, void* y, int y_cs, int N, int H, int W, int C, int dtype, void* stream) {
     MGDT_CHECK(x && y, "affine_act: null pointer");
     MGDT_CHECK(N > 0 && H > 0 && W > 0 && C > 0 && x_cs >= C && y_cs >= C, "affine_act: bad shape");
-    const long long total = (long long)N * H * W * C;
+    MGDT_CHECK((long long)N * H * W * C < (1LL << 31), "affine_act: tensor too large for 32-bit indexing");
     MGDT_DTYPE_SWITCH(dtype, T, {
-        affine_act_kernel<T><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
-            (const T*)x, x_cs, a, b, (const T*)other, o_cs, act, (T*)y, y_cs, (long long)H * W, C, total);
+        const bool vec = C % 8 == 0 && aligned8(x, x_cs, sizeof(T)) && aligned8(y, y_cs, sizeof(T)) &&
+                         aligned8(other, other ? o_cs : 0, sizeof(T));
+        MGDT_VEC_SWITCH(vec, V, {
+            const unsigned total = (unsigned)((long long)N * H * W * (C / V));
+            affine_act_kernel<T, V><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
+                (const T*)x, x_cs, a, b, (const T*)other, o_cs, act, (T*)y, y_cs, (unsigned)(H * W), (unsigned)C, total);
+        });
     });
     MGDT_LAUNCH_CHECK("affine_act");
     return 0;
@@ -212,10 +314,15 @@ extern "C" int mgdt_resample(const void* x, int x_cs, int Hi, int Wi, void* y, i
     MGDT_CHECK(N > 0 && C > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && x_cs >= C && y_cs >= C, "resample: bad shape");
     MGDT_CHECK(mode >= 0 && mode <= 3, "resample: bad mode %d", mode);
     MGDT_CHECK(mode != MGDT_RS_COPY || (Hi == Ho && Wi == Wo), "resample: copy needs equal sizes");
-    const long long total = (long long)N * Ho * Wo * C;
+    MGDT_CHECK((long long)N * Ho * Wo * C < (1LL << 31) && (long long)N * Hi * Wi * C < (1LL << 31),
+               "resample: tensor too large for 32-bit indexing");
     MGDT_DTYPE_SWITCH(dtype, T, {
-        resample_kernel<T><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const T*)x, x_cs, Hi, Wi, (T*)y,
-                                                                                     y_cs, Ho, Wo, C, mode, total);
+        const bool vec = C % 8 == 0 && aligned8(x, x_cs, sizeof(T)) && aligned8(y, y_cs, sizeof(T));
+        MGDT_VEC_SWITCH(vec, V, {
+            const unsigned total = (unsigned)((long long)N * Ho * Wo * (C / V));
+            resample_kernel<T, V><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
+                (const T*)x, x_cs, Hi, Wi, (T*)y, y_cs, Ho, Wo, (unsigned)C, mode, total);
+        });
     });
     MGDT_LAUNCH_CHECK("resample");
     return 0;
@@ -225,10 +332,15 @@ extern "C" int mgdt_sppf_pool(const void* x, int x_cs, void* y1, void* y2, void*
                               int C, int k, int dtype, void* stream) {
     MGDT_CHECK(x && y1 && y2 && y3, "sppf_pool: null pointer");
     MGDT_CHECK(N > 0 && H > 0 && W > 0 && C > 0 && (k & 1) && k >= 1, "sppf_pool: bad shape/k");
-    const long long total = (long long)N * H * W * C;
+    MGDT_CHECK((long long)N * H * W * C < (1LL << 31), "sppf_pool: tensor too large for 32-bit indexing");
     MGDT_DTYPE_SWITCH(dtype, T, {
-        sppf_pool_kernel<T><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
-            (const T*)x, x_cs, (T*)y1, (T*)y2, (T*)y3, y_cs, H, W, C, k / 2, total);
+        const bool vec = C % 8 == 0 && aligned8(x, x_cs, sizeof(T)) && aligned8(y1, y_cs, sizeof(T)) &&
+                         aligned8(y2, y_cs, sizeof(T)) && aligned8(y3, y_cs, sizeof(T));
+        MGDT_VEC_SWITCH(vec, V, {
+            const unsigned total = (unsigned)((long long)N * H * W * (C / V));
+            sppf_pool_kernel<T, V><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
+                (const T*)x, x_cs, (T*)y1, (T*)y2, (T*)y3, y_cs, H, W, (unsigned)C, k / 2, total);
+        });
     });
     MGDT_LAUNCH_CHECK("sppf_pool");
     return 0;
@@ -238,10 +350,17 @@ extern "C" int mgdt_inject(const void* local, int l_cs, const void* gact, int a_
                            void* y, int y_cs, int N, int H, int W, int Hg, int Wg, int C, int dtype, void* stream) {
     MGDT_CHECK(local && gact && gfeat && y, "inject: null pointer");
     MGDT_CHECK(N > 0 && H > 0 && W > 0 && Hg > 0 && Wg > 0 && C > 0, "inject: bad shape");
-    const long long total = (long long)N * H * W * C;
+    MGDT_CHECK((long long)N * H * W * C < (1LL << 31) && (long long)N * Hg * Wg * C < (1LL << 31),
+               "inject: tensor too large for 32-bit indexing");
     MGDT_DTYPE_SWITCH(dtype, T, {
-        inject_kernel<T><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
-            (const T*)local, l_cs, (const T*)gact, a_cs, (const T*)gfeat, f_cs, (T*)y, y_cs, H, W, Hg, Wg, C, total);
+        const bool vec = C % 8 == 0 && aligned8(local, l_cs, sizeof(T)) && aligned8(gact, a_cs, sizeof(T)) &&
+                         aligned8(gfeat, f_cs, sizeof(T)) && aligned8(y, y_cs, sizeof(T));
+        MGDT_VEC_SWITCH(vec, V, {
+            const unsigned total = (unsigned)((long long)N * H * W * (C / V));
+            inject_kernel<T, V><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
+                (const T*)local, l_cs, (const T*)gact, a_cs, (const T*)gfeat, f_cs, (T*)y, y_cs, H, W, Hg, Wg,
+                (unsigned)C, total);
+        });
     });
     MGDT_LAUNCH_CHECK("inject");
     return 0;
@@ -250,16 +369,17 @@ extern "C" int mgdt_inject(const void* local, int l_cs, const void* gact, int a_
 extern "C" int mgdt_preprocess(const void* src, int src_is_u8, void* y, int y_cs, int N, int C, int H, int W, int dtype,
                                void* stream) {
     MGDT_CHECK(src && y && N > 0 && C > 0 && H > 0 && W > 0 && y_cs >= C, "preprocess: bad args");
-    const long long total = (long long)N * H * W * C;
-    const long long HW = (long long)H * W;
+    MGDT_CHECK((long long)N * H * W * C < (1LL << 31), "preprocess: tensor too large for 32-bit indexing");
+    const unsigned npix = (unsigned)((long long)N * H * W);
+    const unsigned HW = (unsigned)(H * W);
     cudaStream_t s = (cudaStream_t)stream;
     MGDT_DTYPE_SWITCH(dtype, T, {
         if (src_is_u8)
-            preprocess_kernel<uint8_t, T><<<ew_grid(total), EW_THREADS, 0, s>>>((const uint8_t*)src, (T*)y, y_cs, C, HW,
-                                                                                255.0f, total);
+            preprocess_kernel<uint8_t, T><<<ew_grid(npix), EW_THREADS, 0, s>>>((const uint8_t*)src, (T*)y, y_cs, C, HW,
+                                                                               255.0f, npix);
         else
-            preprocess_kernel<float, T><<<ew_grid(total), EW_THREADS, 0, s>>>((const float*)src, (T*)y, y_cs, C, HW,
-                                                                              1.0f, total);
+            preprocess_kernel<float, T><<<ew_grid(npix), EW_THREADS, 0, s>>>((const float*)src, (T*)y, y_cs, C, HW,
+                                                                             1.0f, npix);
     });
     MGDT_LAUNCH_CHECK("preprocess");
     return 0;

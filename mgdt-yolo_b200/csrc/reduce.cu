@@ -5,18 +5,38 @@
 namespace mgdt {
 
 // ------------------------------------------------------------------ chan_stats
-// Stage 1: grid (chunks, N).  A block walks a strip of pixels; thread = (pixel group, channel).
-// Partials: part[n][chunk][Q][C] (sum) and partsq[n][chunk][C].
+// Stage 1: grid (chunks, N).  A block walks a strip of pixels; thread = (pixel group, channel vector
+// of V channels); partial sums go to part[n][chunk][Q][C] and partsq[n][chunk][C].
 constexpr int CS_THREADS = 256;
 
-template <typename T>
+template <typename T, int V> struct StatLd;
+template <typename T> struct StatLd<T, 1> {
+    static __device__ __forceinline__ void ld(const T* p, float* f) { f[0] = ldf(p); }
+};
+template <> struct StatLd<__nv_bfloat16, 8> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+    }
+};
+template <> struct StatLd<float, 8> {
+    static __device__ __forceinline__ void ld(const float* p, float* f) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+};
+
+template <typename T, int V, int Q>
 __global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __restrict__ x, int x_cs, int H, int W, int C,
-                                                                 int Q, int pix_per_chunk, float* __restrict__ part,
+                                                                 int pix_per_chunk, float* __restrict__ part,
                                                                  float* __restrict__ partsq) {
-    extern __shared__ float sm[];  // [PG][Q+1][Cw]
+    __shared__ float sm[CS_THREADS * V];  // [PG][Cw * V]
     const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const int CV = C / V;
     int Cw = 1;
-    while (Cw < C && Cw < CS_THREADS) Cw <<= 1;  // channel lanes per pass (pow2 <= 256)
+    while (Cw < CV && Cw < CS_THREADS) Cw <<= 1;  // channel-vector lanes per pass (pow2 <= 256)
     const int PG = CS_THREADS / Cw;
     const int cl = threadIdx.x % Cw, pg = threadIdx.x / Cw;
     const int HW = H * W;
@@ -25,43 +45,61 @@ __global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __rest
     // adaptive_avg_pool2d(2) windows: [floor(i*H/2), ceil((i+1)*H/2))
     const int h_top_end = (H + 1) / 2, h_bot_begin = H / 2;
     const int w_left_end = (W + 1) / 2, w_right_begin = W / 2;
-    const T* xn = x + (long long)n * HW * x_cs;
+    const T* xn = x + (size_t)n * HW * x_cs;
 
-    for (int cb = 0; cb < C; cb += Cw) {
-        const int c = cb + cl;
-        float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        float sq = 0.f;
-        if (c < C) {
+    for (int cb = 0; cb < CV; cb += Cw) {
+        const int cv = cb + cl;
+        float s[Q][V];
+        float sq[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            sq[j] = 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) s[q][j] = 0.f;
+        }
+        if (cv < CV) {
             for (int pidx = p_begin + pg; pidx < p_end; pidx += PG) {
-                const float v = ldf(xn + (long long)pidx * x_cs + c);
-                s[0] += v;
-                sq += v * v;
+                float v[V];
+                StatLd<T, V>::ld(xn + (size_t)pidx * x_cs + cv * V, v);
+                bool m[4] = {false, false, false, false};
                 if (Q == 5) {
                     const int h = pidx / W, w = pidx - h * W;
                     const bool top = h < h_top_end, bot = h >= h_bot_begin;
                     const bool left = w < w_left_end, right = w >= w_right_begin;
-                    if (top && left) s[1] += v;
-                    if (top && right) s[2] += v;
-                    if (bot && left) s[3] += v;
-                    if (bot && right) s[4] += v;
+                    m[0] = top && left; m[1] = top && right; m[2] = bot && left; m[3] = bot && right;
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    s[0][j] += v[j];
+                    sq[j] += v[j] * v[j];
+                    if (Q == 5) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (m[q]) s[1 + q][j] += v[j];
+                    }
                 }
             }
         }
-        // reduce over pixel groups through shared memory (fixed order -> deterministic)
-        for (int q = 0; q < Q; ++q) sm[(pg * (Q + 1) + q) * Cw + cl] = s[q];
-        sm[(pg * (Q + 1) + Q) * Cw + cl] = sq;
-        __syncthreads();
-        if (pg == 0 && c < C) {
-            for (int q = 0; q <= Q; ++q) {
-                float t = 0.f;
-                for (int g = 0; g < PG; ++g) t += sm[(g * (Q + 1) + q) * Cw + cl];
-                if (q < Q)
-                    part[(((long long)n * nchunks + chunk) * Q + q) * C + c] = t;
-                else if (partsq)
-                    partsq[((long long)n * nchunks + chunk) * C + c] = t;
+        // reduce over pixel groups through shared memory, one statistic at a time (fixed order -> deterministic)
+#pragma unroll
+        for (int q = 0; q <= Q; ++q) {
+            if (q == Q && !partsq) break;
+#pragma unroll
+            for (int j = 0; j < V; ++j) sm[(pg * Cw + cl) * V + j] = (q < Q) ? s[q < Q ? q : 0][j] : sq[j];
+            __syncthreads();
+            if (pg == 0 && cv < CV) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    float t = 0.f;
+                    for (int g = 0; g < PG; ++g) t += sm[(g * Cw + cl) * V + j];
+                    if (q < Q)
+                        part[(((size_t)n * nchunks + chunk) * Q + q) * C + cv * V + j] = t;
+                    else
+                        partsq[((size_t)n * nchunks + chunk) * C + cv * V + j] = t;
+                }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -117,14 +155,14 @@ extern "C" int mgdt_chan_stats(const void* x, int x_cs, int N, int H, int W, int
     const int ppc = cdiv(H * W, nch);
     float* part = (float*)ws;
     float* partsq = part + (size_t)N * nch * Q * C;
-    int Cw = 1;
-    while (Cw < C && Cw < CS_THREADS) Cw <<= 1;
-    const int PG = CS_THREADS / Cw;
-    const size_t smem = sizeof(float) * PG * (Q + 1) * Cw;
     cudaStream_t s = (cudaStream_t)stream;
     MGDT_DTYPE_SWITCH(dtype, T, {
-        chan_stats_partial<T><<<dim3(nch, N), CS_THREADS, smem, s>>>((const T*)x, x_cs, H, W, C, Q, ppc, part,
-                                                                     out_sumsq ? partsq : nullptr);
+        const bool vec = C % 8 == 0 && (x_cs % 8) == 0 && (((uintptr_t)x) % (8 * sizeof(T))) == 0;
+        float* psq = out_sumsq ? partsq : nullptr;
+        if (vec && quads) chan_stats_partial<T, 8, 5><<<dim3(nch, N), CS_THREADS, 0, s>>>((const T*)x, x_cs, H, W, C, ppc, part, psq);
+        else if (vec) chan_stats_partial<T, 8, 1><<<dim3(nch, N), CS_THREADS, 0, s>>>((const T*)x, x_cs, H, W, C, ppc, part, psq);
+        else if (quads) chan_stats_partial<T, 1, 5><<<dim3(nch, N), CS_THREADS, 0, s>>>((const T*)x, x_cs, H, W, C, ppc, part, psq);
+        else chan_stats_partial<T, 1, 1><<<dim3(nch, N), CS_THREADS, 0, s>>>((const T*)x, x_cs, H, W, C, ppc, part, psq);
     });
     MGDT_LAUNCH_CHECK("chan_stats_partial");
     const long long total = (long long)N * (Q + 1) * C;

@@ -367,6 +367,8 @@ class DyDCNv2(KernelModule):
 
         def build():
             wp = w.detach().float().permute(0, 2, 3, 1).contiguous().to(device=device, dtype=dtype)
+            # [Cout][9][Cin] == OHWI of a 1x1 conv over 9*Cin virtual channels (the tensor-core DCN path)
+            wp = ops.PackedConv(wp.reshape(wp.shape[0], 1, 1, -1), 1)
             if not self.with_norm:
                 return wp, None, None
             return wp, f32(self.norm.weight, device), f32(self.norm.bias, device)

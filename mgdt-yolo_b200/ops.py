@@ -217,7 +217,8 @@ def dcn3x3(x, offset, mask, w, cout, mask_is_logit, out=None):
     if out is None:
         out = new_act(n, cout, h, wd, x.dtype, x.device)
     yp, *_, ycs = view(out)
-    _invoke("mgdt_dcn3x3", dict(shape=f"dcn {cin}->{cout} {n}x{h}x{wd}", bytes=_nb(x, offset, mask, out), flops=2.0 * 9 * cin * cout * n * h * wd), xp, xcs, op, ocs, mp, mcs, 1 if mask_is_logit else 0, w.data_ptr(), yp, ycs, n, h, wd,
+    _invoke("mgdt_dcn3x3", dict(shape=f"dcn {cin}->{cout} {n}x{h}x{wd}", bytes=_nb(x, offset, mask, out), flops=2.0 * 9 * cin * cout * n * h * wd), xp, xcs, op, ocs, mp, mcs, 1 if mask_is_logit else 0, w.data_ptr(),
+            None if getattr(w, "umma", None) is None else w.umma.data_ptr(), yp, ycs, n, h, wd,
                             cin, cout, dtype_code(x.dtype), stream_ptr())
     return out
 
