@@ -1,0 +1,731 @@
+// Persistent, warp-specialised tcgen05 / TMEM implicit-GEMM convolution for sm_100a.
+//
+// Same GEMM mapping and shared-memory layouts as described in conv_umma.cu (pixels on M = 128,
+// channel planes [Cin/8][parity][P][16 B] in the no-swizzle K-major UMMA layout, taps as shifted
+// descriptors, stride 2 as four parity sub-images), restructured as ONE resident CTA per SM that
+// loops over output tiles with three overlapped roles:
+//
+//   warps 0-7   producers  stage A (and, for K-sliced layers, the matching weight slice) of work item i+1
+//               into a ring of S shared-memory stages: 16-byte LDG -> fused input transform -> STS,
+//               fence.proxy.async, mbarrier arrive (full[s])
+//   warp  16    MMA        one lane waits full[s], issues the tcgen05.mma chain of the item into one of two
+//               TMEM accumulator buffers, tcgen05.commit -> empty[s]  (+ accfull[a] on the last K slice)
+//   warps 8-15  epilogue   wait accfull[a]; tcgen05.ld 32x32b -> bias/act (SFU)/residual -> bf16 -> NHWC stores;
+//               arrive accempty[a]
+//
+// so the global loads of tile i+1, the tensor-core work of tile i and the stores of tile i-1 overlap,
+// and TMEM allocation, barrier setup and the (resident) weight image are paid once per SM instead of
+// once per tile.  Layers whose whole K extent does not fit next to its weights are K-sliced (nks > 1):
+// each work item is (tile, K slice) and carries its own weight slice through the ring.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace mgdt {
+
+constexpr int U2_PRODUCER_WARPS = 8;
+constexpr int U2_EPI_WARPS = 8;      // two per TMEM lane quadrant
+constexpr int U2_MMA_WARP = U2_PRODUCER_WARPS + U2_EPI_WARPS;
+constexpr int U2_THREADS = (U2_MMA_WARP + 1) * 32;
+constexpr int U2_MAX_SMEM = 220 * 1024;
+constexpr int U2_MAX_STAGES = 4;
+constexpr int U2_MAX_MMA = 160;   // K=16 instructions per (slice, 128-row block) the descriptor table holds
+constexpr int U2_TAIL = 128 + 2 * 8 * U2_MAX_MMA + 4 * 256;  // barriers + TMEM slot, two descriptor tables, bias[Nc]
+
+struct FastDiv {  // exact n / d for 0 <= n < 2^31
+    uint32_t mul, shr, d;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;
+    const uint32_t s = 31 + l;
+    f.shr = s;
+    f.mul = (uint32_t)((((unsigned long long)1 << s) + d - 1) / d);
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+    return (uint32_t)(((unsigned long long)n * f.mul) >> f.shr);
+}
+
+struct Plan2 {
+    int mode;      // 0: 1x1 s1 (also DCN), 1: 3x3 s1, 2: 3x3 s2
+    int planes, npar, taps;
+    int Npad, Nc, nsplit;
+    int PS, nks;   // planes per K slice, number of slices
+    int nmma_s;    // K=16 instructions per (slice, 128-row block) = ceil(taps*PS / 2)
+    int tap_par[9], tap_dy[9], tap_dx[9];
+    bool ok;
+};
+
+struct Run2 {
+    int MB, S, NACC, P, Wq, halo, pstride16, tiles_per_img, tmem_cols;
+    long long tiles;
+    unsigned a_bytes, w_slice_bytes, stage_bytes, wres_bytes, smem_total;
+};
+
+static Plan2 make_plan2(int Cin, int Cout, int k, int stride) {
+    Plan2 p{};
+    p.ok = false;
+    if (Cin % 8 != 0 || Cin < 8 || Cout < 1 || Cout > 1024) return p;
+    if (k == 1 && stride == 1) p.mode = 0;
+    else if (k == 3 && stride == 1) p.mode = 1;
+    else if (k == 3 && stride == 2) p.mode = 2;
+    else return p;
+    p.planes = Cin / 8;
+    p.npar = p.mode == 2 ? 4 : 1;
+    p.taps = p.mode == 0 ? 1 : 9;
+    p.Npad = (Cout + 15) / 16 * 16;
+    int n = 0;
+    if (p.mode == 0) {
+        p.tap_par[0] = 0; p.tap_dy[0] = 0; p.tap_dx[0] = 0;
+    } else if (p.mode == 1) {
+        for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx) { p.tap_par[n] = 0; p.tap_dy[n] = dy; p.tap_dx[n] = dx; ++n; }
+    } else {  // ascending (parity plane, shift): chunk pairs that straddle taps get a positive LBO
+        for (int par = 0; par < 4; ++par)
+            for (int dy = 0; dy < 3; ++dy)
+                for (int dx = 0; dx < 3; ++dx)
+                    if (((dy & 1) * 2 + (dx & 1)) == par) { p.tap_par[n] = par; p.tap_dy[n] = dy; p.tap_dx[n] = dx; ++n; }
+    }
+    // columns per CTA (<= 256, dividing Npad) and K slicing: the largest plane count per slice whose weight
+    // slice and (nominal) A slice stay under ~80 KB each with two ring stages under ~200 KB; whole-K layers
+    // keep their weights resident instead.
+    const int a_plane_est = p.mode == 0 ? 2048 : (p.mode == 1 ? 4096 : 10240);
+    int best = 0, Nc = p.Npad;
+    while (Nc > 256 && Nc % 32 == 0) Nc /= 2;
+    if (Nc > 256 || p.Npad % Nc != 0) return p;
+    for (; Nc >= 16 && !best; Nc = (Nc % 32 == 0) ? Nc / 2 : 0) {
+        for (int ps = p.planes; ps >= 1; --ps) {
+            if (p.planes % ps) continue;
+            if (p.taps > 1 && (ps & 1) && !(ps == 1 && p.planes == 1)) continue;  // pairs would straddle taps backwards
+            const long long nm = (p.taps * ps + 1) / 2;
+            if (nm > U2_MAX_MMA) continue;
+            const long long wbytes = nm * 2 * Nc * 16;
+            const long long abytes = (long long)ps * a_plane_est;
+            const bool whole = ps == p.planes && wbytes <= 100 * 1024 && abytes <= 100 * 1024 && wbytes + 2 * abytes <= 200 * 1024;
+            const bool sliced = wbytes <= 80 * 1024 && abytes <= 80 * 1024 && 2 * (wbytes + abytes) <= 200 * 1024;
+            if (whole || sliced) { best = ps; break; }
+        }
+        if (best) break;
+    }
+    if (!best) return p;
+    p.Nc = Nc;
+    p.nsplit = p.Npad / Nc;
+    p.PS = best;
+    p.nks = p.planes / best;
+    p.nmma_s = (p.taps * p.PS + 1) / 2;
+    p.ok = true;
+    return p;
+}
+
+static bool try_run2(const Plan2& p, int MB, int N, int H, int W, int Ho, int Wo, Run2& r) {
+    r.MB = MB;
+    r.NACC = (2 * MB * p.Nc <= 512) ? 2 : 1;
+    if (MB * p.Nc > 512) return false;
+    if (p.mode == 0) {
+        r.Wq = W; r.halo = 0; r.P = 128 * MB;
+        r.tiles_per_img = 1;
+        r.tiles = ((long long)N * H * W + 128 * MB - 1) / (128 * MB);
+    } else if (p.mode == 1) {
+        r.Wq = W + 2; r.halo = r.Wq + 1; r.P = 128 * MB + 2 * r.halo;
+        r.tiles_per_img = (H * r.Wq + 128 * MB - 1) / (128 * MB);
+        r.tiles = (long long)r.tiles_per_img * N;
+    } else {
+        r.Wq = Wo + 1; r.halo = 0; r.P = 128 * MB + r.Wq + 1;
+        r.tiles_per_img = (Ho * r.Wq + 128 * MB - 1) / (128 * MB);
+        r.tiles = (long long)r.tiles_per_img * N;
+    }
+    r.P = (r.P + 7) / 8 * 8 + 8;
+    r.pstride16 = p.npar * r.P;
+    if ((r.pstride16 & 1) == 0) r.pstride16 += 1;
+    r.a_bytes = (unsigned)(((size_t)p.PS * r.pstride16 * 16 + 127) / 128 * 128);
+    const unsigned wall = (unsigned)((size_t)p.nmma_s * 2 * p.Nc * 16);
+    r.w_slice_bytes = p.nks > 1 ? wall : 0;
+    r.wres_bytes = p.nks > 1 ? 0 : wall;
+    r.stage_bytes = r.a_bytes + r.w_slice_bytes;
+    int S = U2_MAX_STAGES;
+    while (S >= 2 && (size_t)r.wres_bytes + (size_t)S * r.stage_bytes + U2_TAIL > (size_t)U2_MAX_SMEM) --S;
+    if (S < 2) return false;
+    r.S = S;
+    r.smem_total = r.wres_bytes + S * r.stage_bytes + U2_TAIL;
+    int cols = 32;
+    while (cols < r.NACC * MB * p.Nc) cols <<= 1;
+    r.tmem_cols = cols;
+    return true;
+}
+
+static bool make_run2(const Plan2& p, int N, int H, int W, int Ho, int Wo, Run2& r) {
+    const int mbs[3] = {4, 2, 1};
+    bool found = false;
+    for (int i = 0; i < 3; ++i) {
+        Run2 t;
+        if (!try_run2(p, mbs[i], N, H, W, Ho, Wo, t)) continue;
+        if (t.NACC < 2 && mbs[i] > 1) continue;           // keep two accumulator buffers when a smaller tile allows it
+        r = t;
+        found = true;
+        if (t.tiles * p.nsplit >= 3 * 148) break;          // enough tiles for every persistent CTA to pipeline
+    }
+    if (!found) {
+        Run2 t;
+        if (try_run2(p, 1, N, H, W, Ho, Wo, t)) { r = t; found = true; }
+    }
+    return found;
+}
+
+// ---------------------------------------------------------------------------------- weight packing
+// OHWI bf16 [Cout][k][k][Cin] -> [nsplit][nks][2*nmma_s chunks: (tap, plane-in-slice)][Nc][8], zero padded
+__global__ void umma2_pack_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, Plan2 p,
+                                  int Cin, int Cout, int k) {
+    const int cps = p.nmma_s * 2;
+    const long long total = (long long)p.nsplit * p.nks * cps * p.Nc * 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % 8);
+        const int nl = (int)((i / 8) % p.Nc);
+        const int chunk = (int)((i / (8LL * p.Nc)) % cps);
+        const int ks = (int)((i / (8LL * p.Nc * cps)) % p.nks);
+        const int ns = (int)(i / (8LL * p.Nc * cps * p.nks));
+        const int co = ns * p.Nc + nl;
+        __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+        if (chunk < p.taps * p.PS && co < Cout) {
+            const int t = chunk / p.PS, plane = ks * p.PS + chunk % p.PS;
+            v = w[(((long long)co * k + p.tap_dy[t]) * k + p.tap_dx[t]) * Cin + plane * 8 + j];
+        }
+        out[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t mk_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // K-major, SWIZZLE_NONE shared-memory matrix descriptor, version 1 (Blackwell)
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    // bounded spin: a protocol bug traps (CUDA error) instead of hanging the GPU
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// Epilogue activations on the SFU (bf16 outputs: 2^-9 relative rounding dominates their error).
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <int ACT> __device__ __forceinline__ float act_fast(float v) {
+    if (ACT == MGDT_ACT_SILU) return v * fmaf(0.5f, tanh_fast(0.5f * v), 0.5f);         // x * sigmoid(x)
+    if (ACT == MGDT_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == MGDT_ACT_SIGMOID) return fmaf(0.5f, tanh_fast(0.5f * v), 0.5f);
+    if (ACT == MGDT_ACT_HSIGMOID) return __saturatef(fmaf(v, 1.0f / 6.0f, 0.5f));
+    if (ACT == MGDT_ACT_GELU) {
+        // exact-erf GELU through Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7)
+        const float z = fabsf(v) * 0.70710678118654752440f;
+        const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+        const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+        const float e = 1.0f - poly * __expf(-z * z);
+        return 0.5f * v * (1.0f + copysignf(e, v));
+    }
+    return v;
+}
+
+struct P2 {
+    const __nv_bfloat16 *x, *w, *pre_add, *pix_scale, *residual;
+    const float *bias, *in_scale;
+    __nv_bfloat16* y;
+    int N, H, W, Cin, Cout, Ho, Wo;
+    int x_cs, y_cs, add_cs, ps_cs, res_cs, act, in_relu;
+    int y_vec, res_vec;
+    Plan2 pl;
+    Run2 rn;
+    unsigned M_total;            // mode 0: N*H*W
+    FastDiv d_ps, d_P, d_Wq, d_HW, d_tpi, d_W, d_cgs;
+    const __nv_bfloat16 *dcn_off, *dcn_mask;   // DCNv2 staging (see conv_umma.cu)
+    int off_cs, mask_cs, mask_logit, dcn_cin;
+};
+
+// tile-relative output row m -> output pixel index, or -1 for junk / out-of-range rows
+__device__ __forceinline__ int out_pixel2(const P2& p, uint32_t tile, uint32_t m) {
+    if (p.pl.mode == 0) {
+        const uint32_t pix = tile * (128u * p.rn.MB) + m;
+        return pix < p.M_total ? (int)pix : -1;
+    }
+    const uint32_t n = fdiv(tile, p.d_tpi);
+    const uint32_t tt = tile - n * p.rn.tiles_per_img;
+    if (p.pl.mode == 1) {
+        const uint32_t q = p.rn.Wq + tt * 128u * p.rn.MB + m;
+        const uint32_t hp = fdiv(q, p.d_Wq), wp = q - hp * p.rn.Wq;
+        if (hp < 1 || hp > (uint32_t)p.H || wp < 1 || wp > (uint32_t)p.W) return -1;
+        return (int)((n * p.H + (hp - 1)) * p.W + (wp - 1));
+    }
+    const uint32_t q = tt * 128u * p.rn.MB + m;
+    const uint32_t ho = fdiv(q, p.d_Wq), wo = q - ho * p.rn.Wq;
+    if (ho >= (uint32_t)p.Ho || wo >= (uint32_t)p.Wo) return -1;
+    return (int)((n * p.Ho + ho) * p.Wo + wo);
+}
+
+// One 16-byte chunk of the A stage: 8 channels (plane) of staged position `pos` (parity `par`).
+__device__ __forceinline__ uint4 load_chunk(const P2& p, uint32_t tile, uint32_t tt, uint32_t n_img, int plane,
+                                            uint32_t pos, uint32_t par) {
+    int pix = -1;
+    uint32_t n = n_img;
+    if (p.pl.mode == 0) {
+        const uint32_t g = tile * (128u * p.rn.MB) + pos;
+        if (g < p.M_total) { pix = (int)g; n = fdiv(g, p.d_HW); }
+    } else if (p.pl.mode == 1) {
+        const int q = (int)(p.rn.Wq + tt * 128u * p.rn.MB + pos) - p.rn.halo;
+        if (q >= 0) {
+            const uint32_t hp = fdiv((uint32_t)q, p.d_Wq), wp = (uint32_t)q - hp * p.rn.Wq;
+            if (hp >= 1 && hp <= (uint32_t)p.H && wp >= 1 && wp <= (uint32_t)p.W)
+                pix = (int)((n * p.H + (hp - 1)) * p.W + (wp - 1));
+        }
+    } else {
+        const uint32_t q = tt * 128u * p.rn.MB + pos;
+        const uint32_t r = fdiv(q, p.d_Wq), c = q - r * p.rn.Wq;
+        const int hi = 2 * (int)r + (int)(par >> 1) - 1, wi = 2 * (int)c + (int)(par & 1) - 1;
+        if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) pix = (int)((n * p.H + hi) * p.W + wi);
+    }
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (pix < 0) return v;
+    v = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)pix * p.x_cs + plane * 8));
+    if (p.pre_add || p.in_scale || p.pix_scale || p.in_relu) {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+        if (p.pre_add) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.pre_add + (size_t)pix * p.add_cs + plane * 8));
+            const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(ah[j]); f[2 * j] += t.x; f[2 * j + 1] += t.y; }
+        }
+        if (p.in_scale) {
+            const float4* s = reinterpret_cast<const float4*>(p.in_scale + (size_t)n * p.Cin + plane * 8);
+            const float4 s0 = __ldg(s), s1 = __ldg(s + 1);
+            f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w; f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+        }
+        if (p.pix_scale) {
+            const float s = __bfloat162float(p.pix_scale[(size_t)pix * p.ps_cs]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] *= s;
+        }
+        if (p.in_relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    }
+    return v;
+}
+
+// DCNv2: chunk = 8 channels (cg) of tap `tap` at output pixel g: mask * bilinear(x, p0 + offset)
+__device__ __forceinline__ uint4 dcn_chunk(const P2& p, uint32_t g, int plane) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (g < p.M_total) {
+        const int tap = (int)fdiv((uint32_t)plane, p.d_cgs), cg = plane - tap * (p.dcn_cin / 8);
+        const uint32_t n = fdiv(g, p.d_HW);
+        const uint32_t rem = g - n * (uint32_t)(p.H * p.W);
+        const int hq = (int)fdiv(rem, p.d_W), wq = (int)rem - hq * p.W;
+        const __nv_bfloat16* ofp = p.dcn_off + (size_t)g * p.off_cs + 2 * tap;
+        const float dy = __bfloat162float(ofp[0]), dx = __bfloat162float(ofp[1]);
+        float m = __bfloat162float(p.dcn_mask[(size_t)g * p.mask_cs + tap]);
+        if (p.mask_logit) m = sigmoidf_(m);
+        const float py = (float)(hq + tap / 3 - 1) + dy, px = (float)(wq + tap % 3 - 1) + dx;
+        if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
+            const int y0 = (int)floorf(py), x0 = (int)floorf(px);
+            const float ly = py - (float)y0, lx = px - (float)x0;
+            const float hy = 1.f - ly, hx = 1.f - lx;
+            const __nv_bfloat16* xn = p.x + (size_t)n * p.H * p.W * p.x_cs + cg * 8;
+            const float wgt[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+            const int yy[4] = {y0, y0, y0 + 1, y0 + 1}, xx[4] = {x0, x0 + 1, x0, x0 + 1};
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                if (yy[c4] >= 0 && yy[c4] <= p.H - 1 && xx[c4] >= 0 && xx[c4] <= p.W - 1) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xn + (size_t)(yy[c4] * p.W + xx[c4]) * p.x_cs));
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 t = __bfloat1622float2(h[j]);
+                        f[2 * j] = fmaf(wgt[c4], t.x, f[2 * j]);
+                        f[2 * j + 1] = fmaf(wgt[c4], t.y, f[2 * j + 1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] *= m;
+        }
+    }
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    return o;
+}
+
+__global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_constant__ P2 p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const Plan2& pl = p.pl;
+    const Run2& rn = p.rn;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ns = blockIdx.y;
+
+    unsigned char* sWres = smem;
+    unsigned char* sStage = smem + rn.wres_bytes;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + rn.wres_bytes + (size_t)rn.S * rn.stage_bytes);
+    // barrier slots: full[S] | empty[S] | accfull[2] | accempty[2] | wready
+    const uint32_t bar0 = s_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (U2_MAX_STAGES + s); };
+    auto ACCFULL = [&](int a) { return bar0 + 8u * (2 * U2_MAX_STAGES + a); };
+    auto ACCEMPTY = [&](int a) { return bar0 + 8u * (2 * U2_MAX_STAGES + 2 + a); };
+    const uint32_t WREADY = bar0 + 8u * (2 * U2_MAX_STAGES + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * U2_MAX_STAGES + 5);
+    // per-instruction descriptor templates (tile independent): start offsets relative to the stage / weight base
+    unsigned long long* adesc_t = bars + 16;
+    unsigned long long* bdesc_t = adesc_t + U2_MAX_MMA;
+    float* sBias = reinterpret_cast<float*>(bdesc_t + U2_MAX_MMA);
+    for (int i = tid; i < pl.Nc; i += U2_THREADS) {
+        const int co = ns * pl.Nc + i;
+        sBias[i] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
+    }
+    for (int i = tid; i < pl.nmma_s; i += U2_THREADS) {
+        const int c0 = 2 * i, c1 = 2 * i + 1;
+        auto off = [&](int c) -> uint32_t {
+            const int t = c / pl.PS, pll = c - t * pl.PS;
+            int shift;
+            if (pl.mode == 0) shift = 0;
+            else if (pl.mode == 1) shift = rn.halo + (pl.tap_dy[t] - 1) * rn.Wq + (pl.tap_dx[t] - 1);
+            else shift = (pl.tap_dy[t] >> 1) * rn.Wq + (pl.tap_dx[t] >> 1);
+            return ((uint32_t)pll * rn.pstride16 + (uint32_t)pl.tap_par[t] * rn.P + shift) * 16u;
+        };
+        const uint32_t o0 = off(c0);
+        const uint32_t lbo = (c1 < pl.taps * pl.PS) ? (off(c1) - o0) : 16u;  // dummy chunk: its weights are zero
+        const uint32_t b_lbo = (uint32_t)pl.Nc * 16;
+        adesc_t[i] = mk_desc(o0, lbo, 128u);
+        bdesc_t[i] = mk_desc((uint32_t)c0 * b_lbo, b_lbo, 128u);
+    }
+
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)),
+                     "r"((uint32_t)rn.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < rn.S; ++s) { mbar_init(FULL(s), U2_PRODUCER_WARPS); mbar_init(EMPTY(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(ACCFULL(a), 1); mbar_init(ACCEMPTY(a), U2_EPI_WARPS); }
+        mbar_init(WREADY, U2_PRODUCER_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t tiles = (uint32_t)rn.tiles;
+    const int nks = pl.nks;
+    const size_t w_slice_elems = (size_t)pl.nmma_s * 2 * pl.Nc * 8;  // bf16 elements of one (ns, ks) weight slice
+
+    if (warp < U2_PRODUCER_WARPS) {
+        // =============================================================== producers
+        const int ptid = tid;  // 0..255
+        constexpr int NP = U2_PRODUCER_WARPS * 32;
+        if (nks == 1) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)ns * w_slice_elems);
+            uint4* dst = reinterpret_cast<uint4*>(sWres);
+            const int n16 = (int)(rn.wres_bytes / 16);
+            for (int i = ptid; i < n16; i += NP) dst[i] = __ldg(src + i);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(WREADY);
+        }
+        const uint32_t chunks = (uint32_t)(pl.PS * pl.npar * rn.P);
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            uint32_t n_img = 0, tt = 0;
+            if (pl.mode != 0) { n_img = fdiv(tile, p.d_tpi); tt = tile - n_img * rn.tiles_per_img; }
+            for (int ks = 0; ks < nks; ++ks, ++it) {
+                const int s = it % rn.S;
+                mbar_wait(EMPTY(s), ((it / rn.S) & 1) ^ 1);
+                unsigned char* sA = sStage + (size_t)s * rn.stage_bytes;
+                if (nks > 1) {
+                    const uint4* src = reinterpret_cast<const uint4*>(p.w + ((size_t)ns * nks + ks) * w_slice_elems);
+                    uint4* dst = reinterpret_cast<uint4*>(sA + rn.a_bytes);
+                    const int n16 = (int)(rn.w_slice_bytes / 16);
+                    for (int i = ptid; i < n16; i += NP) dst[i] = __ldg(src + i);
+                }
+                const int plane0 = ks * pl.PS;
+                // 4 chunks in flight per thread: loads first, then stores
+                for (uint32_t e0 = ptid; e0 < chunks; e0 += NP * 4) {
+                    uint4 v[4];
+                    uint32_t dsto[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t e = e0 + u * NP;
+                        dsto[u] = 0xffffffffu;
+                        if (e < chunks) {
+                            const uint32_t rest = fdiv(e, p.d_ps);
+                            const int pll = (int)(e - rest * pl.PS);
+                            uint32_t pos = rest, par = 0;
+                            if (pl.npar > 1) { par = fdiv(rest, p.d_P); pos = rest - par * rn.P; }
+                            v[u] = p.dcn_off ? dcn_chunk(p, tile * (128u * rn.MB) + pos, plane0 + pll)
+                                             : load_chunk(p, tile, tt, n_img, plane0 + pll, pos, par);
+                            dsto[u] = ((uint32_t)pll * rn.pstride16 + par * rn.P + pos) * 16u;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (dsto[u] != 0xffffffffu) *reinterpret_cast<uint4*>(sA + dsto[u]) = v[u];
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(FULL(s));
+            }
+        }
+    } else if (warp == U2_MMA_WARP) {
+        // =============================================================== MMA issuer (one lane)
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.Nc >> 3) << 17) | ((128u >> 4) << 24);
+            if (nks == 1) mbar_wait(WREADY, 0);
+            uint32_t it = 0, ti = 0;
+            for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+                const int a = rn.NACC == 2 ? (int)(ti & 1) : 0;
+                const uint32_t aphase = rn.NACC == 2 ? ((ti >> 1) & 1) : (ti & 1);
+                mbar_wait(ACCEMPTY(a), aphase ^ 1);
+                for (int ks = 0; ks < nks; ++ks, ++it) {
+                    const int s = it % rn.S;
+                    mbar_wait(FULL(s), (it / rn.S) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = s_u32(sStage + (size_t)s * rn.stage_bytes);
+                    const uint32_t w0 = nks == 1 ? s_u32(sWres) : a0 + rn.a_bytes;
+                    for (int mb = 0; mb < rn.MB; ++mb) {
+                        const uint32_t d = tmem_base + (uint32_t)(a * rn.MB * pl.Nc + mb * pl.Nc);
+                        const uint64_t abase = (uint64_t)((a0 + (uint32_t)mb * 2048u) >> 4);
+                        const uint64_t wbase = (uint64_t)(w0 >> 4);
+                        for (int i = 0; i < pl.nmma_s; ++i) {
+                            const uint64_t adesc = adesc_t[i] + abase;   // start-address field is the low 14 bits
+                            const uint64_t bdesc = bdesc_t[i] + wbase;
+                            const uint32_t acc = (ks > 0 || i > 0) ? 1u : 0u;
+                            asm volatile(
+                                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                                ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+                        }
+                    }
+                    umma_commit(EMPTY(s));                       // smem stage may be refilled once these MMAs retire
+                    if (ks == nks - 1) umma_commit(ACCFULL(a));  // accumulators complete
+                }
+            }
+        }
+    } else {
+        // =============================================================== epilogue (warps 8..15)
+        // TMEM lane quadrant = warp % 4; the two warps of a quadrant alternate over (block, 16-column) units.
+        const int ew = warp - U2_PRODUCER_WARPS;
+        const int quad = ew & 3, half = ew >> 2;
+        const int ncch = pl.Nc / 16;
+        const int units = rn.MB * ncch;
+        uint32_t ti = 0;
+        for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+            const int a = rn.NACC == 2 ? (int)(ti & 1) : 0;
+            const uint32_t aphase = rn.NACC == 2 ? ((ti >> 1) & 1) : (ti & 1);
+            mbar_wait(ACCFULL(a), aphase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int opix = -1, mb_cached = -1;
+            for (int u = half; u < units; u += 2) {
+                const int mb = u / ncch, cc = u - mb * ncch;
+                if (mb != mb_cached) { opix = out_pixel2(p, tile, (uint32_t)(mb * 128 + quad * 32 + lane)); mb_cached = mb; }
+                uint32_t r[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                       (uint32_t)(a * rn.MB * pl.Nc + mb * pl.Nc + cc * 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int co0 = ns * pl.Nc + cc * 16;
+                if (opix < 0 || co0 >= p.Cout) continue;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + sBias[cc * 16 + j];
+                switch (p.act) {
+#define MGDT_ACT_CASE(A) case A: _Pragma("unroll") for (int j = 0; j < 16; ++j) v[j] = act_fast<A>(v[j]); break;
+                    MGDT_ACT_CASE(MGDT_ACT_SILU)
+                    MGDT_ACT_CASE(MGDT_ACT_RELU)
+                    MGDT_ACT_CASE(MGDT_ACT_SIGMOID)
+                    MGDT_ACT_CASE(MGDT_ACT_HSIGMOID)
+                    MGDT_ACT_CASE(MGDT_ACT_GELU)
+#undef MGDT_ACT_CASE
+                    default: break;
+                }
+                __nv_bfloat16* yp = p.y + (size_t)opix * p.y_cs + co0;
+                const __nv_bfloat16* rp = p.residual ? p.residual + (size_t)opix * p.res_cs + co0 : nullptr;
+#pragma unroll
+                for (int h8 = 0; h8 < 2; ++h8) {          // two 8-channel (16-byte) halves
+                    const int c8 = co0 + 8 * h8;
+                    if (c8 >= p.Cout) break;
+                    float* vv = v + 8 * h8;
+                    const bool full8 = c8 + 8 <= p.Cout;
+                    if (rp) {
+                        if (full8 && p.res_vec) {
+                            const uint4 ra = __ldg(reinterpret_cast<const uint4*>(rp + 8 * h8));
+                            const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&ra);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(ah[j]); vv[2 * j] += t.x; vv[2 * j + 1] += t.y; }
+                        } else {
+                            for (int j = 0; j < 8 && c8 + j < p.Cout; ++j) vv[j] += __bfloat162float(rp[8 * h8 + j]);
+                        }
+                    }
+                    if (full8 && p.y_vec) {
+                        uint4 o;
+                        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(vv[2 * j], vv[2 * j + 1]);
+                        *reinterpret_cast<uint4*>(yp + 8 * h8) = o;
+                    } else {
+                        for (int j = 0; j < 8 && c8 + j < p.Cout; ++j) yp[8 * h8 + j] = __float2bfloat16_rn(vv[j]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ACCEMPTY(a));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)rn.tmem_cols)
+                     : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------- host side
+static bool plan2_for(int Cin, int Cout, int k, int stride, int N, int H, int W, Plan2& pl, Run2& rn, int& Ho, int& Wo) {
+    pl = make_plan2(Cin, Cout, k, stride);
+    if (!pl.ok) return false;
+    const int pad = k / 2;
+    Ho = (H + 2 * pad - k) / stride + 1;
+    Wo = (W + 2 * pad - k) / stride + 1;
+    if ((long long)N * H * W >= (1LL << 30) || (long long)N * Ho * Wo >= (1LL << 30)) return false;
+    if (!make_run2(pl, N, H, W, Ho, Wo, rn)) return false;
+    return rn.tiles < (1LL << 30);
+}
+
+static void fill_divs(P2& p) {
+    p.d_ps = make_fastdiv((uint32_t)p.pl.PS);
+    p.d_P = make_fastdiv((uint32_t)p.rn.P);
+    p.d_Wq = make_fastdiv((uint32_t)p.rn.Wq);
+    p.d_HW = make_fastdiv((uint32_t)(p.H * p.W));
+    p.d_tpi = make_fastdiv((uint32_t)p.rn.tiles_per_img);
+    p.d_W = make_fastdiv((uint32_t)p.W);
+    p.d_cgs = make_fastdiv((uint32_t)(p.dcn_cin > 0 ? p.dcn_cin / 8 : 1));
+}
+
+static int launch2(P2& p, cudaStream_t s) {
+    fill_divs(p);
+    cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_MAX_SMEM);
+    if (e != cudaSuccess) return set_error(-EIO, "conv_umma2: smem attr: %s", cudaGetErrorString(e));
+    const long long tiles = p.rn.tiles;
+    int ctas = (int)(tiles < 148 ? tiles : 148);
+    if (p.pl.nsplit > 1) ctas = (int)std::max(1LL, std::min(tiles, (long long)(148 / p.pl.nsplit)));
+    conv_umma2_kernel<<<dim3((unsigned)ctas, (unsigned)p.pl.nsplit), U2_THREADS, p.rn.smem_total, s>>>(p);
+    MGDT_LAUNCH_CHECK("conv_umma2");
+    return 0;
+}
+
+bool conv2d_umma_supported(const mgdt_conv_args* a) {
+    if (!a->w_umma || a->dtype != MGDT_BF16 || a->kh != a->kw || a->pad != a->kh / 2) return false;
+    Plan2 pl; Run2 rn; int Ho, Wo;
+    if (!plan2_for(a->Cin, a->Cout, a->kh, a->stride, a->N, a->H, a->W, pl, rn, Ho, Wo)) return false;
+    if (((uintptr_t)a->x & 15) || (a->x_cs & 7)) return false;
+    if (a->pre_add && (((uintptr_t)a->pre_add & 15) || (a->add_cs & 7))) return false;
+    if (a->in_scale && ((uintptr_t)a->in_scale & 15)) return false;
+    if ((uintptr_t)a->w_umma & 15) return false;
+    return true;
+}
+
+int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
+    P2 p;
+    int Ho, Wo;
+    if (!plan2_for(a->Cin, a->Cout, a->kh, a->stride, a->N, a->H, a->W, p.pl, p.rn, Ho, Wo))
+        return set_error(-EINVAL, "conv2d_umma: unsupported shape");
+    p.x = (const __nv_bfloat16*)a->x; p.w = (const __nv_bfloat16*)a->w_umma;
+    p.pre_add = (const __nv_bfloat16*)a->pre_add; p.pix_scale = (const __nv_bfloat16*)a->pix_scale;
+    p.residual = (const __nv_bfloat16*)a->residual; p.bias = a->bias; p.in_scale = a->in_scale;
+    p.y = (__nv_bfloat16*)a->y;
+    p.N = a->N; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout; p.Ho = Ho; p.Wo = Wo;
+    p.x_cs = a->x_cs; p.y_cs = a->y_cs; p.add_cs = a->add_cs; p.ps_cs = a->ps_cs; p.res_cs = a->res_cs;
+    p.act = a->act; p.in_relu = a->in_relu;
+    p.y_vec = (((uintptr_t)a->y & 15) == 0 && (a->y_cs & 7) == 0) ? 1 : 0;
+    p.res_vec = (a->residual && ((uintptr_t)a->residual & 15) == 0 && (a->res_cs & 7) == 0) ? 1 : 0;
+    p.M_total = (unsigned)((long long)a->N * a->H * a->W);
+    p.dcn_off = nullptr; p.dcn_mask = nullptr; p.off_cs = p.mask_cs = p.mask_logit = p.dcn_cin = 0;
+    return launch2(p, s);
+}
+
+bool dcn_umma_supported(const void* x, int x_cs, const void* w_umma, int N, int H, int W, int Cin, int Cout) {
+    if (!w_umma || Cin % 8 != 0 || ((uintptr_t)x & 15) || (x_cs & 7) || ((uintptr_t)w_umma & 15)) return false;
+    Plan2 pl; Run2 rn; int Ho, Wo;
+    return plan2_for(9 * Cin, Cout, 1, 1, N, H, W, pl, rn, Ho, Wo);
+}
+
+int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs, int mask_is_logit,
+             const void* w_umma, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, cudaStream_t s) {
+    P2 p;
+    int Ho, Wo;
+    if (!plan2_for(9 * Cin, Cout, 1, 1, N, H, W, p.pl, p.rn, Ho, Wo)) return set_error(-EINVAL, "dcn_umma: unsupported shape");
+    p.x = (const __nv_bfloat16*)x; p.w = (const __nv_bfloat16*)w_umma; p.pre_add = nullptr; p.pix_scale = nullptr;
+    p.residual = nullptr; p.bias = nullptr; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y;
+    p.N = N; p.H = H; p.W = W; p.Cin = 9 * Cin; p.Cout = Cout; p.Ho = H; p.Wo = W;
+    p.x_cs = x_cs; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = MGDT_ACT_NONE; p.in_relu = 0;
+    p.y_vec = (((uintptr_t)y & 15) == 0 && (y_cs & 7) == 0) ? 1 : 0;
+    p.res_vec = 0;
+    p.M_total = (unsigned)((long long)N * H * W);
+    p.dcn_off = (const __nv_bfloat16*)offset; p.dcn_mask = (const __nv_bfloat16*)mask;
+    p.off_cs = off_cs; p.mask_cs = mask_cs; p.mask_logit = mask_is_logit; p.dcn_cin = Cin;
+    return launch2(p, s);
+}
+
+}  // namespace mgdt
+
+using namespace mgdt;
+
+extern "C" size_t mgdt_conv_umma_packed_bytes(int Cin, int Cout, int k, int stride) {
+    const Plan2 pl = make_plan2(Cin, Cout, k, stride);
+    if (!pl.ok) return 0;
+    return (size_t)pl.nsplit * pl.nks * pl.nmma_s * 2 * pl.Nc * 16;
+}
+
+extern "C" int mgdt_conv_umma_pack(const void* w_ohwi, int Cin, int Cout, int k, int stride, void* packed, void* stream) {
+    MGDT_CHECK(w_ohwi && packed, "conv_umma_pack: null pointer");
+    const Plan2 pl = make_plan2(Cin, Cout, k, stride);
+    MGDT_CHECK(pl.ok, "conv_umma_pack: shape %d->%d k%d s%d is not supported by the tcgen05 path", Cin, Cout, k, stride);
+    const long long total = (long long)pl.nsplit * pl.nks * pl.nmma_s * 2 * pl.Nc * 8;
+    umma2_pack_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)w_ohwi,
+                                                                         (__nv_bfloat16*)packed, pl, Cin, Cout, k);
+    MGDT_LAUNCH_CHECK("umma_pack");
+    return 0;
+}
