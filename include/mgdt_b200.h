@@ -86,6 +86,13 @@ int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
 size_t mgdt_conv_umma_packed_bytes(int Cin, int Cout, int k, int stride);
 int mgdt_conv_umma_pack(const void* w_ohwi, int Cin, int Cout, int k, int stride, void* packed, void* stream);
 
+/* Fused input preprocessing + stem convolution on the tensor cores (bf16): 3x3 stride-2 pad-1 Conv+BN+act
+ * (layer 0 of every config, models/v8/*.yaml) read straight from the NCHW uint8 (divided by 255,
+ * predictor.py:127-129) or float32 source.  w_umma = mgdt_conv_umma_pack of the OHWI weights viewed as a
+ * 1x1 conv over round_up(9*C, 16) channels (k = (dy*3+dx)*C + c, zero padded). */
+int mgdt_stem_conv(const void* src, int src_is_u8, const void* w_umma, const float* bias, void* y, int y_cs, int N, int C,
+                   int H, int W, int Cout, int act, int dtype, void* stream);
+
 /* Depthwise 7x7 (pad 3, bias) + channels-last LayerNorm(eps), ConvNeXtV2_Block.forward
  * (nn/modules/convnextv2.py:35-37, nn/modules/utils.py:162-163).  w is [49][C] in dtype,
  * bias/ln_w/ln_b fp32 [C]. */

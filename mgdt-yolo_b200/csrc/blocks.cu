@@ -68,6 +68,123 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv7_ln_kernel(const T* __re
     }
 }
 
+// ------------------------------------------------------------------ dwconv7 + LN, shared-memory tiled
+// CTA = 8x8 output pixels of one image, all C channels: the (8+6)x(8+6)xC input halo tile and the 49xC
+// weights live in shared memory; warp r computes output row r (8 pixels, lanes over channels, CPL
+// channels per lane) re-using every staged input value for the up-to-7 outputs it contributes to, then
+// LayerNorm is a warp reduction per pixel.  ~200 instructions per pixel-lane instead of ~500 global loads.
+constexpr int DT = 8;            // tile edge
+constexpr int DTI = DT + 6;      // input tile edge
+
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256) dwconv7_ln_tiled(const T* __restrict__ x, int x_cs, const T* __restrict__ w,
+                                                        const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                        const float* __restrict__ ln_b, float eps, T* __restrict__ y,
+                                                        int y_cs, int H, int W, int C, int tiles_x, int tiles_y) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int CP = CPL * 32;                                   // padded channel count
+    float* sw = reinterpret_cast<float*>(dsm);                 // [49][CP]
+    T* sx = reinterpret_cast<T*>(dsm + sizeof(float) * 49 * CP);  // [DTI][DTI][CP]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int b = blockIdx.x;
+    const int tx = b % tiles_x; b /= tiles_x;
+    const int ty = b % tiles_y;
+    const int n = b / tiles_y;
+    const int h0 = ty * DT, w0 = tx * DT;
+    for (int i = tid; i < 49 * CP; i += 256) {
+        const int c = i % CP;
+        sw[i] = c < C ? ldf(w + (i / CP) * C + c) : 0.f;
+    }
+    const T* xn = x + (size_t)n * H * W * x_cs;
+    for (int i = tid; i < DTI * DTI * CP; i += 256) {
+        const int c = i % CP, pix = i / CP;
+        const int iy = pix / DTI, ix = pix - iy * DTI;
+        const int hh = h0 + iy - 3, ww = w0 + ix - 3;
+        float v = 0.f;
+        if (c < C && hh >= 0 && hh < H && ww >= 0 && ww < W) v = ldf(xn + (size_t)(hh * W + ww) * x_cs + c);
+        stf(sx + i, v);
+    }
+    __syncthreads();
+    const int r = warp;  // output row inside the tile
+    float acc[DT][CPL];
+#pragma unroll
+    for (int px = 0; px < DT; ++px)
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            const int c = lane + 32 * j;
+            acc[px][j] = c < C ? bias[c] : 0.f;
+        }
+#pragma unroll
+    for (int dy = 0; dy < 7; ++dy) {
+        float wk[7][CPL];
+#pragma unroll
+        for (int dx = 0; dx < 7; ++dx)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) wk[dx][j] = sw[(dy * 7 + dx) * CP + lane + 32 * j];
+        const T* row = sx + (size_t)((r + dy) * DTI) * CP;
+#pragma unroll
+        for (int ix = 0; ix < DTI; ++ix) {
+            float v[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) v[j] = ldf(row + ix * CP + lane + 32 * j);
+#pragma unroll
+            for (int dx = 0; dx < 7; ++dx) {
+                const int px = ix - dx;
+                if (px >= 0 && px < DT) {
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) acc[px][j] = fmaf(v[j], wk[dx][j], acc[px][j]);
+                }
+            }
+        }
+    }
+    const int hq = h0 + r;
+    float lw[CPL], lb[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const int c = lane + 32 * j;
+        lw[j] = c < C ? ln_w[c] : 0.f;
+        lb[j] = c < C ? ln_b[c] : 0.f;
+    }
+#pragma unroll
+    for (int px = 0; px < DT; ++px) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+            if (lane + 32 * j < C) s += acc[px][j];
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+            if (lane + 32 * j < C) {
+                const float d = acc[px][j] - mean;
+                q += d * d;
+            }
+        const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+        const int wq = w0 + px;
+        if (hq < H && wq < W) {
+            T* yp = y + ((size_t)n * H * W + (size_t)hq * W + wq) * y_cs;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const int c = lane + 32 * j;
+                if (c < C) stf(yp + c, (acc[px][j] - mean) * rstd * lw[j] + lb[j]);
+            }
+        }
+    }
+}
+
+template <typename T, int CPL>
+static int launch_dw_tiled(const void* x, int x_cs, const void* w, const float* bias, const float* ln_w,
+                           const float* ln_b, float eps, void* y, int y_cs, int N, int H, int W, int C, cudaStream_t s) {
+    const int CP = CPL * 32;
+    const size_t smem = sizeof(float) * 49 * CP + sizeof(T) * DTI * DTI * CP;
+    cudaError_t e = cudaFuncSetAttribute(dwconv7_ln_tiled<T, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(-EIO, "dwconv7_ln: smem attr: %s", cudaGetErrorString(e));
+    const int tx = (W + DT - 1) / DT, ty = (H + DT - 1) / DT;
+    dwconv7_ln_tiled<T, CPL><<<tx * ty * N, 256, smem, s>>>((const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps, (T*)y,
+                                                            y_cs, H, W, C, tx, ty);
+    return 0;
+}
+
 // ------------------------------------------------------------------ DCNv2 3x3
 // CTA = DCN_PIX output pixels.  Phase 1 builds the modulated bilinear im2col tile
 // cols[pixel][tap*Cin + ci] in shared memory; phase 2 is a small GEMM against w[Cout][9*Cin].
@@ -197,8 +314,22 @@ extern "C" int mgdt_dwconv7_ln(const void* x, int x_cs, const void* w, const flo
                32 * DW_MAXPL);
     MGDT_CHECK(x_cs >= C && y_cs >= C, "dwconv7_ln: bad strides");
     const long long npix = (long long)N * H * W;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (C <= 128) {  // shared-memory tiled kernel, CPL = ceil(C / 32) channels per lane
+        const int cpl = (C + 31) / 32;
+        int rc = 0;
+        MGDT_DTYPE_SWITCH(dtype, T, {
+            if (cpl == 1) rc = launch_dw_tiled<T, 1>(x, x_cs, w, bias, ln_w, ln_b, eps, y, y_cs, N, H, W, C, s);
+            else if (cpl == 2) rc = launch_dw_tiled<T, 2>(x, x_cs, w, bias, ln_w, ln_b, eps, y, y_cs, N, H, W, C, s);
+            else if (cpl == 3) rc = launch_dw_tiled<T, 3>(x, x_cs, w, bias, ln_w, ln_b, eps, y, y_cs, N, H, W, C, s);
+            else rc = launch_dw_tiled<T, 4>(x, x_cs, w, bias, ln_w, ln_b, eps, y, y_cs, N, H, W, C, s);
+        });
+        if (rc) return rc;
+        MGDT_LAUNCH_CHECK("dwconv7_ln_tiled");
+        return 0;
+    }
     MGDT_DTYPE_SWITCH(dtype, T, {
-        dwconv7_ln_kernel<T><<<cdiv(npix, DW_WARPS), DW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        dwconv7_ln_kernel<T><<<cdiv(npix, DW_WARPS), DW_WARPS * 32, 0, s>>>(
             (const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps, (T*)y, y_cs, H, W, C, npix);
     });
     MGDT_LAUNCH_CHECK("dwconv7_ln");

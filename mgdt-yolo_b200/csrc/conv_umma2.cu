@@ -30,7 +30,7 @@ constexpr int U2_THREADS = (U2_MMA_WARP + 1) * 32;
 constexpr int U2_MAX_SMEM = 220 * 1024;
 constexpr int U2_MAX_STAGES = 4;
 constexpr int U2_MAX_MMA = 160;   // K=16 instructions per (slice, 128-row block) the descriptor table holds
-constexpr int U2_TAIL = 128 + 2 * 8 * U2_MAX_MMA + 4 * 256;  // barriers + TMEM slot, two descriptor tables, bias[Nc]
+constexpr int U2_TAIL = 128 + 2 * 8 * U2_MAX_MMA + 4 * 256 + 2 * 256;  // barriers + TMEM slot, descriptor tables, bias[Nc], u8 LUT
 
 struct FastDiv {  // exact n / d for 0 <= n < 2^31
     uint32_t mul, shr, d;
@@ -216,9 +216,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     for (;;) {
         uint32_t ok;
+        // suspend-time hint (ns): the waiting warp sleeps in hardware instead of polling, so the epilogue / MMA
+        // warps do not steal issue slots from the producers while they wait
         asm volatile(
-            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
         if (ok) return;
         if (clock64() - t0 > 8000000000LL) __trap();
     }
@@ -260,8 +262,12 @@ struct P2 {
     Run2 rn;
     unsigned M_total;            // mode 0: N*H*W
     FastDiv d_ps, d_P, d_Wq, d_HW, d_tpi, d_W, d_cgs;
-    const __nv_bfloat16 *dcn_off, *dcn_mask;   // DCNv2 staging (see conv_umma.cu)
+    const __nv_bfloat16 *dcn_off, *dcn_mask;   // DCNv2 staging: virtual 9*dcn_cin-channel input
     int off_cs, mask_cs, mask_logit, dcn_cin;
+    // fused preprocess + stem: 3x3 stride-2 conv read straight from the NCHW uint8 / float source image
+    const void* stem_src;
+    int stem_u8, stem_C, stem_H, stem_W;
+    FastDiv d_Wo;
 };
 
 // tile-relative output row m -> output pixel index, or -1 for junk / out-of-range rows
@@ -385,6 +391,39 @@ __device__ __forceinline__ uint4 dcn_chunk(const P2& p, uint32_t g, int plane) {
     return o;
 }
 
+// Stem: K index k = (dy*3 + dx)*C + c of the 3x3 stride-2 pad-1 window, zero beyond 9*C; value = src/255 for
+// uint8 (BasePredictor.preprocess, predictor.py:127-129), rounded to bf16 exactly as the unfused path does.
+__device__ __forceinline__ uint4 stem_chunk(const P2& p, uint32_t g, int plane) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (g < p.M_total) {
+        const uint32_t n = fdiv(g, p.d_HW);                       // d_HW = Ho*Wo here
+        const uint32_t rem = g - n * (uint32_t)(p.H * p.W);
+        const int ho = (int)fdiv(rem, p.d_Wo), wo = (int)rem - ho * p.W;
+        const int C = p.stem_C, KK = 9 * C;
+        const size_t plane_sz = (size_t)p.stem_H * p.stem_W;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = plane * 8 + j;
+            if (k < KK) {
+                const int tap = k / C, c = k - tap * C;
+                const int hi = 2 * ho + tap / 3 - 1, wi = 2 * wo + tap % 3 - 1;
+                if (hi >= 0 && hi < p.stem_H && wi >= 0 && wi < p.stem_W) {
+                    const size_t idx = ((size_t)n * C + c) * plane_sz + (size_t)hi * p.stem_W + wi;
+                    f[j] = p.stem_u8 ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.stem_src) + idx) / 255.0f
+                                     : __ldg(reinterpret_cast<const float*>(p.stem_src) + idx);
+                }
+            }
+        }
+    }
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    return o;
+}
+
 __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_constant__ P2 p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Plan2& pl = p.pl;
@@ -407,6 +446,10 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     unsigned long long* adesc_t = bars + 16;
     unsigned long long* bdesc_t = adesc_t + U2_MAX_MMA;
     float* sBias = reinterpret_cast<float*>(bdesc_t + U2_MAX_MMA);
+    unsigned short* sLut = reinterpret_cast<unsigned short*>(sBias + 256);   // bf16(u / 255), u = 0..255
+    if (p.stem_src && p.stem_u8) {
+        for (int i = tid; i < 256; i += U2_THREADS) sLut[i] = __bfloat16_as_ushort(__float2bfloat16_rn((float)i / 255.0f));
+    }
     for (int i = tid; i < pl.Nc; i += U2_THREADS) {
         const int co = ns * pl.Nc + i;
         sBias[i] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
@@ -477,6 +520,79 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                     for (int i = ptid; i < n16; i += NP) dst[i] = __ldg(src + i);
                 }
                 const int plane0 = ks * pl.PS;
+                if (p.stem_src && p.stem_C == 3 && pl.PS == 4 && p.stem_u8) {
+                    // uint8 source: bf16(u / 255) comes from a 256-entry shared-memory table (exactly the value the
+                    // unfused preprocess kernel produces; no I2F / IEEE division in the loop)
+                    const size_t plane_sz = (size_t)p.stem_H * p.stem_W;
+                    const uint8_t* src8 = reinterpret_cast<const uint8_t*>(p.stem_src);
+                    for (uint32_t pos = ptid; pos < 128u * rn.MB; pos += NP) {
+                        const uint32_t g = tile * (128u * rn.MB) + pos;
+                        unsigned short hv[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) hv[j] = 0;
+                        if (g < p.M_total) {
+                            const uint32_t n = fdiv(g, p.d_HW);
+                            const uint32_t rem = g - n * (uint32_t)(p.H * p.W);
+                            const int ho = (int)fdiv(rem, p.d_Wo), wo = (int)rem - ho * p.W;
+                            const size_t base = (size_t)n * 3 * plane_sz;
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int hi = 2 * ho + tap / 3 - 1, wi = 2 * wo + tap % 3 - 1;
+                                if (hi >= 0 && hi < p.stem_H && wi >= 0 && wi < p.stem_W) {
+                                    const size_t o = base + (size_t)hi * p.stem_W + wi;
+#pragma unroll
+                                    for (int c = 0; c < 3; ++c) hv[tap * 3 + c] = sLut[__ldg(src8 + o + c * plane_sz)];
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int pll = 0; pll < 4; ++pll) {
+                            uint4 o;
+                            o.x = hv[pll * 8 + 0] | ((uint32_t)hv[pll * 8 + 1] << 16);
+                            o.y = hv[pll * 8 + 2] | ((uint32_t)hv[pll * 8 + 3] << 16);
+                            o.z = hv[pll * 8 + 4] | ((uint32_t)hv[pll * 8 + 5] << 16);
+                            o.w = hv[pll * 8 + 6] | ((uint32_t)hv[pll * 8 + 7] << 16);
+                            *reinterpret_cast<uint4*>(sA + ((uint32_t)pll * rn.pstride16 + pos) * 16u) = o;
+                        }
+                    }
+                } else if (p.stem_src && p.stem_C == 3 && pl.PS == 4) {
+                    // fused preprocess + stem, C = 3: one output pixel per thread; its 27 source values are
+                    // gathered with compile-time (tap, channel) indices and stored as the pixel's 4 K-chunks
+                    const size_t plane_sz = (size_t)p.stem_H * p.stem_W;
+                    for (uint32_t pos = ptid; pos < 128u * rn.MB; pos += NP) {
+                        const uint32_t g = tile * (128u * rn.MB) + pos;
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+                        if (g < p.M_total) {
+                            const uint32_t n = fdiv(g, p.d_HW);
+                            const uint32_t rem = g - n * (uint32_t)(p.H * p.W);
+                            const int ho = (int)fdiv(rem, p.d_Wo), wo = (int)rem - ho * p.W;
+                            const size_t base = (size_t)n * 3 * plane_sz;
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int hi = 2 * ho + tap / 3 - 1, wi = 2 * wo + tap % 3 - 1;
+                                if (hi >= 0 && hi < p.stem_H && wi >= 0 && wi < p.stem_W) {
+                                    const size_t o = base + (size_t)hi * p.stem_W + wi;
+#pragma unroll
+                                    for (int c = 0; c < 3; ++c) {
+                                        f[tap * 3 + c] = p.stem_u8
+                                            ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.stem_src) + o + c * plane_sz) / 255.0f
+                                            : __ldg(reinterpret_cast<const float*>(p.stem_src) + o + c * plane_sz);
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int pll = 0; pll < 4; ++pll) {
+                            uint4 o;
+                            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(f[pll * 8 + 2 * j], f[pll * 8 + 2 * j + 1]);
+                            *reinterpret_cast<uint4*>(sA + ((uint32_t)pll * rn.pstride16 + pos) * 16u) = o;
+                        }
+                    }
+                } else
                 // 4 chunks in flight per thread: loads first, then stores
                 for (uint32_t e0 = ptid; e0 < chunks; e0 += NP * 4) {
                     uint4 v[4];
@@ -490,8 +606,9 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                             const int pll = (int)(e - rest * pl.PS);
                             uint32_t pos = rest, par = 0;
                             if (pl.npar > 1) { par = fdiv(rest, p.d_P); pos = rest - par * rn.P; }
-                            v[u] = p.dcn_off ? dcn_chunk(p, tile * (128u * rn.MB) + pos, plane0 + pll)
-                                             : load_chunk(p, tile, tt, n_img, plane0 + pll, pos, par);
+                            v[u] = p.stem_src ? stem_chunk(p, tile * (128u * rn.MB) + pos, plane0 + pll)
+                                   : p.dcn_off ? dcn_chunk(p, tile * (128u * rn.MB) + pos, plane0 + pll)
+                                               : load_chunk(p, tile, tt, n_img, plane0 + pll, pos, par);
                             dsto[u] = ((uint32_t)pll * rn.pstride16 + par * rn.P + pos) * 16u;
                         }
                     }
@@ -642,6 +759,7 @@ static void fill_divs(P2& p) {
     p.d_tpi = make_fastdiv((uint32_t)p.rn.tiles_per_img);
     p.d_W = make_fastdiv((uint32_t)p.W);
     p.d_cgs = make_fastdiv((uint32_t)(p.dcn_cin > 0 ? p.dcn_cin / 8 : 1));
+    p.d_Wo = make_fastdiv((uint32_t)p.W);
 }
 
 static int launch2(P2& p, cudaStream_t s) {
@@ -683,6 +801,7 @@ int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
     p.res_vec = (a->residual && ((uintptr_t)a->residual & 15) == 0 && (a->res_cs & 7) == 0) ? 1 : 0;
     p.M_total = (unsigned)((long long)a->N * a->H * a->W);
     p.dcn_off = nullptr; p.dcn_mask = nullptr; p.off_cs = p.mask_cs = p.mask_logit = p.dcn_cin = 0;
+    p.stem_src = nullptr; p.stem_u8 = p.stem_C = p.stem_H = p.stem_W = 0;
     return launch2(p, s);
 }
 
@@ -706,12 +825,44 @@ int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void
     p.M_total = (unsigned)((long long)N * H * W);
     p.dcn_off = (const __nv_bfloat16*)offset; p.dcn_mask = (const __nv_bfloat16*)mask;
     p.off_cs = off_cs; p.mask_cs = mask_cs; p.mask_logit = mask_is_logit; p.dcn_cin = Cin;
+    p.stem_src = nullptr; p.stem_u8 = p.stem_C = p.stem_H = p.stem_W = 0;
+    return launch2(p, s);
+}
+
+// Fused preprocess + stem conv (3x3, stride 2, pad 1, C <= 3..8 input channels): a 1x1 GEMM over the virtual
+// K = round_up(9*C, 16) im2col built from the NCHW source while staging; output geometry (Ho, Wo) plays the
+// role of the 1x1 conv's (H, W).
+int stem_umma(const void* src, int src_is_u8, const void* w_umma, const float* bias, void* y, int y_cs, int N, int C,
+              int H, int W, int Cout, int act, cudaStream_t s) {
+    const int Kp = (9 * C + 15) / 16 * 16;
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    P2 p;
+    int ho2, wo2;
+    if (!plan2_for(Kp, Cout, 1, 1, N, Ho, Wo, p.pl, p.rn, ho2, wo2)) return set_error(-EINVAL, "stem_umma: unsupported shape");
+    p.x = nullptr; p.w = (const __nv_bfloat16*)w_umma; p.pre_add = nullptr; p.pix_scale = nullptr; p.residual = nullptr;
+    p.bias = bias; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y;
+    p.N = N; p.H = Ho; p.W = Wo; p.Cin = Kp; p.Cout = Cout; p.Ho = Ho; p.Wo = Wo;
+    p.x_cs = 0; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = act; p.in_relu = 0;
+    p.y_vec = (((uintptr_t)y & 15) == 0 && (y_cs & 7) == 0) ? 1 : 0;
+    p.res_vec = 0;
+    p.M_total = (unsigned)((long long)N * Ho * Wo);
+    p.dcn_off = nullptr; p.dcn_mask = nullptr; p.off_cs = p.mask_cs = p.mask_logit = p.dcn_cin = 0;
+    p.stem_src = src; p.stem_u8 = src_is_u8; p.stem_C = C; p.stem_H = H; p.stem_W = W;
     return launch2(p, s);
 }
 
 }  // namespace mgdt
 
 using namespace mgdt;
+
+extern "C" int mgdt_stem_conv(const void* src, int src_is_u8, const void* w_umma, const float* bias, void* y, int y_cs,
+                              int N, int C, int H, int W, int Cout, int act, int dtype, void* stream) {
+    MGDT_CHECK(src && w_umma && y, "stem_conv: null pointer");
+    MGDT_CHECK(dtype == MGDT_BF16, "stem_conv: the fused tensor-core stem is bf16 only (use preprocess + conv2d for fp32)");
+    MGDT_CHECK(N > 0 && C > 0 && C <= 8 && H > 1 && W > 1 && Cout > 0 && y_cs >= Cout, "stem_conv: bad shape");
+    MGDT_CHECK(((uintptr_t)w_umma & 15) == 0, "stem_conv: packed weights must be 16-byte aligned");
+    return stem_umma(src, src_is_u8, w_umma, bias, y, y_cs, N, C, H, W, Cout, act, (cudaStream_t)stream);
+}
 
 extern "C" size_t mgdt_conv_umma_packed_bytes(int Cin, int Cout, int k, int stride) {
     const Plan2 pl = make_plan2(Cin, Cout, k, stride);

@@ -198,7 +198,10 @@ __global__ void __launch_bounds__(EW_THREADS) sppf_pool_kernel(const T* __restri
 }
 
 // ------------------------------------------------------------------ injection gate
-__device__ __forceinline__ float hsig(float v) { return fminf(fmaxf(v + 3.0f, 0.0f), 6.0f) / 6.0f; }
+// relu6(x + 3) / 6: exact IEEE form in the fp32 validation mode, saturate(x/6 + 0.5) (2 instructions) for bf16
+template <typename T> __device__ __forceinline__ float hsig(float v);
+template <> __device__ __forceinline__ float hsig<float>(float v) { return fminf(fmaxf(v + 3.0f, 0.0f), 6.0f) / 6.0f; }
+template <> __device__ __forceinline__ float hsig<__nv_bfloat16>(float v) { return __saturatef(fmaf(v, 1.0f / 6.0f, 0.5f)); }
 
 template <typename T, int V>
 __global__ void __launch_bounds__(EW_THREADS) inject_kernel(const T* __restrict__ local, int l_cs,
@@ -248,8 +251,8 @@ __global__ void __launch_bounds__(EW_THREADS) inject_kernel(const T* __restrict_
             VecIO<T, V>::ld(fn + o10 * f_cs, f10); VecIO<T, V>::ld(fn + o11 * f_cs, f11);
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-                sig[j] = (1.f - lh) * ((1.f - lw) * hsig(a00[j]) + lw * hsig(a01[j])) +
-                         lh * ((1.f - lw) * hsig(a10[j]) + lw * hsig(a11[j]));
+                sig[j] = (1.f - lh) * ((1.f - lw) * hsig<T>(a00[j]) + lw * hsig<T>(a01[j])) +
+                         lh * ((1.f - lw) * hsig<T>(a10[j]) + lw * hsig<T>(a11[j]));
                 gf[j] = (1.f - lh) * ((1.f - lw) * f00[j] + lw * f01[j]) + lh * ((1.f - lw) * f10[j] + lw * f11[j]);
             }
         }

@@ -41,6 +41,8 @@ class Engine:
         self.ch = self.model.yaml.get("ch", 3)
         self.use_graph = use_graph
         self.launches_per_step = 0
+        # bf16: preprocessing is fused into the stem conv (the graph then starts at the raw source buffer)
+        self.fused_stem = dtype == torch.bfloat16 and self.model.stem_fusable()
         with torch.cuda.device(self.device):
             self._classes = None if classes is None else torch.as_tensor(list(classes), dtype=torch.int32,
                                                                          device=self.device)
@@ -49,8 +51,11 @@ class Engine:
 
     # ------------------------------------------------------------------ construction
     def _body(self, s):
-        """Everything after preprocess, on the current stream, into the slot's static outputs."""
-        y, _ = self.model(s.x)
+        """Everything after the input copy, on the current stream, into the slot's static outputs."""
+        if self.fused_stem:
+            y, _ = self.model.predict_from(s.x0, 1)    # layer 0 ran outside the graph, straight from the source
+        else:
+            y, _ = self.model(s.x)
         s.pred = y
         nb = lib().mgdt_nms_ws_bytes(self.batch, y.shape[1] - 4, y.shape[2], 1 if self.nms_args["multi_label"] else 0,
                                      self.nms_args["max_nms"])
@@ -65,7 +70,8 @@ class Engine:
         B, C, H, W = self.batch, self.ch, self.h, self.w
         s.stream = torch.cuda.Stream(device=self.device)
         s.src = torch.zeros((B, C, H, W), dtype=self.input_dtype, device=self.device)
-        s.x = ops.new_act(B, C, H, W, self.dtype, self.device)
+        s.x = ops.new_act(B, C, H, W, self.dtype, self.device) if not self.fused_stem else None
+        s.x0 = None
         s.out = torch.zeros((B, self.max_det, 6), dtype=torch.float32, device=self.device)
         s.counts = torch.zeros((B,), dtype=torch.int32, device=self.device)
         s.ws = None
@@ -77,7 +83,7 @@ class Engine:
             # warm-up (packs weights, sizes the NMS workspace) on the slot's stream, then capture
             s.stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(s.stream):
-                ops.preprocess(s.src, self.dtype, out=s.x)
+                self._head(s, s.src)
                 for _ in range(2):
                     self._body(s)
             s.stream.synchronize()
@@ -87,7 +93,7 @@ class Engine:
                 with torch.cuda.graph(g, stream=s.stream):
                     self._body(s)
                 s.graph = g
-                self.launches_per_step = int(lib().mgdt_launch_count() - c0) + 1  # + preprocess
+                self.launches_per_step = int(lib().mgdt_launch_count() - c0) + 1
             else:
                 c0 = lib().mgdt_launch_count()
                 with torch.cuda.stream(s.stream):
@@ -97,10 +103,22 @@ class Engine:
         return s
 
     # ------------------------------------------------------------------ execution
-    def _run(self, s, src):
-        """Enqueue preprocess(src) + forward + decode + NMS on the slot's stream (no sync)."""
-        with torch.cuda.stream(s.stream), torch.no_grad():
+    def _head(self, s, src):
+        """The one launch outside the graph (its source pointer changes per call): preprocessing, fused
+        into the stem conv in bf16."""
+        if self.fused_stem:
+            m0 = self.model.model[0]
+            if s.x0 is None:
+                s.x0 = m0.forward_image(src)
+            else:
+                m0.forward_image(src, out=s.x0)
+        else:
             ops.preprocess(src, self.dtype, out=s.x)
+
+    def _run(self, s, src):
+        """Enqueue preprocess/stem(src) + forward + decode + NMS on the slot's stream (no sync)."""
+        with torch.cuda.stream(s.stream), torch.no_grad():
+            self._head(s, src)
             if s.graph is not None:
                 s.graph.replay()
             else:

@@ -66,6 +66,31 @@ class Conv(KernelModule):
 
     forward_fuse = forward  # after fuse() the reference swaps forward := forward_fuse (tasks.py:137)
 
+    def can_fuse_preprocess(self):
+        c = self.conv
+        return (c.kernel_size == (3, 3) and c.stride == (2, 2) and c.padding == (1, 1) and c.groups == 1
+                and c.in_channels <= 8)
+
+    def forward_image(self, src, out=None):
+        """Layer-0 fast path of the engine: `src` is the raw NCHW uint8 (or float32) batch; preprocessing
+        (/255, NCHW->NHWC, bf16) is fused into this conv's loader on the tensor cores."""
+        c = self.conv
+        bn = getattr(self, "bn", None)
+        tensors = [c.weight] + ([c.bias] if c.bias is not None else [])
+        if bn is not None:
+            tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+        def build():
+            w, b = fold_conv_bn(c, bn)                                   # (Cout, Cin, 3, 3)
+            k = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)            # k = (dy*3+dx)*Cin + ci
+            kp = (k.shape[1] + 15) // 16 * 16
+            wp = torch.zeros((w.shape[0], 1, 1, kp), dtype=torch.float32, device=src.device)
+            wp[:, 0, 0, :k.shape[1]] = k.to(src.device)
+            return ops.PackedConv(wp.to(torch.bfloat16), 1), f32(b, src.device)
+
+        pw, b = self._packed("stem", torch.bfloat16, src.device, tensors, build)
+        return ops.stem_conv(src, pw, b, c.out_channels, act_name(self.act), out=out)
+
     def fuse(self):
         """Fold BN into self.conv the way BaseModel.fuse does (nn/tasks.py:133-137)."""
         if hasattr(self, "bn"):

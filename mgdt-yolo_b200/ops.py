@@ -196,6 +196,25 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
     return out
 
 
+def stem_conv(src, w: "PackedConv", bias, cout, act, out=None):
+    """Fused preprocess + 3x3/s2 stem conv from an NCHW uint8 (/255) or float32 image batch (bf16 out)."""
+    require_cuda(src, "stem input")
+    if not src.is_contiguous() or src.dtype not in (torch.uint8, torch.float32) or w.umma is None:
+        raise ValueError("stem_conv: needs a contiguous uint8/float32 NCHW source and tcgen05-packed weights")
+    n, c, h, wd = src.shape
+    ho, wo = (h - 1) // 2 + 1, (wd - 1) // 2 + 1
+    if out is None:
+        out = new_act(n, cout, ho, wo, torch.bfloat16, src.device)
+    yp, yn, yc, yh, yw, ycs = view(out)
+    if (yn, yc, yh, yw) != (n, cout, ho, wo):
+        raise ValueError("stem_conv: bad output shape")
+    meta = dict(shape=f"stem {c}->{cout} k3s2 {n}x{h}x{wd}", flops=2.0 * n * ho * wo * cout * c * 9,
+                bytes=_nb(src, out))
+    _invoke("mgdt_stem_conv", meta, src.data_ptr(), 1 if src.dtype == torch.uint8 else 0, w.umma.data_ptr(), _p(bias),
+            yp, ycs, n, c, h, wd, cout, ACTS[act], BF16, stream_ptr())
+    return out
+
+
 def dwconv7_ln(x, w49c, bias, ln_w, ln_b, eps=1e-6, out=None):
     xp, n, c, h, w, xcs = view(x)
     if out is None:

@@ -184,6 +184,32 @@ class BaseModel(nn.Module):
                 y.append(x if m.i in self.save else None)
             return x
 
+    def stem_fusable(self):
+        m0 = self.model[0]
+        return isinstance(m0, Conv) and m0.can_fuse_preprocess() and bool(ops.lib().mgdt_has_umma())
+
+    def predict_from(self, x, start):
+        """Continue the graph walk of _predict_once from layer `start`, x being layer start-1's output."""
+        with torch.cuda.device(x.device):
+            y = [None] * start
+            if start > 0 and self.model[start - 1].i in self.save:
+                y[start - 1] = x
+            for m in self.model[start:]:
+                if m.f != -1:
+                    x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
+                x = m(x)
+                y.append(x if m.i in self.save else None)
+            return x
+
+    def predict_image(self, src):
+        """Forward from a raw NCHW uint8 (or float32 in [0,1]) batch: the /255 + NCHW->NHWC + bf16
+        preprocessing of BasePredictor.preprocess (predictor.py:115-130) is fused into layer 0."""
+        ops.require_cuda(src, "model input")
+        if not self.stem_fusable():
+            return self._predict_once(ops.preprocess(src.contiguous(), torch.bfloat16))
+        with torch.cuda.device(src.device):
+            return self.predict_from(self.model[0].forward_image(src.contiguous()), 1)
+
     def fuse(self, verbose=True):
         """tasks.py:121-146: fold every Conv's BatchNorm into its Conv2d."""
         for m in self.model.modules():

@@ -77,21 +77,57 @@ def test_cpu_tensor_fails_loudly():
 
 
 def test_engine_matches_module_path():
-    """CUDA-graph engine (uint8 in, packed detections out) == eager modules + non_max_suppression."""
+    """CUDA-graph engine (uint8 in, fused preprocess+stem, packed detections out) against the eager module
+    path: same decode output up to bf16 rounding of the differently-ordered stem sums, and its NMS output
+    is exactly non_max_suppression() of its own decode tensor, from host and from device input."""
     from mgdt_yolo_b200.engine import Engine
     from mgdt_yolo_b200.postprocess import non_max_suppression
     m, _ = parity.build_model("mspa_c2f_gd_tood_yolov8n.yaml", cls_bias=-1.238)
     g = torch.Generator().manual_seed(0)
     u8 = torch.randint(0, 256, (2, 3, 128, 160), dtype=torch.uint8, generator=g)
     eng = Engine(m, 2, (128, 160), torch.bfloat16, "cuda:0", conf=0.25, iou=0.7)
-    got = eng(u8.pin_memory())
-    got2 = eng(u8.cuda())
-    with torch.no_grad():
-        y, _ = m((u8.cuda().float() / 255).to(torch.bfloat16))
-    want = non_max_suppression(y, 0.25, 0.7)
-    for a, b, c in zip(got, got2, want):
+    assert eng.fused_stem
+    got_host = eng(u8.pin_memory())
+    pred_host = eng.slots[0].pred.clone()
+    got_dev = eng(u8.cuda())
+    pred_dev = eng.slots[0].pred.clone()
+    assert torch.equal(pred_host, pred_dev)
+    want = non_max_suppression(pred_dev, 0.25, 0.7)
+    for a, b, c in zip(got_host, got_dev, want):
         assert torch.equal(a, c.cpu()) and torch.equal(b.cpu(), c.cpu())
     assert sum(int(t.shape[0]) for t in want) > 0
+    with torch.no_grad():
+        y, _ = m((u8.cuda().float() / 255).to(torch.bfloat16))
+    mx, l2 = parity.errs(pred_dev, y)
+    assert l2 <= 1e-2, f"engine vs eager decode output: rel-L2 {l2:.3e}"
+    # fp32 engine (no fused stem) == eager fp32 modules (torch's CUDA `/ 255` multiplies by a reciprocal, the
+    # kernel divides like the reference's CPU path: inputs differ by an ulp, hence allclose, not equal)
+    eng32 = Engine(m, 2, (128, 160), torch.float32, "cuda:0", conf=0.25, iou=0.7, slots=1)
+    assert not eng32.fused_stem
+    got32 = eng32(u8.cuda())
+    with torch.no_grad():
+        y32, _ = m((u8.float() / 255).cuda())
+    for a, b in zip(got32, non_max_suppression(y32, 0.25, 0.7)):
+        assert a.shape == b.shape and torch.allclose(a, b, rtol=1e-5, atol=1e-3)
+
+
+def test_fused_stem_matches_preprocess_plus_conv():
+    from mgdt_yolo_b200 import ops
+    from mgdt_yolo_b200.modules import Conv
+    from mgdt_yolo_b200.synth import synth_state_dict
+    c = Conv(3, 16, 3, 2)
+    c.load_state_dict(synth_state_dict(c.state_dict(), seed=11))
+    c = c.cuda().eval()
+    g = torch.Generator().manual_seed(2)
+    for shape in ((2, 3, 64, 96), (1, 3, 37, 51)):
+        u8 = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g).cuda()
+        with torch.no_grad():
+            fused = c.forward_image(u8)
+            plain = c(ops.preprocess(u8, torch.bfloat16))
+            fused_f = c.forward_image(u8.float() / 255)
+        mx, _ = parity.errs(fused, plain)
+        assert fused.shape == plain.shape and mx <= 2 ** -7, f"fused stem vs preprocess+conv: {mx:.3e}"
+        assert parity.errs(fused_f, plain)[0] <= 2 ** -7
 
 
 def test_full_size_properties():
