@@ -45,6 +45,8 @@ const char* mgdt_last_error(void);
 /* Number of kernels this library has enqueued so far in this process (every launch counts once;
  * a launch recorded into a CUDA graph counts when recorded, not per replay). */
 unsigned long long mgdt_launch_count(void);
+/* Debug: device buffer of 64 u64 per CTA receiving %globaltimer stamps of the tcgen05 conv's phases (NULL = off). */
+void mgdt_debug_set_trace(void* buf);
 /* Compiled-in facts for tests: returns 1 if the tcgen05/TMA conv path was built. */
 int mgdt_has_umma(void);
 
@@ -77,6 +79,7 @@ typedef struct mgdt_conv_args {
     int32_t act, in_relu, dtype;
     int32_t impl;          /* 0 auto, 1 force CUDA-core path, 2 force tcgen05 path */
     const void* w_umma;    /* NULL, or the weights packed by mgdt_conv_umma_pack (bf16 tcgen05 path) */
+    int32_t w_umma_f16;    /* 1 if w_umma was packed as fp16 (B operand F16, A stays bf16): 8x finer weight rounding */
 } mgdt_conv_args;
 int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
 
@@ -84,14 +87,15 @@ int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
  * mgdt_conv_umma_packed_bytes returns 0 when (Cin, Cout, k, stride) is not taken by that path
  * (needs bf16, Cin % 8 == 0, k in {1,3} with pad k/2, stride 1 or (k=3) 2). */
 size_t mgdt_conv_umma_packed_bytes(int Cin, int Cout, int k, int stride);
-int mgdt_conv_umma_pack(const void* w_ohwi, int Cin, int Cout, int k, int stride, void* packed, void* stream);
+int mgdt_conv_umma_pack(const void* w_ohwi, int w_dtype, int Cin, int Cout, int k, int stride, int out_f16, void* packed,
+                        void* stream);
 
 /* Fused input preprocessing + stem convolution on the tensor cores (bf16): 3x3 stride-2 pad-1 Conv+BN+act
  * (layer 0 of every config, models/v8/*.yaml) read straight from the NCHW uint8 (divided by 255,
  * predictor.py:127-129) or float32 source.  w_umma = mgdt_conv_umma_pack of the OHWI weights viewed as a
  * 1x1 conv over round_up(9*C, 16) channels (k = (dy*3+dx)*C + c, zero padded). */
-int mgdt_stem_conv(const void* src, int src_is_u8, const void* w_umma, const float* bias, void* y, int y_cs, int N, int C,
-                   int H, int W, int Cout, int act, int dtype, void* stream);
+int mgdt_stem_conv(const void* src, int src_is_u8, const void* w_umma, int w_umma_f16, const float* bias, void* y, int y_cs,
+                   int N, int C, int H, int W, int Cout, int act, int dtype, void* stream);
 
 /* Depthwise 7x7 (pad 3, bias) + channels-last LayerNorm(eps), ConvNeXtV2_Block.forward
  * (nn/modules/convnextv2.py:35-37, nn/modules/utils.py:162-163).  w is [49][C] in dtype,
@@ -107,8 +111,8 @@ int mgdt_dwconv7_ln(const void* x, int x_cs, const void* w, const float* bias, c
  * a 1x1 conv over 9*Cin channels: the tensor-core path builds the modulated bilinear im2col tile in
  * shared memory and runs it through tcgen05. */
 int mgdt_dcn3x3(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs,
-                int mask_is_logit, const void* w, const void* w_umma, void* y, int y_cs, int N, int H, int W, int Cin,
-                int Cout, int dtype, void* stream);
+                int mask_is_logit, const void* w, const void* w_umma, int w_umma_f16, void* y, int y_cs, int N, int H, int W,
+                int Cin, int Cout, int dtype, void* stream);
 
 /* ---------------------------------------------------------------- reductions
  * Per-(n,c) sums over the image, optionally per adaptive 2x2 window as well.

@@ -26,7 +26,7 @@ class ConvArgs(C.Structure):
                 ("N", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32),
                 ("kh", i32), ("kw", i32), ("stride", i32), ("pad", i32),
                 ("x_cs", i32), ("y_cs", i32), ("add_cs", i32), ("ps_cs", i32), ("res_cs", i32),
-                ("act", i32), ("in_relu", i32), ("dtype", i32), ("impl", i32), ("w_umma", vp)]
+                ("act", i32), ("in_relu", i32), ("dtype", i32), ("impl", i32), ("w_umma", vp), ("w_umma_f16", i32)]
 
 
 class DecodeLevel(C.Structure):
@@ -39,12 +39,13 @@ SIGNATURES = {
     "mgdt_last_error": (C.c_char_p, []),
     "mgdt_launch_count": (C.c_ulonglong, []),
     "mgdt_has_umma": (C.c_int, []),
+    "mgdt_debug_set_trace": (None, [vp]),
     "mgdt_conv2d": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "mgdt_conv_umma_packed_bytes": (sz, [i32, i32, i32, i32]),
-    "mgdt_conv_umma_pack": (C.c_int, [vp, i32, i32, i32, i32, vp, vp]),
-    "mgdt_stem_conv": (C.c_int, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_conv_umma_pack": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "mgdt_stem_conv": (C.c_int, [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_dwconv7_ln": (C.c_int, [vp, i32, vp, vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]),
-    "mgdt_dcn3x3": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_dcn3x3": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_chan_stats_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
     "mgdt_chan_stats": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, i32, vp]),
     "mgdt_mspa_gate": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),

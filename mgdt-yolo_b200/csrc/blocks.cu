@@ -340,18 +340,18 @@ extern "C" int mgdt_dwconv7_ln(const void* x, int x_cs, const void* w, const flo
 namespace mgdt {
 bool dcn_umma_supported(const void* x, int x_cs, const void* w_umma, int N, int H, int W, int Cin, int Cout);
 int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs, int mask_is_logit,
-             const void* w_umma, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
+             const void* w_umma, int w_f16, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
 }
 #endif
 
 extern "C" int mgdt_dcn3x3(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs,
-                           int mask_is_logit, const void* w, const void* w_umma, void* y, int y_cs, int N, int H, int W,
-                           int Cin, int Cout, int dtype, void* stream) {
+                           int mask_is_logit, const void* w, const void* w_umma, int w_umma_f16, void* y, int y_cs, int N,
+                           int H, int W, int Cin, int Cout, int dtype, void* stream) {
     MGDT_CHECK(x && offset && mask && w && y, "dcn3x3: null pointer");
     MGDT_CHECK(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && off_cs >= 18 && mask_cs >= 9, "dcn3x3: bad shape");
 #ifdef MGDT_WITH_UMMA
     if (dtype == MGDT_BF16 && dcn_umma_supported(x, x_cs, w_umma, N, H, W, Cin, Cout))
-        return dcn_umma(x, x_cs, offset, off_cs, mask, mask_cs, mask_is_logit, w_umma, y, y_cs, N, H, W, Cin, Cout,
+        return dcn_umma(x, x_cs, offset, off_cs, mask, mask_cs, mask_is_logit, w_umma, w_umma_f16, y, y_cs, N, H, W, Cin, Cout,
                         (cudaStream_t)stream);
 #endif
     const size_t smem = sizeof(float) * DCN_PIX * (9 * Cin + 1);

@@ -19,6 +19,8 @@
 // each work item is (tile, K slice) and carries its own weight slice through the ring.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 namespace mgdt {
@@ -29,6 +31,7 @@ constexpr int U2_MMA_WARP = U2_PRODUCER_WARPS + U2_EPI_WARPS;
 constexpr int U2_THREADS = (U2_MMA_WARP + 1) * 32;
 constexpr int U2_MAX_SMEM = 220 * 1024;
 constexpr int U2_MAX_STAGES = 4;
+constexpr int U2_MLP = 8;          // 16-byte loads in flight per producer thread
 constexpr int U2_MAX_MMA = 160;   // K=16 instructions per (slice, 128-row block) the descriptor table holds
 constexpr int U2_TAIL = 128 + 2 * 8 * U2_MAX_MMA + 4 * 256 + 2 * 256;  // barriers + TMEM slot, descriptor tables, bias[Nc], u8 LUT
 
@@ -176,8 +179,14 @@ static bool make_run2(const Plan2& p, int N, int H, int W, int Ho, int Wo, Run2&
 
 // ---------------------------------------------------------------------------------- weight packing
 // OHWI bf16 [Cout][k][k][Cin] -> [nsplit][nks][2*nmma_s chunks: (tap, plane-in-slice)][Nc][8], zero padded
-__global__ void umma2_pack_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, Plan2 p,
-                                  int Cin, int Cout, int k) {
+template <typename S, typename D> __device__ __forceinline__ D cvt_w(S v);
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_w<__nv_bfloat16, __nv_bfloat16>(__nv_bfloat16 v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_w<float, __nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half cvt_w<float, __half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __half cvt_w<__nv_bfloat16, __half>(__nv_bfloat16 v) { return __float2half_rn(__bfloat162float(v)); }
+
+template <typename S, typename D>
+__global__ void umma2_pack_kernel(const S* __restrict__ w, D* __restrict__ out, Plan2 p, int Cin, int Cout, int k) {
     const int cps = p.nmma_s * 2;
     const long long total = (long long)p.nsplit * p.nks * cps * p.Nc * 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -187,10 +196,10 @@ __global__ void umma2_pack_kernel(const __nv_bfloat16* __restrict__ w, __nv_bflo
         const int ks = (int)((i / (8LL * p.Nc * cps)) % p.nks);
         const int ns = (int)(i / (8LL * p.Nc * cps * p.nks));
         const int co = ns * p.Nc + nl;
-        __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+        D v = cvt_w<float, D>(0.f);
         if (chunk < p.taps * p.PS && co < Cout) {
             const int t = chunk / p.PS, plane = ks * p.PS + chunk % p.PS;
-            v = w[(((long long)co * k + p.tap_dy[t]) * k + p.tap_dx[t]) * Cin + plane * 8 + j];
+            v = cvt_w<S, D>(w[(((long long)co * k + p.tap_dy[t]) * k + p.tap_dx[t]) * Cin + plane * 8 + j]);
         }
         out[i] = v;
     }
@@ -258,6 +267,7 @@ struct P2 {
     int N, H, W, Cin, Cout, Ho, Wo;
     int x_cs, y_cs, add_cs, ps_cs, res_cs, act, in_relu;
     int y_vec, res_vec;
+    int w_f16;                   // weights packed as fp16 (B operand format F16), activations stay bf16
     Plan2 pl;
     Run2 rn;
     unsigned M_total;            // mode 0: N*H*W
@@ -268,6 +278,7 @@ struct P2 {
     const void* stem_src;
     int stem_u8, stem_C, stem_H, stem_W;
     FastDiv d_Wo;
+    unsigned long long* trace;   // debug: per-CTA phase timestamps (mgdt_debug_set_trace), normally NULL
 };
 
 // tile-relative output row m -> output pixel index, or -1 for junk / out-of-range rows
@@ -424,6 +435,17 @@ __device__ __forceinline__ uint4 stem_chunk(const P2& p, uint32_t g, int plane) 
     return o;
 }
 
+// Debug timeline: trace[(cta * 64 + slot)] = globaltimer ns.  slots: 0 start, 1 setup done, 2 weights resident,
+// 3 end; per tile t (< 6): 8+8t fill done (producer warp 0), 9+8t MMAs issued, 10+8t accumulators ready
+// (epilogue warp 8), 11+8t epilogue done.
+__device__ __forceinline__ void trace_mark(const P2& p, int slot) {
+    if (p.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + slot] = t;
+    }
+}
+
 __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_constant__ P2 p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Plan2& pl = p.pl;
@@ -431,6 +453,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ns = blockIdx.y;
 
+    if (tid == 0) trace_mark(p, 0);
     unsigned char* sWres = smem;
     unsigned char* sStage = smem + rn.wres_bytes;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + rn.wres_bytes + (size_t)rn.S * rn.stage_bytes);
@@ -486,6 +509,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) trace_mark(p, 1);
 
     const uint32_t tiles = (uint32_t)rn.tiles;
     const int nks = pl.nks;
@@ -503,6 +527,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(WREADY);
+            if (tid == 0) trace_mark(p, 2);
         }
         const uint32_t chunks = (uint32_t)(pl.PS * pl.npar * rn.P);
         uint32_t it = 0;
@@ -593,12 +618,12 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                         }
                     }
                 } else
-                // 4 chunks in flight per thread: loads first, then stores
-                for (uint32_t e0 = ptid; e0 < chunks; e0 += NP * 4) {
-                    uint4 v[4];
-                    uint32_t dsto[4];
+                // U2_MLP chunks in flight per thread: loads first, then stores
+                for (uint32_t e0 = ptid; e0 < chunks; e0 += NP * U2_MLP) {
+                    uint4 v[U2_MLP];
+                    uint32_t dsto[U2_MLP];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < U2_MLP; ++u) {
                         const uint32_t e = e0 + u * NP;
                         dsto[u] = 0xffffffffu;
                         if (e < chunks) {
@@ -613,18 +638,20 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                    for (int u = 0; u < U2_MLP; ++u)
                         if (dsto[u] != 0xffffffffu) *reinterpret_cast<uint4*>(sA + dsto[u]) = v[u];
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(FULL(s));
+                if (tid == 0 && it < 6) trace_mark(p, 8 + 8 * (int)it);
             }
         }
     } else if (warp == U2_MMA_WARP) {
         // =============================================================== MMA issuer (one lane)
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.Nc >> 3) << 17) | ((128u >> 4) << 24);
+            // instruction descriptor: D = f32, A = bf16, B = bf16 or f16, both K-major, N = Nc, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | ((p.w_f16 ? 0u : 1u) << 10) | ((uint32_t)(pl.Nc >> 3) << 17) | ((128u >> 4) << 24);
             if (nks == 1) mbar_wait(WREADY, 0);
             uint32_t it = 0, ti = 0;
             for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
@@ -653,6 +680,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                     }
                     umma_commit(EMPTY(s));                       // smem stage may be refilled once these MMAs retire
                     if (ks == nks - 1) umma_commit(ACCFULL(a));  // accumulators complete
+                    if (it < 6) trace_mark(p, 9 + 8 * (int)it);
                 }
             }
         }
@@ -669,6 +697,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             const uint32_t aphase = rn.NACC == 2 ? ((ti >> 1) & 1) : (ti & 1);
             mbar_wait(ACCFULL(a), aphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (warp == U2_PRODUCER_WARPS && lane == 0 && ti < 6) trace_mark(p, 10 + 8 * (int)ti);
             int opix = -1, mb_cached = -1;
             for (int u = half; u < units; u += 2) {
                 const int mb = u / ncch, cc = u - mb * ncch;
@@ -729,10 +758,12 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(ACCEMPTY(a));
+            if (warp == U2_PRODUCER_WARPS && lane == 0 && ti < 6) trace_mark(p, 11 + 8 * (int)ti);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (tid == 0) trace_mark(p, 3);
     if (warp == 8) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)rn.tmem_cols)
                      : "memory");
@@ -762,8 +793,11 @@ static void fill_divs(P2& p) {
     p.d_Wo = make_fastdiv((uint32_t)p.W);
 }
 
+static unsigned long long* g_trace = nullptr;
+
 static int launch2(P2& p, cudaStream_t s) {
     fill_divs(p);
+    p.trace = g_trace;
     cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_MAX_SMEM);
     if (e != cudaSuccess) return set_error(-EIO, "conv_umma2: smem attr: %s", cudaGetErrorString(e));
     const long long tiles = p.rn.tiles;
@@ -797,6 +831,7 @@ int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
     p.N = a->N; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout; p.Ho = Ho; p.Wo = Wo;
     p.x_cs = a->x_cs; p.y_cs = a->y_cs; p.add_cs = a->add_cs; p.ps_cs = a->ps_cs; p.res_cs = a->res_cs;
     p.act = a->act; p.in_relu = a->in_relu;
+    p.w_f16 = a->w_umma_f16;
     p.y_vec = (((uintptr_t)a->y & 15) == 0 && (a->y_cs & 7) == 0) ? 1 : 0;
     p.res_vec = (a->residual && ((uintptr_t)a->residual & 15) == 0 && (a->res_cs & 7) == 0) ? 1 : 0;
     p.M_total = (unsigned)((long long)a->N * a->H * a->W);
@@ -812,7 +847,7 @@ bool dcn_umma_supported(const void* x, int x_cs, const void* w_umma, int N, int 
 }
 
 int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs, int mask_is_logit,
-             const void* w_umma, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, cudaStream_t s) {
+             const void* w_umma, int w_f16, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, cudaStream_t s) {
     P2 p;
     int Ho, Wo;
     if (!plan2_for(9 * Cin, Cout, 1, 1, N, H, W, p.pl, p.rn, Ho, Wo)) return set_error(-EINVAL, "dcn_umma: unsupported shape");
@@ -820,6 +855,7 @@ int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void
     p.residual = nullptr; p.bias = nullptr; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y;
     p.N = N; p.H = H; p.W = W; p.Cin = 9 * Cin; p.Cout = Cout; p.Ho = H; p.Wo = W;
     p.x_cs = x_cs; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = MGDT_ACT_NONE; p.in_relu = 0;
+    p.w_f16 = w_f16;
     p.y_vec = (((uintptr_t)y & 15) == 0 && (y_cs & 7) == 0) ? 1 : 0;
     p.res_vec = 0;
     p.M_total = (unsigned)((long long)N * H * W);
@@ -832,8 +868,8 @@ int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void
 // Fused preprocess + stem conv (3x3, stride 2, pad 1, C <= 3..8 input channels): a 1x1 GEMM over the virtual
 // K = round_up(9*C, 16) im2col built from the NCHW source while staging; output geometry (Ho, Wo) plays the
 // role of the 1x1 conv's (H, W).
-int stem_umma(const void* src, int src_is_u8, const void* w_umma, const float* bias, void* y, int y_cs, int N, int C,
-              int H, int W, int Cout, int act, cudaStream_t s) {
+int stem_umma(const void* src, int src_is_u8, const void* w_umma, int w_f16, const float* bias, void* y, int y_cs, int N,
+              int C, int H, int W, int Cout, int act, cudaStream_t s) {
     const int Kp = (9 * C + 15) / 16 * 16;
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     P2 p;
@@ -843,6 +879,7 @@ int stem_umma(const void* src, int src_is_u8, const void* w_umma, const float* b
     p.bias = bias; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y;
     p.N = N; p.H = Ho; p.W = Wo; p.Cin = Kp; p.Cout = Cout; p.Ho = Ho; p.Wo = Wo;
     p.x_cs = 0; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = act; p.in_relu = 0;
+    p.w_f16 = w_f16;
     p.y_vec = (((uintptr_t)y & 15) == 0 && (y_cs & 7) == 0) ? 1 : 0;
     p.res_vec = 0;
     p.M_total = (unsigned)((long long)N * Ho * Wo);
@@ -855,13 +892,15 @@ int stem_umma(const void* src, int src_is_u8, const void* w_umma, const float* b
 
 using namespace mgdt;
 
-extern "C" int mgdt_stem_conv(const void* src, int src_is_u8, const void* w_umma, const float* bias, void* y, int y_cs,
-                              int N, int C, int H, int W, int Cout, int act, int dtype, void* stream) {
+extern "C" void mgdt_debug_set_trace(void* buf) { mgdt::g_trace = (unsigned long long*)buf; }
+
+extern "C" int mgdt_stem_conv(const void* src, int src_is_u8, const void* w_umma, int w_umma_f16, const float* bias,
+                              void* y, int y_cs, int N, int C, int H, int W, int Cout, int act, int dtype, void* stream) {
     MGDT_CHECK(src && w_umma && y, "stem_conv: null pointer");
     MGDT_CHECK(dtype == MGDT_BF16, "stem_conv: the fused tensor-core stem is bf16 only (use preprocess + conv2d for fp32)");
     MGDT_CHECK(N > 0 && C > 0 && C <= 8 && H > 1 && W > 1 && Cout > 0 && y_cs >= Cout, "stem_conv: bad shape");
     MGDT_CHECK(((uintptr_t)w_umma & 15) == 0, "stem_conv: packed weights must be 16-byte aligned");
-    return stem_umma(src, src_is_u8, w_umma, bias, y, y_cs, N, C, H, W, Cout, act, (cudaStream_t)stream);
+    return stem_umma(src, src_is_u8, w_umma, w_umma_f16, bias, y, y_cs, N, C, H, W, Cout, act, (cudaStream_t)stream);
 }
 
 extern "C" size_t mgdt_conv_umma_packed_bytes(int Cin, int Cout, int k, int stride) {
@@ -870,13 +909,23 @@ extern "C" size_t mgdt_conv_umma_packed_bytes(int Cin, int Cout, int k, int stri
     return (size_t)pl.nsplit * pl.nks * pl.nmma_s * 2 * pl.Nc * 16;
 }
 
-extern "C" int mgdt_conv_umma_pack(const void* w_ohwi, int Cin, int Cout, int k, int stride, void* packed, void* stream) {
+extern "C" int mgdt_conv_umma_pack(const void* w_ohwi, int w_dtype, int Cin, int Cout, int k, int stride, int out_f16,
+                                   void* packed, void* stream) {
     MGDT_CHECK(w_ohwi && packed, "conv_umma_pack: null pointer");
+    MGDT_CHECK(w_dtype == MGDT_F32 || w_dtype == MGDT_BF16, "conv_umma_pack: weights must be fp32 or bf16");
     const Plan2 pl = make_plan2(Cin, Cout, k, stride);
     MGDT_CHECK(pl.ok, "conv_umma_pack: shape %d->%d k%d s%d is not supported by the tcgen05 path", Cin, Cout, k, stride);
     const long long total = (long long)pl.nsplit * pl.nks * pl.nmma_s * 2 * pl.Nc * 8;
-    umma2_pack_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)w_ohwi,
-                                                                         (__nv_bfloat16*)packed, pl, Cin, Cout, k);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int g = cdiv(total, 256);
+    if (w_dtype == MGDT_F32 && out_f16)
+        umma2_pack_kernel<float, __half><<<g, 256, 0, s>>>((const float*)w_ohwi, (__half*)packed, pl, Cin, Cout, k);
+    else if (w_dtype == MGDT_F32)
+        umma2_pack_kernel<float, __nv_bfloat16><<<g, 256, 0, s>>>((const float*)w_ohwi, (__nv_bfloat16*)packed, pl, Cin, Cout, k);
+    else if (out_f16)
+        umma2_pack_kernel<__nv_bfloat16, __half><<<g, 256, 0, s>>>((const __nv_bfloat16*)w_ohwi, (__half*)packed, pl, Cin, Cout, k);
+    else
+        umma2_pack_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)w_ohwi, (__nv_bfloat16*)packed, pl, Cin, Cout, k);
     MGDT_LAUNCH_CHECK("umma_pack");
     return 0;
 }

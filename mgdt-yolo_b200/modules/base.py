@@ -58,8 +58,8 @@ def act_name(m) -> str | None:
 def ohwi(w: torch.Tensor, dtype, device, stride: int = 1) -> "ops.PackedConv":
     """(Cout, Cin, kh, kw) -> kernel weight pack: contiguous OHWI (Cout, kh, kw, Cin) in the compute dtype
     for the CUDA-core path plus, for bf16 shapes the tcgen05 path takes, its K-major shared-memory image."""
-    t = w.detach().to(device=device, dtype=torch.float32).permute(0, 2, 3, 1).contiguous().to(dtype)
-    return ops.PackedConv(t, stride)
+    t32 = w.detach().to(device=device, dtype=torch.float32).permute(0, 2, 3, 1).contiguous()
+    return ops.PackedConv(t32.to(dtype), stride, w32=t32)
 
 
 def f32(t: torch.Tensor, device) -> torch.Tensor:

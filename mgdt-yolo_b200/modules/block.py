@@ -15,6 +15,12 @@ __all__ = ("DFL", "SPPF", "Bottleneck", "C2f", "MSPA_C2f", "SPRModule", "SimFusi
            "ConvNeXtV2_Block", "LayerNorm", "GRN", "h_sigmoid", "InjectionMultiSum_Auto_pool", "DyDCNv2")
 
 
+def _pk1x1(w32_ohwi, dtype, device):
+    """PackedConv of a (Cout,1,1,K) fp32 weight matrix."""
+    w32 = w32_ohwi.to(device=device, dtype=torch.float32).contiguous()
+    return ops.PackedConv(w32.to(dtype), 1, w32=w32)
+
+
 class DFL(KernelModule):
     """Distribution-focal-loss integral (nn/modules/block.py:36-54): softmax over c1 bins and
     expectation with the fixed weights 0..c1-1.  Inside the heads it is fused into mgdt_decode."""
@@ -271,9 +277,9 @@ class ConvNeXtV2_Block(KernelModule):
             return dict(
                 dw=self.dwconv.weight.detach().float().reshape(c, 49).t().contiguous().to(device=device, dtype=dtype),
                 dwb=f32(self.dwconv.bias, device), lnw=f32(self.norm.weight, device), lnb=f32(self.norm.bias, device),
-                w1=ops.PackedConv(self.pwconv1.weight.detach().float().reshape(4 * c, 1, 1, c).contiguous().to(device=device, dtype=dtype)),
+                w1=_pk1x1(self.pwconv1.weight.detach().float().reshape(4 * c, 1, 1, c), dtype, device),
                 b1=f32(self.pwconv1.bias, device), gamma=f32(self.grn.gamma.reshape(-1), device),
-                w2=ops.PackedConv(w2.reshape(c, 1, 1, 4 * c).contiguous().to(device=device, dtype=dtype)), b2=f32(b2, device))
+                w2=_pk1x1(w2.reshape(c, 1, 1, 4 * c), dtype, device), b2=f32(b2, device))
 
         return self._packed("blk", dtype, device, t, build)
 
@@ -366,9 +372,8 @@ class DyDCNv2(KernelModule):
         t = [w] + ([self.norm.weight, self.norm.bias] if self.with_norm else [])
 
         def build():
-            wp = w.detach().float().permute(0, 2, 3, 1).contiguous().to(device=device, dtype=dtype)
             # [Cout][9][Cin] == OHWI of a 1x1 conv over 9*Cin virtual channels (the tensor-core DCN path)
-            wp = ops.PackedConv(wp.reshape(wp.shape[0], 1, 1, -1), 1)
+            wp = _pk1x1(w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], 1, 1, -1), dtype, device)
             if not self.with_norm:
                 return wp, None, None
             return wp, f32(self.norm.weight, device), f32(self.norm.bias, device)

@@ -112,11 +112,14 @@ def _invoke(name, meta, *args):
 class PackedConv:
     """Weights of one convolution in the kernels' layouts: `.ohwi` (Cout,k,k,Cin) for the CUDA-core
     path and, when the tcgen05 path takes the shape (bf16 on a CUDA device), `.umma`, the K-major
-    shared-memory image built by mgdt_conv_umma_pack for the stride it will be used with."""
+    shared-memory image built by mgdt_conv_umma_pack for the stride it will be used with.  If the fp32
+    master weights `w32` (same OHWI shape) are given and WEIGHT_F16 is on, the image is packed in fp16:
+    the MMA then runs bf16 activations x fp16 weights, removing the weights' share of the rounding error."""
 
-    def __init__(self, ohwi: torch.Tensor, stride: int = 1):
+    def __init__(self, ohwi: torch.Tensor, stride: int = 1, w32: torch.Tensor | None = None):
         self.ohwi = ohwi
         self.umma = None
+        self.f16 = False
         self.shape = ohwi.shape
         self.dtype = ohwi.dtype
         cout, k, k2, cin = ohwi.shape
@@ -124,15 +127,22 @@ class PackedConv:
             nbytes = lib().mgdt_conv_umma_packed_bytes(cin, cout, k, stride)
             if nbytes:
                 self.umma = torch.empty((nbytes,), dtype=torch.uint8, device=ohwi.device)
+                self.f16 = bool(WEIGHT_F16 and w32 is not None)
+                src = w32.contiguous() if self.f16 else ohwi
                 with torch.cuda.device(ohwi.device):
-                    check(lib().mgdt_conv_umma_pack(ohwi.data_ptr(), cin, cout, k, stride, self.umma.data_ptr(),
-                                                    stream_ptr()), "conv_umma_pack")
+                    check(lib().mgdt_conv_umma_pack(src.data_ptr(), F32 if self.f16 else BF16, cin, cout, k, stride,
+                                                    1 if self.f16 else 0, self.umma.data_ptr(), stream_ptr()),
+                          "conv_umma_pack")
                 self.stride = stride
 
     def data_ptr(self):
         return self.ohwi.data_ptr()
 
 
+# tcgen05 path: pack weights as fp16 while activations stay bf16.  Measured on B200: tcgen05.mma kind::f16 with
+# A = BF16 and B = F16 in the instruction descriptor raises 'illegal instruction' -- both operands must share one
+# format -- so this stays off; the packer keeps the option for an all-fp16 mode.
+WEIGHT_F16 = False
 USE_UMMA = True  # tests flip this to compare the tcgen05 path with the CUDA-core path
 
 
@@ -142,10 +152,10 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
     `w` is a PackedConv (or a plain OHWI (Cout, k, k, Cin) tensor) in x's dtype; `out` may be a channel
     slice of a concat buffer."""
     xp, n, cin, h, wd, xcs = view(x)
-    w_umma = None
+    w_umma, w_f16 = None, False
     if isinstance(w, PackedConv):
         if w.umma is not None and w.stride == s:
-            w_umma = w.umma
+            w_umma, w_f16 = w.umma, w.f16
         w = w.ohwi
     cout = cout if cout is not None else w.shape[0]
     p = k // 2 if p is None else p
@@ -187,6 +197,7 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
     a.dtype = dtype_code(x.dtype)
     a.impl = impl
     a.w_umma = None if (w_umma is None or impl == 1) else w_umma.data_ptr()
+    a.w_umma_f16 = 1 if w_f16 else 0
     es = x.element_size()
     meta = dict(shape=f"{cin}->{cout} k{k}s{s} {n}x{h}x{wd}", flops=2.0 * n * ho * wo * cout * cin * k * k,
                 bytes=es * (n * h * wd * cin * (2 if pre_add is not None else 1)
@@ -210,7 +221,8 @@ def stem_conv(src, w: "PackedConv", bias, cout, act, out=None):
         raise ValueError("stem_conv: bad output shape")
     meta = dict(shape=f"stem {c}->{cout} k3s2 {n}x{h}x{wd}", flops=2.0 * n * ho * wo * cout * c * 9,
                 bytes=_nb(src, out))
-    _invoke("mgdt_stem_conv", meta, src.data_ptr(), 1 if src.dtype == torch.uint8 else 0, w.umma.data_ptr(), _p(bias),
+    _invoke("mgdt_stem_conv", meta, src.data_ptr(), 1 if src.dtype == torch.uint8 else 0, w.umma.data_ptr(),
+            1 if w.f16 else 0, _p(bias),
             yp, ycs, n, c, h, wd, cout, ACTS[act], BF16, stream_ptr())
     return out
 
@@ -237,7 +249,8 @@ def dcn3x3(x, offset, mask, w, cout, mask_is_logit, out=None):
         out = new_act(n, cout, h, wd, x.dtype, x.device)
     yp, *_, ycs = view(out)
     _invoke("mgdt_dcn3x3", dict(shape=f"dcn {cin}->{cout} {n}x{h}x{wd}", bytes=_nb(x, offset, mask, out), flops=2.0 * 9 * cin * cout * n * h * wd), xp, xcs, op, ocs, mp, mcs, 1 if mask_is_logit else 0, w.data_ptr(),
-            None if getattr(w, "umma", None) is None else w.umma.data_ptr(), yp, ycs, n, h, wd,
+            None if getattr(w, "umma", None) is None else w.umma.data_ptr(), 1 if getattr(w, "f16", False) else 0,
+            yp, ycs, n, h, wd,
                             cin, cout, dtype_code(x.dtype), stream_ptr())
     return out
 

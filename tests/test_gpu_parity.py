@@ -43,15 +43,27 @@ def test_model_fp32(cfg):
         assert mx <= 1e-4, f"{cfg} {k}: max-rel {mx:.3e}"
 
 
+# bf16 whole-model bounds in the relative-L2 norm (measured values in DESIGN.md §5).  The four configs BASELINE.json
+# names are held to the north_star's 1e-2 on every feature map and on the decoded boxes/scores; the stock-backbone
+# variants and the raw head logit maps (pre-softmax/sigmoid, not feature maps) get the stated looser bounds.
+BF16_FEATURE_TOL = {"mspa_c2f_gd_tood_yolov8n.yaml": 1e-2, "mspa_c2f_gd_yolov8n.yaml": 1e-2, "mspa_c2f_yolov8n.yaml": 1e-2,
+                    "yolov8n.yaml": 1.5e-2}
+BF16_Y_TOL = {"mspa_c2f_gd_tood_yolov8n.yaml": 1e-2, "mspa_c2f_gd_yolov8n.yaml": 1e-2, "mspa_c2f_yolov8n.yaml": 1e-2,
+              "yolov8n.yaml": 1e-2}
+BF16_RAW_TOL = 3e-2
+
+
 @pytest.mark.parametrize("cfg", MODEL_CFGS)
 def test_model_bf16(cfg):
     res = parity.run_model_case(cfg, torch.bfloat16, layers=cfg in LAYER_CFGS)
     for k, (mx, l2) in res.items():
         if k.startswith("raw"):
-            assert l2 <= 3e-2, f"{cfg} {k}: rel-L2 {l2:.3e}"
-        elif "MGDT" or True:
-            lim = 1e-2 if ("mspa" in cfg and "tood" in cfg) or k.startswith("y") else 1.5e-2
-            assert l2 <= lim, f"{cfg} {k}: rel-L2 {l2:.3e} > {lim}"
+            lim = BF16_RAW_TOL
+        elif k.startswith("y"):
+            lim = BF16_Y_TOL.get(cfg, 1.5e-2)
+        else:
+            lim = BF16_FEATURE_TOL.get(cfg, 1.5e-2)
+        assert l2 <= lim, f"{cfg} {k}: rel-L2 {l2:.3e} > {lim}"
 
 
 @pytest.mark.parametrize("ci", range(len(NMS_CASES)), ids=[c[0] for c in NMS_CASES])

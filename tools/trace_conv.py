@@ -1,0 +1,42 @@
+"""Phase timeline of the persistent tcgen05 conv kernel for a few shapes (debug tool)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from mgdt_yolo_b200 import ops
+from mgdt_yolo_b200._lib import lib
+from mgdt_yolo_b200.modules import Conv
+from mgdt_yolo_b200.synth import synth_state_dict
+
+B = 32
+cases = [("c32_3x3", 32, 32, 3, 1, 80, 80), ("c8_1x1", 8, 8, 1, 1, 160, 160), ("c64_256", 64, 256, 1, 1, 80, 80),
+         ("c96_384", 96, 384, 1, 1, 40, 40), ("c16_3x3", 16, 16, 3, 1, 80, 80)]
+trace = torch.zeros(148 * 2 * 64, dtype=torch.int64, device="cuda")
+for name, cin, cout, k, s, H, W in cases:
+    m = Conv(cin, cout, k, s)
+    m.load_state_dict(synth_state_dict(m.state_dict(), seed=3))
+    m = m.cuda().eval()
+    x = ops.as_act(torch.randn(B, cin, H, W, device="cuda").to(torch.bfloat16))
+    with torch.no_grad():
+        for _ in range(3):
+            m(x)
+        torch.cuda.synchronize()
+        trace.zero_()
+        lib().mgdt_debug_set_trace(trace.data_ptr())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); m(x); e1.record()
+        torch.cuda.synchronize()
+        lib().mgdt_debug_set_trace(None)
+    t = trace.view(-1, 64).cpu()
+    act = t[:, 0] > 0
+    t = t[act]
+    t0 = int(t[:, 0].min())
+    rel = lambda col: [(int(v) - t0) / 1000 for v in col if v > 0]
+    def stat(slot):
+        r = rel(t[:, slot])
+        return f"{min(r):7.1f}/{sum(r)/len(r):7.1f}/{max(r):7.1f}" if r else "   -"
+    print(f"== {name}: event time {e0.elapsed_time(e1)*1000:.1f} us, CTAs {len(t)}   (us since first CTA start: min/mean/max)")
+    print("   start", stat(0), " setup", stat(1), " W", stat(2), " end", stat(3))
+    for ti in range(6):
+        if (t[:, 8 + 8 * ti] > 0).any():
+            print(f"   tile{ti}: fill {stat(8+8*ti)}  mma_issued {stat(9+8*ti)}  acc_ready {stat(10+8*ti)}  epi_done {stat(11+8*ti)}")
