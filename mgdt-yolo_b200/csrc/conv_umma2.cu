@@ -33,7 +33,7 @@ constexpr int U2_MAX_SMEM = 220 * 1024;
 constexpr int U2_MAX_STAGES = 4;
 constexpr int U2_MLP = 8;          // 16-byte loads in flight per producer thread
 constexpr int U2_MAX_MMA = 160;   // K=16 instructions per (slice, 128-row block) the descriptor table holds
-constexpr int U2_TAIL = 128 + 2 * 8 * U2_MAX_MMA + 4 * 256 + 2 * 256;  // barriers + TMEM slot, descriptor tables, bias[Nc], u8 LUT
+constexpr int U2_TAIL = 128 + 2 * 8 * U2_MAX_MMA + 4 * 256 + 2 * 256 + U2_EPI_WARPS * 2048;  // barriers + TMEM slot, descriptor tables, bias[Nc], u8 LUT, epilogue staging
 
 struct FastDiv {  // exact n / d for 0 <= n < 2^31
     uint32_t mul, shr, d;
@@ -301,61 +301,6 @@ __device__ __forceinline__ int out_pixel2(const P2& p, uint32_t tile, uint32_t m
     return (int)((n * p.Ho + ho) * p.Wo + wo);
 }
 
-// One 16-byte chunk of the A stage: 8 channels (plane) of staged position `pos` (parity `par`).
-__device__ __forceinline__ uint4 load_chunk(const P2& p, uint32_t tile, uint32_t tt, uint32_t n_img, int plane,
-                                            uint32_t pos, uint32_t par) {
-    int pix = -1;
-    uint32_t n = n_img;
-    if (p.pl.mode == 0) {
-        const uint32_t g = tile * (128u * p.rn.MB) + pos;
-        if (g < p.M_total) { pix = (int)g; n = fdiv(g, p.d_HW); }
-    } else if (p.pl.mode == 1) {
-        const int q = (int)(p.rn.Wq + tt * 128u * p.rn.MB + pos) - p.rn.halo;
-        if (q >= 0) {
-            const uint32_t hp = fdiv((uint32_t)q, p.d_Wq), wp = (uint32_t)q - hp * p.rn.Wq;
-            if (hp >= 1 && hp <= (uint32_t)p.H && wp >= 1 && wp <= (uint32_t)p.W)
-                pix = (int)((n * p.H + (hp - 1)) * p.W + (wp - 1));
-        }
-    } else {
-        const uint32_t q = tt * 128u * p.rn.MB + pos;
-        const uint32_t r = fdiv(q, p.d_Wq), c = q - r * p.rn.Wq;
-        const int hi = 2 * (int)r + (int)(par >> 1) - 1, wi = 2 * (int)c + (int)(par & 1) - 1;
-        if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) pix = (int)((n * p.H + hi) * p.W + wi);
-    }
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (pix < 0) return v;
-    v = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)pix * p.x_cs + plane * 8));
-    if (p.pre_add || p.in_scale || p.pix_scale || p.in_relu) {
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
-        if (p.pre_add) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.pre_add + (size_t)pix * p.add_cs + plane * 8));
-            const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(ah[j]); f[2 * j] += t.x; f[2 * j + 1] += t.y; }
-        }
-        if (p.in_scale) {
-            const float4* s = reinterpret_cast<const float4*>(p.in_scale + (size_t)n * p.Cin + plane * 8);
-            const float4 s0 = __ldg(s), s1 = __ldg(s + 1);
-            f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w; f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
-        }
-        if (p.pix_scale) {
-            const float s = __bfloat162float(p.pix_scale[(size_t)pix * p.ps_cs]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] *= s;
-        }
-        if (p.in_relu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-    }
-    return v;
-}
-
 // DCNv2: chunk = 8 channels (cg) of tap `tap` at output pixel g: mask * bilinear(x, p0 + offset)
 __device__ __forceinline__ uint4 dcn_chunk(const P2& p, uint32_t g, int plane) {
     float f[8];
@@ -446,6 +391,125 @@ __device__ __forceinline__ void trace_mark(const P2& p, int slot) {
     }
 }
 
+// ---------------------------------------------------------------------------------- async copy helpers
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    // 16-byte global -> shared copy that bypasses the register file; src_bytes = 0 zero-fills (halo / tail rows)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    // the mbarrier arrival fires once every cp.async this thread issued so far has landed
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+enum : int { LD_ASYNC = 0, LD_XFORM = 1, LD_DCN = 2, LD_STEM_U8 = 3, LD_STEM_GEN = 4 };
+
+constexpr int U2_NP = U2_PRODUCER_WARPS * 32;   // producer threads; every full[] / wready arrival count
+
+// Source pixel of staged position `pos` (parity `par`) of a tile, or -1 (zero fill); n = image of that pixel.
+template <int MODE>
+__device__ __forceinline__ int src_pixel(const P2& p, uint32_t tile, uint32_t tt, uint32_t n_img, uint32_t pos, uint32_t par,
+                                         uint32_t& n) {
+    n = n_img;
+    if (MODE == 0) {
+        const uint32_t g = tile * (128u * p.rn.MB) + pos;
+        if (g >= p.M_total) return -1;
+        n = fdiv(g, p.d_HW);
+        return (int)g;
+    } else if (MODE == 1) {
+        const int q = (int)(p.rn.Wq + tt * 128u * p.rn.MB + pos) - p.rn.halo;
+        if (q < 0) return -1;
+        const uint32_t hp = fdiv((uint32_t)q, p.d_Wq), wp = (uint32_t)q - hp * p.rn.Wq;
+        if (hp < 1 || hp > (uint32_t)p.H || wp < 1 || wp > (uint32_t)p.W) return -1;
+        return (int)((n * p.H + (hp - 1)) * p.W + (wp - 1));
+    } else {
+        const uint32_t q = tt * 128u * p.rn.MB + pos;
+        const uint32_t r = fdiv(q, p.d_Wq), c = q - r * p.rn.Wq;
+        const int hi = 2 * (int)r + (int)(par >> 1) - 1, wi = 2 * (int)c + (int)(par & 1) - 1;
+        if (hi < 0 || hi >= p.H || wi < 0 || wi >= p.W) return -1;
+        return (int)((n * p.H + hi) * p.W + wi);
+    }
+}
+
+// One 16-byte chunk (8 channels of plane `plane`) of source pixel `pix` with the fused input transforms.
+__device__ __forceinline__ uint4 xform_chunk(const P2& p, int pix, uint32_t n, int plane) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (pix < 0) return v;
+    v = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)pix * p.x_cs + plane * 8));
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+    if (p.pre_add) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.pre_add + (size_t)pix * p.add_cs + plane * 8));
+        const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(ah[j]); f[2 * j] += t.x; f[2 * j + 1] += t.y; }
+    }
+    if (p.in_scale) {
+        const float4* s = reinterpret_cast<const float4*>(p.in_scale + (size_t)n * p.Cin + plane * 8);
+        const float4 s0 = __ldg(s), s1 = __ldg(s + 1);
+        f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w; f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+    }
+    if (p.pix_scale) {
+        const float s = __bfloat162float(p.pix_scale[(size_t)pix * p.ps_cs]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= s;
+    }
+    if (p.in_relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    return v;
+}
+
+// Epilogue arithmetic on NV accumulator columns of one output row: bias, activation, residual, bf16 pack.
+template <int NV>
+__device__ __forceinline__ void epi_math(const P2& p, const uint32_t* r, const float* sBias, int cbase, int co0, int opix,
+                                         uint32_t* packed) {
+    float v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(sBias + cbase + j);
+        v[j] = __uint_as_float(r[j]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+        v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+    }
+    switch (p.act) {
+#define MGDT_ACT_CASE(A) case A: _Pragma("unroll") for (int j = 0; j < NV; ++j) v[j] = act_fast<A>(v[j]); break;
+        MGDT_ACT_CASE(MGDT_ACT_SILU)
+        MGDT_ACT_CASE(MGDT_ACT_RELU)
+        MGDT_ACT_CASE(MGDT_ACT_SIGMOID)
+        MGDT_ACT_CASE(MGDT_ACT_HSIGMOID)
+        MGDT_ACT_CASE(MGDT_ACT_GELU)
+#undef MGDT_ACT_CASE
+        default: break;
+    }
+    if (p.residual && opix >= 0) {
+        const __nv_bfloat16* rp = p.residual + (size_t)opix * p.res_cs + co0;
+#pragma unroll
+        for (int c8 = 0; c8 < NV; c8 += 8) {
+            if (co0 + c8 >= p.Cout) break;
+            if (co0 + c8 + 8 <= p.Cout && p.res_vec) {
+                const uint4 ra = __ldg(reinterpret_cast<const uint4*>(rp + c8));
+                const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&ra);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(ah[j]); v[c8 + 2 * j] += t.x; v[c8 + 2 * j + 1] += t.y; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (co0 + c8 + j < p.Cout) v[c8 + j] += __bfloat162float(rp[c8 + j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NV / 2; ++j) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        packed[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+}
+
+template <int MODE, int LOADER>
 __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_constant__ P2 p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Plan2& pl = p.pl;
@@ -470,7 +534,8 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     unsigned long long* bdesc_t = adesc_t + U2_MAX_MMA;
     float* sBias = reinterpret_cast<float*>(bdesc_t + U2_MAX_MMA);
     unsigned short* sLut = reinterpret_cast<unsigned short*>(sBias + 256);   // bf16(u / 255), u = 0..255
-    if (p.stem_src && p.stem_u8) {
+    unsigned char* sOut = reinterpret_cast<unsigned char*>(sLut + 256);      // epilogue staging: 2 KB per epilogue warp
+    if (LOADER == LD_STEM_U8) {
         for (int i = tid; i < 256; i += U2_THREADS) sLut[i] = __bfloat16_as_ushort(__float2bfloat16_rn((float)i / 255.0f));
     }
     for (int i = tid; i < pl.Nc; i += U2_THREADS) {
@@ -482,8 +547,8 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         auto off = [&](int c) -> uint32_t {
             const int t = c / pl.PS, pll = c - t * pl.PS;
             int shift;
-            if (pl.mode == 0) shift = 0;
-            else if (pl.mode == 1) shift = rn.halo + (pl.tap_dy[t] - 1) * rn.Wq + (pl.tap_dx[t] - 1);
+            if (MODE == 0) shift = 0;
+            else if (MODE == 1) shift = rn.halo + (pl.tap_dy[t] - 1) * rn.Wq + (pl.tap_dx[t] - 1);
             else shift = (pl.tap_dy[t] >> 1) * rn.Wq + (pl.tap_dx[t] >> 1);
             return ((uint32_t)pll * rn.pstride16 + (uint32_t)pl.tap_par[t] * rn.P + shift) * 16u;
         };
@@ -500,9 +565,9 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int s = 0; s < rn.S; ++s) { mbar_init(FULL(s), U2_PRODUCER_WARPS); mbar_init(EMPTY(s), 1); }
+        for (int s = 0; s < rn.S; ++s) { mbar_init(FULL(s), U2_NP); mbar_init(EMPTY(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(ACCFULL(a), 1); mbar_init(ACCEMPTY(a), U2_EPI_WARPS); }
-        mbar_init(WREADY, U2_PRODUCER_WARPS);
+        mbar_init(WREADY, U2_NP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -518,133 +583,117 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     if (warp < U2_PRODUCER_WARPS) {
         // =============================================================== producers
         const int ptid = tid;  // 0..255
-        constexpr int NP = U2_PRODUCER_WARPS * 32;
+        constexpr int NP = U2_NP;
         if (nks == 1) {
             const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)ns * w_slice_elems);
-            uint4* dst = reinterpret_cast<uint4*>(sWres);
+            const uint32_t dst = s_u32(sWres);
             const int n16 = (int)(rn.wres_bytes / 16);
-            for (int i = ptid; i < n16; i += NP) dst[i] = __ldg(src + i);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(WREADY);
+            for (int i = ptid; i < n16; i += NP) cp_async16(dst + 16u * i, src + i, 16u);
+            cp_async_arrive_noinc(WREADY);
             if (tid == 0) trace_mark(p, 2);
         }
         const uint32_t chunks = (uint32_t)(pl.PS * pl.npar * rn.P);
         uint32_t it = 0;
+        int s = 0;
+        uint32_t ph = 0;   // phase of the stage's current use (flips each time the ring wraps)
         for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             uint32_t n_img = 0, tt = 0;
-            if (pl.mode != 0) { n_img = fdiv(tile, p.d_tpi); tt = tile - n_img * rn.tiles_per_img; }
+            if (MODE != 0) { n_img = fdiv(tile, p.d_tpi); tt = tile - n_img * rn.tiles_per_img; }
             for (int ks = 0; ks < nks; ++ks, ++it) {
-                const int s = it % rn.S;
-                mbar_wait(EMPTY(s), ((it / rn.S) & 1) ^ 1);
+                mbar_wait(EMPTY(s), ph ^ 1);
                 unsigned char* sA = sStage + (size_t)s * rn.stage_bytes;
+                const uint32_t sA32 = s_u32(sA);
                 if (nks > 1) {
                     const uint4* src = reinterpret_cast<const uint4*>(p.w + ((size_t)ns * nks + ks) * w_slice_elems);
-                    uint4* dst = reinterpret_cast<uint4*>(sA + rn.a_bytes);
+                    const uint32_t dst = sA32 + rn.a_bytes;
                     const int n16 = (int)(rn.w_slice_bytes / 16);
-                    for (int i = ptid; i < n16; i += NP) dst[i] = __ldg(src + i);
+                    for (int i = ptid; i < n16; i += NP) cp_async16(dst + 16u * i, src + i, 16u);
                 }
                 const int plane0 = ks * pl.PS;
-                if (p.stem_src && p.stem_C == 3 && pl.PS == 4 && p.stem_u8) {
-                    // uint8 source: bf16(u / 255) comes from a 256-entry shared-memory table (exactly the value the
-                    // unfused preprocess kernel produces; no I2F / IEEE division in the loop)
-                    const size_t plane_sz = (size_t)p.stem_H * p.stem_W;
-                    const uint8_t* src8 = reinterpret_cast<const uint8_t*>(p.stem_src);
-                    for (uint32_t pos = ptid; pos < 128u * rn.MB; pos += NP) {
-                        const uint32_t g = tile * (128u * rn.MB) + pos;
-                        unsigned short hv[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) hv[j] = 0;
-                        if (g < p.M_total) {
-                            const uint32_t n = fdiv(g, p.d_HW);
-                            const uint32_t rem = g - n * (uint32_t)(p.H * p.W);
-                            const int ho = (int)fdiv(rem, p.d_Wo), wo = (int)rem - ho * p.W;
-                            const size_t base = (size_t)n * 3 * plane_sz;
-#pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const int hi = 2 * ho + tap / 3 - 1, wi = 2 * wo + tap % 3 - 1;
-                                if (hi >= 0 && hi < p.stem_H && wi >= 0 && wi < p.stem_W) {
-                                    const size_t o = base + (size_t)hi * p.stem_W + wi;
-#pragma unroll
-                                    for (int c = 0; c < 3; ++c) hv[tap * 3 + c] = sLut[__ldg(src8 + o + c * plane_sz)];
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int pll = 0; pll < 4; ++pll) {
-                            uint4 o;
-                            o.x = hv[pll * 8 + 0] | ((uint32_t)hv[pll * 8 + 1] << 16);
-                            o.y = hv[pll * 8 + 2] | ((uint32_t)hv[pll * 8 + 3] << 16);
-                            o.z = hv[pll * 8 + 4] | ((uint32_t)hv[pll * 8 + 5] << 16);
-                            o.w = hv[pll * 8 + 6] | ((uint32_t)hv[pll * 8 + 7] << 16);
-                            *reinterpret_cast<uint4*>(sA + ((uint32_t)pll * rn.pstride16 + pos) * 16u) = o;
-                        }
+                if (LOADER == LD_ASYNC) {
+                    // transform-free input: every chunk is an asynchronous 16-byte copy (zero-filled outside the image);
+                    // the thread never waits for its data, the stage's full barrier counts the copies' completion
+                    for (uint32_t e = ptid; e < chunks; e += NP) {
+                        const uint32_t rest = fdiv(e, p.d_ps);
+                        const uint32_t pll = e - rest * pl.PS;
+                        uint32_t pos = rest, par = 0, n;
+                        if (MODE == 2) { par = fdiv(rest, p.d_P); pos = rest - par * rn.P; }
+                        const int pix = src_pixel<MODE>(p, tile, tt, n_img, pos, par, n);
+                        const __nv_bfloat16* src = pix >= 0 ? p.x + (size_t)pix * p.x_cs + (plane0 + pll) * 8 : p.x;
+                        cp_async16(sA32 + (pll * rn.pstride16 + par * rn.P + pos) * 16u, src, pix >= 0 ? 16u : 0u);
                     }
-                } else if (p.stem_src && p.stem_C == 3 && pl.PS == 4) {
-                    // fused preprocess + stem, C = 3: one output pixel per thread; its 27 source values are
-                    // gathered with compile-time (tap, channel) indices and stored as the pixel's 4 K-chunks
-                    const size_t plane_sz = (size_t)p.stem_H * p.stem_W;
-                    for (uint32_t pos = ptid; pos < 128u * rn.MB; pos += NP) {
-                        const uint32_t g = tile * (128u * rn.MB) + pos;
-                        float f[32];
+                    cp_async_arrive_noinc(FULL(s));
+                } else {
+                    if (LOADER == LD_STEM_U8) {
+                        // uint8 source: bf16(u / 255) comes from a 256-entry shared-memory table (exactly the value the
+                        // unfused preprocess kernel produces; no I2F / IEEE division in the loop)
+                        const size_t plane_sz = (size_t)p.stem_H * p.stem_W;
+                        const uint8_t* src8 = reinterpret_cast<const uint8_t*>(p.stem_src);
+                        for (uint32_t pos = ptid; pos < 128u * rn.MB; pos += NP) {
+                            const uint32_t g = tile * (128u * rn.MB) + pos;
+                            unsigned short hv[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = 0.f;
-                        if (g < p.M_total) {
-                            const uint32_t n = fdiv(g, p.d_HW);
-                            const uint32_t rem = g - n * (uint32_t)(p.H * p.W);
-                            const int ho = (int)fdiv(rem, p.d_Wo), wo = (int)rem - ho * p.W;
-                            const size_t base = (size_t)n * 3 * plane_sz;
+                            for (int j = 0; j < 32; ++j) hv[j] = 0;
+                            if (g < p.M_total) {
+                                const uint32_t n = fdiv(g, p.d_HW);
+                                const uint32_t rem = g - n * (uint32_t)(p.H * p.W);
+                                const int ho = (int)fdiv(rem, p.d_Wo), wo = (int)rem - ho * p.W;
+                                const size_t base = (size_t)n * 3 * plane_sz;
 #pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const int hi = 2 * ho + tap / 3 - 1, wi = 2 * wo + tap % 3 - 1;
-                                if (hi >= 0 && hi < p.stem_H && wi >= 0 && wi < p.stem_W) {
-                                    const size_t o = base + (size_t)hi * p.stem_W + wi;
+                                for (int tap = 0; tap < 9; ++tap) {
+                                    const int hi = 2 * ho + tap / 3 - 1, wi = 2 * wo + tap % 3 - 1;
+                                    if (hi >= 0 && hi < p.stem_H && wi >= 0 && wi < p.stem_W) {
+                                        const size_t o = base + (size_t)hi * p.stem_W + wi;
 #pragma unroll
-                                    for (int c = 0; c < 3; ++c) {
-                                        f[tap * 3 + c] = p.stem_u8
-                                            ? (float)__ldg(reinterpret_cast<const uint8_t*>(p.stem_src) + o + c * plane_sz) / 255.0f
-                                            : __ldg(reinterpret_cast<const float*>(p.stem_src) + o + c * plane_sz);
+                                        for (int c = 0; c < 3; ++c) hv[tap * 3 + c] = sLut[__ldg(src8 + o + c * plane_sz)];
                                     }
                                 }
                             }
+#pragma unroll
+                            for (int pll = 0; pll < 4; ++pll) {
+                                uint4 o;
+                                o.x = hv[pll * 8 + 0] | ((uint32_t)hv[pll * 8 + 1] << 16);
+                                o.y = hv[pll * 8 + 2] | ((uint32_t)hv[pll * 8 + 3] << 16);
+                                o.z = hv[pll * 8 + 4] | ((uint32_t)hv[pll * 8 + 5] << 16);
+                                o.w = hv[pll * 8 + 6] | ((uint32_t)hv[pll * 8 + 7] << 16);
+                                *reinterpret_cast<uint4*>(sA + ((uint32_t)pll * rn.pstride16 + pos) * 16u) = o;
+                            }
                         }
+                    } else {
+                        // U2_MLP chunks in flight per thread: loads first, then stores
+                        for (uint32_t e0 = ptid; e0 < chunks; e0 += NP * U2_MLP) {
+                            uint4 v[U2_MLP];
+                            uint32_t dsto[U2_MLP];
 #pragma unroll
-                        for (int pll = 0; pll < 4; ++pll) {
-                            uint4 o;
-                            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+                            for (int u = 0; u < U2_MLP; ++u) {
+                                const uint32_t e = e0 + u * NP;
+                                dsto[u] = 0xffffffffu;
+                                if (e < chunks) {
+                                    const uint32_t rest = fdiv(e, p.d_ps);
+                                    const int pll = (int)(e - rest * pl.PS);
+                                    uint32_t pos = rest, par = 0;
+                                    if (MODE == 2) { par = fdiv(rest, p.d_P); pos = rest - par * rn.P; }
+                                    if (LOADER == LD_STEM_GEN) v[u] = stem_chunk(p, tile * (128u * rn.MB) + pos, plane0 + pll);
+                                    else if (LOADER == LD_DCN) v[u] = dcn_chunk(p, tile * (128u * rn.MB) + pos, plane0 + pll);
+                                    else {
+                                        uint32_t n;
+                                        const int pix = src_pixel<MODE>(p, tile, tt, n_img, pos, par, n);
+                                        v[u] = xform_chunk(p, pix, n, plane0 + pll);
+                                    }
+                                    dsto[u] = ((uint32_t)pll * rn.pstride16 + par * rn.P + pos) * 16u;
+                                }
+                            }
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(f[pll * 8 + 2 * j], f[pll * 8 + 2 * j + 1]);
-                            *reinterpret_cast<uint4*>(sA + ((uint32_t)pll * rn.pstride16 + pos) * 16u) = o;
+                            for (int u = 0; u < U2_MLP; ++u)
+                                if (dsto[u] != 0xffffffffu) *reinterpret_cast<uint4*>(sA + dsto[u]) = v[u];
                         }
                     }
-                } else
-                // U2_MLP chunks in flight per thread: loads first, then stores
-                for (uint32_t e0 = ptid; e0 < chunks; e0 += NP * U2_MLP) {
-                    uint4 v[U2_MLP];
-                    uint32_t dsto[U2_MLP];
-#pragma unroll
-                    for (int u = 0; u < U2_MLP; ++u) {
-                        const uint32_t e = e0 + u * NP;
-                        dsto[u] = 0xffffffffu;
-                        if (e < chunks) {
-                            const uint32_t rest = fdiv(e, p.d_ps);
-                            const int pll = (int)(e - rest * pl.PS);
-                            uint32_t pos = rest, par = 0;
-                            if (pl.npar > 1) { par = fdiv(rest, p.d_P); pos = rest - par * rn.P; }
-                            v[u] = p.stem_src ? stem_chunk(p, tile * (128u * rn.MB) + pos, plane0 + pll)
-                                   : p.dcn_off ? dcn_chunk(p, tile * (128u * rn.MB) + pos, plane0 + pll)
-                                               : load_chunk(p, tile, tt, n_img, plane0 + pll, pos, par);
-                            dsto[u] = ((uint32_t)pll * rn.pstride16 + par * rn.P + pos) * 16u;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < U2_MLP; ++u)
-                        if (dsto[u] != 0xffffffffu) *reinterpret_cast<uint4*>(sA + dsto[u]) = v[u];
+                    if (nks > 1) cp_async_wait_all();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(FULL(s));
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(FULL(s));
                 if (tid == 0 && it < 6) trace_mark(p, 8 + 8 * (int)it);
+                if (++s == rn.S) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == U2_MMA_WARP) {
@@ -654,13 +703,16 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             const uint32_t idesc = (1u << 4) | (1u << 7) | ((p.w_f16 ? 0u : 1u) << 10) | ((uint32_t)(pl.Nc >> 3) << 17) | ((128u >> 4) << 24);
             if (nks == 1) mbar_wait(WREADY, 0);
             uint32_t it = 0, ti = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
                 const int a = rn.NACC == 2 ? (int)(ti & 1) : 0;
                 const uint32_t aphase = rn.NACC == 2 ? ((ti >> 1) & 1) : (ti & 1);
                 mbar_wait(ACCEMPTY(a), aphase ^ 1);
                 for (int ks = 0; ks < nks; ++ks, ++it) {
-                    const int s = it % rn.S;
-                    mbar_wait(FULL(s), (it / rn.S) & 1);
+                    mbar_wait(FULL(s), ph);
+                    // the stage was written through the generic proxy (cp.async / st.shared by the producers)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a0 = s_u32(sStage + (size_t)s * rn.stage_bytes);
                     const uint32_t w0 = nks == 1 ? s_u32(sWres) : a0 + rn.a_bytes;
@@ -681,16 +733,20 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                     umma_commit(EMPTY(s));                       // smem stage may be refilled once these MMAs retire
                     if (ks == nks - 1) umma_commit(ACCFULL(a));  // accumulators complete
                     if (it < 6) trace_mark(p, 9 + 8 * (int)it);
+                    if (++s == rn.S) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else {
         // =============================================================== epilogue (warps 8..15)
-        // TMEM lane quadrant = warp % 4; the two warps of a quadrant alternate over (block, 16-column) units.
+        // TMEM lane quadrant = warp % 4; the two warps of a quadrant alternate over (row block, 32-column) units.
+        // A unit is read from TMEM one output row per lane, converted, transposed through a swizzled 2 KB
+        // shared-memory tile and written out with 8 rows x 64 contiguous bytes per store instruction.
         const int ew = warp - U2_PRODUCER_WARPS;
         const int quad = ew & 3, half = ew >> 2;
-        const int ncch = pl.Nc / 16;
-        const int units = rn.MB * ncch;
+        const int ncch = (pl.Nc + 31) / 32;
+        unsigned char* stg = sOut + ew * 2048;
+        const int srow = lane >> 2, schunk = lane & 3;    // store phase: row within a group of 8, 16-byte chunk
         uint32_t ti = 0;
         for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
             const int a = rn.NACC == 2 ? (int)(ti & 1) : 0;
@@ -698,61 +754,68 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             mbar_wait(ACCFULL(a), aphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (warp == U2_PRODUCER_WARPS && lane == 0 && ti < 6) trace_mark(p, 10 + 8 * (int)ti);
-            int opix = -1, mb_cached = -1;
-            for (int u = half; u < units; u += 2) {
-                const int mb = u / ncch, cc = u - mb * ncch;
-                if (mb != mb_cached) { opix = out_pixel2(p, tile, (uint32_t)(mb * 128 + quad * 32 + lane)); mb_cached = mb; }
-                uint32_t r[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                       (uint32_t)(a * rn.MB * pl.Nc + mb * pl.Nc + cc * 16);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int co0 = ns * pl.Nc + cc * 16;
-                if (opix < 0 || co0 >= p.Cout) continue;
-                float v[16];
+            int u = 0;
+            for (int mb = 0; mb < rn.MB; ++mb) {
+                const int opix = out_pixel2(p, tile, (uint32_t)(mb * 128 + quad * 32 + lane));
+                const bool any_row = __any_sync(0xffffffffu, opix >= 0);
+                for (int cc = 0; cc < ncch; ++cc, ++u) {
+                    if ((u & 1) != half) continue;
+                    const int cl = cc * 32;                       // first column of the unit within this CTA's Nc
+                    const int co0 = ns * pl.Nc + cl;
+                    if (!any_row || co0 >= p.Cout) continue;
+                    const int nv = min(32, pl.Nc - cl);           // 32, or 16 for the last unit when Nc % 32 == 16
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                           (uint32_t)(a * rn.MB * pl.Nc + mb * pl.Nc + cl);
+                    uint32_t r[32], pk[16];
+                    if (nv == 32) {
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                            : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        epi_math<32>(p, r, sBias, cl, co0, opix, pk);
+                    } else {
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                            : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        epi_math<16>(p, r, sBias, cl, co0, opix, pk);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + sBias[cc * 16 + j];
-                switch (p.act) {
-#define MGDT_ACT_CASE(A) case A: _Pragma("unroll") for (int j = 0; j < 16; ++j) v[j] = act_fast<A>(v[j]); break;
-                    MGDT_ACT_CASE(MGDT_ACT_SILU)
-                    MGDT_ACT_CASE(MGDT_ACT_RELU)
-                    MGDT_ACT_CASE(MGDT_ACT_SIGMOID)
-                    MGDT_ACT_CASE(MGDT_ACT_HSIGMOID)
-                    MGDT_ACT_CASE(MGDT_ACT_GELU)
-#undef MGDT_ACT_CASE
-                    default: break;
-                }
-                __nv_bfloat16* yp = p.y + (size_t)opix * p.y_cs + co0;
-                const __nv_bfloat16* rp = p.residual ? p.residual + (size_t)opix * p.res_cs + co0 : nullptr;
+                        for (int j = 8; j < 16; ++j) pk[j] = 0u;
+                    }
+                    // row `lane` -> staging: 64 bytes per row, 16-byte chunk c at slot c ^ ((row >> 1) & 3)
+                    {
+                        const int sw = (lane >> 1) & 3;
 #pragma unroll
-                for (int h8 = 0; h8 < 2; ++h8) {          // two 8-channel (16-byte) halves
-                    const int c8 = co0 + 8 * h8;
-                    if (c8 >= p.Cout) break;
-                    float* vv = v + 8 * h8;
-                    const bool full8 = c8 + 8 <= p.Cout;
-                    if (rp) {
-                        if (full8 && p.res_vec) {
-                            const uint4 ra = __ldg(reinterpret_cast<const uint4*>(rp + 8 * h8));
-                            const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&ra);
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ sw) << 4)) =
+                                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    }
+                    __syncwarp();
+                    const int c8 = co0 + schunk * 8;              // first output channel of this lane's chunk
+                    const bool chunk_on = schunk * 8 < nv && c8 < p.Cout;
+                    const bool full8 = c8 + 8 <= p.Cout && p.y_vec;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(ah[j]); vv[2 * j] += t.x; vv[2 * j + 1] += t.y; }
-                        } else {
-                            for (int j = 0; j < 8 && c8 + j < p.Cout; ++j) vv[j] += __bfloat162float(rp[8 * h8 + j]);
+                    for (int g = 0; g < 4; ++g) {
+                        const int row = g * 8 + srow;
+                        const int orow = __shfl_sync(0xffffffffu, opix, row);
+                        const uint4 o = *reinterpret_cast<const uint4*>(stg + row * 64 + ((schunk ^ ((row >> 1) & 3)) << 4));
+                        if (orow >= 0 && chunk_on) {
+                            __nv_bfloat16* yp = p.y + (size_t)orow * p.y_cs + c8;
+                            if (full8) *reinterpret_cast<uint4*>(yp) = o;
+                            else {
+                                const __nv_bfloat16* oh = reinterpret_cast<const __nv_bfloat16*>(&o);
+                                for (int j = 0; j < 8 && c8 + j < p.Cout; ++j) yp[j] = oh[j];
+                            }
                         }
                     }
-                    if (full8 && p.y_vec) {
-                        uint4 o;
-                        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(vv[2 * j], vv[2 * j + 1]);
-                        *reinterpret_cast<uint4*>(yp + 8 * h8) = o;
-                    } else {
-                        for (int j = 0; j < 8 && c8 + j < p.Cout; ++j) yp[8 * h8 + j] = __float2bfloat16_rn(vv[j]);
-                    }
+                    __syncwarp();
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -795,17 +858,36 @@ static void fill_divs(P2& p) {
 
 static unsigned long long* g_trace = nullptr;
 
+template <int MODE, int LOADER>
+static int launch2t(const P2& p, dim3 grid, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<MODE, LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_MAX_SMEM);
+    if (e != cudaSuccess) return set_error(-EIO, "conv_umma2: smem attr: %s", cudaGetErrorString(e));
+    conv_umma2_kernel<MODE, LOADER><<<grid, U2_THREADS, p.rn.smem_total, s>>>(p);
+    MGDT_LAUNCH_CHECK("conv_umma2");
+    return 0;
+}
+
 static int launch2(P2& p, cudaStream_t s) {
     fill_divs(p);
     p.trace = g_trace;
-    cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_MAX_SMEM);
-    if (e != cudaSuccess) return set_error(-EIO, "conv_umma2: smem attr: %s", cudaGetErrorString(e));
     const long long tiles = p.rn.tiles;
     int ctas = (int)(tiles < 148 ? tiles : 148);
     if (p.pl.nsplit > 1) ctas = (int)std::max(1LL, std::min(tiles, (long long)(148 / p.pl.nsplit)));
-    conv_umma2_kernel<<<dim3((unsigned)ctas, (unsigned)p.pl.nsplit), U2_THREADS, p.rn.smem_total, s>>>(p);
-    MGDT_LAUNCH_CHECK("conv_umma2");
-    return 0;
+    const dim3 grid((unsigned)ctas, (unsigned)p.pl.nsplit);
+    if (p.stem_src) {
+        if (p.stem_C == 3 && p.pl.PS == 4 && p.stem_u8) return launch2t<0, LD_STEM_U8>(p, grid, s);
+        return launch2t<0, LD_STEM_GEN>(p, grid, s);
+    }
+    if (p.dcn_off) return launch2t<0, LD_DCN>(p, grid, s);
+    const bool xform = p.pre_add || p.in_scale || p.pix_scale || p.in_relu;
+    switch (p.pl.mode * 2 + (xform ? 1 : 0)) {
+        case 0: return launch2t<0, LD_ASYNC>(p, grid, s);
+        case 1: return launch2t<0, LD_XFORM>(p, grid, s);
+        case 2: return launch2t<1, LD_ASYNC>(p, grid, s);
+        case 3: return launch2t<1, LD_XFORM>(p, grid, s);
+        case 4: return launch2t<2, LD_ASYNC>(p, grid, s);
+        default: return launch2t<2, LD_XFORM>(p, grid, s);
+    }
 }
 
 bool conv2d_umma_supported(const mgdt_conv_args* a) {
