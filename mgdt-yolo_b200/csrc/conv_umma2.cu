@@ -25,15 +25,17 @@
 
 namespace mgdt {
 
-constexpr int U2_PRODUCER_WARPS = 8;
-constexpr int U2_EPI_WARPS = 8;      // two per TMEM lane quadrant
-constexpr int U2_MMA_WARP = U2_PRODUCER_WARPS + U2_EPI_WARPS;
-constexpr int U2_THREADS = (U2_MMA_WARP + 1) * 32;
-constexpr int U2_MAX_SMEM = 220 * 1024;
+// 20 warps (five per SM sub-partition, so 96 registers per thread): producers | one MMA warp | epilogue.  The cp.async
+// loader needs few issuing threads and runs with 3 producer + 16 epilogue warps (four per TMEM lane quadrant); the
+// register-staged loaders use 7 + 12.
+constexpr int U2_WARPS = 20;
+constexpr int U2_THREADS = U2_WARPS * 32;
+constexpr int U2_MAX_EPI_WARPS = 16;
+constexpr int U2_MAX_SMEM = 226 * 1024;
 constexpr int U2_MAX_STAGES = 4;
 constexpr int U2_MLP = 8;          // 16-byte loads in flight per producer thread
 constexpr int U2_MAX_MMA = 160;   // K=16 instructions per (slice, 128-row block) the descriptor table holds
-constexpr int U2_TAIL = 128 + 2 * 8 * U2_MAX_MMA + 4 * 256 + 2 * 256 + U2_EPI_WARPS * 2048;  // barriers + TMEM slot, descriptor tables, bias[Nc], u8 LUT, epilogue staging
+constexpr int U2_TAIL = 128 + 2 * 8 * U2_MAX_MMA + 4 * 256 + 2 * 256 + U2_MAX_EPI_WARPS * 2048;  // barriers + TMEM slot, descriptor tables, bias[Nc], u8 LUT, epilogue staging
 
 struct FastDiv {  // exact n / d for 0 <= n < 2^31
     uint32_t mul, shr, d;
@@ -67,6 +69,8 @@ struct Run2 {
     long long tiles;
     unsigned a_bytes, w_slice_bytes, stage_bytes, wres_bytes, smem_total;
 };
+
+constexpr long long U2_STAGE_BUDGET = U2_MAX_SMEM - U2_TAIL - 6 * 1024;   // weights + ring (estimates run a little low)
 
 static Plan2 make_plan2(int Cin, int Cout, int k, int stride) {
     Plan2 p{};
@@ -107,8 +111,8 @@ static Plan2 make_plan2(int Cin, int Cout, int k, int stride) {
             if (nm > U2_MAX_MMA) continue;
             const long long wbytes = nm * 2 * Nc * 16;
             const long long abytes = (long long)ps * a_plane_est;
-            const bool whole = ps == p.planes && wbytes <= 100 * 1024 && abytes <= 100 * 1024 && wbytes + 2 * abytes <= 200 * 1024;
-            const bool sliced = wbytes <= 80 * 1024 && abytes <= 80 * 1024 && 2 * (wbytes + abytes) <= 200 * 1024;
+            const bool whole = ps == p.planes && wbytes <= 100 * 1024 && abytes <= 100 * 1024 && wbytes + 2 * abytes <= U2_STAGE_BUDGET;
+            const bool sliced = wbytes <= 80 * 1024 && abytes <= 80 * 1024 && 2 * (wbytes + abytes) <= U2_STAGE_BUDGET;
             if (whole || sliced) { best = ps; break; }
         }
         if (best) break;
@@ -233,6 +237,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (ok) return;
         if (clock64() - t0 > 8000000000LL) __trap();
     }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -404,7 +413,38 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 enum : int { LD_ASYNC = 0, LD_XFORM = 1, LD_DCN = 2, LD_STEM_U8 = 3, LD_STEM_GEN = 4 };
 
-constexpr int U2_NP = U2_PRODUCER_WARPS * 32;   // producer threads; every full[] / wready arrival count
+template <int LOADER> struct Roles {
+    static constexpr int NPW = LOADER == LD_ASYNC ? 3 : 7;   // producer warps 0 .. NPW-1
+    static constexpr int MMAW = NPW;                          // the MMA warp
+    static constexpr int EPI0 = NPW + 1;                      // first epilogue warp (a multiple of 4: quadrant = warp % 4)
+    static constexpr int NEW = U2_WARPS - EPI0;               // epilogue warps (16 or 12), NEW / 4 per lane quadrant
+    static constexpr int NP = NPW * 32;                       // producer threads = arrival count of full[] / wready
+};
+
+// packed fp32 pair arithmetic (FADD2 / FMUL2 / FFMA2): halves the epilogue's ALU instruction count
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void up2(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 
 // Source pixel of staged position `pos` (parity `par`) of a tile, or -1 (zero fill); n = image of that pixel.
 template <int MODE>
@@ -470,17 +510,32 @@ template <int NV>
 __device__ __forceinline__ void epi_math(const P2& p, const uint32_t* r, const float* sBias, int cbase, int co0, int opix,
                                          uint32_t* packed) {
     float v[NV];
+    unsigned long long a[NV / 2];
+    const unsigned long long half2 = pk2(0.5f, 0.5f);
+    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(sBias + cbase);
 #pragma unroll
-    for (int j = 0; j < NV; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(sBias + cbase + j);
-        v[j] = __uint_as_float(r[j]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
-        v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+    for (int j = 0; j < NV / 4; ++j) {
+        const ulonglong2 b = b2[j];
+        a[2 * j] = add2(pk2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), b.x);
+        a[2 * j + 1] = add2(pk2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), b.y);
     }
+    if (p.act == MGDT_ACT_SILU || p.act == MGDT_ACT_SIGMOID) {
+        // h = v/2, t = tanh(h) on the SFU: silu = h + h*t, sigmoid = 0.5 + 0.5*t
+        const bool silu = p.act == MGDT_ACT_SILU;
+#pragma unroll
+        for (int j = 0; j < NV / 2; ++j) {
+            const unsigned long long h = mul2(a[j], half2);
+            float h0, h1;
+            up2(h, h0, h1);
+            const unsigned long long t = pk2(tanh_fast(h0), tanh_fast(h1));
+            a[j] = silu ? fma2(h, t, h) : fma2(t, half2, half2);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NV / 2; ++j) up2(a[j], v[2 * j], v[2 * j + 1]);
     switch (p.act) {
 #define MGDT_ACT_CASE(A) case A: _Pragma("unroll") for (int j = 0; j < NV; ++j) v[j] = act_fast<A>(v[j]); break;
-        MGDT_ACT_CASE(MGDT_ACT_SILU)
         MGDT_ACT_CASE(MGDT_ACT_RELU)
-        MGDT_ACT_CASE(MGDT_ACT_SIGMOID)
         MGDT_ACT_CASE(MGDT_ACT_HSIGMOID)
         MGDT_ACT_CASE(MGDT_ACT_GELU)
 #undef MGDT_ACT_CASE
@@ -516,6 +571,8 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     const Run2& rn = p.rn;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ns = blockIdx.y;
+    constexpr int NPW = Roles<LOADER>::NPW, NEW = Roles<LOADER>::NEW, NP = Roles<LOADER>::NP;
+    constexpr int MMAW = Roles<LOADER>::MMAW, EPI0 = Roles<LOADER>::EPI0;
 
     if (tid == 0) trace_mark(p, 0);
     unsigned char* sWres = smem;
@@ -530,9 +587,8 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     const uint32_t WREADY = bar0 + 8u * (2 * U2_MAX_STAGES + 4);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * U2_MAX_STAGES + 5);
     // per-instruction descriptor templates (tile independent): start offsets relative to the stage / weight base
-    unsigned long long* adesc_t = bars + 16;
-    unsigned long long* bdesc_t = adesc_t + U2_MAX_MMA;
-    float* sBias = reinterpret_cast<float*>(bdesc_t + U2_MAX_MMA);
+    ulonglong2* desc_t = reinterpret_cast<ulonglong2*>(bars + 16);         // {A descriptor, B descriptor} per MMA
+    float* sBias = reinterpret_cast<float*>(desc_t + U2_MAX_MMA);
     unsigned short* sLut = reinterpret_cast<unsigned short*>(sBias + 256);   // bf16(u / 255), u = 0..255
     unsigned char* sOut = reinterpret_cast<unsigned char*>(sLut + 256);      // epilogue staging: 2 KB per epilogue warp
     if (LOADER == LD_STEM_U8) {
@@ -555,19 +611,18 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         const uint32_t o0 = off(c0);
         const uint32_t lbo = (c1 < pl.taps * pl.PS) ? (off(c1) - o0) : 16u;  // dummy chunk: its weights are zero
         const uint32_t b_lbo = (uint32_t)pl.Nc * 16;
-        adesc_t[i] = mk_desc(o0, lbo, 128u);
-        bdesc_t[i] = mk_desc((uint32_t)c0 * b_lbo, b_lbo, 128u);
+        desc_t[i] = make_ulonglong2(mk_desc(o0, lbo, 128u), mk_desc((uint32_t)c0 * b_lbo, b_lbo, 128u));
     }
 
-    if (warp == 8) {
+    if (warp == MMAW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)),
                      "r"((uint32_t)rn.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int s = 0; s < rn.S; ++s) { mbar_init(FULL(s), U2_NP); mbar_init(EMPTY(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(ACCFULL(a), 1); mbar_init(ACCEMPTY(a), U2_EPI_WARPS); }
-        mbar_init(WREADY, U2_NP);
+        for (int s = 0; s < rn.S; ++s) { mbar_init(FULL(s), NP); mbar_init(EMPTY(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(ACCFULL(a), 1); mbar_init(ACCEMPTY(a), NEW); }
+        mbar_init(WREADY, NP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -580,10 +635,9 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     const int nks = pl.nks;
     const size_t w_slice_elems = (size_t)pl.nmma_s * 2 * pl.Nc * 8;  // bf16 elements of one (ns, ks) weight slice
 
-    if (warp < U2_PRODUCER_WARPS) {
+    if (warp < NPW) {
         // =============================================================== producers
-        const int ptid = tid;  // 0..255
-        constexpr int NP = U2_NP;
+        const int ptid = tid;  // 0..NP-1
         if (nks == 1) {
             const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)ns * w_slice_elems);
             const uint32_t dst = s_u32(sWres);
@@ -593,6 +647,9 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             if (tid == 0) trace_mark(p, 2);
         }
         const uint32_t chunks = (uint32_t)(pl.PS * pl.npar * rn.P);
+        const bool ps_divides = NP % pl.PS == 0;
+        const uint32_t pstep = ps_divides ? (uint32_t)(NP / pl.PS) : 1u;
+        const uint32_t pos_fix = fdiv((uint32_t)ptid, p.d_ps), pll_fix = (uint32_t)ptid - pos_fix * pl.PS;
         uint32_t it = 0;
         int s = 0;
         uint32_t ph = 0;   // phase of the stage's current use (flips each time the ring wraps)
@@ -613,6 +670,61 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                 if (LOADER == LD_ASYNC) {
                     // transform-free input: every chunk is an asynchronous 16-byte copy (zero-filled outside the image);
                     // the thread never waits for its data, the stage's full barrier counts the copies' completion
+                    if (ps_divides) {
+                        // NP % PS == 0: this thread always stages the same plane and its positions advance by a constant
+                        // step.  Four independent chunks per iteration (index arithmetic by multiply-shift division, no
+                        // data-dependent branches) so the address chains overlap.
+                        const __nv_bfloat16* xpl = p.x + (plane0 + pll_fix) * 8;
+                        const uint32_t dpl = sA32 + (uint32_t)pll_fix * rn.pstride16 * 16u;
+                        const uint32_t Pn = (uint32_t)rn.P;
+                        if (MODE == 0) {
+                            const uint32_t g0 = tile * (128u * rn.MB);
+                            for (uint32_t pos0 = pos_fix; pos0 < Pn; pos0 += 4 * pstep) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const uint32_t pos = pos0 + u * pstep;
+                                    const uint32_t g = g0 + pos;
+                                    const bool ok = g < p.M_total;
+                                    if (pos < Pn) cp_async16(dpl + pos * 16u, ok ? xpl + (size_t)g * p.x_cs : p.x, ok ? 16u : 0u);
+                                }
+                            }
+                        } else if (MODE == 1) {
+                            // padded-linear index shifted by one padded row so that it is never negative:
+                            // hp = padded row + 1, valid rows 2 .. H+1, valid columns 1 .. W
+                            const uint32_t q1 = tt * 128u * rn.MB + (uint32_t)rn.Wq - 1u;
+                            const int pixc = (int)(n_img * p.H * p.W) - 2 * p.W - 1;
+                            for (uint32_t pos0 = pos_fix; pos0 < Pn; pos0 += 4 * pstep) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const uint32_t pos = pos0 + u * pstep;
+                                    const uint32_t q = q1 + pos;
+                                    const uint32_t hp = fdiv(q, p.d_Wq), wp = q - hp * rn.Wq;
+                                    const bool ok = (hp - 2u) < (uint32_t)p.H && (wp - 1u) < (uint32_t)p.W;
+                                    const int pix = (int)(hp * p.W + wp) + pixc;
+                                    if (pos < Pn) cp_async16(dpl + pos * 16u, ok ? xpl + (size_t)pix * p.x_cs : p.x, ok ? 16u : 0u);
+                                }
+                            }
+                        } else {
+                            const uint32_t q0 = tt * 128u * rn.MB;
+                            const int pixc = (int)(n_img * p.H * p.W);
+                            for (uint32_t par = 0; par < 4; ++par) {
+                                const int dh = (int)(par >> 1) - 1, dw = (int)(par & 1) - 1;
+                                const uint32_t dpar = dpl + par * Pn * 16u;
+                                for (uint32_t pos0 = pos_fix; pos0 < Pn; pos0 += 4 * pstep) {
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const uint32_t pos = pos0 + u * pstep;
+                                        const uint32_t q = q0 + pos;
+                                        const uint32_t r = fdiv(q, p.d_Wq), c = q - r * rn.Wq;
+                                        const int hi = 2 * (int)r + dh, wi = 2 * (int)c + dw;
+                                        const bool ok = (uint32_t)hi < (uint32_t)p.H && (uint32_t)wi < (uint32_t)p.W;
+                                        const int pix = hi * p.W + wi + pixc;
+                                        if (pos < Pn) cp_async16(dpar + pos * 16u, ok ? xpl + (size_t)pix * p.x_cs : p.x, ok ? 16u : 0u);
+                                    }
+                                }
+                            }
+                        }
+                    } else
                     for (uint32_t e = ptid; e < chunks; e += NP) {
                         const uint32_t rest = fdiv(e, p.d_ps);
                         const uint32_t pll = e - rest * pl.PS;
@@ -696,77 +808,106 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                 if (++s == rn.S) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == U2_MMA_WARP) {
-        // =============================================================== MMA issuer (one lane)
-        if (lane == 0) {
-            // instruction descriptor: D = f32, A = bf16, B = bf16 or f16, both K-major, N = Nc, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | ((p.w_f16 ? 0u : 1u) << 10) | ((uint32_t)(pl.Nc >> 3) << 17) | ((128u >> 4) << 24);
-            if (nks == 1) mbar_wait(WREADY, 0);
-            uint32_t it = 0, ti = 0;
-            int s = 0;
-            uint32_t ph = 0;
-            for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
-                const int a = rn.NACC == 2 ? (int)(ti & 1) : 0;
-                const uint32_t aphase = rn.NACC == 2 ? ((ti >> 1) & 1) : (ti & 1);
-                mbar_wait(ACCEMPTY(a), aphase ^ 1);
-                for (int ks = 0; ks < nks; ++ks, ++it) {
-                    mbar_wait(FULL(s), ph);
-                    // the stage was written through the generic proxy (cp.async / st.shared by the producers)
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    } else if (warp == MMAW) {
+        // =============================================================== MMA issuer
+        // The whole warp walks the pipeline (uniform control flow); the tcgen05 instructions are issued by the one
+        // lane elect.sync picks, which lets ptxas emit them without a per-lane waterfall loop.
+        // instruction descriptor: D = f32, A = bf16, B = bf16 or f16, both K-major, N = Nc, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | ((p.w_f16 ? 0u : 1u) << 10) | ((uint32_t)(pl.Nc >> 3) << 17) | ((128u >> 4) << 24);
+        if (nks == 1) mbar_wait(WREADY, 0);
+        uint32_t it = 0, ti = 0;
+        int s = 0;
+        uint32_t ph = 0;
+        for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+            const int a = rn.NACC == 2 ? (int)(ti & 1) : 0;
+            const uint32_t aphase = rn.NACC == 2 ? ((ti >> 1) & 1) : (ti & 1);
+            mbar_wait(ACCEMPTY(a), aphase ^ 1);
+            for (int ks = 0; ks < nks; ++ks, ++it) {
+                mbar_wait(FULL(s), ph);
+                // the stage was written through the generic proxy (cp.async / st.shared by the producers)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
                     const uint32_t a0 = s_u32(sStage + (size_t)s * rn.stage_bytes);
                     const uint32_t w0 = nks == 1 ? s_u32(sWres) : a0 + rn.a_bytes;
-                    for (int mb = 0; mb < rn.MB; ++mb) {
-                        const uint32_t d = tmem_base + (uint32_t)(a * rn.MB * pl.Nc + mb * pl.Nc);
-                        const uint64_t abase = (uint64_t)((a0 + (uint32_t)mb * 2048u) >> 4);
-                        const uint64_t wbase = (uint64_t)(w0 >> 4);
-                        for (int i = 0; i < pl.nmma_s; ++i) {
-                            const uint64_t adesc = adesc_t[i] + abase;   // start-address field is the low 14 bits
-                            const uint64_t bdesc = bdesc_t[i] + wbase;
-                            const uint32_t acc = (ks > 0 || i > 0) ? 1u : 0u;
-                            asm volatile(
-                                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-                                ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+                    const uint32_t d0 = tmem_base + (uint32_t)(a * rn.MB * pl.Nc);
+                    const uint64_t abase = (uint64_t)(a0 >> 4), wbase = (uint64_t)(w0 >> 4);
+                    // descriptors are fetched four at a time ahead of the instructions that use them
+                    for (int i0 = 0; i0 < pl.nmma_s; i0 += 4) {
+                        ulonglong2 dsc[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) dsc[u] = desc_t[min(i0 + u, pl.nmma_s - 1)];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (i0 + u < pl.nmma_s) {
+                                const uint64_t bdesc = dsc[u].y + wbase;
+                                const uint32_t acc = (ks > 0 || i0 + u > 0) ? 1u : 0u;
+                                for (int mb = 0; mb < rn.MB; ++mb) {
+                                    const uint64_t adesc = dsc[u].x + abase + (uint64_t)(mb * 128);   // 2048 B per row block
+                                    asm volatile(
+                                        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                                        ::"r"(d0 + (uint32_t)(mb * pl.Nc)), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
+                                }
+                            }
                         }
                     }
                     umma_commit(EMPTY(s));                       // smem stage may be refilled once these MMAs retire
                     if (ks == nks - 1) umma_commit(ACCFULL(a));  // accumulators complete
                     if (it < 6) trace_mark(p, 9 + 8 * (int)it);
-                    if (++s == rn.S) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++s == rn.S) { s = 0; ph ^= 1; }
             }
         }
     } else {
-        // =============================================================== epilogue (warps 8..15)
-        // TMEM lane quadrant = warp % 4; the two warps of a quadrant alternate over (row block, 32-column) units.
-        // A unit is read from TMEM one output row per lane, converted, transposed through a swizzled 2 KB
+        // =============================================================== epilogue (warps EPI0 .. 19)
+        // TMEM lane quadrant = warp % 4; the NEW/4 warps of a quadrant take the (row block, 32-column) units round
+        // robin.  A unit is read from TMEM one output row per lane, converted, transposed through a swizzled 2 KB
         // shared-memory tile and written out with 8 rows x 64 contiguous bytes per store instruction.
-        const int ew = warp - U2_PRODUCER_WARPS;
-        const int quad = ew & 3, half = ew >> 2;
+        const int ew = warp - EPI0;
+        const int quad = warp & 3, sub = ew >> 2;
+        constexpr int NSUB = NEW / 4;
         const int ncch = (pl.Nc + 31) / 32;
         unsigned char* stg = sOut + ew * 2048;
         const int srow = lane >> 2, schunk = lane & 3;    // store phase: row within a group of 8, 16-byte chunk
+        const uint32_t st_wr = s_u32(stg) + lane * 64, sw_wr = (uint32_t)((lane >> 1) & 3);
+        uint32_t st_rd[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int row = g * 8 + srow;
+            st_rd[g] = s_u32(stg) + row * 64 + ((schunk ^ ((row >> 1) & 3)) << 4);
+        }
+        const bool trw = p.trace && ew == 0 && lane == 0;
         uint32_t ti = 0;
         for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
             const int a = rn.NACC == 2 ? (int)(ti & 1) : 0;
             const uint32_t aphase = rn.NACC == 2 ? ((ti >> 1) & 1) : (ti & 1);
             mbar_wait(ACCFULL(a), aphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (warp == U2_PRODUCER_WARPS && lane == 0 && ti < 6) trace_mark(p, 10 + 8 * (int)ti);
-            int u = 0;
+            if (trw && ti < 6) trace_mark(p, 10 + 8 * (int)ti);
+            int u = sub;                                           // units are numbered mb * ncch + cc
             for (int mb = 0; mb < rn.MB; ++mb) {
+                if (u >= (mb + 1) * ncch) continue;                // no unit of this row block is ours
                 const int opix = out_pixel2(p, tile, (uint32_t)(mb * 128 + quad * 32 + lane));
                 const bool any_row = __any_sync(0xffffffffu, opix >= 0);
-                for (int cc = 0; cc < ncch; ++cc, ++u) {
-                    if ((u & 1) != half) continue;
-                    const int cl = cc * 32;                       // first column of the unit within this CTA's Nc
+                __nv_bfloat16* yrow[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int orow = __shfl_sync(0xffffffffu, opix, g * 8 + srow);
+                    yrow[g] = orow >= 0 ? p.y + (size_t)orow * p.y_cs : nullptr;
+                }
+                for (; u < (mb + 1) * ncch; u += NSUB) {
+                    const int cl = (u - mb * ncch) * 32;          // first column of the unit within this CTA's Nc
                     const int co0 = ns * pl.Nc + cl;
                     if (!any_row || co0 >= p.Cout) continue;
                     const int nv = min(32, pl.Nc - cl);           // 32, or 16 for the last unit when Nc % 32 == 16
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
                                            (uint32_t)(a * rn.MB * pl.Nc + mb * pl.Nc + cl);
                     uint32_t r[32], pk[16];
+                    const bool tr = trw && ti == 1;
+                    long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
+                    if (tr) tc0 = clock64();
                     if (nv == 32) {
                         asm volatile(
                             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -777,6 +918,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                             : "r"(taddr));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (tr) tc1 = clock64();
                         epi_math<32>(p, r, sBias, cl, co0, opix, pk);
                     } else {
                         asm volatile(
@@ -785,29 +927,27 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                             : "r"(taddr));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (tr) tc1 = clock64();
                         epi_math<16>(p, r, sBias, cl, co0, opix, pk);
 #pragma unroll
                         for (int j = 8; j < 16; ++j) pk[j] = 0u;
                     }
                     // row `lane` -> staging: 64 bytes per row, 16-byte chunk c at slot c ^ ((row >> 1) & 3)
-                    {
-                        const int sw = (lane >> 1) & 3;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ sw) << 4)) =
-                                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                    }
+                    for (int c = 0; c < 4; ++c)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_wr + ((c ^ sw_wr) << 4)), "r"(pk[4 * c]),
+                                     "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
                     __syncwarp();
+                    if (tr) tc2 = clock64();
                     const int c8 = co0 + schunk * 8;              // first output channel of this lane's chunk
                     const bool chunk_on = schunk * 8 < nv && c8 < p.Cout;
                     const bool full8 = c8 + 8 <= p.Cout && p.y_vec;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const int row = g * 8 + srow;
-                        const int orow = __shfl_sync(0xffffffffu, opix, row);
-                        const uint4 o = *reinterpret_cast<const uint4*>(stg + row * 64 + ((schunk ^ ((row >> 1) & 3)) << 4));
-                        if (orow >= 0 && chunk_on) {
-                            __nv_bfloat16* yp = p.y + (size_t)orow * p.y_cs + c8;
+                        uint4 o;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(st_rd[g]));
+                        if (yrow[g] != nullptr && chunk_on) {
+                            __nv_bfloat16* yp = yrow[g] + c8;
                             if (full8) *reinterpret_cast<uint4*>(yp) = o;
                             else {
                                 const __nv_bfloat16* oh = reinterpret_cast<const __nv_bfloat16*>(&o);
@@ -816,18 +956,24 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                         }
                     }
                     __syncwarp();
+                    if (tr) {
+                        tc3 = clock64();
+                        unsigned long long* t = p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + 56;
+                        t[0] += 1; t[1] += (unsigned long long)(tc1 - tc0); t[2] += (unsigned long long)(tc2 - tc1);
+                        t[3] += (unsigned long long)(tc3 - tc2);
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(ACCEMPTY(a));
-            if (warp == U2_PRODUCER_WARPS && lane == 0 && ti < 6) trace_mark(p, 11 + 8 * (int)ti);
+            if (trw && ti < 6) trace_mark(p, 11 + 8 * (int)ti);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0) trace_mark(p, 3);
-    if (warp == 8) {
+    if (warp == MMAW) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)rn.tmem_cols)
                      : "memory");
     }

@@ -9,11 +9,16 @@ from mgdt_yolo_b200.modules import Conv
 from mgdt_yolo_b200.synth import synth_state_dict
 
 B = 32
+import torch.nn as nn
 cases = [("c32_3x3", 32, 32, 3, 1, 80, 80), ("c8_1x1", 8, 8, 1, 1, 160, 160), ("c64_256", 64, 256, 1, 1, 80, 80),
+         ("c64_256_noact", 64, 256, 1, 1, 80, 80), ("c64_256_relu", 64, 256, 1, 1, 80, 80),
          ("c96_384", 96, 384, 1, 1, 40, 40), ("c16_3x3", 16, 16, 3, 1, 80, 80)]
+sel = sys.argv[1:]
+if sel:
+    cases = [c for c in cases if c[0] in sel]
 trace = torch.zeros(148 * 2 * 64, dtype=torch.int64, device="cuda")
 for name, cin, cout, k, s, H, W in cases:
-    m = Conv(cin, cout, k, s)
+    m = Conv(cin, cout, k, s, act=(False if 'noact' in name else nn.ReLU() if 'relu' in name else True))
     m.load_state_dict(synth_state_dict(m.state_dict(), seed=3))
     m = m.cuda().eval()
     x = ops.as_act(torch.randn(B, cin, H, W, device="cuda").to(torch.bfloat16))
@@ -40,3 +45,7 @@ for name, cin, cout, k, s, H, W in cases:
     for ti in range(6):
         if (t[:, 8 + 8 * ti] > 0).any():
             print(f"   tile{ti}: fill {stat(8+8*ti)}  mma_issued {stat(9+8*ti)}  acc_ready {stat(10+8*ti)}  epi_done {stat(11+8*ti)}")
+    ph = t[:, 56:60].float()
+    n = ph[:, 0].clamp(min=1)
+    print(f"   epilogue unit phases (cycles, warp 8, tile 1): units {ph[:,0].mean():.1f}  tmem-ld {(ph[:,1]/n).mean():.0f}"
+          f"  math+stage {(ph[:,2]/n).mean():.0f}  store {(ph[:,3]/n).mean():.0f}")
