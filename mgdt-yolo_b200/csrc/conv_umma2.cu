@@ -25,9 +25,8 @@
 
 namespace mgdt {
 
-// 20 warps (five per SM sub-partition, so 96 registers per thread): producers | one MMA warp | epilogue.  The cp.async
-// loader needs few issuing threads and runs with 3 producer + 16 epilogue warps (four per TMEM lane quadrant); the
-// register-staged loaders use 7 + 12.
+// 20 warps (five per SM sub-partition, so 96 registers per thread): producers | one MMA warp | epilogue; the split
+// depends on the loader (struct Roles).
 constexpr int U2_WARPS = 20;
 constexpr int U2_THREADS = U2_WARPS * 32;
 constexpr int U2_MAX_EPI_WARPS = 16;
@@ -277,6 +276,7 @@ struct P2 {
     int x_cs, y_cs, add_cs, ps_cs, res_cs, act, in_relu;
     int y_vec, res_vec;
     int w_f16;                   // weights packed as fp16 (B operand format F16), activations stay bf16
+    float out_scale;             // accumulator scale applied with the bias (1/255 for the uint8 stem, else 1)
     Plan2 pl;
     Run2 rn;
     unsigned M_total;            // mode 0: N*H*W
@@ -414,7 +414,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 enum : int { LD_ASYNC = 0, LD_XFORM = 1, LD_DCN = 2, LD_STEM_U8 = 3, LD_STEM_GEN = 4 };
 
 template <int LOADER> struct Roles {
-    static constexpr int NPW = LOADER == LD_ASYNC ? 3 : 7;   // producer warps 0 .. NPW-1
+    // producer warps 0 .. NPW-1: the cp.async loader only issues copies (3 warps); the fused-transform loader stages
+    // through registers (7); DCN sampling and the stem's byte gather are instruction-bound and take most of the CTA
+    static constexpr int NPW = LOADER == LD_ASYNC ? 3 : LOADER == LD_XFORM ? 7 : LOADER == LD_DCN ? 15 : 11;
     static constexpr int MMAW = NPW;                          // the MMA warp
     static constexpr int EPI0 = NPW + 1;                      // first epilogue warp (a multiple of 4: quadrant = warp % 4)
     static constexpr int NEW = U2_WARPS - EPI0;               // epilogue warps (16 or 12), NEW / 4 per lane quadrant
@@ -512,12 +514,13 @@ __device__ __forceinline__ void epi_math(const P2& p, const uint32_t* r, const f
     float v[NV];
     unsigned long long a[NV / 2];
     const unsigned long long half2 = pk2(0.5f, 0.5f);
+    const unsigned long long sc2 = pk2(p.out_scale, p.out_scale);
     const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(sBias + cbase);
 #pragma unroll
-    for (int j = 0; j < NV / 4; ++j) {
+    for (int j = 0; j < NV / 4; ++j) {   // acc * out_scale + bias (out_scale = 1 except for the uint8 stem)
         const ulonglong2 b = b2[j];
-        a[2 * j] = add2(pk2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), b.x);
-        a[2 * j + 1] = add2(pk2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), b.y);
+        a[2 * j] = fma2(pk2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), sc2, b.x);
+        a[2 * j + 1] = fma2(pk2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), sc2, b.y);
     }
     if (p.act == MGDT_ACT_SILU || p.act == MGDT_ACT_SIGMOID) {
         // h = v/2, t = tanh(h) on the SFU: silu = h + h*t, sigmoid = 0.5 + 0.5*t
@@ -737,38 +740,127 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                     cp_async_arrive_noinc(FULL(s));
                 } else {
                     if (LOADER == LD_STEM_U8) {
-                        // uint8 source: bf16(u / 255) comes from a 256-entry shared-memory table (exactly the value the
-                        // unfused preprocess kernel produces; no I2F / IEEE division in the loop)
+                        // uint8 NCHW source, C = 3, K = 32: one pair of horizontally adjacent output pixels per thread
+                        // iteration.  Per (row, channel) two aligned 32-bit loads cover the five source bytes of the
+                        // pair; bytes become EXACT bf16 integers 0..255 (PRMT into the 2^23 magic float, subtract, take
+                        // the high half) and the 1/255 of BasePredictor.preprocess is applied to the fp32 accumulator in
+                        // the epilogue (out_scale), which is closer to the fp32 reference than rounding u/255 to bf16.
                         const size_t plane_sz = (size_t)p.stem_H * p.stem_W;
                         const uint8_t* src8 = reinterpret_cast<const uint8_t*>(p.stem_src);
-                        for (uint32_t pos = ptid; pos < 128u * rn.MB; pos += NP) {
-                            const uint32_t g = tile * (128u * rn.MB) + pos;
-                            unsigned short hv[32];
+                        const uint32_t rows = 128u * rn.MB;
+                        for (uint32_t pp = ptid; pp < rows / 2; pp += NP) {
+                            const uint32_t pos = 2 * pp, g = tile * rows + pos;
+                            uint32_t wa[9], wb[9];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) hv[j] = 0;
+                            for (int j = 0; j < 9; ++j) { wa[j] = 0u; wb[j] = 0u; }
                             if (g < p.M_total) {
                                 const uint32_t n = fdiv(g, p.d_HW);
                                 const uint32_t rem = g - n * (uint32_t)(p.H * p.W);
-                                const int ho = (int)fdiv(rem, p.d_Wo), wo = (int)rem - ho * p.W;
-                                const size_t base = (size_t)n * 3 * plane_sz;
+                                const int ho = (int)fdiv(rem, p.d_Wo), wo = (int)rem - ho * p.W;   // wo is even
+                                const uint8_t* base = src8 + (size_t)n * 3 * plane_sz + 2 * wo;
 #pragma unroll
-                                for (int tap = 0; tap < 9; ++tap) {
-                                    const int hi = 2 * ho + tap / 3 - 1, wi = 2 * wo + tap % 3 - 1;
-                                    if (hi >= 0 && hi < p.stem_H && wi >= 0 && wi < p.stem_W) {
-                                        const size_t o = base + (size_t)hi * p.stem_W + wi;
+                                for (int dy = 0; dy < 3; ++dy) {
+                                    const int hi = 2 * ho + dy - 1;
+                                    if (hi >= 0 && hi < p.stem_H) {
 #pragma unroll
-                                        for (int c = 0; c < 3; ++c) hv[tap * 3 + c] = sLut[__ldg(src8 + o + c * plane_sz)];
+                                        for (int c = 0; c < 3; ++c) {
+                                            const uint32_t* rp = reinterpret_cast<const uint32_t*>(base + c * plane_sz + (size_t)hi * p.stem_W);
+                                            wb[dy * 3 + c] = __ldg(rp);
+                                            if (wo > 0) wa[dy * 3 + c] = __ldg(rp - 1);
+                                        }
                                     }
                                 }
                             }
 #pragma unroll
-                            for (int pll = 0; pll < 4; ++pll) {
+                            for (int px = 0; px < 2; ++px) {
+                                float f[32];
+#pragma unroll
+                                for (int j = 27; j < 32; ++j) f[j] = 0.f;
+#pragma unroll
+                                for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                                    for (int c = 0; c < 3; ++c) {
+                                        // low three bytes = source columns 2*wo'-1, 2*wo', 2*wo'+1 of output column wo' = wo + px
+                                        const uint32_t x3 = px == 0 ? __funnelshift_r(wa[dy * 3 + c], wb[dy * 3 + c], 24) : (wb[dy * 3 + c] >> 8);
+#pragma unroll
+                                        for (int dx = 0; dx < 3; ++dx)
+                                            f[(dy * 3 + dx) * 3 + c] = __uint_as_float(__byte_perm(x3, 0x4B000000u, 0x7650 | dx)) - 8388608.0f;
+                                    }
+                                }
+#pragma unroll
+                                for (int pll = 0; pll < 4; ++pll) {
+                                    uint4 o;   // exact small integers: the bf16 value is the float's high half
+                                    o.x = __byte_perm(__float_as_uint(f[pll * 8 + 0]), __float_as_uint(f[pll * 8 + 1]), 0x7632);
+                                    o.y = __byte_perm(__float_as_uint(f[pll * 8 + 2]), __float_as_uint(f[pll * 8 + 3]), 0x7632);
+                                    o.z = __byte_perm(__float_as_uint(f[pll * 8 + 4]), __float_as_uint(f[pll * 8 + 5]), 0x7632);
+                                    o.w = __byte_perm(__float_as_uint(f[pll * 8 + 6]), __float_as_uint(f[pll * 8 + 7]), 0x7632);
+                                    *reinterpret_cast<uint4*>(sA + ((uint32_t)pll * rn.pstride16 + pos + px) * 16u) = o;
+                                }
+                            }
+                        }
+                    } else if (LOADER == LD_DCN && pl.PS % (p.dcn_cin / 8) == 0) {
+                        // DCNv2 sampling, one (position, tap) item per thread iteration: offset / mask / bilinear weights
+                        // are decoded once and reused for all channel groups of the tap (mask folded into the weights,
+                        // out-of-image corners get weight 0 and a clamped address, so the loop is branch-free)
+                        const int cgs = p.dcn_cin / 8;
+                        const int tap0 = plane0 / cgs, ntap = pl.PS / cgs;
+                        const uint32_t rows = 128u * rn.MB;
+                        const uint32_t items = rows * (uint32_t)ntap;
+                        for (uint32_t e = ptid; e < items; e += NP) {
+                            const uint32_t tl = e / rows, pos = e - tl * rows;   // consecutive threads -> consecutive pixels
+                            const int tap = tap0 + (int)tl;
+                            const uint32_t g = tile * rows + pos;
+                            float wgt[4] = {0.f, 0.f, 0.f, 0.f};
+                            const __nv_bfloat16* cp[4] = {p.x, p.x, p.x, p.x};
+                            if (g < p.M_total) {
+                                const uint32_t n = fdiv(g, p.d_HW);
+                                const uint32_t rem = g - n * (uint32_t)(p.H * p.W);
+                                const int hq = (int)fdiv(rem, p.d_W), wq = (int)rem - hq * p.W;
+                                const __nv_bfloat16* ofp = p.dcn_off + (size_t)g * p.off_cs + 2 * tap;
+                                const float dy = __bfloat162float(ofp[0]), dx = __bfloat162float(ofp[1]);
+                                float m = __bfloat162float(p.dcn_mask[(size_t)g * p.mask_cs + tap]);
+                                if (p.mask_logit) m = sigmoidf_(m);
+                                const float py = (float)(hq + tap / 3 - 1) + dy, px = (float)(wq + tap % 3 - 1) + dx;
+                                if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
+                                    const int y0 = (int)floorf(py), x0 = (int)floorf(px);
+                                    const float ly = py - (float)y0, lx = px - (float)x0;
+                                    const float hy = 1.f - ly, hx = 1.f - lx;
+                                    const bool y0v = y0 >= 0, y1v = y0 + 1 <= p.H - 1, x0v = x0 >= 0, x1v = x0 + 1 <= p.W - 1;
+                                    wgt[0] = (y0v && x0v) ? hy * hx * m : 0.f;
+                                    wgt[1] = (y0v && x1v) ? hy * lx * m : 0.f;
+                                    wgt[2] = (y1v && x0v) ? ly * hx * m : 0.f;
+                                    wgt[3] = (y1v && x1v) ? ly * lx * m : 0.f;
+                                    const int yc0 = max(y0, 0), yc1 = min(y0 + 1, p.H - 1), xc0 = max(x0, 0), xc1 = min(x0 + 1, p.W - 1);
+                                    const __nv_bfloat16* xn = p.x + (size_t)n * p.H * p.W * p.x_cs;
+                                    cp[0] = xn + (size_t)(yc0 * p.W + xc0) * p.x_cs;
+                                    cp[1] = xn + (size_t)(yc0 * p.W + xc1) * p.x_cs;
+                                    cp[2] = xn + (size_t)(yc1 * p.W + xc0) * p.x_cs;
+                                    cp[3] = xn + (size_t)(yc1 * p.W + xc1) * p.x_cs;
+                                }
+                            }
+                            unsigned char* dst = sA + ((uint32_t)((tap - tap0) * cgs) * rn.pstride16 + pos) * 16u;
+                            for (int cg = 0; cg < cgs; ++cg) {
+                                uint4 v[4];
+#pragma unroll
+                                for (int c4 = 0; c4 < 4; ++c4) v[c4] = __ldg(reinterpret_cast<const uint4*>(cp[c4] + cg * 8));
+                                float f[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = 0.f;
+#pragma unroll
+                                for (int c4 = 0; c4 < 4; ++c4) {
+                                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[c4]);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float2 t = __bfloat1622float2(h[j]);
+                                        f[2 * j] = fmaf(wgt[c4], t.x, f[2 * j]);
+                                        f[2 * j + 1] = fmaf(wgt[c4], t.y, f[2 * j + 1]);
+                                    }
+                                }
                                 uint4 o;
-                                o.x = hv[pll * 8 + 0] | ((uint32_t)hv[pll * 8 + 1] << 16);
-                                o.y = hv[pll * 8 + 2] | ((uint32_t)hv[pll * 8 + 3] << 16);
-                                o.z = hv[pll * 8 + 4] | ((uint32_t)hv[pll * 8 + 5] << 16);
-                                o.w = hv[pll * 8 + 6] | ((uint32_t)hv[pll * 8 + 7] << 16);
-                                *reinterpret_cast<uint4*>(sA + ((uint32_t)pll * rn.pstride16 + pos) * 16u) = o;
+                                __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                                *reinterpret_cast<uint4*>(dst + (size_t)cg * rn.pstride16 * 16u) = o;
                             }
                         }
                     } else {
@@ -1021,7 +1113,7 @@ static int launch2(P2& p, cudaStream_t s) {
     if (p.pl.nsplit > 1) ctas = (int)std::max(1LL, std::min(tiles, (long long)(148 / p.pl.nsplit)));
     const dim3 grid((unsigned)ctas, (unsigned)p.pl.nsplit);
     if (p.stem_src) {
-        if (p.stem_C == 3 && p.pl.PS == 4 && p.stem_u8) return launch2t<0, LD_STEM_U8>(p, grid, s);
+        if (p.out_scale != 1.0f) return launch2t<0, LD_STEM_U8>(p, grid, s);
         return launch2t<0, LD_STEM_GEN>(p, grid, s);
     }
     if (p.dcn_off) return launch2t<0, LD_DCN>(p, grid, s);
@@ -1059,7 +1151,7 @@ int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
     p.N = a->N; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout; p.Ho = Ho; p.Wo = Wo;
     p.x_cs = a->x_cs; p.y_cs = a->y_cs; p.add_cs = a->add_cs; p.ps_cs = a->ps_cs; p.res_cs = a->res_cs;
     p.act = a->act; p.in_relu = a->in_relu;
-    p.w_f16 = a->w_umma_f16;
+    p.w_f16 = a->w_umma_f16; p.out_scale = 1.0f;
     p.y_vec = (((uintptr_t)a->y & 15) == 0 && (a->y_cs & 7) == 0) ? 1 : 0;
     p.res_vec = (a->residual && ((uintptr_t)a->residual & 15) == 0 && (a->res_cs & 7) == 0) ? 1 : 0;
     p.M_total = (unsigned)((long long)a->N * a->H * a->W);
@@ -1083,7 +1175,7 @@ int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void
     p.residual = nullptr; p.bias = nullptr; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y;
     p.N = N; p.H = H; p.W = W; p.Cin = 9 * Cin; p.Cout = Cout; p.Ho = H; p.Wo = W;
     p.x_cs = x_cs; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = MGDT_ACT_NONE; p.in_relu = 0;
-    p.w_f16 = w_f16;
+    p.w_f16 = w_f16; p.out_scale = 1.0f;
     p.y_vec = (((uintptr_t)y & 15) == 0 && (y_cs & 7) == 0) ? 1 : 0;
     p.res_vec = 0;
     p.M_total = (unsigned)((long long)N * H * W);
@@ -1108,6 +1200,9 @@ int stem_umma(const void* src, int src_is_u8, const void* w_umma, int w_f16, con
     p.N = N; p.H = Ho; p.W = Wo; p.Cin = Kp; p.Cout = Cout; p.Ho = Ho; p.Wo = Wo;
     p.x_cs = 0; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = act; p.in_relu = 0;
     p.w_f16 = w_f16;
+    // the fast uint8 loader stages exact integers and leaves the /255 to the epilogue
+    const bool u8_fast = src_is_u8 && C == 3 && p.pl.PS == 4 && W % 4 == 0 && ((uintptr_t)src & 3) == 0;
+    p.out_scale = u8_fast ? 1.0f / 255.0f : 1.0f;
     p.y_vec = (((uintptr_t)y & 15) == 0 && (y_cs & 7) == 0) ? 1 : 0;
     p.res_vec = 0;
     p.M_total = (unsigned)((long long)N * Ho * Wo);
