@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv7_ln_kernel(const T* __re
 constexpr int DT = 8;            // tile edge
 constexpr int DTI = DT + 6;      // input tile edge
 
-template <typename T, int CPL>
+template <typename T, int CPL, bool VEC>
 __global__ void __launch_bounds__(256) dwconv7_ln_tiled(const T* __restrict__ x, int x_cs, const T* __restrict__ w,
                                                         const float* __restrict__ bias, const float* __restrict__ ln_w,
                                                         const float* __restrict__ ln_b, float eps, T* __restrict__ y,
@@ -84,25 +84,56 @@ __global__ void __launch_bounds__(256) dwconv7_ln_tiled(const T* __restrict__ x,
     extern __shared__ __align__(16) unsigned char dsm[];
     const int CP = CPL * 32;                                   // padded channel count
     float* sw = reinterpret_cast<float*>(dsm);                 // [49][CP]
-    T* sx = reinterpret_cast<T*>(dsm + sizeof(float) * 49 * CP);  // [DTI][DTI][CP]
+    float* sx = sw + 49 * CP;                                  // [DTI][DTI][CP], staged as fp32
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int b = blockIdx.x;
     const int tx = b % tiles_x; b /= tiles_x;
     const int ty = b % tiles_y;
     const int n = b / tiles_y;
     const int h0 = ty * DT, w0 = tx * DT;
-    for (int i = tid; i < 49 * CP; i += 256) {
-        const int c = i % CP;
-        sw[i] = c < C ? ldf(w + (i / CP) * C + c) : 0.f;
-    }
     const T* xn = x + (size_t)n * H * W * x_cs;
-    for (int i = tid; i < DTI * DTI * CP; i += 256) {
-        const int c = i % CP, pix = i / CP;
-        const int iy = pix / DTI, ix = pix - iy * DTI;
-        const int hh = h0 + iy - 3, ww = w0 + ix - 3;
-        float v = 0.f;
-        if (c < C && hh >= 0 && hh < H && ww >= 0 && ww < W) v = ldf(xn + (size_t)(hh * W + ww) * x_cs + c);
-        stf(sx + i, v);
+    if (VEC) {
+        // bf16, C % 8 == 0, 16-byte aligned rows: 8 channels per load, converted to fp32 once while staging
+        constexpr int C8 = CPL * 4;   // 8-channel chunks per padded pixel
+        for (int i = tid; i < 49 * C8; i += 256) {
+            const int tap = i / C8, c8 = (i - tap * C8) * 8;
+            float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+            if (c8 < C) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(w) + tap * C + c8));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+                const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]), c = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
+                lo = make_float4(a.x, a.y, b.x, b.y); hi = make_float4(c.x, c.y, d.x, d.y);
+            }
+            float4* dst = reinterpret_cast<float4*>(sw + tap * CP + c8);
+            dst[0] = lo; dst[1] = hi;
+        }
+        for (int i = tid; i < DTI * DTI * C8; i += 256) {
+            const int pix = i / C8, c8 = (i - pix * C8) * 8;
+            const int iy = pix / DTI, ix = pix - iy * DTI;
+            const int hh = h0 + iy - 3, ww = w0 + ix - 3;
+            float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+            if (c8 < C && hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(xn) + (size_t)(hh * W + ww) * x_cs + c8));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+                const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]), c = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
+                lo = make_float4(a.x, a.y, b.x, b.y); hi = make_float4(c.x, c.y, d.x, d.y);
+            }
+            float4* dst = reinterpret_cast<float4*>(sx + (size_t)pix * CP + c8);
+            dst[0] = lo; dst[1] = hi;
+        }
+    } else {
+        for (int i = tid; i < 49 * CP; i += 256) {
+            const int c = i % CP;
+            sw[i] = c < C ? ldf(w + (i / CP) * C + c) : 0.f;
+        }
+        for (int i = tid; i < DTI * DTI * CP; i += 256) {
+            const int c = i % CP, pix = i / CP;
+            const int iy = pix / DTI, ix = pix - iy * DTI;
+            const int hh = h0 + iy - 3, ww = w0 + ix - 3;
+            float v = 0.f;
+            if (c < C && hh >= 0 && hh < H && ww >= 0 && ww < W) v = ldf(xn + (size_t)(hh * W + ww) * x_cs + c);
+            sx[i] = v;
+        }
     }
     __syncthreads();
     const int r = warp;  // output row inside the tile
@@ -121,12 +152,12 @@ __global__ void __launch_bounds__(256) dwconv7_ln_tiled(const T* __restrict__ x,
         for (int dx = 0; dx < 7; ++dx)
 #pragma unroll
             for (int j = 0; j < CPL; ++j) wk[dx][j] = sw[(dy * 7 + dx) * CP + lane + 32 * j];
-        const T* row = sx + (size_t)((r + dy) * DTI) * CP;
+        const float* row = sx + (size_t)((r + dy) * DTI) * CP;
 #pragma unroll
         for (int ix = 0; ix < DTI; ++ix) {
             float v[CPL];
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) v[j] = ldf(row + ix * CP + lane + 32 * j);
+            for (int j = 0; j < CPL; ++j) v[j] = row[ix * CP + lane + 32 * j];
 #pragma unroll
             for (int dx = 0; dx < 7; ++dx) {
                 const int px = ix - dx;
@@ -176,12 +207,21 @@ template <typename T, int CPL>
 static int launch_dw_tiled(const void* x, int x_cs, const void* w, const float* bias, const float* ln_w,
                            const float* ln_b, float eps, void* y, int y_cs, int N, int H, int W, int C, cudaStream_t s) {
     const int CP = CPL * 32;
-    const size_t smem = sizeof(float) * 49 * CP + sizeof(T) * DTI * DTI * CP;
-    cudaError_t e = cudaFuncSetAttribute(dwconv7_ln_tiled<T, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(-EIO, "dwconv7_ln: smem attr: %s", cudaGetErrorString(e));
+    const size_t smem = sizeof(float) * 49 * CP + sizeof(float) * DTI * DTI * CP;
     const int tx = (W + DT - 1) / DT, ty = (H + DT - 1) / DT;
-    dwconv7_ln_tiled<T, CPL><<<tx * ty * N, 256, smem, s>>>((const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps, (T*)y,
-                                                            y_cs, H, W, C, tx, ty);
+    const bool vec = sizeof(T) == 2 && C % 8 == 0 && x_cs % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0;
+    cudaError_t e;
+    if (vec) {
+        e = cudaFuncSetAttribute(dwconv7_ln_tiled<T, CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(-EIO, "dwconv7_ln: smem attr: %s", cudaGetErrorString(e));
+        dwconv7_ln_tiled<T, CPL, true><<<tx * ty * N, 256, smem, s>>>((const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps,
+                                                                      (T*)y, y_cs, H, W, C, tx, ty);
+    } else {
+        e = cudaFuncSetAttribute(dwconv7_ln_tiled<T, CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(-EIO, "dwconv7_ln: smem attr: %s", cudaGetErrorString(e));
+        dwconv7_ln_tiled<T, CPL, false><<<tx * ty * N, 256, smem, s>>>((const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps,
+                                                                       (T*)y, y_cs, H, W, C, tx, ty);
+    }
     return 0;
 }
 

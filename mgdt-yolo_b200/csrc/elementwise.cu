@@ -197,6 +197,54 @@ __global__ void __launch_bounds__(EW_THREADS) sppf_pool_kernel(const T* __restri
     }
 }
 
+// SPPF pooling chain for maps that fit in shared memory (bf16, 8-aligned): one CTA per (image, 8-channel chunk).
+// pool_{k}(pool_{k}(x)) = pool_{2k-1}(x) with -inf padding, so the three outputs are three cascaded separable
+// (row max, then column max) passes over a ping-pong pair of [H*W] x 16-byte tiles; the max of packed bf16 pairs
+// is a selection, hence exact.
+__device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
+    uint4 r;
+    const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = __hmax2(x[j], y[j]);
+    return r;
+}
+
+__global__ void __launch_bounds__(EW_THREADS) sppf_pool_tile(const __nv_bfloat16* __restrict__ x, int x_cs,
+                                                             __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2,
+                                                             __nv_bfloat16* __restrict__ y3, int y_cs, int H, int W, int C8,
+                                                             int r) {
+    extern __shared__ uint4 sp_buf[];
+    const int HW = H * W;
+    uint4* A = sp_buf;
+    uint4* B = sp_buf + HW;
+    const int n = blockIdx.x / C8, c = (blockIdx.x - n * C8) * 8;
+    const size_t pix0 = (size_t)n * HW;
+    for (int i = threadIdx.x; i < HW; i += EW_THREADS) A[i] = __ldg(reinterpret_cast<const uint4*>(x + (pix0 + i) * x_cs + c));
+    __syncthreads();
+    __nv_bfloat16* outs[3] = {y1, y2, y3};
+    for (int st = 0; st < 3; ++st) {
+        for (int i = threadIdx.x; i < HW; i += EW_THREADS) {
+            const int h = i / W, w = i - h * W;
+            const int lo = max(w - r, 0), hi = min(w + r, W - 1);
+            uint4 m = A[h * W + lo];
+            for (int ww = lo + 1; ww <= hi; ++ww) m = max8(m, A[h * W + ww]);
+            B[i] = m;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < HW; i += EW_THREADS) {
+            const int h = i / W, w = i - h * W;
+            const int lo = max(h - r, 0), hi = min(h + r, H - 1);
+            uint4 m = B[lo * W + w];
+            for (int hh = lo + 1; hh <= hi; ++hh) m = max8(m, B[hh * W + w]);
+            A[i] = m;
+            *reinterpret_cast<uint4*>(outs[st] + (pix0 + i) * y_cs + c) = m;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ injection gate
 // relu6(x + 3) / 6: exact IEEE form in the fp32 validation mode, saturate(x/6 + 0.5) (2 instructions) for bf16
 template <typename T> __device__ __forceinline__ float hsig(float v);
@@ -336,6 +384,16 @@ extern "C" int mgdt_sppf_pool(const void* x, int x_cs, void* y1, void* y2, void*
     MGDT_CHECK(x && y1 && y2 && y3, "sppf_pool: null pointer");
     MGDT_CHECK(N > 0 && H > 0 && W > 0 && C > 0 && (k & 1) && k >= 1, "sppf_pool: bad shape/k");
     MGDT_CHECK((long long)N * H * W * C < (1LL << 31), "sppf_pool: tensor too large for 32-bit indexing");
+    if (dtype == MGDT_BF16 && C % 8 == 0 && aligned8(x, x_cs, 2) && aligned8(y1, y_cs, 2) && aligned8(y2, y_cs, 2) &&
+        aligned8(y3, y_cs, 2) && (size_t)H * W * 32 <= 96 * 1024) {
+        const size_t smem = (size_t)H * W * 32;
+        cudaError_t e = cudaFuncSetAttribute(sppf_pool_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(-EIO, "sppf_pool: smem attr: %s", cudaGetErrorString(e));
+        sppf_pool_tile<<<N * (C / 8), EW_THREADS, smem, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, x_cs, (__nv_bfloat16*)y1, (__nv_bfloat16*)y2, (__nv_bfloat16*)y3, y_cs, H, W, C / 8, k / 2);
+        MGDT_LAUNCH_CHECK("sppf_pool_tile");
+        return 0;
+    }
     MGDT_DTYPE_SWITCH(dtype, T, {
         const bool vec = C % 8 == 0 && aligned8(x, x_cs, sizeof(T)) && aligned8(y1, y_cs, sizeof(T)) &&
                          aligned8(y2, y_cs, sizeof(T)) && aligned8(y3, y_cs, sizeof(T));

@@ -136,6 +136,7 @@ __device__ __forceinline__ bool iou_gt(const Box& a, float area_a, const Box& b,
     const float xx2 = fminf(a.x2, b.x2), yy2 = fminf(a.y2, b.y2);
     const float w = fmaxf(xx2 - xx1, 0.f), h = fmaxf(yy2 - yy1, 0.f);
     const float inter = w * h;
+    if (!(inter > 0.f)) return false;   // 0 / u > thr is false for every thr >= 0 (and NaN compares false): skip the divide
     return inter / (area_a + area_b - inter) > thr;
 }
 
@@ -190,10 +191,14 @@ __global__ void __launch_bounds__(NMS_CHUNK) nms_scan(NmsP p, float* __restrict_
         for (int wd = 0; wd < NMS_WORDS; ++wd) {
             unsigned m = 0;
             if (live && wd >= (tid >> 5)) {
-                const unsigned aw = alive[wd];
-                for (int b = 0; b < 32; ++b) {
+                // live candidates after this one only (words past the last valid candidate are empty)
+                unsigned bits = alive[wd];
+                if (wd == (tid >> 5)) bits &= ~((2u << (tid & 31)) - 1u);
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1u;
                     const int j = wd * 32 + b;
-                    if (j > tid && ((aw >> b) & 1u) && iou_gt(ob, area, cbox[j], carea[j], p.iou)) m |= (1u << b);
+                    if (iou_gt(ob, area, cbox[j], carea[j], p.iou)) m |= (1u << b);
                 }
             }
             cmask[tid * NMS_WORDS + wd] = m;

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __rest
             for (int q = 0; q < Q; ++q) s[q][j] = 0.f;
         }
         if (cv < CV) {
+#pragma unroll 4
             for (int pidx = p_begin + pg; pidx < p_end; pidx += PG) {
                 float v[V];
                 StatLd<T, V>::ld(xn + (size_t)pidx * x_cs + cv * V, v);
@@ -80,22 +81,36 @@ __global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __rest
                 }
             }
         }
-        // reduce over pixel groups through shared memory, one statistic at a time (fixed order -> deterministic)
+        // reduce over pixel groups, one statistic at a time: xor-shuffles inside the warp (lanes that share a channel
+        // lane are Cw apart), then at most 8 partial rows through shared memory (fixed order -> deterministic)
+        const int lane = threadIdx.x & 31;
+        const int rows = Cw <= 32 ? CS_THREADS / 32 : PG;
+        const int row = Cw <= 32 ? (threadIdx.x >> 5) : pg;
 #pragma unroll
         for (int q = 0; q <= Q; ++q) {
             if (q == Q && !partsq) break;
+            float t[V];
 #pragma unroll
-            for (int j = 0; j < V; ++j) sm[(pg * Cw + cl) * V + j] = (q < Q) ? s[q < Q ? q : 0][j] : sq[j];
+            for (int j = 0; j < V; ++j) t[j] = (q < Q) ? s[q < Q ? q : 0][j] : sq[j];
+            for (int off = 16; off >= Cw; off >>= 1) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) t[j] += __shfl_xor_sync(0xffffffffu, t[j], off);
+            }
+            if (Cw >= 32 || lane < Cw) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) sm[(row * Cw + cl) * V + j] = t[j];
+            }
             __syncthreads();
-            if (pg == 0 && cv < CV) {
+            if ((int)threadIdx.x < Cw && cb + (int)threadIdx.x < CV) {
+                const int cvo = cb + (int)threadIdx.x;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    float t = 0.f;
-                    for (int g = 0; g < PG; ++g) t += sm[(g * Cw + cl) * V + j];
+                    float tot = 0.f;
+                    for (int g = 0; g < rows; ++g) tot += sm[(g * Cw + (int)threadIdx.x) * V + j];
                     if (q < Q)
-                        part[(((size_t)n * nchunks + chunk) * Q + q) * C + cv * V + j] = t;
+                        part[(((size_t)n * nchunks + chunk) * Q + q) * C + cvo * V + j] = tot;
                     else
-                        partsq[((size_t)n * nchunks + chunk) * C + cv * V + j] = t;
+                        partsq[((size_t)n * nchunks + chunk) * C + cvo * V + j] = tot;
                 }
             }
             __syncthreads();
