@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-json", default="", help="write the per-launch table here")
+    ap.add_argument("--launch-list", action="store_true",
+                    help="eager warm-up + timed steps only (no e2e / per-launch / CPU legs): the run to put under ncu")
     return ap.parse_args()
 
 
@@ -252,6 +254,14 @@ def run_ours(args):
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop(t_wall0, t_wall1)
     n_det = int(eng.slots[(args.steps - 1) % nslot].counts.sum().item())
+
+    if args.launch_list:
+        if rank == 0:
+            print(json.dumps({"launch_list": True, "steps": args.steps, "ms_per_step": ms_dev / args.steps,
+                              "launches_per_step": eng.launches_per_step}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     # ---- (2) end to end from pinned host memory (H2D + D2H inside the timed region)
     for i in range(args.warmup):

@@ -473,11 +473,8 @@ __device__ __forceinline__ int src_pixel(const P2& p, uint32_t tile, uint32_t tt
     }
 }
 
-// One 16-byte chunk (8 channels of plane `plane`) of source pixel `pix` with the fused input transforms.
-__device__ __forceinline__ uint4 xform_chunk(const P2& p, int pix, uint32_t n, int plane) {
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (pix < 0) return v;
-    v = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)pix * p.x_cs + plane * 8));
+// The fused input transforms on one staged 16-byte chunk (8 channels of plane `plane`) of source pixel `pix`.
+__device__ __forceinline__ uint4 xform_apply(const P2& p, uint4 v, int pix, uint32_t n, int plane) {
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
     float f[8];
 #pragma unroll
@@ -505,6 +502,30 @@ __device__ __forceinline__ uint4 xform_chunk(const P2& p, int pix, uint32_t n, i
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
     return v;
+}
+
+// In-place transform of the chunks thread `ptid` copied into stage `sA` (zero-filled chunks stay zero, as in the
+// reference where padding is applied after the producing op).
+template <int MODE, int NP>
+__device__ __forceinline__ void xform_stage(const P2& p, unsigned char* sA, uint32_t tile, uint32_t tt, uint32_t n_img,
+                                            int plane0, uint32_t chunks, int ptid) {
+    for (uint32_t e0 = ptid; e0 < chunks; e0 += NP * 2) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t e = e0 + u * NP;
+            if (e < chunks) {
+                const uint32_t rest = fdiv(e, p.d_ps);
+                const uint32_t pll = e - rest * p.pl.PS;
+                uint32_t pos = rest, par = 0, n;
+                if (MODE == 2) { par = fdiv(rest, p.d_P); pos = rest - par * p.rn.P; }
+                const int pix = src_pixel<MODE>(p, tile, tt, n_img, pos, par, n);
+                if (pix >= 0) {
+                    uint4* q = reinterpret_cast<uint4*>(sA + (pll * p.rn.pstride16 + par * p.rn.P + pos) * 16u);
+                    *q = xform_apply(p, *q, pix, n, plane0 + (int)pll);
+                }
+            }
+        }
+    }
 }
 
 // Epilogue arithmetic on NV accumulator columns of one output row: bias, activation, residual, bf16 pack.
@@ -650,12 +671,17 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             if (tid == 0) trace_mark(p, 2);
         }
         const uint32_t chunks = (uint32_t)(pl.PS * pl.npar * rn.P);
-        const bool ps_divides = NP % pl.PS == 0;
+        // (the in-place transform revisits chunks through the generic mapping, which matches the fast path's except for
+        // the stride-2 parity loop)
+        const bool ps_divides = NP % pl.PS == 0 && !(LOADER == LD_XFORM && MODE == 2);
         const uint32_t pstep = ps_divides ? (uint32_t)(NP / pl.PS) : 1u;
         const uint32_t pos_fix = fdiv((uint32_t)ptid, p.d_ps), pll_fix = (uint32_t)ptid - pos_fix * pl.PS;
         uint32_t it = 0;
         int s = 0;
         uint32_t ph = 0;   // phase of the stage's current use (flips each time the ring wraps)
+        bool xf_valid = false;   // LD_XFORM: the item whose raw copies are in flight and still to be transformed
+        int xf_s = 0, xf_plane0 = 0;
+        uint32_t xf_tile = 0, xf_tt = 0, xf_nimg = 0;
         for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             uint32_t n_img = 0, tt = 0;
             if (MODE != 0) { n_img = fdiv(tile, p.d_tpi); tt = tile - n_img * rn.tiles_per_img; }
@@ -670,7 +696,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                     for (int i = ptid; i < n16; i += NP) cp_async16(dst + 16u * i, src + i, 16u);
                 }
                 const int plane0 = ks * pl.PS;
-                if (LOADER == LD_ASYNC) {
+                if (LOADER == LD_ASYNC || LOADER == LD_XFORM) {
                     // transform-free input: every chunk is an asynchronous 16-byte copy (zero-filled outside the image);
                     // the thread never waits for its data, the stage's full barrier counts the copies' completion
                     if (ps_divides) {
@@ -737,7 +763,20 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                         const __nv_bfloat16* src = pix >= 0 ? p.x + (size_t)pix * p.x_cs + (plane0 + pll) * 8 : p.x;
                         cp_async16(sA32 + (pll * rn.pstride16 + par * rn.P + pos) * 16u, src, pix >= 0 ? 16u : 0u);
                     }
-                    cp_async_arrive_noinc(FULL(s));
+                    if (LOADER == LD_ASYNC) cp_async_arrive_noinc(FULL(s));
+                    else {
+                        // fused input transforms: the raw copies of THIS item stay in flight while the thread transforms,
+                        // in place, the chunks it copied for the PREVIOUS item (same thread -> chunk mapping, so no
+                        // cross-thread synchronisation), then publishes that stage
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                        if (xf_valid) {
+                            asm volatile("cp.async.wait_group 1;" ::: "memory");
+                            xform_stage<MODE, NP>(p, sStage + (size_t)xf_s * rn.stage_bytes, xf_tile, xf_tt, xf_nimg, xf_plane0, chunks, ptid);
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            mbar_arrive(FULL(xf_s));
+                        }
+                        xf_valid = true; xf_s = s; xf_tile = tile; xf_tt = tt; xf_nimg = n_img; xf_plane0 = plane0;
+                    }
                 } else {
                     if (LOADER == LD_STEM_U8) {
                         // uint8 NCHW source, C = 3, K = 32: one pair of horizontally adjacent output pixels per thread
@@ -879,11 +918,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                                     if (MODE == 2) { par = fdiv(rest, p.d_P); pos = rest - par * rn.P; }
                                     if (LOADER == LD_STEM_GEN) v[u] = stem_chunk(p, tile * (128u * rn.MB) + pos, plane0 + pll);
                                     else if (LOADER == LD_DCN) v[u] = dcn_chunk(p, tile * (128u * rn.MB) + pos, plane0 + pll);
-                                    else {
-                                        uint32_t n;
-                                        const int pix = src_pixel<MODE>(p, tile, tt, n_img, pos, par, n);
-                                        v[u] = xform_chunk(p, pix, n, plane0 + pll);
-                                    }
+                                    else v[u] = make_uint4(0u, 0u, 0u, 0u);
                                     dsto[u] = ((uint32_t)pll * rn.pstride16 + par * rn.P + pos) * 16u;
                                 }
                             }
@@ -899,6 +934,12 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                 if (tid == 0 && it < 6) trace_mark(p, 8 + 8 * (int)it);
                 if (++s == rn.S) { s = 0; ph ^= 1; }
             }
+        }
+        if (LOADER == LD_XFORM && xf_valid) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            xform_stage<MODE, NP>(p, sStage + (size_t)xf_s * rn.stage_bytes, xf_tile, xf_tt, xf_nimg, xf_plane0, chunks, ptid);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(FULL(xf_s));
         }
     } else if (warp == MMAW) {
         // =============================================================== MMA issuer
