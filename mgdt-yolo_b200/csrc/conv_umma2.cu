@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace mgdt {
 
@@ -413,10 +414,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 enum : int { LD_ASYNC = 0, LD_XFORM = 1, LD_DCN = 2, LD_STEM_U8 = 3, LD_STEM_GEN = 4 };
 
-template <int LOADER> struct Roles {
-    // producer warps 0 .. NPW-1: the cp.async loader only issues copies (3 warps); the fused-transform loader stages
-    // through registers (7); DCN sampling and the stem's byte gather are instruction-bound and take most of the CTA
-    static constexpr int NPW = LOADER == LD_ASYNC ? 3 : LOADER == LD_XFORM ? 7 : LOADER == LD_DCN ? 15 : 11;
+template <int LOADER, int SPLIT> struct Roles {
+    // producer warps 0 .. NPW-1.  cp.async loaders: a warp sustains about one 512-byte LDGSTS per ~200 cycles in this
+    // kernel (measured; tools/ubench/cpasync.cu gives 50-115 cycles for a bare loop), so the producer/epilogue split
+    // is chosen per layer by the host cost model (SPLIT 0/1/2 = 3/16, 7/12, 11/8 producer/epilogue warps).  DCN
+    // sampling and the stem's byte gather are instruction-bound and take most of the CTA.
+    static constexpr int NPW = (LOADER == LD_ASYNC || LOADER == LD_XFORM) ? (SPLIT == 0 ? 3 : SPLIT == 1 ? 7 : 11)
+                               : LOADER == LD_DCN ? 15 : 11;
     static constexpr int MMAW = NPW;                          // the MMA warp
     static constexpr int EPI0 = NPW + 1;                      // first epilogue warp (a multiple of 4: quadrant = warp % 4)
     static constexpr int NEW = U2_WARPS - EPI0;               // epilogue warps (16 or 12), NEW / 4 per lane quadrant
@@ -588,15 +592,15 @@ __device__ __forceinline__ void epi_math(const P2& p, const uint32_t* r, const f
     }
 }
 
-template <int MODE, int LOADER>
+template <int MODE, int LOADER, int SPLIT>
 __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_constant__ P2 p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Plan2& pl = p.pl;
     const Run2& rn = p.rn;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ns = blockIdx.y;
-    constexpr int NPW = Roles<LOADER>::NPW, NEW = Roles<LOADER>::NEW, NP = Roles<LOADER>::NP;
-    constexpr int MMAW = Roles<LOADER>::MMAW, EPI0 = Roles<LOADER>::EPI0;
+    constexpr int NPW = Roles<LOADER, SPLIT>::NPW, NEW = Roles<LOADER, SPLIT>::NEW, NP = Roles<LOADER, SPLIT>::NP;
+    constexpr int MMAW = Roles<LOADER, SPLIT>::MMAW, EPI0 = Roles<LOADER, SPLIT>::EPI0;
 
     if (tid == 0) trace_mark(p, 0);
     unsigned char* sWres = smem;
@@ -1136,17 +1140,40 @@ static void fill_divs(P2& p) {
 }
 
 static unsigned long long* g_trace = nullptr;
+static int g_force_split = -1;   // debug (MGDT_CONV_SPLIT=0/1/2): override the producer/epilogue warp split
 
-template <int MODE, int LOADER>
+template <int MODE, int LOADER, int SPLIT>
 static int launch2t(const P2& p, dim3 grid, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<MODE, LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<MODE, LOADER, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_MAX_SMEM);
     if (e != cudaSuccess) return set_error(-EIO, "conv_umma2: smem attr: %s", cudaGetErrorString(e));
-    conv_umma2_kernel<MODE, LOADER><<<grid, U2_THREADS, p.rn.smem_total, s>>>(p);
+    conv_umma2_kernel<MODE, LOADER, SPLIT><<<grid, U2_THREADS, p.rn.smem_total, s>>>(p);
     MGDT_LAUNCH_CHECK("conv_umma2");
     return 0;
 }
 
+template <int MODE, int LOADER>
+static int launch2s(const P2& p, int split, dim3 grid, cudaStream_t s) {
+    if (split == 0) return launch2t<MODE, LOADER, 0>(p, grid, s);
+    if (split == 1) return launch2t<MODE, LOADER, 1>(p, grid, s);
+    return launch2t<MODE, LOADER, 2>(p, grid, s);
+}
+
+// Producer / epilogue warp split of the cp.async loaders.  Measured on the full model (profiles/, per-shape sweep of
+// MGDT_CONV_SPLIT): a warp sustains only one 512-byte LDGSTS per ~200 cycles here, so 11 producer warps win almost
+// everywhere; only tiles with many 32-column epilogue units (wide Cout) want the epilogue-heavy splits.
+static int pick_split(const P2& p, bool xform) {
+    (void)xform;
+    const int units = p.rn.MB * ((p.pl.Nc + 31) / 32);
+    return units >= 8 ? 0 : units >= 6 ? 1 : 2;
+}
+
 static int launch2(P2& p, cudaStream_t s) {
+    static bool env_read = false;
+    if (!env_read) {
+        const char* e = getenv("MGDT_CONV_SPLIT");
+        if (e && e[0] >= '0' && e[0] <= '2') g_force_split = e[0] - '0';
+        env_read = true;
+    }
     fill_divs(p);
     p.trace = g_trace;
     const long long tiles = p.rn.tiles;
@@ -1154,18 +1181,19 @@ static int launch2(P2& p, cudaStream_t s) {
     if (p.pl.nsplit > 1) ctas = (int)std::max(1LL, std::min(tiles, (long long)(148 / p.pl.nsplit)));
     const dim3 grid((unsigned)ctas, (unsigned)p.pl.nsplit);
     if (p.stem_src) {
-        if (p.out_scale != 1.0f) return launch2t<0, LD_STEM_U8>(p, grid, s);
-        return launch2t<0, LD_STEM_GEN>(p, grid, s);
+        if (p.out_scale != 1.0f) return launch2t<0, LD_STEM_U8, 0>(p, grid, s);
+        return launch2t<0, LD_STEM_GEN, 0>(p, grid, s);
     }
-    if (p.dcn_off) return launch2t<0, LD_DCN>(p, grid, s);
+    if (p.dcn_off) return launch2t<0, LD_DCN, 0>(p, grid, s);
     const bool xform = p.pre_add || p.in_scale || p.pix_scale || p.in_relu;
+    const int split = g_force_split >= 0 ? g_force_split : pick_split(p, xform);
     switch (p.pl.mode * 2 + (xform ? 1 : 0)) {
-        case 0: return launch2t<0, LD_ASYNC>(p, grid, s);
-        case 1: return launch2t<0, LD_XFORM>(p, grid, s);
-        case 2: return launch2t<1, LD_ASYNC>(p, grid, s);
-        case 3: return launch2t<1, LD_XFORM>(p, grid, s);
-        case 4: return launch2t<2, LD_ASYNC>(p, grid, s);
-        default: return launch2t<2, LD_XFORM>(p, grid, s);
+        case 0: return launch2s<0, LD_ASYNC>(p, split, grid, s);
+        case 1: return launch2s<0, LD_XFORM>(p, split, grid, s);
+        case 2: return launch2s<1, LD_ASYNC>(p, split, grid, s);
+        case 3: return launch2s<1, LD_XFORM>(p, split, grid, s);
+        case 4: return launch2s<2, LD_ASYNC>(p, split, grid, s);
+        default: return launch2s<2, LD_XFORM>(p, split, grid, s);
     }
 }
 

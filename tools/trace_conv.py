@@ -12,7 +12,8 @@ B = 32
 import torch.nn as nn
 cases = [("c32_3x3", 32, 32, 3, 1, 80, 80), ("c8_1x1", 8, 8, 1, 1, 160, 160), ("c64_256", 64, 256, 1, 1, 80, 80),
          ("c64_256_noact", 64, 256, 1, 1, 80, 80), ("c64_256_relu", 64, 256, 1, 1, 80, 80),
-         ("c96_384", 96, 384, 1, 1, 40, 40), ("c16_3x3", 16, 16, 3, 1, 80, 80)]
+         ("c96_384", 96, 384, 1, 1, 40, 40), ("c16_3x3", 16, 16, 3, 1, 80, 80), ("c32_64", 32, 64, 1, 1, 80, 80),
+         ("c256_64", 256, 64, 1, 1, 80, 80), ("c16_32_s2", 16, 32, 3, 2, 320, 320), ("c384_96", 384, 96, 1, 1, 40, 40)]
 sel = sys.argv[1:]
 if sel:
     cases = [c for c in cases if c[0] in sel]
