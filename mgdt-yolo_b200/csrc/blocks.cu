@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv7_ln_kernel(const T* __re
                                                                    const float* __restrict__ ln_b, float eps,
                                                                    T* __restrict__ y, int y_cs, int H, int W, int C,
                                                                    long long npix) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long pix = (long long)blockIdx.x * DW_WARPS + (threadIdx.x >> 5);
     if (pix >= npix) return;
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(256) dwconv7_ln_tiled(const T* __restrict__ x,
                                                         const float* __restrict__ bias, const float* __restrict__ ln_w,
                                                         const float* __restrict__ ln_b, float eps, T* __restrict__ y,
                                                         int y_cs, int H, int W, int C, int tiles_x, int tiles_y) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char dsm[];
     const int CP = CPL * 32;                                   // padded channel count
     float* sw = reinterpret_cast<float*>(dsm);                 // [49][CP]
@@ -214,12 +218,12 @@ static int launch_dw_tiled(const void* x, int x_cs, const void* w, const float* 
     if (vec) {
         e = cudaFuncSetAttribute(dwconv7_ln_tiled<T, CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(-EIO, "dwconv7_ln: smem attr: %s", cudaGetErrorString(e));
-        dwconv7_ln_tiled<T, CPL, true><<<tx * ty * N, 256, smem, s>>>((const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps,
+        launch_k(dwconv7_ln_tiled<T, CPL, true>, dim3(tx * ty * N), dim3(256), smem, s, (const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps,
                                                                       (T*)y, y_cs, H, W, C, tx, ty);
     } else {
         e = cudaFuncSetAttribute(dwconv7_ln_tiled<T, CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(-EIO, "dwconv7_ln: smem attr: %s", cudaGetErrorString(e));
-        dwconv7_ln_tiled<T, CPL, false><<<tx * ty * N, 256, smem, s>>>((const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps,
+        launch_k(dwconv7_ln_tiled<T, CPL, false>, dim3(tx * ty * N), dim3(256), smem, s, (const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps,
                                                                        (T*)y, y_cs, H, W, C, tx, ty);
     }
     return 0;
@@ -237,6 +241,8 @@ __global__ void __launch_bounds__(DCN_THREADS) dcn3x3_kernel(const T* __restrict
                                                              const T* __restrict__ msk, int msk_cs, int mask_is_logit,
                                                              const T* __restrict__ w, T* __restrict__ y, int y_cs,
                                                              int H, int W, int Cin, int Cout, long long npix) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float cols[];  // [DCN_PIX][K + 1]
     const int K = 9 * Cin;
     const int ld = K + 1;
@@ -298,6 +304,8 @@ struct DecodeLevels {
 template <typename T>
 __global__ void __launch_bounds__(128) decode_kernel(DecodeLevels L, int reg_max, int nc, int dist_only,
                                                      float* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = blockIdx.y;
     if (a >= L.A) return;
@@ -369,8 +377,7 @@ extern "C" int mgdt_dwconv7_ln(const void* x, int x_cs, const void* w, const flo
         return 0;
     }
     MGDT_DTYPE_SWITCH(dtype, T, {
-        dwconv7_ln_kernel<T><<<cdiv(npix, DW_WARPS), DW_WARPS * 32, 0, s>>>(
-            (const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps, (T*)y, y_cs, H, W, C, npix);
+        launch_k(dwconv7_ln_kernel<T>, dim3(cdiv(npix, DW_WARPS)), dim3(DW_WARPS * 32), 0, s, (const T*)x, x_cs, (const T*)w, bias, ln_w, ln_b, eps, (T*)y, y_cs, H, W, C, npix);
     });
     MGDT_LAUNCH_CHECK("dwconv7_ln");
     return 0;
@@ -403,7 +410,7 @@ extern "C" int mgdt_dcn3x3(const void* x, int x_cs, const void* offset, int off_
             cudaError_t e = cudaFuncSetAttribute(dcn3x3_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return set_error(-EIO, "dcn3x3: smem attr: %s", cudaGetErrorString(e));
         }
-        dcn3x3_kernel<T><<<cdiv(npix, DCN_PIX), DCN_THREADS, smem, s>>>((const T*)x, x_cs, (const T*)offset, off_cs,
+        launch_k(dcn3x3_kernel<T>, dim3(cdiv(npix, DCN_PIX)), dim3(DCN_THREADS), smem, s, (const T*)x, x_cs, (const T*)offset, off_cs,
                                                                         (const T*)mask, mask_cs, mask_is_logit,
                                                                         (const T*)w, (T*)y, y_cs, H, W, Cin, Cout, npix);
     });
@@ -432,7 +439,7 @@ extern "C" int mgdt_decode(const mgdt_decode_level* levels, int nl, int N, int r
     }
     L.A = a0;
     MGDT_DTYPE_SWITCH(dtype, T, {
-        decode_kernel<T><<<dim3(cdiv(L.A, 128), N), 128, 0, (cudaStream_t)stream>>>(L, reg_max, nc, dist_only, y);
+        launch_k(decode_kernel<T>, dim3(dim3(cdiv(L.A, 128), N)), dim3(128), 0, (cudaStream_t)stream, L, reg_max, nc, dist_only, y);
     });
     MGDT_LAUNCH_CHECK("decode");
     return 0;

@@ -1,10 +1,21 @@
 // C-ABI glue: error strings, version, conv dispatch between the CUDA-core and tcgen05 paths.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace mgdt {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+int g_pdl = -1;
+
+int pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("MGDT_PDL");
+        g_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_pdl;
+}
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;

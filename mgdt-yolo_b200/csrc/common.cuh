@@ -31,6 +31,30 @@ extern unsigned long long g_launches;  // kernels enqueued by this library (see 
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL): every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may be scheduled while the previous kernel of the
+// stream is still draining.  Contract: a kernel calls pdl_trigger() first (lets ITS successor be scheduled early)
+// and pdl_wait() before it reads or writes any global memory another kernel may touch; pdl_wait() returns once every
+// prerequisite grid has completed and its writes are visible.  MGDT_PDL=0 in the environment launches plainly.
+extern int g_pdl;  // -1 unread, 0 off, 1 on
+int pdl_enabled();
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- storage-type helpers: T is float or __nv_bfloat16, arithmetic is always fp32
 template <typename T> __device__ __forceinline__ float ldf(const T* p);
 template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }

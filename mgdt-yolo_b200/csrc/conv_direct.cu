@@ -24,6 +24,8 @@ constexpr int NTHREADS = 256;
 
 template <typename T, int BN>
 __global__ void __launch_bounds__(NTHREADS) conv_direct_kernel(ConvP p) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NT_N = BN / 4;          // threads along N
     constexpr int NT_M = NTHREADS / NT_N; // threads along M
     constexpr int BM = NT_M * 4;
@@ -132,7 +134,7 @@ template <typename T, int BN>
 static int launch(const ConvP& p, cudaStream_t s) {
     constexpr int BM = (NTHREADS / (BN / 4)) * 4;
     dim3 grid(cdiv(p.M, BM), cdiv(p.Cout, BN));
-    conv_direct_kernel<T, BN><<<grid, NTHREADS, 0, s>>>(p);
+    launch_k(conv_direct_kernel<T, BN>, dim3(grid), dim3(NTHREADS), 0, s, p);
     MGDT_LAUNCH_CHECK("conv_direct");
     return 0;
 }

@@ -191,6 +191,8 @@ template <> __device__ __forceinline__ __half cvt_w<__nv_bfloat16, __half>(__nv_
 
 template <typename S, typename D>
 __global__ void umma2_pack_kernel(const S* __restrict__ w, D* __restrict__ out, Plan2 p, int Cin, int Cout, int k) {
+    pdl_trigger();
+    pdl_wait();
     const int cps = p.nmma_s * 2;
     const long long total = (long long)p.nsplit * p.nks * cps * p.Nc * 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -594,6 +596,7 @@ __device__ __forceinline__ void epi_math(const P2& p, const uint32_t* r, const f
 
 template <int MODE, int LOADER, int SPLIT>
 __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_constant__ P2 p) {
+    pdl_trigger();
     extern __shared__ __align__(128) unsigned char smem[];
     const Plan2& pl = p.pl;
     const Run2& rn = p.rn;
@@ -658,6 +661,9 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     if (tid == 0) trace_mark(p, 1);
+    // Everything above touched only shared memory, TMEM and this layer's constant parameters.  The activations may
+    // still be being written by the previous kernel of the stream: each role calls pdl_wait() before its first access
+    // to them (the producers after they have started the copy of the resident weights).
 
     const uint32_t tiles = (uint32_t)rn.tiles;
     const int nks = pl.nks;
@@ -674,6 +680,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             cp_async_arrive_noinc(WREADY);
             if (tid == 0) trace_mark(p, 2);
         }
+        pdl_wait();
         const uint32_t chunks = (uint32_t)(pl.PS * pl.npar * rn.P);
         // (the in-place transform revisits chunks through the generic mapping, which matches the fast path's except for
         // the stride-2 parity loop)
@@ -1002,6 +1009,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         // TMEM lane quadrant = warp % 4; the NEW/4 warps of a quadrant take the (row block, 32-column) units round
         // robin.  A unit is read from TMEM one output row per lane, converted, transposed through a swizzled 2 KB
         // shared-memory tile and written out with 8 rows x 64 contiguous bytes per store instruction.
+        pdl_wait();
         const int ew = warp - EPI0;
         const int quad = warp & 3, sub = ew >> 2;
         constexpr int NSUB = NEW / 4;
@@ -1146,7 +1154,7 @@ template <int MODE, int LOADER, int SPLIT>
 static int launch2t(const P2& p, dim3 grid, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<MODE, LOADER, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_MAX_SMEM);
     if (e != cudaSuccess) return set_error(-EIO, "conv_umma2: smem attr: %s", cudaGetErrorString(e));
-    conv_umma2_kernel<MODE, LOADER, SPLIT><<<grid, U2_THREADS, p.rn.smem_total, s>>>(p);
+    launch_k(conv_umma2_kernel<MODE, LOADER, SPLIT>, dim3(grid), dim3(U2_THREADS), p.rn.smem_total, s, p);
     MGDT_LAUNCH_CHECK("conv_umma2");
     return 0;
 }
@@ -1311,13 +1319,13 @@ extern "C" int mgdt_conv_umma_pack(const void* w_ohwi, int w_dtype, int Cin, int
     cudaStream_t s = (cudaStream_t)stream;
     const int g = cdiv(total, 256);
     if (w_dtype == MGDT_F32 && out_f16)
-        umma2_pack_kernel<float, __half><<<g, 256, 0, s>>>((const float*)w_ohwi, (__half*)packed, pl, Cin, Cout, k);
+        launch_k(umma2_pack_kernel<float, __half>, dim3(g), dim3(256), 0, s, (const float*)w_ohwi, (__half*)packed, pl, Cin, Cout, k);
     else if (w_dtype == MGDT_F32)
-        umma2_pack_kernel<float, __nv_bfloat16><<<g, 256, 0, s>>>((const float*)w_ohwi, (__nv_bfloat16*)packed, pl, Cin, Cout, k);
+        launch_k(umma2_pack_kernel<float, __nv_bfloat16>, dim3(g), dim3(256), 0, s, (const float*)w_ohwi, (__nv_bfloat16*)packed, pl, Cin, Cout, k);
     else if (out_f16)
-        umma2_pack_kernel<__nv_bfloat16, __half><<<g, 256, 0, s>>>((const __nv_bfloat16*)w_ohwi, (__half*)packed, pl, Cin, Cout, k);
+        launch_k(umma2_pack_kernel<__nv_bfloat16, __half>, dim3(g), dim3(256), 0, s, (const __nv_bfloat16*)w_ohwi, (__half*)packed, pl, Cin, Cout, k);
     else
-        umma2_pack_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)w_ohwi, (__nv_bfloat16*)packed, pl, Cin, Cout, k);
+        launch_k(umma2_pack_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(g), dim3(256), 0, s, (const __nv_bfloat16*)w_ohwi, (__nv_bfloat16*)packed, pl, Cin, Cout, k);
     MGDT_LAUNCH_CHECK("umma_pack");
     return 0;
 }

@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(EW_THREADS) affine_act_kernel(const T* __restr
                                                                 const T* __restrict__ other, int o_cs, int act,
                                                                 T* __restrict__ y, int y_cs, unsigned HW, unsigned C,
                                                                 unsigned total) {
+    pdl_trigger();
+    pdl_wait();
     const unsigned CV = C / V;
     for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
         const unsigned cv = i % CV, pix = i / CV;
@@ -103,6 +105,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(EW_THREADS) resample_kernel(const T* __restrict__ x, int x_cs, int Hi, int Wi,
                                                               T* __restrict__ y, int y_cs, int Ho, int Wo, unsigned C,
                                                               int mode, unsigned total) {
+    pdl_trigger();
+    pdl_wait();
     const unsigned CV = C / V;
     for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
         const unsigned cv = i % CV, pix = i / CV;
@@ -160,6 +164,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(EW_THREADS) sppf_pool_kernel(const T* __restrict__ x, int x_cs, T* __restrict__ y1,
                                                                T* __restrict__ y2, T* __restrict__ y3, int y_cs, int H,
                                                                int W, unsigned C, int r, unsigned total) {
+    pdl_trigger();
+    pdl_wait();
     const unsigned CV = C / V;
     for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
         const unsigned cv = i % CV, pix = i / CV;
@@ -215,6 +221,8 @@ __global__ void __launch_bounds__(EW_THREADS) sppf_pool_tile(const __nv_bfloat16
                                                              __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2,
                                                              __nv_bfloat16* __restrict__ y3, int y_cs, int H, int W, int C8,
                                                              int r) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ uint4 sp_buf[];
     const int HW = H * W;
     uint4* A = sp_buf;
@@ -257,6 +265,8 @@ __global__ void __launch_bounds__(EW_THREADS) inject_kernel(const T* __restrict_
                                                             const T* __restrict__ gfeat, int f_cs, T* __restrict__ y,
                                                             int y_cs, int H, int W, int Hg, int Wg, unsigned C,
                                                             unsigned total) {
+    pdl_trigger();
+    pdl_wait();
     const bool pool = H < Hg;
     const unsigned CV = C / V;
     for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
@@ -316,6 +326,8 @@ __global__ void __launch_bounds__(EW_THREADS) inject_kernel(const T* __restrict_
 template <typename S, typename T>
 __global__ void __launch_bounds__(EW_THREADS) preprocess_kernel(const S* __restrict__ src, T* __restrict__ y, int y_cs,
                                                                 int C, unsigned HW, float div, unsigned npix) {
+    pdl_trigger();
+    pdl_wait();
     // thread <-> pixel: per-plane reads are contiguous across the warp; the C outputs of a pixel are
     // adjacent, so the warp's stores cover one contiguous span.
     for (unsigned pix = blockIdx.x * EW_THREADS + threadIdx.x; pix < npix; pix += gridDim.x * EW_THREADS) {
@@ -351,8 +363,7 @@ extern "C" int mgdt_affine_act(const void* x, int x_cs, const float* a, const fl
                          aligned8(other, other ? o_cs : 0, sizeof(T));
         MGDT_VEC_SWITCH(vec, V, {
             const unsigned total = (unsigned)((long long)N * H * W * (C / V));
-            affine_act_kernel<T, V><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
-                (const T*)x, x_cs, a, b, (const T*)other, o_cs, act, (T*)y, y_cs, (unsigned)(H * W), (unsigned)C, total);
+            launch_k(affine_act_kernel<T, V>, dim3(ew_grid(total)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, a, b, (const T*)other, o_cs, act, (T*)y, y_cs, (unsigned)(H * W), (unsigned)C, total);
         });
     });
     MGDT_LAUNCH_CHECK("affine_act");
@@ -371,8 +382,7 @@ extern "C" int mgdt_resample(const void* x, int x_cs, int Hi, int Wi, void* y, i
         const bool vec = C % 8 == 0 && aligned8(x, x_cs, sizeof(T)) && aligned8(y, y_cs, sizeof(T));
         MGDT_VEC_SWITCH(vec, V, {
             const unsigned total = (unsigned)((long long)N * Ho * Wo * (C / V));
-            resample_kernel<T, V><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
-                (const T*)x, x_cs, Hi, Wi, (T*)y, y_cs, Ho, Wo, (unsigned)C, mode, total);
+            launch_k(resample_kernel<T, V>, dim3(ew_grid(total)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, Hi, Wi, (T*)y, y_cs, Ho, Wo, (unsigned)C, mode, total);
         });
     });
     MGDT_LAUNCH_CHECK("resample");
@@ -389,8 +399,7 @@ extern "C" int mgdt_sppf_pool(const void* x, int x_cs, void* y1, void* y2, void*
         const size_t smem = (size_t)H * W * 32;
         cudaError_t e = cudaFuncSetAttribute(sppf_pool_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(-EIO, "sppf_pool: smem attr: %s", cudaGetErrorString(e));
-        sppf_pool_tile<<<N * (C / 8), EW_THREADS, smem, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, x_cs, (__nv_bfloat16*)y1, (__nv_bfloat16*)y2, (__nv_bfloat16*)y3, y_cs, H, W, C / 8, k / 2);
+        launch_k(sppf_pool_tile, dim3(N * (C / 8)), dim3(EW_THREADS), smem, (cudaStream_t)stream, (const __nv_bfloat16*)x, x_cs, (__nv_bfloat16*)y1, (__nv_bfloat16*)y2, (__nv_bfloat16*)y3, y_cs, H, W, C / 8, k / 2);
         MGDT_LAUNCH_CHECK("sppf_pool_tile");
         return 0;
     }
@@ -399,8 +408,7 @@ extern "C" int mgdt_sppf_pool(const void* x, int x_cs, void* y1, void* y2, void*
                          aligned8(y2, y_cs, sizeof(T)) && aligned8(y3, y_cs, sizeof(T));
         MGDT_VEC_SWITCH(vec, V, {
             const unsigned total = (unsigned)((long long)N * H * W * (C / V));
-            sppf_pool_kernel<T, V><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
-                (const T*)x, x_cs, (T*)y1, (T*)y2, (T*)y3, y_cs, H, W, (unsigned)C, k / 2, total);
+            launch_k(sppf_pool_kernel<T, V>, dim3(ew_grid(total)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, (T*)y1, (T*)y2, (T*)y3, y_cs, H, W, (unsigned)C, k / 2, total);
         });
     });
     MGDT_LAUNCH_CHECK("sppf_pool");
@@ -418,8 +426,7 @@ extern "C" int mgdt_inject(const void* local, int l_cs, const void* gact, int a_
                          aligned8(gfeat, f_cs, sizeof(T)) && aligned8(y, y_cs, sizeof(T));
         MGDT_VEC_SWITCH(vec, V, {
             const unsigned total = (unsigned)((long long)N * H * W * (C / V));
-            inject_kernel<T, V><<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
-                (const T*)local, l_cs, (const T*)gact, a_cs, (const T*)gfeat, f_cs, (T*)y, y_cs, H, W, Hg, Wg,
+            launch_k(inject_kernel<T, V>, dim3(ew_grid(total)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)local, l_cs, (const T*)gact, a_cs, (const T*)gfeat, f_cs, (T*)y, y_cs, H, W, Hg, Wg,
                 (unsigned)C, total);
         });
     });
@@ -436,10 +443,10 @@ extern "C" int mgdt_preprocess(const void* src, int src_is_u8, void* y, int y_cs
     cudaStream_t s = (cudaStream_t)stream;
     MGDT_DTYPE_SWITCH(dtype, T, {
         if (src_is_u8)
-            preprocess_kernel<uint8_t, T><<<ew_grid(npix), EW_THREADS, 0, s>>>((const uint8_t*)src, (T*)y, y_cs, C, HW,
+            launch_k(preprocess_kernel<uint8_t, T>, dim3(ew_grid(npix)), dim3(EW_THREADS), 0, s, (const uint8_t*)src, (T*)y, y_cs, C, HW,
                                                                                255.0f, npix);
         else
-            preprocess_kernel<float, T><<<ew_grid(npix), EW_THREADS, 0, s>>>((const float*)src, (T*)y, y_cs, C, HW,
+            launch_k(preprocess_kernel<float, T>, dim3(ew_grid(npix)), dim3(EW_THREADS), 0, s, (const float*)src, (T*)y, y_cs, C, HW,
                                                                              1.0f, npix);
     });
     MGDT_LAUNCH_CHECK("preprocess");

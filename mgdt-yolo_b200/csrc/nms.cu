@@ -70,6 +70,8 @@ __device__ __forceinline__ int anchor_candidates(const NmsP& p, int n, int a, un
 }
 
 __global__ void __launch_bounds__(NMS_T) nms_count(NmsP p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ int wsum[NMS_T / 32];
     const int n = blockIdx.y, a = blockIdx.x * NMS_T + threadIdx.x;
     int c = (a < p.A) ? anchor_candidates(p, n, a, nullptr) : 0;
@@ -84,6 +86,8 @@ __global__ void __launch_bounds__(NMS_T) nms_count(NmsP p) {
 }
 
 __global__ void __launch_bounds__(NMS_T) nms_compact(NmsP p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ int wpre[NMS_T / 32];
     __shared__ int base_s;
     const int n = blockIdx.y, a = blockIdx.x * NMS_T + threadIdx.x;
@@ -111,6 +115,8 @@ __global__ void __launch_bounds__(NMS_T) nms_compact(NmsP p) {
 }
 
 __global__ void __launch_bounds__(NMS_T) nms_rank(NmsP p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ unsigned long long tile[1024];
     const int n = blockIdx.y;
     const int nc_ = p.ncand[n];
@@ -141,6 +147,8 @@ __device__ __forceinline__ bool iou_gt(const Box& a, float area_a, const Box& b,
 }
 
 __global__ void __launch_bounds__(NMS_CHUNK) nms_scan(NmsP p, float* __restrict__ out, int32_t* __restrict__ counts) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smraw[];
     // kept boxes (offset coords) + areas, chunk boxes, chunk masks
     Box* kbox = (Box*)smraw;                                  // [max_det]
@@ -297,11 +305,11 @@ extern "C" int mgdt_nms(const float* pred, int N, int nc, int A, float conf_thre
     p.blockcnt = (int*)(base + L.blockcnt); p.ncand = (int*)(base + L.ncand);
     p.keys = (unsigned long long*)(base + L.keys); p.sorted = (unsigned long long*)(base + L.sorted);
     cudaStream_t s = (cudaStream_t)stream;
-    nms_count<<<dim3(L.nchunks, N), NMS_T, 0, s>>>(p);
+    launch_k(nms_count, dim3(dim3(L.nchunks, N)), dim3(NMS_T), 0, s, p);
     MGDT_LAUNCH_CHECK("nms_count");
-    nms_compact<<<dim3(L.nchunks, N), NMS_T, 0, s>>>(p);
+    launch_k(nms_compact, dim3(dim3(L.nchunks, N)), dim3(NMS_T), 0, s, p);
     MGDT_LAUNCH_CHECK("nms_compact");
-    nms_rank<<<dim3(cdiv(L.cap, NMS_T), N), NMS_T, 0, s>>>(p);
+    launch_k(nms_rank, dim3(dim3(cdiv(L.cap, NMS_T), N)), dim3(NMS_T), 0, s, p);
     MGDT_LAUNCH_CHECK("nms_rank");
     const size_t smem = (sizeof(Box) + sizeof(float)) * (size_t)(max_det + NMS_CHUNK) +
                         sizeof(unsigned) * (size_t)(NMS_CHUNK * NMS_WORDS + NMS_WORDS);
@@ -309,7 +317,7 @@ extern "C" int mgdt_nms(const float* pred, int N, int nc, int A, float conf_thre
         cudaError_t e = cudaFuncSetAttribute(nms_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(-EIO, "nms: smem attr: %s", cudaGetErrorString(e));
     }
-    nms_scan<<<N, NMS_CHUNK, smem, s>>>(p, out, counts);
+    launch_k(nms_scan, dim3(N), dim3(NMS_CHUNK), smem, s, p, out, counts);
     MGDT_LAUNCH_CHECK("nms_scan");
     return 0;
 }

@@ -32,6 +32,8 @@ template <typename T, int V, int Q>
 __global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __restrict__ x, int x_cs, int H, int W, int C,
                                                                  int pix_per_chunk, float* __restrict__ part,
                                                                  float* __restrict__ partsq) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sm[CS_THREADS * V];  // [PG][Cw * V]
     const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
     const int CV = C / V;
@@ -120,6 +122,8 @@ __global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __rest
 
 __global__ void chan_stats_final(const float* __restrict__ part, const float* __restrict__ partsq, int nchunks, int Q,
                                  int C, float* __restrict__ out_sum, float* __restrict__ out_sumsq, int N) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)N * Q * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total + (long long)N * C;
          i += (long long)gridDim.x * blockDim.x) {
@@ -174,14 +178,14 @@ extern "C" int mgdt_chan_stats(const void* x, int x_cs, int N, int H, int W, int
     MGDT_DTYPE_SWITCH(dtype, T, {
         const bool vec = C % 8 == 0 && (x_cs % 8) == 0 && (((uintptr_t)x) % (8 * sizeof(T))) == 0;
         float* psq = out_sumsq ? partsq : nullptr;
-        if (vec && quads) chan_stats_partial<T, 8, 5><<<dim3(nch, N), CS_THREADS, 0, s>>>((const T*)x, x_cs, H, W, C, ppc, part, psq);
-        else if (vec) chan_stats_partial<T, 8, 1><<<dim3(nch, N), CS_THREADS, 0, s>>>((const T*)x, x_cs, H, W, C, ppc, part, psq);
-        else if (quads) chan_stats_partial<T, 1, 5><<<dim3(nch, N), CS_THREADS, 0, s>>>((const T*)x, x_cs, H, W, C, ppc, part, psq);
-        else chan_stats_partial<T, 1, 1><<<dim3(nch, N), CS_THREADS, 0, s>>>((const T*)x, x_cs, H, W, C, ppc, part, psq);
+        if (vec && quads) launch_k(chan_stats_partial<T, 8, 5>, dim3(dim3(nch, N)), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, ppc, part, psq);
+        else if (vec) launch_k(chan_stats_partial<T, 8, 1>, dim3(dim3(nch, N)), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, ppc, part, psq);
+        else if (quads) launch_k(chan_stats_partial<T, 1, 5>, dim3(dim3(nch, N)), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, ppc, part, psq);
+        else launch_k(chan_stats_partial<T, 1, 1>, dim3(dim3(nch, N)), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, ppc, part, psq);
     });
     MGDT_LAUNCH_CHECK("chan_stats_partial");
     const long long total = (long long)N * (Q + 1) * C;
-    chan_stats_final<<<cdiv(total, 256), 256, 0, s>>>(part, partsq, nch, Q, C, out_sum, out_sumsq, N);
+    launch_k(chan_stats_final, dim3(cdiv(total, 256)), dim3(256), 0, s, part, partsq, nch, Q, C, out_sum, out_sumsq, N);
     MGDT_LAUNCH_CHECK("chan_stats_final");
     return 0;
 }
@@ -193,6 +197,8 @@ __global__ void mspa_gate_kernel(const float* __restrict__ stats, int H, int W, 
                                  const float* __restrict__ w1, const float* __restrict__ b1,
                                  const float* __restrict__ w2, const float* __restrict__ b2, int hidden,
                                  float* __restrict__ scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];  // feat[G][5*ow] | hid[G][hidden] | gate[G][ow]
     const int n = blockIdx.x;
     const int ow = C / G;
@@ -241,6 +247,8 @@ __global__ void mspa_gate_kernel(const float* __restrict__ stats, int H, int W, 
 
 __global__ void grn_scale_kernel(const float* __restrict__ sumsq, const float* __restrict__ gamma, int C,
                                  float* __restrict__ scale) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[32];
     const int n = blockIdx.x;
     float part = 0.f;
@@ -258,6 +266,8 @@ __global__ void grn_scale_kernel(const float* __restrict__ sumsq, const float* _
 __global__ void gn_affine_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, int C, int groups,
                                  int hw, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float* __restrict__ a, float* __restrict__ b) {
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.x;
     const int cpg = C / groups;
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
@@ -284,6 +294,8 @@ __global__ void td_attn_kernel(const float* __restrict__ sum, int N, int C, int 
                                const float* __restrict__ w1, const float* __restrict__ b1,
                                const float* __restrict__ w2, const float* __restrict__ b2,
                                float* __restrict__ in_scale) {
+    pdl_trigger();
+    pdl_wait();
     // grid (N, ndec): blockIdx.y selects the decomposition (0 = cls, 1 = reg); weights are packed per
     // decomposition back to back.
     extern __shared__ float sm[];  // mean[C] | hid[hidden] | att[stacked]
@@ -324,7 +336,7 @@ extern "C" int mgdt_mspa_gate(const float* stats, int N, int H, int W, int C, in
     const int ow = C / groups;
     const size_t smem = sizeof(float) * (size_t)groups * (5 * ow + hidden + ow);
     MGDT_CHECK(smem <= 48 * 1024, "mspa_gate: C=%d too large", C);
-    mspa_gate_kernel<<<N, 128, smem, (cudaStream_t)stream>>>(stats, H, W, C, groups, softmax, fc1_w, fc1_b, fc2_w, fc2_b,
+    launch_k(mspa_gate_kernel, dim3(N), dim3(128), smem, (cudaStream_t)stream, stats, H, W, C, groups, softmax, fc1_w, fc1_b, fc2_w, fc2_b,
                                                              hidden, scale);
     MGDT_LAUNCH_CHECK("mspa_gate");
     return 0;
@@ -332,7 +344,7 @@ extern "C" int mgdt_mspa_gate(const float* stats, int N, int H, int W, int C, in
 
 extern "C" int mgdt_grn_scale(const float* sumsq, const float* gamma, int N, int C, float* scale, void* stream) {
     MGDT_CHECK(sumsq && gamma && scale && N > 0 && C > 0, "grn_scale: bad args");
-    grn_scale_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(sumsq, gamma, C, scale);
+    launch_k(grn_scale_kernel, dim3(N), dim3(128), 0, (cudaStream_t)stream, sumsq, gamma, C, scale);
     MGDT_LAUNCH_CHECK("grn_scale");
     return 0;
 }
@@ -341,7 +353,7 @@ extern "C" int mgdt_gn_affine(const float* sum, const float* sumsq, int N, int C
                               const float* gamma, const float* beta, float* a, float* b, void* stream) {
     MGDT_CHECK(sum && sumsq && gamma && beta && a && b, "gn_affine: null pointer");
     MGDT_CHECK(N > 0 && groups > 0 && C % groups == 0 && hw > 0, "gn_affine: bad shape");
-    gn_affine_kernel<<<N, 32, 0, (cudaStream_t)stream>>>(sum, sumsq, C, groups, hw, eps, gamma, beta, a, b);
+    launch_k(gn_affine_kernel, dim3(N), dim3(32), 0, (cudaStream_t)stream, sum, sumsq, C, groups, hw, eps, gamma, beta, a, b);
     MGDT_LAUNCH_CHECK("gn_affine");
     return 0;
 }
@@ -352,7 +364,7 @@ extern "C" int mgdt_td_attn(const float* sum, int N, int C, int hw, int hidden, 
     MGDT_CHECK(sum && la1_w && la1_b && la2_w && la2_b && in_scale, "td_attn: null pointer");
     MGDT_CHECK(N > 0 && C > 0 && stacked > 0 && C % stacked == 0 && hidden > 0 && ndec > 0, "td_attn: bad shape");
     const size_t smem = sizeof(float) * (C + hidden + stacked);
-    td_attn_kernel<<<dim3(N, ndec), 64, smem, (cudaStream_t)stream>>>(sum, N, C, hw, hidden, stacked, la1_w, la1_b, la2_w,
+    launch_k(td_attn_kernel, dim3(dim3(N, ndec)), dim3(64), smem, (cudaStream_t)stream, sum, N, C, hw, hidden, stacked, la1_w, la1_b, la2_w,
                                                                    la2_b, in_scale);
     MGDT_LAUNCH_CHECK("td_attn");
     return 0;
