@@ -49,6 +49,9 @@ unsigned long long mgdt_launch_count(void);
 void mgdt_debug_set_trace(void* buf);
 /* Compiled-in facts for tests: returns 1 if the tcgen05/TMA conv path was built. */
 int mgdt_has_umma(void);
+/* Programmatic dependent launch (every kernel is launched with the programmatic-stream-serialization attribute and
+ * orders itself with griddepcontrol.wait): 1 = on (default, or MGDT_PDL in the environment), 0 = plain launches. */
+void mgdt_set_pdl(int on);
 
 /* ---------------------------------------------------------------- convolution
  * Replaces Conv.forward/forward_fuse (nn/modules/conv.py:36-42) with BatchNorm folded
@@ -82,6 +85,9 @@ typedef struct mgdt_conv_args {
     int32_t w_umma_f16;    /* 1 if w_umma was packed as fp16 (B operand F16, A stays bf16): 8x finer weight rounding */
 } mgdt_conv_args;
 int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
+/* Which kernel mgdt_conv2d would run for these arguments: 2 = conv_umma2_kernel (tcgen05), 1 = conv_direct_kernel
+ * (CUDA cores).  Used by the bench to attribute launches to kernels. */
+int mgdt_conv2d_path(const mgdt_conv_args* a);
 
 /* tcgen05 path: K-major shared-memory image of the weights, [col split][16-byte K chunk][Nc][8].
  * mgdt_conv_umma_packed_bytes returns 0 when (Cin, Cout, k, stride) is not taken by that path

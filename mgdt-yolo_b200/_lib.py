@@ -40,6 +40,8 @@ SIGNATURES = {
     "mgdt_launch_count": (C.c_ulonglong, []),
     "mgdt_has_umma": (C.c_int, []),
     "mgdt_debug_set_trace": (None, [vp]),
+    "mgdt_set_pdl": (None, [i32]),
+    "mgdt_conv2d_path": (C.c_int, [C.POINTER(ConvArgs)]),
     "mgdt_conv2d": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "mgdt_conv_umma_packed_bytes": (sz, [i32, i32, i32, i32]),
     "mgdt_conv_umma_pack": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),

@@ -38,6 +38,13 @@ using namespace mgdt;
 extern "C" int mgdt_abi_version(void) { return MGDT_ABI_VERSION; }
 extern "C" const char* mgdt_last_error(void) { return g_err; }
 extern "C" unsigned long long mgdt_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+extern "C" void mgdt_set_pdl(int on) { g_pdl = on ? 1 : 0; }
+extern "C" int mgdt_conv2d_path(const mgdt_conv_args* a) {
+#ifdef MGDT_WITH_UMMA
+    if (a && a->impl != 1 && conv2d_umma_supported(a)) return 2;
+#endif
+    return 1;
+}
 extern "C" int mgdt_has_umma(void) {
 #ifdef MGDT_WITH_UMMA
     return 1;

@@ -203,6 +203,8 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
                 bytes=es * (n * h * wd * cin * (2 if pre_add is not None else 1)
                             + n * ho * wo * cout * (2 if residual is not None else 1) + cout * cin * k * k)
                 + (n * h * wd * es if pix_scale is not None else 0))
+    if PROFILE is not None:  # attribute the launch to the kernel the library will actually run
+        meta["kernel"] = "conv_umma2_kernel" if lib().mgdt_conv2d_path(C.byref(a)) == 2 else "conv_direct_kernel"
     _invoke("mgdt_conv2d", meta, C.byref(a), stream_ptr())
     return out
 
@@ -220,7 +222,7 @@ def stem_conv(src, w: "PackedConv", bias, cout, act, out=None):
     if (yn, yc, yh, yw) != (n, cout, ho, wo):
         raise ValueError("stem_conv: bad output shape")
     meta = dict(shape=f"stem {c}->{cout} k3s2 {n}x{h}x{wd}", flops=2.0 * n * ho * wo * cout * c * 9,
-                bytes=_nb(src, out))
+                bytes=_nb(src, out), kernel="conv_umma2_kernel")
     _invoke("mgdt_stem_conv", meta, src.data_ptr(), 1 if src.dtype == torch.uint8 else 0, w.umma.data_ptr(),
             1 if w.f16 else 0, _p(bias),
             yp, ycs, n, c, h, wd, cout, ACTS[act], BF16, stream_ptr())
@@ -248,7 +250,8 @@ def dcn3x3(x, offset, mask, w, cout, mask_is_logit, out=None):
     if out is None:
         out = new_act(n, cout, h, wd, x.dtype, x.device)
     yp, *_, ycs = view(out)
-    _invoke("mgdt_dcn3x3", dict(shape=f"dcn {cin}->{cout} {n}x{h}x{wd}", bytes=_nb(x, offset, mask, out), flops=2.0 * 9 * cin * cout * n * h * wd), xp, xcs, op, ocs, mp, mcs, 1 if mask_is_logit else 0, w.data_ptr(),
+    _invoke("mgdt_dcn3x3", dict(shape=f"dcn {cin}->{cout} {n}x{h}x{wd}", bytes=_nb(x, offset, mask, out), flops=2.0 * 9 * cin * cout * n * h * wd,
+                                kernel="conv_umma2_kernel" if (getattr(w, "umma", None) is not None and x.dtype == torch.bfloat16) else "dcn3x3_kernel"), xp, xcs, op, ocs, mp, mcs, 1 if mask_is_logit else 0, w.data_ptr(),
             None if getattr(w, "umma", None) is None else w.umma.data_ptr(), 1 if getattr(w, "f16", False) else 0,
             yp, ycs, n, h, wd,
                             cin, cout, dtype_code(x.dtype), stream_ptr())
