@@ -201,6 +201,21 @@ int mgdt_nms(const float* pred, int N, int nc, int A, float conf_thres, float io
              int max_det, int max_nms, float max_wh, const int32_t* classes, int n_classes, float* out,
              int32_t* counts, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- pre / post-processing
+ * LetterBox (yolo/data/augment.py:538-593: cv2.resize INTER_LINEAR to (new_h, new_w), constant border) fused with the
+ * BGR->RGB / HWC->CHW of BasePredictor.preprocess (yolo/engine/predictor.py:121-125).  src is one HWC uint8 image with
+ * 3 channels and `pitch` bytes per row; dst is one (3, H, W) image slot of the NCHW batch (or an (H, W, 3) image when
+ * out_hwc).  The geometry (new size, top / left border) is computed by the caller exactly as LetterBox does.
+ * Bit-exact with OpenCV's fixed-point uint8 bilinear resize. */
+int mgdt_letterbox_u8(const void* src, int h0, int w0, int pitch, void* dst, int H, int W, int new_h, int new_w, int top,
+                      int left, int swap_rb, int pad_value, int out_hwc, void* stream);
+
+/* ops.scale_boxes + clip_boxes (yolo/utils/ops.py:90-117, 269-285) in place on packed detections
+ * dets[N][max_rows][row_stride] (xyxy first); counts[N] rows are valid per image (NULL = all max_rows);
+ * params[N][5] = gain, pad_w, pad_h, h0, w0 as the reference computes them. */
+int mgdt_scale_boxes(float* dets, int row_stride, const int32_t* counts, int N, int max_rows, const float* params,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,8 @@ SIGNATURES = {
     "mgdt_has_umma": (C.c_int, []),
     "mgdt_debug_set_trace": (None, [vp]),
     "mgdt_set_pdl": (None, [i32]),
+    "mgdt_letterbox_u8": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_scale_boxes": (C.c_int, [vp, i32, vp, i32, i32, vp, vp]),
     "mgdt_conv2d_path": (C.c_int, [C.POINTER(ConvArgs)]),
     "mgdt_conv2d": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "mgdt_conv_umma_packed_bytes": (sz, [i32, i32, i32, i32]),

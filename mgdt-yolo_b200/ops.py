@@ -416,3 +416,34 @@ def nms_packed(pred, conf_thres, iou_thres, multi_label=False, agnostic=False, m
                          0 if cls_t is None else cls_t.numel(), out.data_ptr(), counts.data_ptr(), ws.data_ptr(),
                          ws.numel(), stream_ptr())
     return out, counts
+
+
+# ------------------------------------------------------------------------------------- pre / post-processing
+def letterbox_u8(src, dst, new_hw, top_left, swap_rb=True, pad_value=114, out_hwc=False):
+    """One HWC uint8 image (CUDA, 3 channels, contiguous rows) -> `dst`: a (3, H, W) slot of an NCHW uint8 batch
+    (or an (H, W, 3) image when out_hwc), resized to new_hw at offset top_left, the rest filled with pad_value."""
+    require_cuda(src, "image")
+    if src.dtype != torch.uint8 or src.dim() != 3 or src.shape[2] != 3 or src.stride(2) != 1 or src.stride(1) != 3:
+        raise ValueError("letterbox_u8: expects an (h, w, 3) uint8 image with contiguous pixels")
+    if dst.dtype != torch.uint8 or not dst.is_contiguous():
+        raise ValueError("letterbox_u8: dst must be a contiguous uint8 tensor")
+    h0, w0 = int(src.shape[0]), int(src.shape[1])
+    H, W = (int(dst.shape[0]), int(dst.shape[1])) if out_hwc else (int(dst.shape[1]), int(dst.shape[2]))
+    _invoke("mgdt_letterbox_u8", dict(shape=f"letterbox {h0}x{w0}->{H}x{W}", bytes=_nb(src, dst), flops=0.0), src.data_ptr(),
+            h0, w0, int(src.stride(0)), dst.data_ptr(), H, W, int(new_hw[0]), int(new_hw[1]), int(top_left[0]),
+            int(top_left[1]), 1 if swap_rb else 0, int(pad_value), 1 if out_hwc else 0, stream_ptr())
+    return dst
+
+
+def scale_boxes_packed(dets, counts, params):
+    """In place: dets (N, max_rows, >=4) fp32 xyxy..., counts (N,) int32 or None, params (N, 5) fp32
+    [gain, pad_w, pad_h, h0, w0] -> boxes mapped back to the original images and clipped."""
+    require_cuda(dets, "detections")
+    if dets.dtype != torch.float32 or not dets.is_contiguous() or dets.dim() != 3:
+        raise ValueError("scale_boxes_packed: dets must be a contiguous fp32 (N, rows, >=4) tensor")
+    n, rows, row = dets.shape
+    if rows == 0:
+        return dets
+    _invoke("mgdt_scale_boxes", dict(shape=f"scale_boxes N{n}", bytes=_nb(dets), flops=0.0), dets.data_ptr(), row, _p(counts),
+            n, rows, params.data_ptr(), stream_ptr())
+    return dets

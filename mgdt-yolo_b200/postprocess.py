@@ -5,7 +5,7 @@ import torch
 
 from . import ops
 
-__all__ = ("non_max_suppression", "nms_packed")
+__all__ = ("non_max_suppression", "nms_packed", "scale_boxes", "clip_boxes", "scale_boxes_params")
 
 nms_packed = ops.nms_packed
 
@@ -39,3 +39,35 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
                                  max_det=max_det, max_nms=max_nms, max_wh=float(max_wh), classes=classes)
     cnt = counts.tolist()  # the single host sync of the whole call
     return [out[i, :cnt[i]] for i in range(bs)]
+
+
+def scale_boxes_params(img1_shape, img0_shape, ratio_pad=None):
+    """(gain, pad_w, pad_h, h0, w0) exactly as ops.scale_boxes derives them (yolo/utils/ops.py:104-109)."""
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad = round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1), round(
+            (img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1)
+    else:
+        gain = ratio_pad[0][0]
+        pad = ratio_pad[1]
+    return float(gain), float(pad[0]), float(pad[1]), float(img0_shape[0]), float(img0_shape[1])
+
+
+def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None):
+    """Drop-in for ops.scale_boxes (yolo/utils/ops.py:90-117): rescales (n, >=4) xyxy boxes from the letterboxed
+    image shape to the original image shape and clips them, in place, on the device (bit-exact with the reference)."""
+    if boxes.shape[0] == 0:
+        return boxes
+    if boxes.dtype != torch.float32 or not boxes.is_contiguous() or boxes.dim() != 2:
+        raise ValueError("scale_boxes: expects a contiguous fp32 (n, >=4) CUDA tensor")
+    prm = torch.tensor([scale_boxes_params(img1_shape, img0_shape, ratio_pad)], dtype=torch.float32, device=boxes.device)
+    ops.scale_boxes_packed(boxes.unsqueeze(0), None, prm)
+    return boxes
+
+
+def clip_boxes(boxes, shape):
+    """ops.clip_boxes (yolo/utils/ops.py:269-285) through the same kernel (gain 1, no padding)."""
+    if boxes.shape[0] == 0:
+        return
+    prm = torch.tensor([[1.0, 0.0, 0.0, float(shape[0]), float(shape[1])]], dtype=torch.float32, device=boxes.device)
+    ops.scale_boxes_packed(boxes.unsqueeze(0), None, prm)

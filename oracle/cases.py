@@ -48,6 +48,41 @@ NMS_CASES = [  # name, nc, anchors, batch, kwargs
 
 
 
+# pre-processing (LetterBox + BGR->RGB + HWC->CHW): name, source (h, w), new_shape, auto
+LETTERBOX_CASES = [
+    ("vga_to_384", (480, 640), (384, 384), False),
+    ("voc_auto", (375, 500), (320, 320), True),
+    ("hd_to_256", (720, 1280), (256, 256), False),
+    ("tall_upscale", (100, 37), (320, 320), False),
+    ("tiny_rect", (33, 47), (96, 160), False),
+    ("odd_auto", (641, 480), (320, 320), True),
+    ("same_size", (64, 96), (64, 96), False),
+    ("up_to_640", (120, 213), (640, 640), True),
+]
+# post-processing (scale_boxes + clip_boxes): name, img1 (letterboxed) shape, img0 (original) shape, boxes
+SCALE_CASES = [
+    ("vga", (640, 640), (480, 640), 300),
+    ("voc_auto", (480, 640), (375, 500), 57),
+    ("hd", (640, 640), (720, 1280), 300),
+    ("tall", (640, 640), (100, 37), 11),
+    ("empty", (640, 640), (480, 640), 0),
+]
+
+
+def synth_bgr(h, w, seed):
+    import numpy as np
+    return np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+
+def synth_boxes(n, shape, seed):
+    """xyxy boxes around a letterboxed image of `shape`, some of them outside it (exercise the clip)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand(n, 2, generator=g) * torch.tensor([shape[1] * 1.2, shape[0] * 1.2]) - torch.tensor([shape[1] * 0.1, shape[0] * 0.1])
+    wh = torch.rand(n, 2, generator=g) * 200 + 2
+    return torch.cat([c - wh / 2, c + wh / 2], 1)
+
+
 def module_inputs(name, shapes):
     from mgdt_yolo_b200.synth import synth_images
     return [synth_images(s[0], ch=s[1], h=s[2], w=s[3], seed=100 + i) * 2 - 0.5 for i, s in enumerate(shapes)]

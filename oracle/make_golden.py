@@ -12,6 +12,7 @@ Fixture index (tests/golden/):
   model_<cfg>.npz    y, raw maps (B=2, 64x96) + every layer output (B=1, 64x64), un-fused eval
   modules.npz        one entry per module class on odd/ragged shapes
   nms.npz            reference non_max_suppression outputs for a parameter grid
+  prepost.npz        LetterBox + BGR->RGB/CHW outputs (live cv2.resize) and ops.scale_boxes outputs
 """
 from __future__ import annotations
 
@@ -29,7 +30,8 @@ from oracle import ref_live  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
-from oracle.cases import LAYER_CFGS, MODEL_CFGS, MODULE_CASES, NMS_CASES, module_inputs  # noqa: E402
+from oracle.cases import (LAYER_CFGS, LETTERBOX_CASES, MODEL_CFGS, MODULE_CASES, NMS_CASES, SCALE_CASES,  # noqa: E402
+                          module_inputs, synth_bgr, synth_boxes)
 
 
 def gen_models():
@@ -108,9 +110,33 @@ def gen_nms():
     print(path, os.path.getsize(path) // 1024, "KiB")
 
 
+def gen_prepost():
+    """LetterBox + the BGR->RGB / HWC->CHW of BasePredictor.preprocess (predictor.py:121-125, augment.py:538-593, whose
+    resize is the live cv2.resize), and ops.scale_boxes (ops.py:90-117)."""
+    ref_live.load()
+    from ultralytics.yolo.data.augment import LetterBox
+    from ultralytics.yolo.utils import ops
+    blob = {}
+    for ci, (name, shape, new_shape, auto) in enumerate(LETTERBOX_CASES):
+        img = synth_bgr(shape[0], shape[1], 300 + ci)
+        out = LetterBox(new_shape, auto=auto, stride=32)(image=img)
+        im = np.ascontiguousarray(np.stack([out])[..., ::-1].transpose((0, 3, 1, 2)))
+        blob[f"lb.{name}"] = im[0]
+        print("letterbox", name, shape, "->", im.shape)
+    for ci, (name, s1, s0, n) in enumerate(SCALE_CASES):
+        b = synth_boxes(n, s1, 400 + ci)
+        out = ops.scale_boxes(s1, b.clone(), s0)
+        blob[f"sb.{name}"] = out.numpy()
+    path = os.path.join(OUT, "prepost.npz")
+    np.savez_compressed(path, **blob)
+    print(path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    gen_models()
-    gen_modules()
-    gen_nms()
+    if "--only-prepost" not in sys.argv:
+        gen_models()
+        gen_modules()
+        gen_nms()
+    gen_prepost()

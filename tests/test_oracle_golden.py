@@ -108,3 +108,26 @@ def test_dcn_restatement_matches_torchvision():
     mask = torch.rand(2, 9, 9, 11, generator=g)
     w = torch.randn(5, 6, 3, 3, generator=g)
     close(O.modulated_deform_conv3x3(x, off, mask, w), torchvision.ops.deform_conv2d(x, off, w, None, 1, 1, 1, mask), 1e-5)
+
+
+# ------------------------------------------------------------------ pre / post-processing rows
+from oracle.cases import LETTERBOX_CASES, SCALE_CASES, synth_bgr, synth_boxes  # noqa: E402
+
+
+@pytest.mark.parametrize("ci", range(len(LETTERBOX_CASES)), ids=[c[0] for c in LETTERBOX_CASES])
+def test_letterbox_bit_exact(ci, golden_dir):
+    """oracle.preprocess_images == LetterBox (live cv2.resize) + BGR->RGB + HWC->CHW, byte for byte."""
+    name, shape, new_shape, auto = LETTERBOX_CASES[ci]
+    g = np.load(os.path.join(golden_dir, "prepost.npz"))
+    out = O.preprocess_images([synth_bgr(shape[0], shape[1], 300 + ci)], new_shape, auto=auto, stride=32)[0]
+    ref = g[f"lb.{name}"]
+    assert out.shape == ref.shape and out.dtype == np.uint8
+    assert np.array_equal(out, ref), f"{int((out != ref).sum())} bytes differ"
+
+
+@pytest.mark.parametrize("ci", range(len(SCALE_CASES)), ids=[c[0] for c in SCALE_CASES])
+def test_scale_boxes_bit_exact(ci, golden_dir):
+    name, s1, s0, n = SCALE_CASES[ci]
+    g = np.load(os.path.join(golden_dir, "prepost.npz"))
+    out = O.scale_boxes(s1, synth_boxes(n, s1, 400 + ci), s0)
+    assert torch.equal(out, torch.from_numpy(g[f"sb.{name}"]))
