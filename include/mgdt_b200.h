@@ -85,8 +85,9 @@ typedef struct mgdt_conv_args {
     int32_t w_umma_f16;    /* 1 if w_umma was packed as fp16 (B operand F16, A stays bf16): 8x finer weight rounding */
 } mgdt_conv_args;
 int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
-/* Which kernel mgdt_conv2d would run for these arguments: 2 = conv_umma2_kernel (tcgen05), 1 = conv_direct_kernel
- * (CUDA cores).  Used by the bench to attribute launches to kernels. */
+/* Which kernel mgdt_conv2d would run for these arguments: 3 = conv_pointwise_kernel (narrow 1x1 layers, CUDA cores,
+ * HBM-bound), 2 = conv_umma2_kernel (tcgen05), 1 = conv_direct_kernel (CUDA cores).  Used by the bench to attribute
+ * launches to kernels. */
 int mgdt_conv2d_path(const mgdt_conv_args* a);
 
 /* tcgen05 path: K-major shared-memory image of the weights, [col split][16-byte K chunk][Nc][8].
@@ -126,10 +127,12 @@ int mgdt_dcn3x3(const void* x, int x_cs, const void* offset, int off_cs, const v
  * adaptive_avg_pool2d(2) windows [floor(i*H/2), ceil((i+1)*H/2)).  out_sumsq (same layout, total
  * only -> [N][C]) may be NULL.  Feeds SPRModule (spr_module.py:22-24), GRN (utils.py:180),
  * GroupNorm (head.py:76, block.py:425) and TaskDecomposition's GAP (head.py:507).
- * Deterministic two-stage reduction; `ws` needs mgdt_chan_stats_ws_bytes(). */
+ * One launch, deterministic: blocks write chunk partials into `ws` (mgdt_chan_stats_ws_bytes()), the last block of
+ * each image (atomic ticket) sums them in chunk order.  counters: int32[N] tickets, ZERO on entry and left zero on
+ * exit; an array may be reused by consecutive calls on one stream, not by calls that can run concurrently. */
 size_t mgdt_chan_stats_ws_bytes(int N, int H, int W, int C, int quads);
 int mgdt_chan_stats(const void* x, int x_cs, int N, int H, int W, int C, int quads, float* out_sum, float* out_sumsq,
-                    void* ws, size_t ws_bytes, int dtype, void* stream);
+                    void* ws, size_t ws_bytes, int32_t* counters, int dtype, void* stream);
 
 /* SPR gate of MSPA_C2f (block.py:270-279 + spr_module.py:20-31): stats[N][5][C] (sums) ->
  * scale[N][C] = softmax over the `groups` (4) channel groups of sigmoid(fc2(relu(fc1([mean | 2x2 means])))).

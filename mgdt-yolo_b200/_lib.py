@@ -51,7 +51,7 @@ SIGNATURES = {
     "mgdt_dwconv7_ln": (C.c_int, [vp, i32, vp, vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_dcn3x3": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_chan_stats_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
-    "mgdt_chan_stats": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, i32, vp]),
+    "mgdt_chan_stats": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, i32, vp]),
     "mgdt_mspa_gate": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
     "mgdt_grn_scale": (C.c_int, [vp, vp, i32, i32, vp, vp]),
     "mgdt_gn_affine": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp]),

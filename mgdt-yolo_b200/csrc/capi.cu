@@ -26,6 +26,8 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 int conv2d_direct(const mgdt_conv_args* a, cudaStream_t s);
+bool conv2d_pointwise_supported(const mgdt_conv_args* a);
+int conv2d_pointwise(const mgdt_conv_args* a, cudaStream_t s);
 #ifdef MGDT_WITH_UMMA
 bool conv2d_umma_supported(const mgdt_conv_args* a);
 int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s);
@@ -40,6 +42,7 @@ extern "C" const char* mgdt_last_error(void) { return g_err; }
 extern "C" unsigned long long mgdt_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" void mgdt_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 extern "C" int mgdt_conv2d_path(const mgdt_conv_args* a) {
+    if (a && a->impl == 0 && conv2d_pointwise_supported(a)) return 3;
 #ifdef MGDT_WITH_UMMA
     if (a && a->impl != 1 && conv2d_umma_supported(a)) return 2;
 #endif
@@ -65,6 +68,7 @@ extern "C" int mgdt_conv2d(const mgdt_conv_args* a, void* stream) {
     MGDT_CHECK(!a->pix_scale || a->ps_cs >= 1, "conv2d: bad pix_scale stride");
     MGDT_CHECK(a->act >= MGDT_ACT_NONE && a->act <= MGDT_ACT_GELU, "conv2d: bad act %d", a->act);
     cudaStream_t s = (cudaStream_t)stream;
+    if (a->impl == 0 && conv2d_pointwise_supported(a)) return conv2d_pointwise(a, s);   // narrow 1x1 layers: HBM-bound SIMT
 #ifdef MGDT_WITH_UMMA
     if (a->impl != 1 && conv2d_umma_supported(a)) return conv2d_umma(a, s);
     MGDT_CHECK(a->impl != 2, "conv2d: tcgen05 path does not support this shape");

@@ -249,28 +249,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// Epilogue activations on the SFU (bf16 outputs: 2^-9 relative rounding dominates their error).
-__device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-template <int ACT> __device__ __forceinline__ float act_fast(float v) {
-    if (ACT == MGDT_ACT_SILU) return v * fmaf(0.5f, tanh_fast(0.5f * v), 0.5f);         // x * sigmoid(x)
-    if (ACT == MGDT_ACT_RELU) return fmaxf(v, 0.f);
-    if (ACT == MGDT_ACT_SIGMOID) return fmaf(0.5f, tanh_fast(0.5f * v), 0.5f);
-    if (ACT == MGDT_ACT_HSIGMOID) return __saturatef(fmaf(v, 1.0f / 6.0f, 0.5f));
-    if (ACT == MGDT_ACT_GELU) {
-        // exact-erf GELU through Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7)
-        const float z = fabsf(v) * 0.70710678118654752440f;
-        const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-        const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-        const float e = 1.0f - poly * __expf(-z * z);
-        return 0.5f * v * (1.0f + copysignf(e, v));
-    }
-    return v;
-}
-
 struct P2 {
     const __nv_bfloat16 *x, *w, *pre_add, *pix_scale, *residual;
     const float *bias, *in_scale;

@@ -2,11 +2,11 @@
 // consume them.  All reductions are deterministic (two-stage, no float atomics).
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace mgdt {
 
 // ------------------------------------------------------------------ chan_stats
-// Stage 1: grid (chunks, N).  A block walks a strip of pixels; thread = (pixel group, channel vector
-// of V channels); partial sums go to part[n][chunk][Q][C] and partsq[n][chunk][C].
 constexpr int CS_THREADS = 256;
 
 template <typename T, int V> struct StatLd;
@@ -28,72 +28,63 @@ template <> struct StatLd<float, 8> {
     }
 };
 
-template <typename T, int V, int Q>
-__global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __restrict__ x, int x_cs, int H, int W, int C,
-                                                                 int pix_per_chunk, float* __restrict__ part,
-                                                                 float* __restrict__ partsq) {
+// Stage 1: grid (chunks, N, rects).  rects = 1 (whole image) or, with quads, the four adaptive_avg_pool2d(2) windows
+// [floor(i*H/2), ceil((i+1)*H/2)) (+ a fifth whole-image rect when H or W is odd and the windows overlap; for even
+// sizes the total is the sum of the four).  A block walks a strip of its rectangle's pixels; thread = (pixel group,
+// channel vector of V channels) with 8 (+8) accumulators, so the kernel stays at full occupancy.  Partial sums go to
+// part[n][chunk][rect][C] and partsq[n][chunk][rect][C]; the LAST block of an image to finish (atomic ticket) reduces
+// them in chunk order (fixed order -> deterministic) into out_sum[n][Q][C] / out_sumsq[n][C].
+template <typename T, int V>
+__global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __restrict__ x, int x_cs, int H, int W, int C, int Q,
+                                                                 float* __restrict__ part, float* __restrict__ partsq,
+                                                                 int* __restrict__ counters, float* __restrict__ out_sum,
+                                                                 float* __restrict__ out_sumsq) {
     pdl_trigger();
     pdl_wait();
-    __shared__ float sm[CS_THREADS * V];  // [PG][Cw * V]
-    const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    __shared__ float sm[CS_THREADS * V];  // [rows][Cw * V]
+    const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x, rect = blockIdx.z, nrect = gridDim.z;
     const int CV = C / V;
     int Cw = 1;
     while (Cw < CV && Cw < CS_THREADS) Cw <<= 1;  // channel-vector lanes per pass (pow2 <= 256)
     const int PG = CS_THREADS / Cw;
     const int cl = threadIdx.x % Cw, pg = threadIdx.x / Cw;
-    const int HW = H * W;
-    const int p_begin = chunk * pix_per_chunk;
-    const int p_end = min(HW, p_begin + pix_per_chunk);
-    // adaptive_avg_pool2d(2) windows: [floor(i*H/2), ceil((i+1)*H/2))
-    const int h_top_end = (H + 1) / 2, h_bot_begin = H / 2;
-    const int w_left_end = (W + 1) / 2, w_right_begin = W / 2;
-    const T* xn = x + (size_t)n * HW * x_cs;
+    // rectangle of this block
+    int rh0 = 0, rh1 = H, rw0 = 0, rw1 = W;
+    if (Q == 5 && rect < 4) {
+        if ((rect >> 1) == 0) rh1 = (H + 1) / 2; else rh0 = H / 2;
+        if ((rect & 1) == 0) rw1 = (W + 1) / 2; else rw0 = W / 2;
+    }
+    const int rw = rw1 - rw0, npx = (rh1 - rh0) * rw;
+    const int ppc = (npx + nchunks - 1) / nchunks;
+    const int p_begin = chunk * ppc, p_end = min(npx, p_begin + ppc);
+    // the sum of squares is only wanted over the whole image: every window when they partition it, else the full rect
+    const bool want_sq = partsq != nullptr && (nrect != 5 || rect == 4);
+    const T* xn = x + (size_t)n * H * W * x_cs;
+    const int lane = threadIdx.x & 31;
+    const int rows = Cw <= 32 ? CS_THREADS / 32 : PG;
+    const int row = Cw <= 32 ? (threadIdx.x >> 5) : pg;
 
     for (int cb = 0; cb < CV; cb += Cw) {
         const int cv = cb + cl;
-        float s[Q][V];
-        float sq[V];
+        float s[V], sq[V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            sq[j] = 0.f;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) s[q][j] = 0.f;
-        }
+        for (int j = 0; j < V; ++j) s[j] = sq[j] = 0.f;
         if (cv < CV) {
 #pragma unroll 4
-            for (int pidx = p_begin + pg; pidx < p_end; pidx += PG) {
+            for (int i = p_begin + pg; i < p_end; i += PG) {
+                const int hh = i / rw, ww = i - hh * rw;
                 float v[V];
-                StatLd<T, V>::ld(xn + (size_t)pidx * x_cs + cv * V, v);
-                bool m[4] = {false, false, false, false};
-                if (Q == 5) {
-                    const int h = pidx / W, w = pidx - h * W;
-                    const bool top = h < h_top_end, bot = h >= h_bot_begin;
-                    const bool left = w < w_left_end, right = w >= w_right_begin;
-                    m[0] = top && left; m[1] = top && right; m[2] = bot && left; m[3] = bot && right;
-                }
+                StatLd<T, V>::ld(xn + (size_t)((rh0 + hh) * W + rw0 + ww) * x_cs + cv * V, v);
 #pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    s[0][j] += v[j];
-                    sq[j] += v[j] * v[j];
-                    if (Q == 5) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (m[q]) s[1 + q][j] += v[j];
-                    }
-                }
+                for (int j = 0; j < V; ++j) { s[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
             }
         }
-        // reduce over pixel groups, one statistic at a time: xor-shuffles inside the warp (lanes that share a channel
-        // lane are Cw apart), then at most 8 partial rows through shared memory (fixed order -> deterministic)
-        const int lane = threadIdx.x & 31;
-        const int rows = Cw <= 32 ? CS_THREADS / 32 : PG;
-        const int row = Cw <= 32 ? (threadIdx.x >> 5) : pg;
 #pragma unroll
-        for (int q = 0; q <= Q; ++q) {
-            if (q == Q && !partsq) break;
+        for (int st = 0; st < 2; ++st) {
+            if (st == 1 && !want_sq) break;
             float t[V];
 #pragma unroll
-            for (int j = 0; j < V; ++j) t[j] = (q < Q) ? s[q < Q ? q : 0][j] : sq[j];
+            for (int j = 0; j < V; ++j) t[j] = st ? sq[j] : s[j];
             for (int off = 16; off >= Cw; off >>= 1) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) t[j] += __shfl_xor_sync(0xffffffffu, t[j], off);
@@ -109,41 +100,45 @@ __global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __rest
                 for (int j = 0; j < V; ++j) {
                     float tot = 0.f;
                     for (int g = 0; g < rows; ++g) tot += sm[(g * Cw + (int)threadIdx.x) * V + j];
-                    if (q < Q)
-                        part[(((size_t)n * nchunks + chunk) * Q + q) * C + cvo * V + j] = tot;
-                    else
-                        partsq[((size_t)n * nchunks + chunk) * C + cvo * V + j] = tot;
+                    float* dst = st == 0 ? part : partsq;
+                    dst[(((size_t)n * nchunks + chunk) * nrect + rect) * C + cvo * V + j] = tot;
                 }
             }
             __syncthreads();
         }
     }
+    // finalisation by the last block of the image
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[n], 1) == nchunks * nrect - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < Q * C + (partsq ? C : 0); i += CS_THREADS) {
+        const bool is_sq = i >= Q * C;
+        const int q = is_sq ? 0 : i / C, c = is_sq ? i - Q * C : i - q * C;
+        const float* src = is_sq ? partsq : part;
+        float t = 0.f;
+        if (q == 0 && nrect == 4) {
+            // even H and W: the windows partition the image; total = (q00 + q01) + (q10 + q11), each in chunk order
+            float tq[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < nchunks; ++k)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) tq[r] += __ldcg(&src[(((size_t)n * nchunks + k) * nrect + r) * C + c]);
+            t = (tq[0] + tq[1]) + (tq[2] + tq[3]);
+        } else {
+            const int r = nrect == 1 ? 0 : (q == 0 ? 4 : q - 1);
+#pragma unroll 4
+            for (int k = 0; k < nchunks; ++k) t += __ldcg(&src[(((size_t)n * nchunks + k) * nrect + r) * C + c]);
+        }
+        if (is_sq) out_sumsq[(size_t)n * C + c] = t;
+        else out_sum[(size_t)n * Q * C + i] = t;
+    }
+    if (threadIdx.x == 0) counters[n] = 0;
 }
 
-__global__ void chan_stats_final(const float* __restrict__ part, const float* __restrict__ partsq, int nchunks, int Q,
-                                 int C, float* __restrict__ out_sum, float* __restrict__ out_sumsq, int N) {
-    pdl_trigger();
-    pdl_wait();
-    const long long total = (long long)N * Q * C;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total + (long long)N * C;
-         i += (long long)gridDim.x * blockDim.x) {
-        if (i < total) {
-            const int c = (int)(i % C);
-            const int q = (int)((i / C) % Q);
-            const int n = (int)(i / ((long long)C * Q));
-            float t = 0.f;
-            for (int k = 0; k < nchunks; ++k) t += part[(((long long)n * nchunks + k) * Q + q) * C + c];
-            out_sum[i] = t;
-        } else if (out_sumsq) {
-            const long long j = i - total;
-            const int c = (int)(j % C);
-            const int n = (int)(j / C);
-            float t = 0.f;
-            for (int k = 0; k < nchunks; ++k) t += partsq[((long long)n * nchunks + k) * C + c];
-            out_sumsq[j] = t;
-        }
-    }
-}
+static int stats_rects(int H, int W, int quads) { return quads ? ((H % 2 == 0 && W % 2 == 0) ? 4 : 5) : 1; }
 
 static int stats_chunks(int N, int H, int W) {
     // enough blocks to fill 148 SMs a few times, at least 64 pixels per chunk
@@ -159,34 +154,29 @@ static int stats_chunks(int N, int H, int W) {
 using namespace mgdt;
 
 extern "C" size_t mgdt_chan_stats_ws_bytes(int N, int H, int W, int C, int quads) {
-    const int Q = quads ? 5 : 1;
-    const size_t nch = (size_t)stats_chunks(N, H, W);
-    return sizeof(float) * (size_t)N * nch * (size_t)(Q + 1) * (size_t)C;
+    const size_t nch = (size_t)stats_chunks(N, H, W), nrect = (size_t)stats_rects(H, W, quads);
+    return sizeof(float) * (size_t)N * nch * nrect * 2 * (size_t)C;
 }
 
 extern "C" int mgdt_chan_stats(const void* x, int x_cs, int N, int H, int W, int C, int quads, float* out_sum,
-                               float* out_sumsq, void* ws, size_t ws_bytes, int dtype, void* stream) {
-    MGDT_CHECK(x && out_sum && ws, "chan_stats: null pointer");
+                               float* out_sumsq, void* ws, size_t ws_bytes, int32_t* counters, int dtype, void* stream) {
+    MGDT_CHECK(x && out_sum && ws && counters, "chan_stats: null pointer");
     MGDT_CHECK(N > 0 && H > 0 && W > 0 && C > 0 && x_cs >= C, "chan_stats: bad shape");
     MGDT_CHECK(ws_bytes >= mgdt_chan_stats_ws_bytes(N, H, W, C, quads), "chan_stats: workspace too small");
     const int Q = quads ? 5 : 1;
-    const int nch = stats_chunks(N, H, W);
-    const int ppc = cdiv(H * W, nch);
+    const int nrect = stats_rects(H, W, quads);
+    // chunks per rectangle (the workspace is sized for stats_chunks() of them; the four windows share that budget)
+    const int nch = std::max(1, stats_chunks(N, H, W) / (nrect >= 4 ? 4 : 1));
     float* part = (float*)ws;
-    float* partsq = part + (size_t)N * nch * Q * C;
+    float* partsq = part + (size_t)N * nch * nrect * C;
     cudaStream_t s = (cudaStream_t)stream;
     MGDT_DTYPE_SWITCH(dtype, T, {
         const bool vec = C % 8 == 0 && (x_cs % 8) == 0 && (((uintptr_t)x) % (8 * sizeof(T))) == 0;
         float* psq = out_sumsq ? partsq : nullptr;
-        if (vec && quads) launch_k(chan_stats_partial<T, 8, 5>, dim3(dim3(nch, N)), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, ppc, part, psq);
-        else if (vec) launch_k(chan_stats_partial<T, 8, 1>, dim3(dim3(nch, N)), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, ppc, part, psq);
-        else if (quads) launch_k(chan_stats_partial<T, 1, 5>, dim3(dim3(nch, N)), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, ppc, part, psq);
-        else launch_k(chan_stats_partial<T, 1, 1>, dim3(dim3(nch, N)), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, ppc, part, psq);
+        if (vec) launch_k(chan_stats_partial<T, 8>, dim3(nch, N, nrect), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, Q, part, psq, (int*)counters, out_sum, out_sumsq);
+        else launch_k(chan_stats_partial<T, 1>, dim3(nch, N, nrect), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, Q, part, psq, (int*)counters, out_sum, out_sumsq);
     });
-    MGDT_LAUNCH_CHECK("chan_stats_partial");
-    const long long total = (long long)N * (Q + 1) * C;
-    launch_k(chan_stats_final, dim3(cdiv(total, 256)), dim3(256), 0, s, part, partsq, nch, Q, C, out_sum, out_sumsq, N);
-    MGDT_LAUNCH_CHECK("chan_stats_final");
+    MGDT_LAUNCH_CHECK("chan_stats");
     return 0;
 }
 

@@ -146,6 +146,28 @@ class Engine:
             s.done.record(s.stream)
         return s
 
+    def submit_images(self, ims, auto=False, stride=32):
+        """The reference's predictor path for a list of (h, w, 3) BGR uint8 images (numpy or torch, host or device):
+        device LetterBox + BGR->RGB + HWC->CHW (preprocess.py) -> pipeline -> scale_boxes back to each original image
+        (postprocess.py) -> D2H.  Asynchronous like submit(); collect(slot) returns boxes in original-image pixels."""
+        from .postprocess import scale_boxes_params
+        from .preprocess import preprocess_images
+        if len(ims) != self.batch:
+            raise ValueError(f"Engine was built for batches of {self.batch} images, got {len(ims)}")
+        s = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        with torch.cuda.stream(s.stream), torch.no_grad():
+            _, metas = preprocess_images(ims, (self.h, self.w), auto=auto, stride=stride, device=self.device, out=s.src)
+            prm = torch.tensor([scale_boxes_params((self.h, self.w), m[0]) for m in metas], dtype=torch.float32)
+            s.scale_prm = prm.to(self.device, non_blocking=True)
+        self._run(s, s.src)
+        with torch.cuda.stream(s.stream):
+            ops.scale_boxes_packed(s.out, s.counts, s.scale_prm)
+            s.host_out.copy_(s.out, non_blocking=True)
+            s.host_counts.copy_(s.counts, non_blocking=True)
+            s.done.record(s.stream)
+        return s
+
     def collect(self, s):
         """Wait for a submitted batch; returns the reference's format: list of (n_i, 6) CPU tensors."""
         s.done.synchronize()

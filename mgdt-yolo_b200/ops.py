@@ -204,7 +204,8 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
                             + n * ho * wo * cout * (2 if residual is not None else 1) + cout * cin * k * k)
                 + (n * h * wd * es if pix_scale is not None else 0))
     if PROFILE is not None:  # attribute the launch to the kernel the library will actually run
-        meta["kernel"] = "conv_umma2_kernel" if lib().mgdt_conv2d_path(C.byref(a)) == 2 else "conv_direct_kernel"
+        meta["kernel"] = {3: "conv_pointwise_kernel", 2: "conv_umma2_kernel"}.get(lib().mgdt_conv2d_path(C.byref(a)),
+                                                                                  "conv_direct_kernel")
     _invoke("mgdt_conv2d", meta, C.byref(a), stream_ptr())
     return out
 
@@ -268,8 +269,23 @@ def chan_stats(x, quads=False, sumsq=False):
     nbytes = lib().mgdt_chan_stats_ws_bytes(n, h, w, c, 1 if quads else 0)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
     _invoke("mgdt_chan_stats", dict(shape=f"stats C{c} {n}x{h}x{w} q{q}", bytes=_nb(x), flops=0.0), xp, xcs, n, h, w, c, 1 if quads else 0, s.data_ptr(), _p(ss), ws.data_ptr(), nbytes,
-                                dtype_code(x.dtype), stream_ptr())
+                                _stats_tickets(x.device, n).data_ptr(), dtype_code(x.dtype), stream_ptr())
     return s, ss
+
+
+_TICKETS = {}
+
+
+def _stats_tickets(device, n):
+    """Zero-initialised int32 tickets for the single-launch chan_stats (the kernel leaves them zero).  One array per
+    (device, stream): calls on one stream are ordered, calls on different streams may overlap.  Allocated outside
+    any graph capture pool on first use (warm-up passes always precede capture)."""
+    key = (device.index, stream_ptr())
+    t = _TICKETS.get(key)
+    if t is None or t.numel() < n:
+        t = torch.zeros((max(n, 1024),), dtype=torch.int32, device=device)
+        _TICKETS[key] = t
+    return t
 
 
 def mspa_gate(stats, h, w, c, fc1_w, fc1_b, fc2_w, fc2_b, groups=4, softmax=True):

@@ -66,3 +66,30 @@ def test_scale_boxes_packed_batch():
         c = int(counts[i])
         assert torch.equal(out[i, :c], O.scale_boxes((640, 640), dets[i, :c].clone(), s0))
         assert torch.equal(out[i, c:], dets[i, c:])                   # rows past the count are untouched
+
+
+def test_engine_submit_images():
+    """Engine.submit_images == preprocess_images -> step_device -> scale_boxes, composed by hand."""
+    from mgdt_yolo_b200 import ops
+    from mgdt_yolo_b200.engine import Engine
+    from mgdt_yolo_b200.postprocess import scale_boxes_params
+    from mgdt_yolo_b200.preprocess import preprocess_images
+    from mgdt_yolo_b200.synth import raise_cls_bias, synth_state_dict
+    from mgdt_yolo_b200.tasks import DetectionModel
+    model = DetectionModel("mspa_c2f_gd_tood_yolov8n.yaml", nc=2, verbose=False)
+    model.load_state_dict(raise_cls_bias(synth_state_dict(model.state_dict(), seed=1), -1.238))
+    eng = Engine(model, 2, (128, 160), torch.bfloat16, "cuda:0", conf=0.25, iou=0.7, slots=1)
+    ims = [synth_bgr(90, 130, 1), synth_bgr(200, 120, 2)]
+    got = eng.collect(eng.submit_images(ims))
+    batch, metas = preprocess_images(ims, (128, 160))
+    s = eng.step_device(batch)
+    s.stream.synchronize()
+    prm = torch.tensor([scale_boxes_params((128, 160), m[0]) for m in metas], dtype=torch.float32, device="cuda")
+    with torch.cuda.stream(s.stream):
+        ops.scale_boxes_packed(s.out, s.counts, prm)
+    s.stream.synchronize()
+    cnt = s.counts.tolist()
+    assert sum(cnt) > 0
+    for i in range(2):
+        assert torch.equal(got[i], s.out[i, :cnt[i]].cpu())
+        assert float(got[i][:, [0, 2]].max()) <= ims[i].shape[1] and float(got[i][:, [1, 3]].max()) <= ims[i].shape[0]
