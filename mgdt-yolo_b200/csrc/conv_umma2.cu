@@ -151,6 +151,13 @@ static bool try_run2(const Plan2& p, int MB, int N, int H, int W, int Ho, int Wo
     const unsigned wall = (unsigned)((size_t)p.nmma_s * 2 * p.Nc * 16);
     r.w_slice_bytes = p.nks > 1 ? wall : 0;
     r.wres_bytes = p.nks > 1 ? 0 : wall;
+    // K-sliced layers whose complete weight image still fits next to two A stages keep it resident (copied once per
+    // CTA) instead of carrying every slice through the ring with every tile (384->96: 74 KB re-read per 128-row tile)
+    if (p.nks > 1 && (size_t)p.nks * wall <= 112 * 1024 &&
+        (size_t)p.nks * wall + 2 * (size_t)r.a_bytes + U2_TAIL <= (size_t)U2_MAX_SMEM) {
+        r.wres_bytes = (unsigned)((size_t)p.nks * wall);
+        r.w_slice_bytes = 0;
+    }
     r.stage_bytes = r.a_bytes + r.w_slice_bytes;
     int S = U2_MAX_STAGES;
     while (S >= 2 && (size_t)r.wres_bytes + (size_t)S * r.stage_bytes + U2_TAIL > (size_t)U2_MAX_SMEM) --S;
@@ -539,13 +546,29 @@ __device__ __forceinline__ void epi_math(const P2& p, const uint32_t* r, const f
             a[j] = silu ? fma2(h, t, h) : fma2(t, half2, half2);
         }
     }
+    if (p.act == MGDT_ACT_GELU) {
+        // packed form of act_fast<GELU>: erf(z) ~= tanh(z * (A + B z^2 + C z^4)), gelu = h + h * t with h = x / 2
+        const unsigned long long kz = pk2(0.70710678118654752440f, 0.70710678118654752440f);
+        const unsigned long long ka = pk2(MGDT_ERF_A, MGDT_ERF_A), kb = pk2(MGDT_ERF_B, MGDT_ERF_B), kc = pk2(MGDT_ERF_C, MGDT_ERF_C);
+#pragma unroll
+        for (int j = 0; j < NV / 2; ++j) {
+            float z0, z1;
+            up2(mul2(a[j], kz), z0, z1);
+            const unsigned long long z = pk2(fminf(fmaxf(z0, -5.0f), 5.0f), fminf(fmaxf(z1, -5.0f), 5.0f));
+            const unsigned long long u = mul2(z, z);
+            float w0, w1;
+            up2(mul2(z, fma2(fma2(kc, u, kb), u, ka)), w0, w1);
+            const unsigned long long t = pk2(tanh_fast(w0), tanh_fast(w1));
+            const unsigned long long h = mul2(a[j], half2);
+            a[j] = fma2(h, t, h);
+        }
+    }
 #pragma unroll
     for (int j = 0; j < NV / 2; ++j) up2(a[j], v[2 * j], v[2 * j + 1]);
     switch (p.act) {
 #define MGDT_ACT_CASE(A) case A: _Pragma("unroll") for (int j = 0; j < NV; ++j) v[j] = act_fast<A>(v[j]); break;
         MGDT_ACT_CASE(MGDT_ACT_RELU)
         MGDT_ACT_CASE(MGDT_ACT_HSIGMOID)
-        MGDT_ACT_CASE(MGDT_ACT_GELU)
 #undef MGDT_ACT_CASE
         default: break;
     }
@@ -650,8 +673,8 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     if (warp < NPW) {
         // =============================================================== producers
         const int ptid = tid;  // 0..NP-1
-        if (nks == 1) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)ns * w_slice_elems);
+        if (rn.wres_bytes) {   // resident weights: the whole (ns) image, all K slices
+            const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)ns * nks * w_slice_elems);
             const uint32_t dst = s_u32(sWres);
             const int n16 = (int)(rn.wres_bytes / 16);
             for (int i = ptid; i < n16; i += NP) cp_async16(dst + 16u * i, src + i, 16u);
@@ -678,7 +701,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                 mbar_wait(EMPTY(s), ph ^ 1);
                 unsigned char* sA = sStage + (size_t)s * rn.stage_bytes;
                 const uint32_t sA32 = s_u32(sA);
-                if (nks > 1) {
+                if (rn.w_slice_bytes) {
                     const uint4* src = reinterpret_cast<const uint4*>(p.w + ((size_t)ns * nks + ks) * w_slice_elems);
                     const uint32_t dst = sA32 + rn.a_bytes;
                     const int n16 = (int)(rn.w_slice_bytes / 16);
@@ -916,7 +939,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                                 if (dsto[u] != 0xffffffffu) *reinterpret_cast<uint4*>(sA + dsto[u]) = v[u];
                         }
                     }
-                    if (nks > 1) cp_async_wait_all();
+                    if (rn.w_slice_bytes) cp_async_wait_all();
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbar_arrive(FULL(s));
                 }
@@ -936,7 +959,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         // lane elect.sync picks, which lets ptxas emit them without a per-lane waterfall loop.
         // instruction descriptor: D = f32, A = bf16, B = bf16 or f16, both K-major, N = Nc, M = 128
         const uint32_t idesc = (1u << 4) | (1u << 7) | ((p.w_f16 ? 0u : 1u) << 10) | ((uint32_t)(pl.Nc >> 3) << 17) | ((128u >> 4) << 24);
-        if (nks == 1) mbar_wait(WREADY, 0);
+        if (rn.wres_bytes) mbar_wait(WREADY, 0);
         uint32_t it = 0, ti = 0;
         int s = 0;
         uint32_t ph = 0;
@@ -951,7 +974,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint32_t a0 = s_u32(sStage + (size_t)s * rn.stage_bytes);
-                    const uint32_t w0 = nks == 1 ? s_u32(sWres) : a0 + rn.a_bytes;
+                    const uint32_t w0 = rn.w_slice_bytes ? a0 + rn.a_bytes : s_u32(sWres) + (uint32_t)ks * (uint32_t)(w_slice_elems * 2);
                     const uint32_t d0 = tmem_base + (uint32_t)(a * rn.MB * pl.Nc);
                     const uint64_t abase = (uint64_t)(a0 >> 4), wbase = (uint64_t)(w0 >> 4);
                     // descriptors are fetched four at a time ahead of the instructions that use them
