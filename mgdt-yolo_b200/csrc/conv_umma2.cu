@@ -112,7 +112,9 @@ static Plan2 make_plan2(int Cin, int Cout, int k, int stride) {
             const long long wbytes = nm * 2 * Nc * 16;
             const long long abytes = (long long)ps * a_plane_est;
             const bool whole = ps == p.planes && wbytes <= 100 * 1024 && abytes <= 100 * 1024 && wbytes + 2 * abytes <= U2_STAGE_BUDGET;
-            const bool sliced = wbytes <= 80 * 1024 && abytes <= 80 * 1024 && 2 * (wbytes + abytes) <= U2_STAGE_BUDGET;
+            // sliced layers: A slices of at most ~40 KB, so that three ring stages fit next to resident weights -- with two
+            // stages the producer of item k+2 waits for the MMAs of item k and the loop serialises (measured on 384->96)
+            const bool sliced = wbytes <= 80 * 1024 && abytes <= 40 * 1024 && 2 * (wbytes + abytes) <= U2_STAGE_BUDGET;
             if (whole || sliced) { best = ps; break; }
         }
         if (best) break;
@@ -465,7 +467,21 @@ __device__ __forceinline__ int src_pixel(const P2& p, uint32_t tile, uint32_t tt
 }
 
 // The fused input transforms on one staged 16-byte chunk (8 channels of plane `plane`) of source pixel `pix`.
-__device__ __forceinline__ uint4 xform_apply(const P2& p, uint4 v, int pix, uint32_t n, int plane) {
+__device__ __forceinline__ uint4 xform_apply(const P2& p, uint4 v, int pix, uint32_t n, int plane, const float* sc = nullptr) {
+    if (sc && p.in_scale && !p.pre_add && !p.pix_scale && !p.in_relu) {
+        // scale-only transform (GRN, TaskDecomposition) with the scales in registers: bf16 pair -> two fp32 by shift /
+        // mask, one packed FMUL2, one F2FP per pair
+        uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned long long x2 = pk2(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u));
+            float lo, hi;
+            up2(mul2(x2, pk2(sc[2 * j], sc[2 * j + 1])), lo, hi);
+            const __nv_bfloat162 o = __floats2bfloat162_rn(lo, hi);
+            w[j] = *reinterpret_cast<const uint32_t*>(&o);
+        }
+        return v;
+    }
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
     float f[8];
 #pragma unroll
@@ -476,7 +492,10 @@ __device__ __forceinline__ uint4 xform_apply(const P2& p, uint4 v, int pix, uint
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(ah[j]); f[2 * j] += t.x; f[2 * j + 1] += t.y; }
     }
-    if (p.in_scale) {
+    if (p.in_scale && sc) {   // the caller keeps this (image, plane)'s scales in registers
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= sc[j];
+    } else if (p.in_scale) {
         const float4* s = reinterpret_cast<const float4*>(p.in_scale + (size_t)n * p.Cin + plane * 8);
         const float4 s0 = __ldg(s), s1 = __ldg(s + 1);
         f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w; f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
@@ -497,9 +516,9 @@ __device__ __forceinline__ uint4 xform_apply(const P2& p, uint4 v, int pix, uint
 
 // In-place transform of the chunks thread `ptid` copied into stage `sA` (zero-filled chunks stay zero, as in the
 // reference where padding is applied after the producing op).
-template <int MODE, int NP>
+template <int MODE>
 __device__ __forceinline__ void xform_stage(const P2& p, unsigned char* sA, uint32_t tile, uint32_t tt, uint32_t n_img,
-                                            int plane0, uint32_t chunks, int ptid) {
+                                            int plane0, uint32_t chunks, int ptid, int NP) {
     for (uint32_t e0 = ptid; e0 < chunks; e0 += NP * 2) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -515,6 +534,37 @@ __device__ __forceinline__ void xform_stage(const P2& p, unsigned char* sA, uint
                     *q = xform_apply(p, *q, pix, n, plane0 + (int)pll);
                 }
             }
+        }
+    }
+}
+
+// Same, for the mapping in which a thread always stages the same plane (positions pos0, pos0 + step, ...): the
+// per-(image, channel) input scales of that plane live in registers and are reloaded only when the image changes.
+template <int MODE>
+__device__ __forceinline__ void xform_stage_fixed(const P2& p, unsigned char* sA, uint32_t tile, uint32_t tt, uint32_t n_img,
+                                                  int plane, uint32_t pll, uint32_t pos0, uint32_t step, float* sc, uint32_t sc_n) {
+    // sc[8] / sc_n: this plane's input scales of image sc_n, prefetched by the caller when the item was issued
+    const uint32_t Pn = (uint32_t)p.rn.P;
+    for (uint32_t pos = pos0; pos < Pn; pos += 4 * step) {   // four independent chunks per iteration
+        int pix[4];
+        uint32_t n[4];
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t ps = pos + u * step;
+            pix[u] = ps < Pn ? src_pixel<MODE>(p, tile, tt, n_img, ps, 0, n[u]) : -1;
+            if (pix[u] >= 0) v[u] = *reinterpret_cast<const uint4*>(sA + (pll * p.rn.pstride16 + ps) * 16u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (pix[u] < 0) continue;
+            if (p.in_scale && n[u] != sc_n) {
+                const float4* s = reinterpret_cast<const float4*>(p.in_scale + (size_t)n[u] * p.Cin + plane * 8);
+                const float4 s0 = __ldg(s), s1 = __ldg(s + 1);
+                sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+                sc_n = n[u];
+            }
+            *reinterpret_cast<uint4*>(sA + (pll * p.rn.pstride16 + pos + u * step) * 16u) = xform_apply(p, v[u], pix[u], n[u], plane, sc);
         }
     }
 }
@@ -685,12 +735,18 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         const uint32_t chunks = (uint32_t)(pl.PS * pl.npar * rn.P);
         // (the in-place transform revisits chunks through the generic mapping, which matches the fast path's except for
         // the stride-2 parity loop)
-        const bool ps_divides = NP % pl.PS == 0 && !(LOADER == LD_XFORM && MODE == 2);
-        const uint32_t pstep = ps_divides ? (uint32_t)(NP / pl.PS) : 1u;
+        // LD_XFORM (not stride 2): use a multiple of PS threads so that every thread owns one plane (its input scales stay
+        // in registers across the in-place transform); the few leftover threads only arrive on the barriers
+        const int NPe = (LOADER == LD_XFORM && MODE != 2 && pl.PS <= NP) ? (NP / pl.PS) * pl.PS : NP;
+        const bool ps_divides = NPe % pl.PS == 0 && !(LOADER == LD_XFORM && MODE == 2);
+        const uint32_t pstep = ps_divides ? (uint32_t)(NPe / pl.PS) : 1u;
+        const bool p_active = ptid < NPe;
         const uint32_t pos_fix = fdiv((uint32_t)ptid, p.d_ps), pll_fix = (uint32_t)ptid - pos_fix * pl.PS;
         uint32_t it = 0;
         int s = 0;
         uint32_t ph = 0;   // phase of the stage's current use (flips each time the ring wraps)
+        float xf_sc[8], xf_sc_new[8];   // LD_XFORM: input scales of the pending item / of the item being issued
+        uint32_t xf_scn = 0xffffffffu, xf_scn_new = 0xffffffffu;
         bool xf_valid = false;   // LD_XFORM: the item whose raw copies are in flight and still to be transformed
         int xf_s = 0, xf_plane0 = 0;
         uint32_t xf_tile = 0, xf_tt = 0, xf_nimg = 0;
@@ -708,10 +764,22 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                     for (int i = ptid; i < n16; i += NP) cp_async16(dst + 16u * i, src + i, 16u);
                 }
                 const int plane0 = ks * pl.PS;
+                if (LOADER == LD_XFORM && p.in_scale && ps_divides && p_active) {
+                    // prefetch this item's per-(image, channel) input scales; they are used one iteration later
+                    uint32_t n0 = n_img;
+                    if (MODE == 0) n0 = fdiv(min(tile * (128u * rn.MB) + pos_fix, p.M_total - 1u), p.d_HW);
+                    const float4* sp = reinterpret_cast<const float4*>(p.in_scale + (size_t)n0 * p.Cin + (plane0 + (int)pll_fix) * 8);
+                    const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+                    xf_sc_new[0] = s0.x; xf_sc_new[1] = s0.y; xf_sc_new[2] = s0.z; xf_sc_new[3] = s0.w;
+                    xf_sc_new[4] = s1.x; xf_sc_new[5] = s1.y; xf_sc_new[6] = s1.z; xf_sc_new[7] = s1.w;
+                    xf_scn_new = n0;
+                }
                 if (LOADER == LD_ASYNC || LOADER == LD_XFORM) {
                     // transform-free input: every chunk is an asynchronous 16-byte copy (zero-filled outside the image);
                     // the thread never waits for its data, the stage's full barrier counts the copies' completion
-                    if (ps_divides) {
+                    if (!p_active) {
+                        // spare thread of the fixed-plane mapping: nothing to copy, it only takes part in the barriers
+                    } else if (ps_divides) {
                         // NP % PS == 0: this thread always stages the same plane and its positions advance by a constant
                         // step.  Four independent chunks per iteration (index arithmetic by multiply-shift division, no
                         // data-dependent branches) so the address chains overlap.
@@ -766,7 +834,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                             }
                         }
                     } else
-                    for (uint32_t e = ptid; e < chunks; e += NP) {
+                    for (uint32_t e = ptid; e < chunks; e += NPe) {
                         const uint32_t rest = fdiv(e, p.d_ps);
                         const uint32_t pll = e - rest * pl.PS;
                         uint32_t pos = rest, par = 0, n;
@@ -783,11 +851,21 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                         asm volatile("cp.async.commit_group;" ::: "memory");
                         if (xf_valid) {
                             asm volatile("cp.async.wait_group 1;" ::: "memory");
-                            xform_stage<MODE, NP>(p, sStage + (size_t)xf_s * rn.stage_bytes, xf_tile, xf_tt, xf_nimg, xf_plane0, chunks, ptid);
+                            if (tid == 0 && it < 6) trace_mark(p, 12 + 8 * (int)it);
+                            if (p_active) {
+                                if (ps_divides) xform_stage_fixed<MODE>(p, sStage + (size_t)xf_s * rn.stage_bytes, xf_tile, xf_tt, xf_nimg,
+                                                                        xf_plane0 + (int)pll_fix, pll_fix, pos_fix, pstep, xf_sc, xf_scn);
+                                else xform_stage<MODE>(p, sStage + (size_t)xf_s * rn.stage_bytes, xf_tile, xf_tt, xf_nimg, xf_plane0, chunks, ptid, NPe);
+                            }
+                            if (tid == 0 && it < 6) trace_mark(p, 14 + 8 * (int)it);
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             mbar_arrive(FULL(xf_s));
+                            if (tid == 0 && it < 6) trace_mark(p, 13 + 8 * (int)it);
                         }
                         xf_valid = true; xf_s = s; xf_tile = tile; xf_tt = tt; xf_nimg = n_img; xf_plane0 = plane0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) xf_sc[j] = xf_sc_new[j];
+                        xf_scn = xf_scn_new;
                     }
                 } else {
                     if (LOADER == LD_STEM_U8) {
@@ -949,7 +1027,11 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         }
         if (LOADER == LD_XFORM && xf_valid) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
-            xform_stage<MODE, NP>(p, sStage + (size_t)xf_s * rn.stage_bytes, xf_tile, xf_tt, xf_nimg, xf_plane0, chunks, ptid);
+            if (p_active) {
+                                if (ps_divides) xform_stage_fixed<MODE>(p, sStage + (size_t)xf_s * rn.stage_bytes, xf_tile, xf_tt, xf_nimg,
+                                                                        xf_plane0 + (int)pll_fix, pll_fix, pos_fix, pstep, xf_sc, xf_scn);
+                                else xform_stage<MODE>(p, sStage + (size_t)xf_s * rn.stage_bytes, xf_tile, xf_tt, xf_nimg, xf_plane0, chunks, ptid, NPe);
+                            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(FULL(xf_s));
         }

@@ -13,7 +13,7 @@ import torch.nn as nn
 cases = [("c32_3x3", 32, 32, 3, 1, 80, 80), ("c8_1x1", 8, 8, 1, 1, 160, 160), ("c64_256", 64, 256, 1, 1, 80, 80),
          ("c64_256_noact", 64, 256, 1, 1, 80, 80), ("c64_256_relu", 64, 256, 1, 1, 80, 80),
          ("c96_384", 96, 384, 1, 1, 40, 40), ("c16_3x3", 16, 16, 3, 1, 80, 80), ("c32_64", 32, 64, 1, 1, 80, 80),
-         ("c256_64", 256, 64, 1, 1, 80, 80), ("c16_32_s2", 16, 32, 3, 2, 320, 320), ("c384_96", 384, 96, 1, 1, 40, 40)]
+         ("c256_64", 256, 64, 1, 1, 80, 80), ("c16_32_s2", 16, 32, 3, 2, 320, 320), ("c384_96", 384, 96, 1, 1, 40, 40), ("c384_96_grn", 384, 96, 1, 1, 40, 40)]
 sel = sys.argv[1:]
 if sel:
     cases = [c for c in cases if c[0] in sel]
@@ -24,13 +24,17 @@ for name, cin, cout, k, s, H, W in cases:
     m = m.cuda().eval()
     x = ops.as_act(torch.randn(B, cin, H, W, device="cuda").to(torch.bfloat16))
     with torch.no_grad():
+        kw = {}
+        if name.endswith("_grn"):   # GRN-scaled input + residual, as ConvNeXtV2_Block's pwconv2
+            kw = dict(in_scale=(torch.rand(B, cin, device="cuda") + 0.5).contiguous(),
+                      residual=ops.as_act(torch.randn(B, cout, H, W, device="cuda").to(torch.bfloat16)))
         for _ in range(3):
-            m(x)
+            m(x, **kw)
         torch.cuda.synchronize()
         trace.zero_()
         lib().mgdt_debug_set_trace(trace.data_ptr())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); m(x); e1.record()
+        e0.record(); m(x, **kw); e1.record()
         torch.cuda.synchronize()
         lib().mgdt_debug_set_trace(None)
     t = trace.view(-1, 64).cpu()
@@ -46,6 +50,8 @@ for name, cin, cout, k, s, H, W in cases:
     for ti in range(6):
         if (t[:, 8 + 8 * ti] > 0).any():
             print(f"   tile{ti}: fill {stat(8+8*ti)}  mma_issued {stat(9+8*ti)}  acc_ready {stat(10+8*ti)}  epi_done {stat(11+8*ti)}")
+            if (t[:, 12 + 8 * ti] > 0).any():
+                print(f"          xform: copies of the previous item landed {stat(12+8*ti)}  transformed {stat(14+8*ti)}  published {stat(13+8*ti)}")
     ph = t[:, 56:60].float()
     n = ph[:, 0].clamp(min=1)
     print(f"   epilogue unit phases (cycles, warp 8, tile 1): units {ph[:,0].mean():.1f}  tmem-ld {(ph[:,1]/n).mean():.0f}"
