@@ -350,6 +350,67 @@ __global__ void __launch_bounds__(128) decode_kernel(DecodeLevels L, int reg_max
     for (int j = 0; j < nc; ++j) yo[(4LL + j) * L.A] = sigmoidf_(ldf(pc + j));
 }
 
+// bf16 variant that stages the block's 128 anchor rows through shared memory: the row-per-thread pattern of
+// decode_kernel issues 2-byte loads at a 132-byte stride (66 channels); here the block copies its contiguous span
+// with coalesced 4-byte loads and each thread then reads its own row from shared memory (odd word pitch, no bank
+// conflicts).  Same arithmetic, same order of operations as decode_kernel.
+__global__ void __launch_bounds__(128) decode_staged_kernel(DecodeLevels L, int reg_max, int nc, int dist_only,
+                                                            float* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ uint32_t dec_sm[];
+    const int a_blk = blockIdx.x * 128, n = blockIdx.y;
+    const int no = 4 * reg_max + nc, nw = no / 2, pitch = nw | 1;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (i < L.nl && a_blk >= L.a0[i]) l = i;
+    const int Wl = L.W[l], Hl = L.H[l];
+    const int la0 = a_blk - L.a0[l];
+    const int cnt = min(128, Hl * Wl - la0);          // the host only takes this path when blocks do not straddle levels
+    const __nv_bfloat16* base = (const __nv_bfloat16*)L.raw[l] + ((long long)n * Hl * Wl + la0) * L.cs[l];
+    for (int e = threadIdx.x; e < cnt * nw; e += 128) {
+        const int r = e / nw, c = e - r * nw;
+        dec_sm[r * pitch + c] = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)r * L.cs[l]) + c);
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= cnt) return;
+    const int a = a_blk + t, la = la0 + t;
+    const int hq = la / Wl, wq = la - hq * Wl;
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(dec_sm + t * pitch);
+    float d[4];
+    for (int side = 0; side < 4; ++side) {
+        if (reg_max > 1) {
+            float mx = -INFINITY;
+            for (int k = 0; k < reg_max; ++k) mx = fmaxf(mx, __bfloat162float(p[side * reg_max + k]));
+            float den = 0.f, num = 0.f;
+            for (int k = 0; k < reg_max; ++k) {
+                const float e = __expf(__bfloat162float(p[side * reg_max + k]) - mx);   // ex2.approx: 2^-21 relative, bf16 inputs
+                den += e;
+                num += e * (float)k;
+            }
+            d[side] = num / den;
+        } else {
+            d[side] = __bfloat162float(p[side]);
+        }
+    }
+    if (dist_only) {
+        float* yd = y + (long long)n * 4 * L.A + a;
+        for (int side = 0; side < 4; ++side) yd[(long long)side * L.A] = d[side];
+        return;
+    }
+    const float ax = (float)wq + 0.5f, ay = (float)hq + 0.5f, st = L.stride[l];
+    const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+    float* yo = y + (long long)n * (4 + nc) * L.A + a;
+    yo[0] = (x1 + x2) / 2.f * st;
+    yo[(long long)L.A] = (y1 + y2) / 2.f * st;
+    yo[2LL * L.A] = (x2 - x1) * st;
+    yo[3LL * L.A] = (y2 - y1) * st;
+    const __nv_bfloat16* pc = p + 4 * reg_max;
+    for (int j = 0; j < nc; ++j) yo[(4LL + j) * L.A] = sigmoidf_(__bfloat162float(pc[j]));
+}
+
 }  // namespace mgdt
 
 using namespace mgdt;
@@ -438,6 +499,20 @@ extern "C" int mgdt_decode(const mgdt_decode_level* levels, int nl, int N, int r
         }
     }
     L.A = a0;
+    // staged bf16 path: even channel count, 4-byte aligned rows, every level a multiple of 128 anchors (so no block
+    // straddles two levels) or a single level
+    bool staged = dtype == MGDT_BF16 && ((4 * reg_max + nc) & 1) == 0;
+    for (int i = 0; i < nl && staged; ++i) {
+        if ((levels[i].cs & 1) || ((uintptr_t)levels[i].raw & 3)) staged = false;
+        if (i + 1 < nl && (levels[i].H * levels[i].W) % 128 != 0) staged = false;
+    }
+    if (staged) {
+        const int nw = (4 * reg_max + nc) / 2;
+        launch_k(decode_staged_kernel, dim3(cdiv(L.A, 128), N), dim3(128), (size_t)128 * (nw | 1) * 4, (cudaStream_t)stream, L,
+                 reg_max, nc, dist_only, y);
+        MGDT_LAUNCH_CHECK("decode_staged");
+        return 0;
+    }
     MGDT_DTYPE_SWITCH(dtype, T, {
         launch_k(decode_kernel<T>, dim3(dim3(cdiv(L.A, 128), N)), dim3(128), 0, (cudaStream_t)stream, L, reg_max, nc, dist_only, y);
     });
