@@ -11,9 +11,9 @@ namespace mgdt {
 
 constexpr int EW_THREADS = 256;
 
-static inline int ew_grid(long long total) {
+static inline int ew_grid(long long total, int waves = 4) {
     long long b = (total + EW_THREADS - 1) / EW_THREADS;
-    const long long cap = 148LL * 32;
+    const long long cap = 148LL * 8 * waves;   // 8 x 256 threads are resident per SM; kernels grid-stride beyond that
     return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
@@ -64,28 +64,58 @@ __global__ void __launch_bounds__(EW_THREADS) affine_act_kernel(const T* __restr
     pdl_trigger();
     pdl_wait();
     const unsigned CV = C / V;
-    for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
-        const unsigned cv = i % CV, pix = i / CV;
-        const unsigned c = cv * V;
-        float f[V];
-        VecIO<T, V>::ld(x + (size_t)pix * x_cs + c, f);
-        if (a || b) {
-            const unsigned n = pix / HW;
+    const unsigned stride = gridDim.x * EW_THREADS;
+    // two independent elements per iteration (all loads first), per-(n,c) scales as vector loads, activation switch
+    // outside the unrolled loops (SFU forms for bf16 storage, exact forms in the fp32 validation mode)
+    for (unsigned i0 = blockIdx.x * EW_THREADS + threadIdx.x; i0 < total; i0 += 2 * stride) {
+        float f[2][V], g[2][V], sa[2][V], sb[2][V];
+        unsigned pixs[2], cs_[2];
+        bool on[2];
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                if (a) f[j] *= a[n * C + c + j];
-                if (b) f[j] += b[n * C + c + j];
+        for (int u = 0; u < 2; ++u) {
+            const unsigned i = i0 + u * stride;
+            on[u] = i < total;
+            if (!on[u]) continue;
+            const unsigned pix = i / CV, cv = i - pix * CV;
+            const unsigned c = cv * V;
+            pixs[u] = pix; cs_[u] = c;
+            VecIO<T, V>::ld(x + (size_t)pix * x_cs + c, f[u]);
+            if (other) VecIO<T, V>::ld(other + (size_t)pix * o_cs + c, g[u]);
+            if (a || b) {
+                const unsigned n = pix / HW;
+                if (a) VecIO<float, V>::ld(a + (size_t)n * C + c, sa[u]);
+                if (b) VecIO<float, V>::ld(b + (size_t)n * C + c, sb[u]);
             }
         }
 #pragma unroll
-        for (int j = 0; j < V; ++j) f[j] = apply_act(f[j], act);
-        if (other) {
-            float g[V];
-            VecIO<T, V>::ld(other + (size_t)pix * o_cs + c, g);
+        for (int u = 0; u < 2; ++u) {
+            if (!on[u]) continue;
 #pragma unroll
-            for (int j = 0; j < V; ++j) f[j] += g[j];
+            for (int j = 0; j < V; ++j) {
+                if (a) f[u][j] *= sa[u][j];
+                if (b) f[u][j] += sb[u][j];
+            }
+            if (sizeof(T) == 2) {
+                switch (act) {
+#define MGDT_ACT_CASE(A) case A: _Pragma("unroll") for (int j = 0; j < V; ++j) f[u][j] = act_fast<A>(f[u][j]); break;
+                    MGDT_ACT_CASE(MGDT_ACT_SILU)
+                    MGDT_ACT_CASE(MGDT_ACT_RELU)
+                    MGDT_ACT_CASE(MGDT_ACT_SIGMOID)
+                    MGDT_ACT_CASE(MGDT_ACT_HSIGMOID)
+                    MGDT_ACT_CASE(MGDT_ACT_GELU)
+#undef MGDT_ACT_CASE
+                    default: break;
+                }
+            } else if (act != MGDT_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) f[u][j] = apply_act(f[u][j], act);
+            }
+            if (other) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) f[u][j] += g[u][j];
+            }
+            VecIO<T, V>::st(y + (size_t)pixs[u] * y_cs + cs_[u], f[u]);
         }
-        VecIO<T, V>::st(y + (size_t)pix * y_cs + c, f);
     }
 }
 
@@ -363,7 +393,7 @@ extern "C" int mgdt_affine_act(const void* x, int x_cs, const float* a, const fl
                          aligned8(other, other ? o_cs : 0, sizeof(T));
         MGDT_VEC_SWITCH(vec, V, {
             const unsigned total = (unsigned)((long long)N * H * W * (C / V));
-            launch_k(affine_act_kernel<T, V>, dim3(ew_grid(total)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, a, b, (const T*)other, o_cs, act, (T*)y, y_cs, (unsigned)(H * W), (unsigned)C, total);
+            launch_k(affine_act_kernel<T, V>, dim3(ew_grid((total + 1) / 2, 1)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, a, b, (const T*)other, o_cs, act, (T*)y, y_cs, (unsigned)(H * W), (unsigned)C, total);
         });
     });
     MGDT_LAUNCH_CHECK("affine_act");
