@@ -134,6 +134,23 @@ size_t mgdt_chan_stats_ws_bytes(int N, int H, int W, int C, int quads);
 int mgdt_chan_stats(const void* x, int x_cs, int N, int H, int W, int C, int quads, float* out_sum, float* out_sumsq,
                     void* ws, size_t ws_bytes, int32_t* counters, int dtype, void* stream);
 
+/* chan_stats whose last block also runs the per-image computation that consumes the statistics (one launch saved):
+ *   MGDT_FIN_GATE  SPRModule MLP + softmax over groups (== mgdt_mspa_gate): p0..p3 = fc1 w, fc1 b, fc2 w, fc2 b,
+ *                  i0 = groups, i1 = softmax, i2 = hidden, o0 = scale[N][C]; needs quads = 1
+ *   MGDT_FIN_GRN   GRN scale (== mgdt_grn_scale): p0 = gamma, o0 = scale[N][C]; needs out_sumsq
+ *   MGDT_FIN_GN    GroupNorm affine (== mgdt_gn_affine): p0 = gamma, p1 = beta, i0 = groups, f0 = eps,
+ *                  o0 = a[N][C], o1 = b[N][C]; needs out_sumsq, quads = 0 */
+enum { MGDT_FIN_NONE = 0, MGDT_FIN_GATE = 1, MGDT_FIN_GRN = 2, MGDT_FIN_GN = 3 };
+typedef struct mgdt_stats_fin {
+    int32_t kind;
+    const float *p0, *p1, *p2, *p3;
+    int32_t i0, i1, i2;
+    float f0;
+    float *o0, *o1;
+} mgdt_stats_fin;
+int mgdt_chan_stats_fin(const void* x, int x_cs, int N, int H, int W, int C, int quads, float* out_sum, float* out_sumsq,
+                        void* ws, size_t ws_bytes, int32_t* counters, const mgdt_stats_fin* fin, int dtype, void* stream);
+
 /* SPR gate of MSPA_C2f (block.py:270-279 + spr_module.py:20-31): stats[N][5][C] (sums) ->
  * scale[N][C] = softmax over the `groups` (4) channel groups of sigmoid(fc2(relu(fc1([mean | 2x2 means])))).
  * fc1_w [hidden][5*ow], fc2_w [ow][hidden] fp32, ow = C/groups.  groups=1, softmax=0 gives

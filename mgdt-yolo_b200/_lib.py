@@ -29,6 +29,12 @@ class ConvArgs(C.Structure):
                 ("act", i32), ("in_relu", i32), ("dtype", i32), ("impl", i32), ("w_umma", vp), ("w_umma_f16", i32)]
 
 
+class StatsFin(C.Structure):
+    fp = C.POINTER(C.c_float)
+    _fields_ = [("kind", i32), ("p0", vp), ("p1", vp), ("p2", vp), ("p3", vp), ("i0", i32), ("i1", i32), ("i2", i32),
+                ("f0", C.c_float), ("o0", vp), ("o1", vp)]
+
+
 class DecodeLevel(C.Structure):
     _fields_ = [("raw", vp), ("H", i32), ("W", i32), ("cs", i32), ("stride", f32)]
 
@@ -52,6 +58,7 @@ SIGNATURES = {
     "mgdt_dcn3x3": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_chan_stats_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
     "mgdt_chan_stats": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, i32, vp]),
+    "mgdt_chan_stats_fin": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, C.POINTER(StatsFin), i32, vp]),
     "mgdt_mspa_gate": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
     "mgdt_grn_scale": (C.c_int, [vp, vp, i32, i32, vp, vp]),
     "mgdt_gn_affine": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp]),

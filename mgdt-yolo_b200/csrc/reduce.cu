@@ -28,6 +28,103 @@ template <> struct StatLd<float, 8> {
     }
 };
 
+// ------------------------------------------------------------------ per-image finalisers
+// Bodies of the tiny per-image kernels (SPR gate MLP, GRN scale, GroupNorm affine) as device functions over one image:
+// they run either as their own one-block-per-image kernels or inside the last block of chan_stats (mgdt_stats_fin),
+// which saves a launch per use.  `sm` is scratch shared memory, blockDim-stride loops throughout.
+struct StatsFin {
+    int kind;                  // 0 none, 1 SPR gate, 2 GRN scale, 3 GroupNorm affine
+    const float *p0, *p1, *p2, *p3;
+    int i0, i1, i2;
+    float f0;
+    float *o0, *o1;
+};
+
+__device__ __forceinline__ void mspa_gate_body(int n, const float* st, int H, int W, int C, int G, int softmax,
+                                               const float* __restrict__ w1, const float* __restrict__ b1,
+                                               const float* __restrict__ w2, const float* __restrict__ b2, int hidden,
+                                               float* __restrict__ scale, float* sm) {
+    const int ow = C / G;
+    float* feat = sm;                    // feat[G][5*ow] | hid[G][hidden] | gate[G][ow]
+    float* hid = feat + G * 5 * ow;
+    float* gate = hid + G * hidden;
+    // window sizes of adaptive_avg_pool2d(2)
+    const int hs[2] = {(H + 1) / 2, H - H / 2};
+    const int ws[2] = {(W + 1) / 2, W - W / 2};
+    for (int i = threadIdx.x; i < G * ow; i += blockDim.x) {
+        const int g = i / ow, c = i % ow;
+        const int ch = g * ow + c;
+        feat[g * 5 * ow + c] = st[0 * C + ch] / (float)(H * W);
+        for (int q = 0; q < 4; ++q)
+            feat[g * 5 * ow + ow + c * 4 + q] = st[(1 + q) * C + ch] / (float)(hs[q >> 1] * ws[q & 1]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G * hidden; i += blockDim.x) {
+        const int g = i / hidden, j = i % hidden;
+        float a = b1[j];
+        const float* wr = w1 + (long long)j * 5 * ow;
+        const float* f = feat + g * 5 * ow;
+        for (int k = 0; k < 5 * ow; ++k) a = fmaf(wr[k], f[k], a);
+        hid[i] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G * ow; i += blockDim.x) {
+        const int g = i / ow, c = i % ow;
+        float a = b2[c];
+        for (int k = 0; k < hidden; ++k) a = fmaf(w2[c * hidden + k], hid[g * hidden + k], a);
+        gate[i] = sigmoidf_(a);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < ow; c += blockDim.x) {
+        if (!softmax) {
+            for (int g = 0; g < G; ++g) scale[(long long)n * C + g * ow + c] = gate[g * ow + c];
+            continue;
+        }
+        float mx = -1e30f, den = 0.f;
+        for (int g = 0; g < G; ++g) mx = fmaxf(mx, gate[g * ow + c]);
+        for (int g = 0; g < G; ++g) den += expf(gate[g * ow + c] - mx);
+        for (int g = 0; g < G; ++g) scale[(long long)n * C + g * ow + c] = expf(gate[g * ow + c] - mx) / den;
+    }
+}
+
+__device__ __forceinline__ void grn_scale_body(int n, const float* sumsq_n, const float* __restrict__ gamma, int C,
+                                               float* __restrict__ scale, float* red) {
+    float part = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) part += sqrtf(sumsq_n[c]);
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    const float denom = tot / (float)C + 1e-6f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        scale[(long long)n * C + c] = 1.0f + gamma[c] * (sqrtf(sumsq_n[c]) / denom);
+}
+
+__device__ __forceinline__ void gn_affine_body(int n, const float* sum_n, const float* sumsq_n, int C, int groups, int hw,
+                                               float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                               float* __restrict__ a, float* __restrict__ b) {
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        for (int k = 0; k < cpg; ++k) {
+            s += (double)sum_n[g * cpg + k];
+            q += (double)sumsq_n[g * cpg + k];
+        }
+        const double cnt = (double)cpg * (double)hw;
+        const double mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        for (int k = 0; k < cpg; ++k) {
+            const int c = g * cpg + k;
+            const float aa = gamma[c] * rstd;
+            a[(long long)n * C + c] = aa;
+            b[(long long)n * C + c] = beta[c] - (float)mean * aa;
+        }
+    }
+}
+
 // Stage 1: grid (chunks, N, rects).  rects = 1 (whole image) or, with quads, the four adaptive_avg_pool2d(2) windows
 // [floor(i*H/2), ceil((i+1)*H/2)) (+ a fifth whole-image rect when H or W is odd and the windows overlap; for even
 // sizes the total is the sum of the four).  A block walks a strip of its rectangle's pixels; thread = (pixel group,
@@ -38,7 +135,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __restrict__ x, int x_cs, int H, int W, int C, int Q,
                                                                  float* __restrict__ part, float* __restrict__ partsq,
                                                                  int* __restrict__ counters, float* __restrict__ out_sum,
-                                                                 float* __restrict__ out_sumsq) {
+                                                                 float* __restrict__ out_sumsq, StatsFin fin) {
     pdl_trigger();
     pdl_wait();
     __shared__ float sm[CS_THREADS * V];  // [rows][Cw * V]
@@ -136,6 +233,18 @@ __global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __rest
         else out_sum[(size_t)n * Q * C + i] = t;
     }
     if (threadIdx.x == 0) counters[n] = 0;
+    if (fin.kind) {
+        // the image's statistics are complete: finish the consumer's per-image computation here (one launch saved)
+        __syncthreads();
+        if (fin.kind == 1)
+            mspa_gate_body(n, out_sum + (size_t)n * Q * C, H, W, C, fin.i0, fin.i1, fin.p0, fin.p1, fin.p2, fin.p3, fin.i2,
+                           fin.o0, sm);
+        else if (fin.kind == 2)
+            grn_scale_body(n, out_sumsq + (size_t)n * C, fin.p0, C, fin.o0, sm);
+        else if (fin.kind == 3)
+            gn_affine_body(n, out_sum + (size_t)n * Q * C, out_sumsq + (size_t)n * C, C, fin.i0, H * W, fin.f0, fin.p0, fin.p1,
+                           fin.o0, fin.o1);
+    }
 }
 
 static int stats_rects(int H, int W, int quads) { return quads ? ((H % 2 == 0 && W % 2 == 0) ? 4 : 5) : 1; }
@@ -158,8 +267,8 @@ extern "C" size_t mgdt_chan_stats_ws_bytes(int N, int H, int W, int C, int quads
     return sizeof(float) * (size_t)N * nch * nrect * 2 * (size_t)C;
 }
 
-extern "C" int mgdt_chan_stats(const void* x, int x_cs, int N, int H, int W, int C, int quads, float* out_sum,
-                               float* out_sumsq, void* ws, size_t ws_bytes, int32_t* counters, int dtype, void* stream) {
+static int chan_stats_impl(const void* x, int x_cs, int N, int H, int W, int C, int quads, float* out_sum, float* out_sumsq,
+                           void* ws, size_t ws_bytes, int32_t* counters, StatsFin fin, int dtype, void* stream) {
     MGDT_CHECK(x && out_sum && ws && counters, "chan_stats: null pointer");
     MGDT_CHECK(N > 0 && H > 0 && W > 0 && C > 0 && x_cs >= C, "chan_stats: bad shape");
     MGDT_CHECK(ws_bytes >= mgdt_chan_stats_ws_bytes(N, H, W, C, quads), "chan_stats: workspace too small");
@@ -173,11 +282,43 @@ extern "C" int mgdt_chan_stats(const void* x, int x_cs, int N, int H, int W, int
     MGDT_DTYPE_SWITCH(dtype, T, {
         const bool vec = C % 8 == 0 && (x_cs % 8) == 0 && (((uintptr_t)x) % (8 * sizeof(T))) == 0;
         float* psq = out_sumsq ? partsq : nullptr;
-        if (vec) launch_k(chan_stats_partial<T, 8>, dim3(nch, N, nrect), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, Q, part, psq, (int*)counters, out_sum, out_sumsq);
-        else launch_k(chan_stats_partial<T, 1>, dim3(nch, N, nrect), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, Q, part, psq, (int*)counters, out_sum, out_sumsq);
+        if (vec) launch_k(chan_stats_partial<T, 8>, dim3(nch, N, nrect), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, Q, part, psq, (int*)counters, out_sum, out_sumsq, fin);
+        else launch_k(chan_stats_partial<T, 1>, dim3(nch, N, nrect), dim3(CS_THREADS), 0, s, (const T*)x, x_cs, H, W, C, Q, part, psq, (int*)counters, out_sum, out_sumsq, fin);
     });
     MGDT_LAUNCH_CHECK("chan_stats");
     return 0;
+}
+
+extern "C" int mgdt_chan_stats(const void* x, int x_cs, int N, int H, int W, int C, int quads, float* out_sum,
+                               float* out_sumsq, void* ws, size_t ws_bytes, int32_t* counters, int dtype, void* stream) {
+    StatsFin fin{};
+    return chan_stats_impl(x, x_cs, N, H, W, C, quads, out_sum, out_sumsq, ws, ws_bytes, counters, fin, dtype, stream);
+}
+
+extern "C" int mgdt_chan_stats_fin(const void* x, int x_cs, int N, int H, int W, int C, int quads, float* out_sum,
+                                   float* out_sumsq, void* ws, size_t ws_bytes, int32_t* counters,
+                                   const mgdt_stats_fin* f, int dtype, void* stream) {
+    MGDT_CHECK(f, "chan_stats_fin: null finaliser");
+    StatsFin fin{};
+    fin.kind = f->kind; fin.p0 = f->p0; fin.p1 = f->p1; fin.p2 = f->p2; fin.p3 = f->p3;
+    fin.i0 = f->i0; fin.i1 = f->i1; fin.i2 = f->i2; fin.f0 = f->f0; fin.o0 = f->o0; fin.o1 = f->o1;
+    const bool vec = C % 8 == 0 && (x_cs % 8) == 0 && (((uintptr_t)x) % (8 * (dtype == MGDT_F32 ? 4 : 2))) == 0;
+    const int smem_floats = CS_THREADS * (vec ? 8 : 1);
+    if (fin.kind == MGDT_FIN_GATE) {
+        MGDT_CHECK(quads && fin.p0 && fin.p1 && fin.p2 && fin.p3 && fin.o0 && fin.i0 > 0 && C % fin.i0 == 0 && fin.i2 > 0,
+                   "chan_stats_fin: bad SPR gate arguments");
+        const int ow = C / fin.i0;
+        MGDT_CHECK(fin.i0 * 5 * ow + fin.i0 * fin.i2 + fin.i0 * ow <= smem_floats,
+                   "chan_stats_fin: gate scratch does not fit (C=%d): use mgdt_mspa_gate", C);
+    } else if (fin.kind == MGDT_FIN_GRN) {
+        MGDT_CHECK(out_sumsq && fin.p0 && fin.o0, "chan_stats_fin: bad GRN arguments");
+    } else if (fin.kind == MGDT_FIN_GN) {
+        MGDT_CHECK(!quads && out_sumsq && fin.p0 && fin.p1 && fin.o0 && fin.o1 && fin.i0 > 0 && C % fin.i0 == 0,
+                   "chan_stats_fin: bad GroupNorm arguments");
+    } else {
+        MGDT_CHECK(fin.kind == 0, "chan_stats_fin: unknown finaliser %d", fin.kind);
+    }
+    return chan_stats_impl(x, x_cs, N, H, W, C, quads, out_sum, out_sumsq, ws, ws_bytes, counters, fin, dtype, stream);
 }
 
 // ------------------------------------------------------------------ MSPA gate
@@ -189,50 +330,8 @@ __global__ void mspa_gate_kernel(const float* __restrict__ stats, int H, int W, 
                                  float* __restrict__ scale) {
     pdl_trigger();
     pdl_wait();
-    extern __shared__ float sm[];  // feat[G][5*ow] | hid[G][hidden] | gate[G][ow]
-    const int n = blockIdx.x;
-    const int ow = C / G;
-    float* feat = sm;
-    float* hid = feat + G * 5 * ow;
-    float* gate = hid + G * hidden;
-    const float* st = stats + (long long)n * 5 * C;
-    // window sizes of adaptive_avg_pool2d(2)
-    const int hs[2] = {(H + 1) / 2, H - H / 2};
-    const int ws[2] = {(W + 1) / 2, W - W / 2};
-    for (int i = threadIdx.x; i < G * ow; i += blockDim.x) {
-        const int g = i / ow, c = i % ow;
-        const int ch = g * ow + c;
-        feat[g * 5 * ow + c] = st[0 * C + ch] / (float)(H * W);
-        for (int q = 0; q < 4; ++q)
-            feat[g * 5 * ow + ow + c * 4 + q] = st[(1 + q) * C + ch] / (float)(hs[q >> 1] * ws[q & 1]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < G * hidden; i += blockDim.x) {
-        const int g = i / hidden, j = i % hidden;
-        float a = b1[j];
-        const float* wr = w1 + (long long)j * 5 * ow;
-        const float* f = feat + g * 5 * ow;
-        for (int k = 0; k < 5 * ow; ++k) a = fmaf(wr[k], f[k], a);
-        hid[i] = fmaxf(a, 0.f);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < G * ow; i += blockDim.x) {
-        const int g = i / ow, c = i % ow;
-        float a = b2[c];
-        for (int k = 0; k < hidden; ++k) a = fmaf(w2[c * hidden + k], hid[g * hidden + k], a);
-        gate[i] = sigmoidf_(a);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < ow; c += blockDim.x) {
-        if (!softmax) {
-            for (int g = 0; g < G; ++g) scale[(long long)n * C + g * ow + c] = gate[g * ow + c];
-            continue;
-        }
-        float mx = -1e30f, den = 0.f;
-        for (int g = 0; g < G; ++g) mx = fmaxf(mx, gate[g * ow + c]);
-        for (int g = 0; g < G; ++g) den += expf(gate[g * ow + c] - mx);
-        for (int g = 0; g < G; ++g) scale[(long long)n * C + g * ow + c] = expf(gate[g * ow + c] - mx) / den;
-    }
+    extern __shared__ float gate_sm[];
+    mspa_gate_body(blockIdx.x, stats + (long long)blockIdx.x * 5 * C, H, W, C, G, softmax, w1, b1, w2, b2, hidden, scale, gate_sm);
 }
 
 __global__ void grn_scale_kernel(const float* __restrict__ sumsq, const float* __restrict__ gamma, int C,
@@ -240,17 +339,7 @@ __global__ void grn_scale_kernel(const float* __restrict__ sumsq, const float* _
     pdl_trigger();
     pdl_wait();
     __shared__ float red[32];
-    const int n = blockIdx.x;
-    float part = 0.f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) part += sqrtf(sumsq[(long long)n * C + c]);
-    part = warp_sum(part);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
-    __syncthreads();
-    float tot = 0.f;
-    for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
-    const float denom = tot / (float)C + 1e-6f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x)
-        scale[(long long)n * C + c] = 1.0f + gamma[c] * (sqrtf(sumsq[(long long)n * C + c]) / denom);
+    grn_scale_body(blockIdx.x, sumsq + (long long)blockIdx.x * C, gamma, C, scale, red);
 }
 
 __global__ void gn_affine_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, int C, int groups,
@@ -258,26 +347,8 @@ __global__ void gn_affine_kernel(const float* __restrict__ sum, const float* __r
                                  float* __restrict__ a, float* __restrict__ b) {
     pdl_trigger();
     pdl_wait();
-    const int n = blockIdx.x;
-    const int cpg = C / groups;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        double s = 0.0, q = 0.0;
-        for (int k = 0; k < cpg; ++k) {
-            s += (double)sum[(long long)n * C + g * cpg + k];
-            q += (double)sumsq[(long long)n * C + g * cpg + k];
-        }
-        const double cnt = (double)cpg * (double)hw;
-        const double mean = s / cnt;
-        double var = q / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        for (int k = 0; k < cpg; ++k) {
-            const int c = g * cpg + k;
-            const float aa = gamma[c] * rstd;
-            a[(long long)n * C + c] = aa;
-            b[(long long)n * C + c] = beta[c] - (float)mean * aa;
-        }
-    }
+    gn_affine_body(blockIdx.x, sum + (long long)blockIdx.x * C, sumsq + (long long)blockIdx.x * C, C, groups, hw, eps, gamma,
+                   beta, a, b);
 }
 
 __global__ void td_attn_kernel(const float* __restrict__ sum, int N, int C, int hw, int hidden, int stacked,

@@ -100,8 +100,7 @@ class SPRModule(KernelModule):
         self._check_mode(x)
         x = ops.as_act(x)
         n, c, h, w = x.shape
-        stats, _ = ops.chan_stats(x, quads=True)
-        gate = ops.mspa_gate(stats, h, w, c, *self._pack(x.device), groups=1, softmax=False)
+        gate = ops.stats_gate(x, *self._pack(x.device), groups=1, softmax=False)   # statistics + MLP in one launch
         return gate.to(x.dtype).view(n, c, 1, 1)
 
 
@@ -149,8 +148,7 @@ class MSPA_C2f(KernelModule):
             sp = m(sp, out=cat[:, (g - 1 + j) * iw:(g + j) * iw])
         feat = self.convs[g - 1](cat)
         co = feat.shape[1]
-        stats, _ = ops.chan_stats(feat, quads=True)
-        scale = ops.mspa_gate(stats, h, w, co, *self.attention._pack(x.device), groups=g, softmax=True)
+        scale = ops.stats_gate(feat, *self.attention._pack(x.device), groups=g, softmax=True)   # stats + gate, one launch
         return ops.affine_act(feat, a=scale)  # feats * softmax_g(gates), written back in group order
 
 
@@ -289,8 +287,7 @@ class ConvNeXtV2_Block(KernelModule):
         p = self._pack(x.dtype, x.device)
         t = ops.dwconv7_ln(x, p["dw"], p["dwb"], p["lnw"], p["lnb"], self.norm.eps)
         hid = ops.conv2d(t, p["w1"], p["b1"], 1, act="gelu")
-        _, sumsq = ops.chan_stats(hid, sumsq=True)
-        scale = ops.grn_scale(sumsq, p["gamma"])
+        scale = ops.stats_grn(hid, p["gamma"])   # sum of squares + GRN scale in one launch
         return ops.conv2d(hid, p["w2"], p["b2"], 1, in_scale=scale, residual=x, out=out)
 
 
@@ -393,6 +390,5 @@ class DyDCNv2(KernelModule):
         if not self.with_norm:
             return y if act is None else ops.affine_act(y, act=act, out=out)
         n, c, h, w = y.shape
-        s, ss = ops.chan_stats(y, sumsq=True)
-        a, b = ops.gn_affine(s, ss, self.norm.num_groups, h * w, self.norm.eps, gnw, gnb)
+        a, b = ops.stats_gn(y, self.norm.num_groups, self.norm.eps, gnw, gnb)   # statistics + affine in one launch
         return ops.affine_act(y, a, b, act=act, out=out)

@@ -57,8 +57,7 @@ class Conv_GN(KernelModule):
         w, gw, gb = self._pack(x.dtype, x.device)
         c = self.conv
         raw = ops.conv2d(x, w, None, c.kernel_size[0], c.stride[0], c.padding[0])
-        s, ss = ops.chan_stats(raw, sumsq=True)
-        a, b = ops.gn_affine(s, ss, self.gn.num_groups, raw.shape[2] * raw.shape[3], self.gn.eps, gw, gb)
+        a, b = ops.stats_gn(raw, self.gn.num_groups, self.gn.eps, gw, gb)   # statistics + affine in one launch
         return ops.affine_act(raw, a, b, act=act_name(self.act), out=out)
 
 

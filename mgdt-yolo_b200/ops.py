@@ -260,17 +260,66 @@ def dcn3x3(x, offset, mask, w, cout, mask_is_logit, out=None):
 
 
 # ------------------------------------------------------------------------------------- reductions
-def chan_stats(x, quads=False, sumsq=False):
-    """-> (sum [N, 5|1, C] fp32, sumsq [N, C] fp32 | None)."""
+def chan_stats(x, quads=False, sumsq=False, fin=None):
+    """-> (sum [N, 5|1, C] fp32, sumsq [N, C] fp32 | None).  `fin` (a _lib.StatsFin) makes the kernel's last block of
+    every image also run the per-image consumer of the statistics (SPR gate / GRN scale / GroupNorm affine)."""
     xp, n, c, h, w, xcs = view(x)
     q = 5 if quads else 1
     s = torch.empty((n, q, c), dtype=torch.float32, device=x.device)
     ss = torch.empty((n, c), dtype=torch.float32, device=x.device) if sumsq else None
     nbytes = lib().mgdt_chan_stats_ws_bytes(n, h, w, c, 1 if quads else 0)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
-    _invoke("mgdt_chan_stats", dict(shape=f"stats C{c} {n}x{h}x{w} q{q}", bytes=_nb(x), flops=0.0), xp, xcs, n, h, w, c, 1 if quads else 0, s.data_ptr(), _p(ss), ws.data_ptr(), nbytes,
-                                _stats_tickets(x.device, n).data_ptr(), dtype_code(x.dtype), stream_ptr())
+    meta = dict(shape=f"stats C{c} {n}x{h}x{w} q{q}", bytes=_nb(x), flops=0.0)
+    if fin is None:
+        _invoke("mgdt_chan_stats", meta, xp, xcs, n, h, w, c, 1 if quads else 0, s.data_ptr(), _p(ss), ws.data_ptr(), nbytes,
+                _stats_tickets(x.device, n).data_ptr(), dtype_code(x.dtype), stream_ptr())
+    else:
+        _invoke("mgdt_chan_stats_fin", meta, xp, xcs, n, h, w, c, 1 if quads else 0, s.data_ptr(), _p(ss), ws.data_ptr(), nbytes,
+                _stats_tickets(x.device, n).data_ptr(), C.byref(fin), dtype_code(x.dtype), stream_ptr())
     return s, ss
+
+
+def _gate_fits(c, groups, hidden, vec):
+    ow = c // groups
+    return groups * 5 * ow + groups * hidden + groups * ow <= 256 * (8 if vec else 1)
+
+
+def stats_gate(x, fc1_w, fc1_b, fc2_w, fc2_b, groups=4, softmax=True):
+    """SPRModule statistics + gate MLP (+ softmax over the groups) of x in ONE launch -> scale [N, C] fp32
+    (== chan_stats(quads) followed by mspa_gate; falls back to the two launches when the scratch does not fit)."""
+    from ._lib import StatsFin
+    _, n, c, h, w, xcs = view(x)
+    vec = c % 8 == 0 and xcs % 8 == 0 and x.data_ptr() % (8 * x.element_size()) == 0
+    if not _gate_fits(c, groups, fc1_w.shape[0], vec):
+        stats, _ = chan_stats(x, quads=True)
+        return mspa_gate(stats, h, w, c, fc1_w, fc1_b, fc2_w, fc2_b, groups=groups, softmax=softmax)
+    scale = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    fin = StatsFin(kind=1, p0=fc1_w.data_ptr(), p1=fc1_b.data_ptr(), p2=fc2_w.data_ptr(), p3=fc2_b.data_ptr(), i0=groups,
+                   i1=1 if softmax else 0, i2=fc1_w.shape[0], f0=0.0, o0=scale.data_ptr(), o1=None)
+    chan_stats(x, quads=True, fin=fin)
+    return scale
+
+
+def stats_grn(x, gamma):
+    """sum of squares + GRN scale of x in one launch -> scale [N, C] fp32 (== chan_stats(sumsq) + grn_scale)."""
+    from ._lib import StatsFin
+    n, c = x.shape[0], x.shape[1]
+    scale = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    fin = StatsFin(kind=2, p0=gamma.data_ptr(), p1=None, p2=None, p3=None, i0=0, i1=0, i2=0, f0=0.0, o0=scale.data_ptr(), o1=None)
+    chan_stats(x, sumsq=True, fin=fin)
+    return scale
+
+
+def stats_gn(x, groups, eps, gamma, beta):
+    """GroupNorm statistics + per-(n,c) affine (a, b) of x in one launch (== chan_stats(sumsq) + gn_affine)."""
+    from ._lib import StatsFin
+    n, c = x.shape[0], x.shape[1]
+    a = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    b = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    fin = StatsFin(kind=3, p0=gamma.data_ptr(), p1=beta.data_ptr(), p2=None, p3=None, i0=groups, i1=0, i2=0, f0=float(eps),
+                   o0=a.data_ptr(), o1=b.data_ptr())
+    chan_stats(x, sumsq=True, fin=fin)
+    return a, b
 
 
 _TICKETS = {}
