@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--slots", type=int, default=2, help="batches in flight (engine slots, one CUDA stream each)")
     ap.add_argument("--profile-json", default="", help="write the per-launch table here")
     ap.add_argument("--launch-list", action="store_true",
                     help="eager warm-up + timed steps only (no e2e / per-launch / CPU legs): the run to put under ncu")
@@ -207,7 +208,7 @@ def run_ours(args):
     model = DetectionModel(cfg, nc=nc, verbose=False)
     model.load_state_dict(raise_cls_bias(synth_state_dict(model.state_dict(), seed=1), cls_bias))
     B = args.batch
-    eng = Engine(model, B, 640, dtype, dev, conf=CONF, iou=IOU, max_det=MAX_DET, slots=2,
+    eng = Engine(model, B, 640, dtype, dev, conf=CONF, iou=IOU, max_det=MAX_DET, slots=args.slots,
                  use_graph=not args.no_graph)
 
     # rotating inputs: 6 x 39 MB uint8 batches on the device (> 126 MB L2) and in pinned host memory
@@ -377,7 +378,7 @@ def run_ours(args):
                          "per-step activation traffic >> L2", "parallelism": f"dp{world} (batch sharded, no collective)"},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 640 * 640,
                 "d2h_bytes_per_step": B * (MAX_DET * 6 * 4 + 4), "ms_per_step": ms_e2e / args.steps,
-                "api": "Engine.submit/collect, 2 batches in flight"},
+                "api": f"Engine.submit/collect, {nslot} batches in flight"},
         "gpu_launches": eng.launches_per_step * args.steps,
         "launches_per_step": eng.launches_per_step,
         "clocks": clocks,
