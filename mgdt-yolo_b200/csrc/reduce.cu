@@ -59,13 +59,15 @@ __device__ __forceinline__ void mspa_gate_body(int n, const float* st, int H, in
             feat[g * 5 * ow + ow + c * 4 + q] = st[(1 + q) * C + ch] / (float)(hs[q >> 1] * ws[q & 1]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < G * hidden; i += blockDim.x) {
+    // fc1: one warp per output, lanes stride the 5*ow inputs (coalesced weight reads), fixed-order butterfly sum
+    for (int i = threadIdx.x >> 5; i < G * hidden; i += (int)(blockDim.x >> 5)) {
         const int g = i / hidden, j = i % hidden;
-        float a = b1[j];
         const float* wr = w1 + (long long)j * 5 * ow;
         const float* f = feat + g * 5 * ow;
-        for (int k = 0; k < 5 * ow; ++k) a = fmaf(wr[k], f[k], a);
-        hid[i] = fmaxf(a, 0.f);
+        float a = 0.f;
+        for (int k = threadIdx.x & 31; k < 5 * ow; k += 32) a = fmaf(wr[k], f[k], a);
+        a = warp_sum(a);
+        if ((threadIdx.x & 31) == 0) hid[i] = fmaxf(a + b1[j], 0.f);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < G * ow; i += blockDim.x) {
@@ -212,25 +214,36 @@ __global__ void __launch_bounds__(CS_THREADS) chan_stats_partial(const T* __rest
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int i = threadIdx.x; i < Q * C + (partsq ? C : 0); i += CS_THREADS) {
+    // four lanes per output (chunks k = sub, sub + 4, ...), combined by a fixed xor butterfly: deterministic, and the
+    // serial tail of the kernel (one block per image) is four times shorter
+    const int sub = threadIdx.x & 3;
+    const int n_out = Q * C + (partsq ? C : 0);
+    for (int i = threadIdx.x >> 2; i < (n_out + 7) / 8 * 8; i += CS_THREADS / 4) {   // whole warps stay in the loop together
+        const bool valid = i < n_out;
         const bool is_sq = i >= Q * C;
         const int q = is_sq ? 0 : i / C, c = is_sq ? i - Q * C : i - q * C;
         const float* src = is_sq ? partsq : part;
         float t = 0.f;
-        if (q == 0 && nrect == 4) {
-            // even H and W: the windows partition the image; total = (q00 + q01) + (q10 + q11), each in chunk order
-            float tq[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int k = 0; k < nchunks; ++k)
+        if (valid) {
+            if (q == 0 && nrect == 4) {
+                // even H and W: the windows partition the image; total = (q00 + q01) + (q10 + q11)
+                float tq[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int k = sub; k < nchunks; k += 4)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) tq[r] += __ldcg(&src[(((size_t)n * nchunks + k) * nrect + r) * C + c]);
-            t = (tq[0] + tq[1]) + (tq[2] + tq[3]);
-        } else {
-            const int r = nrect == 1 ? 0 : (q == 0 ? 4 : q - 1);
-#pragma unroll 4
-            for (int k = 0; k < nchunks; ++k) t += __ldcg(&src[(((size_t)n * nchunks + k) * nrect + r) * C + c]);
+                    for (int r = 0; r < 4; ++r) tq[r] += __ldcg(&src[(((size_t)n * nchunks + k) * nrect + r) * C + c]);
+                t = (tq[0] + tq[1]) + (tq[2] + tq[3]);
+            } else {
+                const int r = nrect == 1 ? 0 : (q == 0 ? 4 : q - 1);
+#pragma unroll 2
+                for (int k = sub; k < nchunks; k += 4) t += __ldcg(&src[(((size_t)n * nchunks + k) * nrect + r) * C + c]);
+            }
         }
-        if (is_sq) out_sumsq[(size_t)n * C + c] = t;
-        else out_sum[(size_t)n * Q * C + i] = t;
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        if (valid && sub == 0) {
+            if (is_sq) out_sumsq[(size_t)n * C + c] = t;
+            else out_sum[(size_t)n * Q * C + i] = t;
+        }
     }
     if (threadIdx.x == 0) counters[n] = 0;
     if (fin.kind) {
