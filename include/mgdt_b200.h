@@ -104,6 +104,17 @@ int mgdt_conv_umma_pack(const void* w_ohwi, int w_dtype, int Cin, int Cout, int 
 int mgdt_stem_conv(const void* src, int src_is_u8, const void* w_umma, int w_umma_f16, const float* bias, void* y, int y_cs,
                    int N, int C, int H, int W, int Cout, int act, int dtype, void* stream);
 
+/* MSPA_C2f hierarchy front (nn/modules/block.py:248-262) in ONE launch (bf16): the chain of pointwise Conv+BN+act
+ * branches  sp_0 = convs[0](spx[0]);  sp_i = convs[i](sp_{i-1} + spx[i]), i < nstage;  sp_in = sp_{nstage-1} + spx[nstage]
+ * where spx[i] = x[:, i*iw:(i+1)*iw].  x has (nstage+1)*iw channels; sp_i is written to ycat[:, i*iw:(i+1)*iw]
+ * (the concat buffer convs[-1] reads), sp_in (the bottleneck input) to ysp (iw channels).  w is fp32
+ * [nstage][ci][co] (BN folded, already rounded to bf16 values), bias fp32 [nstage][iw].  Intermediate values are
+ * rounded to bf16 where the unfused sequence (mgdt_conv2d with pre_add, mgdt_affine_act) stores them, so the two
+ * agree bit for bit.  iw in {8, 16, 32, 64}. */
+int mgdt_mspa_front_supported(int iw, int nstage);
+int mgdt_mspa_front(const void* x, int x_cs, const float* w, const float* bias, int nstage, int iw, int act, void* ycat,
+                    int y_cs, void* ysp, int s_cs, int N, int H, int W, int dtype, void* stream);
+
 /* Depthwise 7x7 (pad 3, bias) + channels-last LayerNorm(eps), ConvNeXtV2_Block.forward
  * (nn/modules/convnextv2.py:35-37, nn/modules/utils.py:162-163).  w is [49][C] in dtype,
  * bias/ln_w/ln_b fp32 [C]. */

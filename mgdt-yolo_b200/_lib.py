@@ -54,6 +54,8 @@ SIGNATURES = {
     "mgdt_conv_umma_packed_bytes": (sz, [i32, i32, i32, i32]),
     "mgdt_conv_umma_pack": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "mgdt_stem_conv": (C.c_int, [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_mspa_front_supported": (C.c_int, [i32, i32]),
+    "mgdt_mspa_front": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "mgdt_dwconv7_ln": (C.c_int, [vp, i32, vp, vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_dcn3x3": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_chan_stats_ws_bytes": (sz, [i32, i32, i32, i32, i32]),

@@ -8,8 +8,8 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .base import KernelModule, f32, ohwi
-from .conv import Conv
+from .base import KernelModule, act_name, f32, ohwi
+from .conv import Conv, fold_conv_bn
 
 __all__ = ("DFL", "SPPF", "Bottleneck", "C2f", "MSPA_C2f", "SPRModule", "SimFusion_4in", "SimFusion_3in", "IFM",
            "ConvNeXtV2_Block", "LayerNorm", "GRN", "h_sigmoid", "InjectionMultiSum_Auto_pool", "DyDCNv2")
@@ -128,6 +128,30 @@ class MSPA_C2f(KernelModule):
         self.attention = SPRModule(self.outwidth)
         self.softmax = nn.Softmax(dim=1)
 
+    def _pack_front(self, dtype, device):
+        """fp32 [g-1][ci][co] weights (BN folded, bf16-rounded values) + biases of the branch convs for
+        mgdt_mspa_front, or None when the fused kernel does not take this block (fp32 mode, other widths)."""
+        g, iw = self.nums, self.inwidth
+        branch = list(self.convs)[:g - 1]
+        acts = {act_name(c.act) for c in branch}
+        if (dtype != torch.bfloat16 or not ops.FUSE_MSPA_FRONT or len(acts) != 1
+                or not ops.lib().mgdt_mspa_front_supported(iw, g - 1)
+                or any(c.conv.kernel_size != (1, 1) or c.conv.groups != 1 for c in branch)):
+            return None
+        tensors = []
+        for c in branch:
+            bn = getattr(c, "bn", None)
+            tensors += [c.conv.weight] + ([c.conv.bias] if c.conv.bias is not None else [])
+            if bn is not None:
+                tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+        def build():
+            ws, bs = zip(*(fold_conv_bn(c.conv, getattr(c, "bn", None)) for c in branch))
+            w = torch.stack([t.flatten(1).to(device).to(torch.bfloat16).float().t().contiguous() for t in ws])
+            return w.contiguous(), torch.stack([f32(b, device) for b in bs]).contiguous(), acts.copy().pop()
+
+        return self._packed("front", dtype, device, tensors, build)
+
     def forward(self, x):
         self._check_mode(x)
         if self.stride != 1:
@@ -138,12 +162,16 @@ class MSPA_C2f(KernelModule):
         if c != g * iw or (g - 1) * iw + nb * iw != self.convs[g - 1].conv.in_channels:
             raise ValueError("MSPA_C2f: channel arithmetic requires inplanes == outplanes, divisible by scale")
         cat = ops.new_act(n, (g - 1 + nb) * iw, h, w, x.dtype, x.device)
-        sp = None
-        for i in range(g - 1):  # sp = convs[i](sp + spx[i]); the add is fused into the conv's loader
-            sp = self.convs[i](x[:, i * iw:(i + 1) * iw] if i == 0 else sp,
-                               pre_add=None if i == 0 else x[:, i * iw:(i + 1) * iw], out=cat[:, i * iw:(i + 1) * iw])
-        last = x[:, (g - 1) * iw:]
-        sp = ops.affine_act(sp, other=last) if g > 1 else last  # sp + spx[-1] feeds bottleneck + its shortcut
+        front = self._pack_front(x.dtype, x.device) if g > 1 else None
+        if front is not None:  # the whole pointwise branch chain + the last add in one launch
+            sp = ops.mspa_front(x, front[0], front[1], iw, front[2], cat)
+        else:
+            sp = None
+            for i in range(g - 1):  # sp = convs[i](sp + spx[i]); the add is fused into the conv's loader
+                sp = self.convs[i](x[:, i * iw:(i + 1) * iw] if i == 0 else sp,
+                                   pre_add=None if i == 0 else x[:, i * iw:(i + 1) * iw], out=cat[:, i * iw:(i + 1) * iw])
+            last = x[:, (g - 1) * iw:]
+            sp = ops.affine_act(sp, other=last) if g > 1 else last  # sp + spx[-1] feeds bottleneck + its shortcut
         for j, m in enumerate(self.bottleneck):
             sp = m(sp, out=cat[:, (g - 1 + j) * iw:(g + j) * iw])
         feat = self.convs[g - 1](cat)

@@ -144,6 +144,7 @@ class PackedConv:
 # format -- so this stays off; the packer keeps the option for an all-fp16 mode.
 WEIGHT_F16 = False
 USE_UMMA = True  # tests flip this to compare the tcgen05 path with the CUDA-core path
+FUSE_MSPA_FRONT = True  # MSPA_C2f branch chain as one launch (bf16); tests flip this to compare with the unfused sequence
 
 
 def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scale=None, pix_scale=None,
@@ -208,6 +209,27 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
                                                                                   "conv_direct_kernel")
     _invoke("mgdt_conv2d", meta, C.byref(a), stream_ptr())
     return out
+
+
+def mspa_front(x, w, bias, iw, act, ycat, ysp=None):
+    """MSPA_C2f branch chain in one launch (bf16): x (N, (nstage+1)*iw, H, W); w fp32 [nstage, iw(ci), iw(co)];
+    bias fp32 [nstage, iw].  Writes sp_i into ycat[:, i*iw:(i+1)*iw] and returns sp_in = sp_last + spx[-1]."""
+    xp, n, c, h, wd, xcs = view(x)
+    nstage = w.shape[0]
+    if c != (nstage + 1) * iw or x.dtype != torch.bfloat16:
+        raise ValueError("mspa_front: x must be bf16 with (nstage+1)*iw channels")
+    if ysp is None:
+        ysp = new_act(n, iw, h, wd, x.dtype, x.device)
+    yp, yn, yc, yh, yw, ycs = view(ycat)
+    sp, sn, sc, sh, sw, scs = view(ysp)
+    if (yn, yh, yw) != (n, h, wd) or yc < nstage * iw or (sn, sc, sh, sw) != (n, iw, h, wd):
+        raise ValueError("mspa_front: bad output shapes")
+    es = x.element_size()
+    meta = dict(shape=f"mspa_front iw{iw}x{nstage} {n}x{h}x{wd}", flops=2.0 * n * h * wd * nstage * iw * iw,
+                bytes=es * n * h * wd * (c + nstage * iw + iw) + 4 * w.numel(), kernel="mspa_front_kernel")
+    _invoke("mgdt_mspa_front", meta, xp, xcs, w.data_ptr(), bias.data_ptr(), nstage, iw, ACTS[act], yp, ycs, sp, scs,
+            n, h, wd, dtype_code(x.dtype), stream_ptr())
+    return ysp
 
 
 def stem_conv(src, w: "PackedConv", bias, cout, act, out=None):

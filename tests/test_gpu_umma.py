@@ -119,3 +119,34 @@ def test_pointwise_narrow_conv(cin, cout):
             err = float((y0.float() - y1.float()).abs().max()) / scale
             assert err <= 2 ** -7, f"{kw.keys()} {act}: {err:.3e}"
     assert float(ybuf[:, :8].float().abs().max()) == 0.0   # the slice write stayed inside its channels
+
+
+@pytest.mark.parametrize("iw,n", [(8, 1), (16, 2), (32, 2), (64, 1)])
+def test_mspa_front_fused_vs_unfused(iw, n):
+    """mgdt_mspa_front (the MSPA_C2f branch chain in one launch) against the unfused sequence of pointwise convs with
+    pre_add + affine_act, through the module, on a ragged shape and as part of the whole block."""
+    from mgdt_yolo_b200 import ops
+    from mgdt_yolo_b200.modules.block import MSPA_C2f
+    from mgdt_yolo_b200.synth import synth_state_dict
+    torch.manual_seed(iw)
+    m = MSPA_C2f(4 * iw, 4 * iw, n, True)
+    m.load_state_dict(synth_state_dict(m.state_dict(), seed=iw))
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(iw + 1)
+    x = ops.as_act(torch.randn(3, 4 * iw, 13, 17, generator=g).cuda().to(torch.bfloat16))
+    outs, launches = {}, {}
+    for rnd in range(2):   # round 0 packs the weights (its kernels count as launches too); round 1 is the one compared
+        for fused in (True, False):
+            ops.FUSE_MSPA_FRONT = fused
+            try:
+                before = ops.lib().mgdt_launch_count()
+                with torch.no_grad():
+                    outs[fused] = m(x).float()
+                torch.cuda.synchronize()
+                launches[fused] = ops.lib().mgdt_launch_count() - before
+            finally:
+                ops.FUSE_MSPA_FRONT = True
+    assert launches[True] == launches[False] - 3, launches   # 3 convs + 1 add -> 1 launch
+    scale = float(outs[False].abs().max())
+    err = float((outs[True] - outs[False]).abs().max()) / scale
+    assert err <= 2 ** -7, f"iw={iw}: {err:.3e}"
