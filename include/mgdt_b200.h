@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGDT_ABI_VERSION 1
+#define MGDT_ABI_VERSION 2
 
 enum { MGDT_F32 = 0, MGDT_BF16 = 1 };
 enum { MGDT_ACT_NONE = 0, MGDT_ACT_SILU = 1, MGDT_ACT_RELU = 2, MGDT_ACT_SIGMOID = 3, MGDT_ACT_HSIGMOID = 4,
@@ -83,6 +83,17 @@ typedef struct mgdt_conv_args {
     int32_t impl;          /* 0 auto, 1 force CUDA-core path, 2 force tcgen05 path */
     const void* w_umma;    /* NULL, or the weights packed by mgdt_conv_umma_pack (bf16 tcgen05 path) */
     int32_t w_umma_f16;    /* 1 if w_umma was packed as fp16 (B operand F16, A stays bf16): 8x finer weight rounding */
+    /* Fused output statistics (tcgen05 path only; mgdt_conv2d fails with -ENOTSUP otherwise, ask mgdt_conv2d_path first):
+     * the epilogue adds, per image n and output channel c, the sums of the bf16-rounded outputs into
+     * stat_acc[n][stat_q + stat_sq][Cout] (fp64, atomics): stat_q = 0 none, 1 total, 5 total + the four
+     * adaptive_avg_pool2d(2) windows (q00, q01, q10, q11); stat_sq = 1 appends the sum of squares as the last plane.
+     * The accumulators are replicated stat_copies (>= 1) times, stat_acc[copy][n][plane][c] with copy = tile % copies,
+     * so that concurrent CTAs do not serialise on one L2 line; with stat_q = 5 and even Ho, Wo the total plane is left
+     * untouched (the windows partition the image).  All copies must be zero on entry; mgdt_stats_finish sums them in
+     * copy order, zeroes them again and runs the consumer (SPR gate / GRN scale / GroupNorm affine).  Replaces a
+     * separate mgdt_chan_stats pass over y. */
+    void* stat_acc;
+    int32_t stat_q, stat_sq, stat_copies;
 } mgdt_conv_args;
 int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
 /* Which kernel mgdt_conv2d would run for these arguments: 3 = conv_pointwise_kernel (narrow 1x1 layers, CUDA cores,
@@ -107,12 +118,15 @@ int mgdt_stem_conv(const void* src, int src_is_u8, const void* w_umma, int w_umm
 /* MSPA_C2f hierarchy front (nn/modules/block.py:248-262) in ONE launch (bf16): the chain of pointwise Conv+BN+act
  * branches  sp_0 = convs[0](spx[0]);  sp_i = convs[i](sp_{i-1} + spx[i]), i < nstage;  sp_in = sp_{nstage-1} + spx[nstage]
  * where spx[i] = x[:, i*iw:(i+1)*iw].  x has (nstage+1)*iw channels; sp_i is written to ycat[:, i*iw:(i+1)*iw]
- * (the concat buffer convs[-1] reads), sp_in (the bottleneck input) to ysp (iw channels).  w is fp32
- * [nstage][ci][co] (BN folded, already rounded to bf16 values), bias fp32 [nstage][iw].  Intermediate values are
- * rounded to bf16 where the unfused sequence (mgdt_conv2d with pre_add, mgdt_affine_act) stores them, so the two
- * agree bit for bit.  iw in {8, 16, 32, 64}. */
+ * (the concat buffer convs[-1] reads), sp_in (the bottleneck input) to ysp (iw channels).  A warp owns 32 pixels and
+ * chains warp-level bf16 MMAs in registers (the accumulator fragment of one stage is the A fragment of the next).
+ * w_packed = mgdt_mspa_front_pack of the fp32 [nstage][ci][co] weights (BN folded): bf16 B fragments; bias fp32
+ * [nstage][iw].  Intermediate values are rounded to bf16 where the unfused sequence (mgdt_conv2d with pre_add,
+ * mgdt_affine_act) stores / stages them.  iw in {8, 16, 32, 64}. */
 int mgdt_mspa_front_supported(int iw, int nstage);
-int mgdt_mspa_front(const void* x, int x_cs, const float* w, const float* bias, int nstage, int iw, int act, void* ycat,
+size_t mgdt_mspa_front_packed_bytes(int iw, int nstage);
+int mgdt_mspa_front_pack(const float* w, int nstage, int iw, void* packed, void* stream);
+int mgdt_mspa_front(const void* x, int x_cs, const void* w_packed, const float* bias, int nstage, int iw, int act, void* ycat,
                     int y_cs, void* ysp, int s_cs, int N, int H, int W, int dtype, void* stream);
 
 /* Depthwise 7x7 (pad 3, bias) + channels-last LayerNorm(eps), ConvNeXtV2_Block.forward
@@ -161,6 +175,14 @@ typedef struct mgdt_stats_fin {
 } mgdt_stats_fin;
 int mgdt_chan_stats_fin(const void* x, int x_cs, int N, int H, int W, int C, int quads, float* out_sum, float* out_sumsq,
                         void* ws, size_t ws_bytes, int32_t* counters, const mgdt_stats_fin* fin, int dtype, void* stream);
+
+/* Consumer of the statistics a convolution accumulated in its epilogue (mgdt_conv_args.stat_acc): reduces
+ * acc[copies][N][q + sq][C] (fp64) to out_sum[N][q][C] / out_sumsq[N][C] (either may be NULL when its planes are
+ * absent; H, W are the map's size: for q = 5 and even H, W the total is the sum of the four windows), zeroes acc for
+ * the next use, then runs the finaliser `fin` (same kinds and arguments as mgdt_chan_stats_fin; NULL or kind 0 =
+ * none).  One block per image. */
+int mgdt_stats_finish(void* acc, int copies, int N, int H, int W, int C, int q, int sq, float* out_sum, float* out_sumsq,
+                      const mgdt_stats_fin* fin, void* stream);
 
 /* SPR gate of MSPA_C2f (block.py:270-279 + spr_module.py:20-31): stats[N][5][C] (sums) ->
  * scale[N][C] = softmax over the `groups` (4) channel groups of sigmoid(fc2(relu(fc1([mean | 2x2 means])))).

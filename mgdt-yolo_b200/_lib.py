@@ -13,6 +13,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmgdt_b200.so")
 
+ABI_VERSION = 2  # include/mgdt_b200.h MGDT_ABI_VERSION
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_RELU, ACT_SIGMOID, ACT_HSIGMOID, ACT_GELU = range(6)
 RS_COPY, RS_AVGPOOL, RS_BILINEAR, RS_NEAREST = range(4)
@@ -26,7 +27,8 @@ class ConvArgs(C.Structure):
                 ("N", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32),
                 ("kh", i32), ("kw", i32), ("stride", i32), ("pad", i32),
                 ("x_cs", i32), ("y_cs", i32), ("add_cs", i32), ("ps_cs", i32), ("res_cs", i32),
-                ("act", i32), ("in_relu", i32), ("dtype", i32), ("impl", i32), ("w_umma", vp), ("w_umma_f16", i32)]
+                ("act", i32), ("in_relu", i32), ("dtype", i32), ("impl", i32), ("w_umma", vp), ("w_umma_f16", i32),
+                ("stat_acc", vp), ("stat_q", i32), ("stat_sq", i32), ("stat_copies", i32)]
 
 
 class StatsFin(C.Structure):
@@ -55,12 +57,15 @@ SIGNATURES = {
     "mgdt_conv_umma_pack": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "mgdt_stem_conv": (C.c_int, [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_mspa_front_supported": (C.c_int, [i32, i32]),
+    "mgdt_mspa_front_packed_bytes": (sz, [i32, i32]),
+    "mgdt_mspa_front_pack": (C.c_int, [vp, i32, i32, vp, vp]),
     "mgdt_mspa_front": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "mgdt_dwconv7_ln": (C.c_int, [vp, i32, vp, vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_dcn3x3": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_chan_stats_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
     "mgdt_chan_stats": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, i32, vp]),
     "mgdt_chan_stats_fin": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, C.POINTER(StatsFin), i32, vp]),
+    "mgdt_stats_finish": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, C.POINTER(StatsFin), vp]),
     "mgdt_mspa_gate": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
     "mgdt_grn_scale": (C.c_int, [vp, vp, i32, i32, vp, vp]),
     "mgdt_gn_affine": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
@@ -90,7 +95,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError if the symbol is missing
             fn.restype, fn.argtypes = res, args
-        if L.mgdt_abi_version() != 1:
+        if L.mgdt_abi_version() != ABI_VERSION:
             raise RuntimeError("mgdt_yolo_b200: ABI version mismatch, rebuild the library")
         _LIB = L
     return _LIB

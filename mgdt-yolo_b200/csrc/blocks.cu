@@ -97,8 +97,24 @@ __global__ void __launch_bounds__(256) dwconv7_ln_tiled(const T* __restrict__ x,
     const int h0 = ty * DT, w0 = tx * DT;
     const T* xn = x + (size_t)n * H * W * x_cs;
     if (VEC) {
-        // bf16, C % 8 == 0, 16-byte aligned rows: 8 channels per load, converted to fp32 once while staging
+        // bf16, C % 8 == 0, 16-byte aligned rows.  The input halo tile stays bf16 in shared memory and is staged by
+        // cp.async (zero-filled outside the image / beyond C) without a register round trip: half the footprint of an
+        // fp32 tile, so four CTAs share an SM and the staging of one overlaps the arithmetic of the others.  The
+        // weights are converted to fp32 once while the copies are in flight.
         constexpr int C8 = CPL * 4;   // 8-channel chunks per padded pixel
+        {
+            const uint32_t sx32 = (uint32_t)__cvta_generic_to_shared(sx);
+            const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(xn);
+            for (int i = tid; i < DTI * DTI * C8; i += 256) {
+                const int pix = i / C8, c8 = (i - pix * C8) * 8;
+                const int iy = pix / DTI, ix = pix - iy * DTI;
+                const int hh = h0 + iy - 3, ww = w0 + ix - 3;
+                const bool ok = c8 < C && hh >= 0 && hh < H && ww >= 0 && ww < W;
+                const __nv_bfloat16* src = ok ? xb + (size_t)(hh * W + ww) * x_cs + c8 : xb;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sx32 + (uint32_t)(pix * CP + c8) * 2u), "l"(src),
+                             "r"(ok ? 16u : 0u) : "memory");
+            }
+        }
         for (int i = tid; i < 49 * C8; i += 256) {
             const int tap = i / C8, c8 = (i - tap * C8) * 8;
             float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
@@ -111,20 +127,7 @@ __global__ void __launch_bounds__(256) dwconv7_ln_tiled(const T* __restrict__ x,
             float4* dst = reinterpret_cast<float4*>(sw + tap * CP + c8);
             dst[0] = lo; dst[1] = hi;
         }
-        for (int i = tid; i < DTI * DTI * C8; i += 256) {
-            const int pix = i / C8, c8 = (i - pix * C8) * 8;
-            const int iy = pix / DTI, ix = pix - iy * DTI;
-            const int hh = h0 + iy - 3, ww = w0 + ix - 3;
-            float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-            if (c8 < C && hh >= 0 && hh < H && ww >= 0 && ww < W) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(xn) + (size_t)(hh * W + ww) * x_cs + c8));
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-                const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]), c = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
-                lo = make_float4(a.x, a.y, b.x, b.y); hi = make_float4(c.x, c.y, d.x, d.y);
-            }
-            float4* dst = reinterpret_cast<float4*>(sx + (size_t)pix * CP + c8);
-            dst[0] = lo; dst[1] = hi;
-        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         for (int i = tid; i < 49 * CP; i += 256) {
             const int c = i % CP;
@@ -157,11 +160,15 @@ __global__ void __launch_bounds__(256) dwconv7_ln_tiled(const T* __restrict__ x,
 #pragma unroll
             for (int j = 0; j < CPL; ++j) wk[dx][j] = sw[(dy * 7 + dx) * CP + lane + 32 * j];
         const float* row = sx + (size_t)((r + dy) * DTI) * CP;
+        const unsigned short* rowh = reinterpret_cast<const unsigned short*>(sx) + (size_t)((r + dy) * DTI) * CP;   // VEC: bf16 tile
 #pragma unroll
         for (int ix = 0; ix < DTI; ++ix) {
             float v[CPL];
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) v[j] = row[ix * CP + lane + 32 * j];
+            for (int j = 0; j < CPL; ++j) {
+                if (VEC) v[j] = __uint_as_float((uint32_t)rowh[ix * CP + lane + 32 * j] << 16);
+                else v[j] = row[ix * CP + lane + 32 * j];
+            }
 #pragma unroll
             for (int dx = 0; dx < 7; ++dx) {
                 const int px = ix - dx;
@@ -211,9 +218,9 @@ template <typename T, int CPL>
 static int launch_dw_tiled(const void* x, int x_cs, const void* w, const float* bias, const float* ln_w,
                            const float* ln_b, float eps, void* y, int y_cs, int N, int H, int W, int C, cudaStream_t s) {
     const int CP = CPL * 32;
-    const size_t smem = sizeof(float) * 49 * CP + sizeof(float) * DTI * DTI * CP;
     const int tx = (W + DT - 1) / DT, ty = (H + DT - 1) / DT;
     const bool vec = sizeof(T) == 2 && C % 8 == 0 && x_cs % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0;
+    const size_t smem = sizeof(float) * 49 * CP + (vec ? 2 : sizeof(float)) * DTI * DTI * CP;
     cudaError_t e;
     if (vec) {
         e = cudaFuncSetAttribute(dwconv7_ln_tiled<T, CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -235,6 +235,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+    // no release fence: the caller's outstanding global stores / reductions need not be performed first
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     // bounded spin: a protocol bug traps (CUDA error) instead of hanging the GPU
     const long long t0 = clock64();
@@ -277,6 +281,16 @@ struct P2 {
     const void* stem_src;
     int stem_u8, stem_C, stem_H, stem_W;
     FastDiv d_Wo;
+    // fused per-(n, c) statistics of the (bf16-rounded) output, accumulated by the epilogue with fp64 atomics into
+    // st_acc[n][st_Q + st_sq][Cout]: st_Q = 0 none / 1 total / 5 total + the four adaptive_avg_pool2d(2) windows
+    // (rows [0, st_h0e) | [st_h1b, Ho), columns [0, st_w0e) | [st_w1b, Wo)), st_sq = sum of squares as the last plane
+    // The accumulators are replicated st_R times (copy = tile % st_R, stride st_rs doubles) so that CTAs working on
+    // neighbouring tiles of one image do not serialise on the same L2 lines; st_tot = 0 skips the total plane when the
+    // windows partition the image (even Ho, Wo: mgdt_stats_finish derives it from the four window sums).
+    double* st_acc;
+    int st_Q, st_sq, st_h0e, st_h1b, st_w0e, st_w1b, st_R, st_tot;
+    long long st_rs;
+    FastDiv d_oHW, d_oW;
     unsigned long long* trace;   // debug: per-CTA phase timestamps (mgdt_debug_set_trace), normally NULL
 };
 
@@ -645,7 +659,67 @@ __device__ __forceinline__ void epi_math(const P2& p, const uint32_t* r, const f
     }
 }
 
-template <int MODE, int LOADER, int SPLIT>
+// Fused output statistics: the calling epilogue warp has just staged a 32-row x 32-column bf16 unit in its swizzled
+// shared-memory tile (row r at r*64, 16-byte chunk c at slot c ^ ((r >> 1) & 3)).  Lane l owns the column PAIR
+// (2*(l & 15), +1) over the 16 rows r = 2*i + (l >> 4) (an even and an odd row per instruction: all 32 banks, no
+// conflict), sums value and square with packed fp32x2 arithmetic, the two half-warps are combined by one shuffle and
+// lanes 0-15 add the result to the per-(image, plane, channel) fp64 accumulators: total, sum of squares and the 2x2
+// adaptive-pool windows the rows belong to.  skey = (image << 4) | window mask of the lane's own OUTPUT row
+// (0xffffffff for junk rows); one masked pass per distinct key among the 32 rows (one in the common case, two or
+// three when the group straddles a window or image boundary).  fp64 atomics make the result independent of the
+// arrival order to ~1e-16, i.e. reproducible after the cast to fp32.
+__device__ __forceinline__ void epi_stats(double* acc, int Q, int sq, int want_tot, int C, uint32_t stg32, uint32_t skey, int lane,
+                                          int nv, int co0, int Cout) {
+    const uint32_t full = 0xffffffffu, INVALID = 0xffffffffu;
+    const uint32_t cp = (uint32_t)lane & 15u, half = (uint32_t)lane >> 4;
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        // row 2i + half: (row >> 1) & 3 == i & 3 for both halves
+        const uint32_t a = stg32 + (uint32_t)(2 * i) * 64u + half * 64u + (((cp >> 2) ^ ((uint32_t)i & 3u)) << 4) + (cp & 3u) * 4u;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[i]) : "r"(a));
+    }
+    const int K = Q + sq;
+    const int c = co0 + 2 * (int)cp;
+    const bool col0 = half == 0 && 2 * (int)cp < nv && c < Cout, col1 = half == 0 && 2 * (int)cp + 1 < nv && c + 1 < Cout;
+    uint32_t rem = __ballot_sync(full, skey != INVALID);
+    while (rem) {
+        const uint32_t k = __shfl_sync(full, skey, __ffs((int)rem) - 1);
+        const uint32_t m = __ballot_sync(full, skey == k);
+        rem &= ~m;
+        const uint32_t mh = m >> half;
+        unsigned long long sa[4], qa[4];   // four independent chains (fixed combination order)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sa[u] = qa[u] = pk2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t t = (m == full || (mh & (1u << (2 * i)))) ? w[i] : 0u;
+            const unsigned long long v2 = pk2(__uint_as_float(t << 16), __uint_as_float(t & 0xffff0000u));
+            sa[i & 3] = add2(v2, sa[i & 3]);
+            qa[i & 3] = fma2(v2, v2, qa[i & 3]);
+        }
+        float s0, s1, q0, q1;
+        up2(add2(add2(sa[0], sa[1]), add2(sa[2], sa[3])), s0, s1);
+        up2(add2(add2(qa[0], qa[1]), add2(qa[2], qa[3])), q0, q1);
+        s0 += __shfl_xor_sync(full, s0, 16); s1 += __shfl_xor_sync(full, s1, 16);
+        q0 += __shfl_xor_sync(full, q0, 16); q1 += __shfl_xor_sync(full, q1, 16);
+        if (col0 && !(want_tot & 256)) {
+            double* base = acc + ((size_t)(k >> 4) * K) * C + c;
+            if (want_tot & 1) { atomicAdd(base, (double)s0); if (col1) atomicAdd(base + 1, (double)s1); }
+            if (Q == 5) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (k & (1u << j)) {
+                        atomicAdd(base + (size_t)(1 + j) * C, (double)s0);
+                        if (col1) atomicAdd(base + (size_t)(1 + j) * C + 1, (double)s1);
+                    }
+            }
+            if (sq) { atomicAdd(base + (size_t)Q * C, (double)q0); if (col1) atomicAdd(base + (size_t)Q * C + 1, (double)q1); }
+        }
+    }
+}
+
+template <int MODE, int LOADER, int SPLIT, int STATS>
 __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_constant__ P2 p) {
     pdl_trigger();
     extern __shared__ __align__(128) unsigned char smem[];
@@ -1119,6 +1193,18 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                 if (u >= (mb + 1) * ncch) continue;                // no unit of this row block is ours
                 const int opix = out_pixel2(p, tile, (uint32_t)(mb * 128 + quad * 32 + lane));
                 const bool any_row = __any_sync(0xffffffffu, opix >= 0);
+                uint32_t skey = 0xffffffffu;   // fused statistics: (image << 4) | adaptive-pool window mask of this lane's row
+                if (STATS && opix >= 0) {
+                    const uint32_t n = fdiv((uint32_t)opix, p.d_oHW);
+                    uint32_t mask = 0;
+                    if (p.st_Q == 5) {
+                        const uint32_t rem = (uint32_t)opix - n * (uint32_t)(p.Ho * p.Wo);
+                        const int h = (int)fdiv(rem, p.d_oW), w = (int)rem - h * p.Wo;
+                        const uint32_t top = h < p.st_h0e, bot = h >= p.st_h1b, lef = w < p.st_w0e, rig = w >= p.st_w1b;
+                        mask = (top & lef) | ((top & rig) << 1) | ((bot & lef) << 2) | ((bot & rig) << 3);
+                    }
+                    skey = (n << 4) | mask;
+                }
                 __nv_bfloat16* yrow[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -1183,6 +1269,9 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                             }
                         }
                     }
+                    if (STATS)
+                        epi_stats(p.st_acc + (size_t)(tile % (uint32_t)p.st_R) * p.st_rs, p.st_Q, p.st_sq, p.st_tot, p.Cout, s_u32(stg), skey,
+                                  lane, nv, co0, p.Cout);
                     __syncwarp();
                     if (tr) {
                         tc3 = clock64();
@@ -1194,7 +1283,9 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(ACCEMPTY(a));
+            // the accumulator buffer is free once this warp's tcgen05.ld's have completed (tcgen05.wait::ld above + the
+            // fence); a relaxed arrival does not wait for the tile's global stores / statistics reductions to drain
+            if (lane == 0) mbar_arrive_relaxed(ACCEMPTY(a));
             if (trw && ti < 6) trace_mark(p, 11 + 8 * (int)ti);
         }
     }
@@ -1228,18 +1319,34 @@ static void fill_divs(P2& p) {
     p.d_W = make_fastdiv((uint32_t)p.W);
     p.d_cgs = make_fastdiv((uint32_t)(p.dcn_cin > 0 ? p.dcn_cin / 8 : 1));
     p.d_Wo = make_fastdiv((uint32_t)p.W);
+    p.d_oHW = make_fastdiv((uint32_t)(p.Ho * p.Wo));
+    p.d_oW = make_fastdiv((uint32_t)p.Wo);
 }
 
 static unsigned long long* g_trace = nullptr;
 static int g_force_split = -1;   // debug (MGDT_CONV_SPLIT=0/1/2): override the producer/epilogue warp split
 
-template <int MODE, int LOADER, int SPLIT>
-static int launch2t(const P2& p, dim3 grid, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<MODE, LOADER, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_MAX_SMEM);
+template <int MODE, int LOADER, int SPLIT, int STATS>
+static int launch2k(const P2& p, dim3 grid, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<MODE, LOADER, SPLIT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_MAX_SMEM);
     if (e != cudaSuccess) return set_error(-EIO, "conv_umma2: smem attr: %s", cudaGetErrorString(e));
-    launch_k(conv_umma2_kernel<MODE, LOADER, SPLIT>, dim3(grid), dim3(U2_THREADS), p.rn.smem_total, s, p);
+    launch_k(conv_umma2_kernel<MODE, LOADER, SPLIT, STATS>, dim3(grid), dim3(U2_THREADS), p.rn.smem_total, s, p);
     MGDT_LAUNCH_CHECK("conv_umma2");
     return 0;
+}
+
+// The statistics epilogue (STATS = 1) is instantiated only for the transform-free 1x1 / 3x3 stride-1 loaders -- the
+// producers of every map the model takes statistics of (MSPA convs[-1], ConvNeXt pwconv1, Conv_GN) -- so that all other
+// instantiations keep their code unchanged.
+template <int MODE, int LOADER> constexpr bool stats_variant() { return LOADER == LD_ASYNC && (MODE == 0 || MODE == 1); }
+
+template <int MODE, int LOADER, int SPLIT>
+static int launch2t(const P2& p, dim3 grid, cudaStream_t s) {
+    if (p.st_acc) {
+        if constexpr (stats_variant<MODE, LOADER>()) return launch2k<MODE, LOADER, SPLIT, 1>(p, grid, s);
+        else return set_error(-ENOTSUP, "conv_umma2: fused statistics are not built for this loader");
+    }
+    return launch2k<MODE, LOADER, SPLIT, 0>(p, grid, s);
 }
 
 template <int MODE, int LOADER>
@@ -1267,6 +1374,7 @@ static int launch2(P2& p, cudaStream_t s) {
     }
     fill_divs(p);
     p.trace = g_trace;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MGDT_STATS_DEBUG"); dbg = e ? atoi(e) : 0; } if (dbg & 1) p.st_tot |= 256; if (dbg & 2) p.st_Q = 0, p.st_sq = 1, p.st_tot |= 256; }
     const long long tiles = p.rn.tiles;
     int ctas = (int)(tiles < 148 ? tiles : 148);
     if (p.pl.nsplit > 1) ctas = (int)std::max(1LL, std::min(tiles, (long long)(148 / p.pl.nsplit)));
@@ -1290,6 +1398,8 @@ static int launch2(P2& p, cudaStream_t s) {
 
 bool conv2d_umma_supported(const mgdt_conv_args* a) {
     if (!a->w_umma || a->dtype != MGDT_BF16 || a->kh != a->kw || a->pad != a->kh / 2) return false;
+    // fused statistics: transform-free stride-1 loaders only (see stats_variant)
+    if (a->stat_acc && (a->stride != 1 || a->pre_add || a->in_scale || a->pix_scale || a->in_relu)) return false;
     Plan2 pl; Run2 rn; int Ho, Wo;
     if (!plan2_for(a->Cin, a->Cout, a->kh, a->stride, a->N, a->H, a->W, pl, rn, Ho, Wo)) return false;
     if (((uintptr_t)a->x & 15) || (a->x_cs & 7)) return false;
@@ -1317,6 +1427,11 @@ int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
     p.M_total = (unsigned)((long long)a->N * a->H * a->W);
     p.dcn_off = nullptr; p.dcn_mask = nullptr; p.off_cs = p.mask_cs = p.mask_logit = p.dcn_cin = 0;
     p.stem_src = nullptr; p.stem_u8 = p.stem_C = p.stem_H = p.stem_W = 0;
+    p.st_acc = (double*)a->stat_acc; p.st_Q = a->stat_q; p.st_sq = a->stat_sq ? 1 : 0;
+    p.st_h0e = (Ho + 1) / 2; p.st_h1b = Ho / 2; p.st_w0e = (Wo + 1) / 2; p.st_w1b = Wo / 2;
+    p.st_R = a->stat_copies > 0 ? a->stat_copies : 1;
+    p.st_rs = (long long)a->N * (p.st_Q + p.st_sq) * a->Cout;
+    p.st_tot = (p.st_Q == 1 || (p.st_Q == 5 && ((Ho | Wo) & 1))) ? 1 : 0;
     return launch2(p, s);
 }
 
@@ -1342,6 +1457,7 @@ int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void
     p.dcn_off = (const __nv_bfloat16*)offset; p.dcn_mask = (const __nv_bfloat16*)mask;
     p.off_cs = off_cs; p.mask_cs = mask_cs; p.mask_logit = mask_is_logit; p.dcn_cin = Cin;
     p.stem_src = nullptr; p.stem_u8 = p.stem_C = p.stem_H = p.stem_W = 0;
+    p.st_acc = nullptr; p.st_Q = p.st_sq = p.st_h0e = p.st_h1b = p.st_w0e = p.st_w1b = p.st_tot = 0; p.st_R = 1; p.st_rs = 0;
     return launch2(p, s);
 }
 
@@ -1368,6 +1484,7 @@ int stem_umma(const void* src, int src_is_u8, const void* w_umma, int w_f16, con
     p.M_total = (unsigned)((long long)N * Ho * Wo);
     p.dcn_off = nullptr; p.dcn_mask = nullptr; p.off_cs = p.mask_cs = p.mask_logit = p.dcn_cin = 0;
     p.stem_src = src; p.stem_u8 = src_is_u8; p.stem_C = C; p.stem_H = H; p.stem_W = W;
+    p.st_acc = nullptr; p.st_Q = p.st_sq = p.st_h0e = p.st_h1b = p.st_w0e = p.st_w1b = p.st_tot = 0; p.st_R = 1; p.st_rs = 0;
     return launch2(p, s);
 }
 

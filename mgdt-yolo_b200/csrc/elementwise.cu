@@ -445,6 +445,143 @@ extern "C" int mgdt_sppf_pool(const void* x, int x_cs, void* y1, void* y2, void*
     return 0;
 }
 
+namespace mgdt {
+// Exact 2x bilinear upsampling (H == 2*Hg, W == 2*Wg, the GD neck's case): output rows {2*bi - 1, 2*bi} and columns
+// {2*bj - 1, 2*bj} all interpolate between source rows {bi - 1, bi} and columns {bj - 1, bj} (clamped), so one thread
+// loads the four corners of both global maps once (8 loads) and produces the whole 2x2 output block: 4 memory
+// instructions per output chunk instead of 10.  Weights come from the same bilinear_src() as the general kernel, so
+// the results are identical to it.
+template <typename T, int V>
+__global__ void __launch_bounds__(EW_THREADS) inject2x_kernel(const T* __restrict__ local, int l_cs, const T* __restrict__ gact,
+                                                              int a_cs, const T* __restrict__ gfeat, int f_cs, T* __restrict__ y,
+                                                              int y_cs, int Hg, int Wg, unsigned C, unsigned total) {
+    pdl_trigger();
+    pdl_wait();
+    const int H = 2 * Hg, W = 2 * Wg;
+    const unsigned CV = C / V;
+    for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
+        const unsigned cv = i % CV, blk = i / CV;
+        const unsigned c = cv * V;
+        const int bj = (int)(blk % (unsigned)(Wg + 1));
+        const unsigned t = blk / (unsigned)(Wg + 1);
+        const int bi = (int)(t % (unsigned)(Hg + 1));
+        const unsigned n = t / (unsigned)(Hg + 1);
+        const int ra = max(bi - 1, 0), rb = min(bi, Hg - 1), ca = max(bj - 1, 0), cb = min(bj, Wg - 1);
+        const T* an = gact + (size_t)n * Hg * Wg * a_cs + c;
+        const T* fn = gfeat + (size_t)n * Hg * Wg * f_cs + c;
+        float a[4][V], f[4][V];   // corners (ra,ca) (ra,cb) (rb,ca) (rb,cb)
+        VecIO<T, V>::ld(an + (size_t)(ra * Wg + ca) * a_cs, a[0]); VecIO<T, V>::ld(an + (size_t)(ra * Wg + cb) * a_cs, a[1]);
+        VecIO<T, V>::ld(an + (size_t)(rb * Wg + ca) * a_cs, a[2]); VecIO<T, V>::ld(an + (size_t)(rb * Wg + cb) * a_cs, a[3]);
+        VecIO<T, V>::ld(fn + (size_t)(ra * Wg + ca) * f_cs, f[0]); VecIO<T, V>::ld(fn + (size_t)(ra * Wg + cb) * f_cs, f[1]);
+        VecIO<T, V>::ld(fn + (size_t)(rb * Wg + ca) * f_cs, f[2]); VecIO<T, V>::ld(fn + (size_t)(rb * Wg + cb) * f_cs, f[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < V; ++j) a[k][j] = hsig<T>(a[k][j]);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const int h = 2 * bi - 1 + dy;
+            if (h < 0 || h >= H) continue;
+            int h0, h1;
+            float lh;
+            bilinear_src(h, Hg, H, h0, h1, lh);   // (h0, h1) == (ra, rb) whenever lh != 0
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int w = 2 * bj - 1 + dx;
+                if (w < 0 || w >= W) continue;
+                int w0, w1;
+                float lw;
+                bilinear_src(w, Wg, W, w0, w1, lw);
+                const size_t pix = ((size_t)n * H + h) * W + w;
+                float l[V];
+                VecIO<T, V>::ld(local + pix * l_cs + c, l);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float sig = (1.f - lh) * ((1.f - lw) * a[0][j] + lw * a[1][j]) + lh * ((1.f - lw) * a[2][j] + lw * a[3][j]);
+                    const float gf = (1.f - lh) * ((1.f - lw) * f[0][j] + lw * f[1][j]) + lh * ((1.f - lw) * f[2][j] + lw * f[3][j]);
+                    l[j] = l[j] * sig + gf;
+                }
+                VecIO<T, V>::st(y + pix * y_cs + c, l);
+            }
+        }
+    }
+}
+// bf16 form of inject2x_kernel: all twelve 16-byte loads of a 2x2 output block (8 corners + 4 local chunks) are issued
+// before any arithmetic and kept packed, so a thread has 192 bytes in flight and three CTAs fit on an SM.
+__device__ __forceinline__ void unpack_bf8(const uint4& v, float* f) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(w[j] << 16); f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+}
+
+__global__ void __launch_bounds__(EW_THREADS, 3) inject2x_bf16_kernel(const __nv_bfloat16* __restrict__ local, int l_cs,
+                                                                     const __nv_bfloat16* __restrict__ gact, int a_cs,
+                                                                     const __nv_bfloat16* __restrict__ gfeat, int f_cs,
+                                                                     __nv_bfloat16* __restrict__ y, int y_cs, int Hg, int Wg,
+                                                                     unsigned C, unsigned total) {
+    pdl_trigger();
+    pdl_wait();
+    using T = __nv_bfloat16;
+    const int H = 2 * Hg, W = 2 * Wg;
+    const unsigned CV = C / 8;
+    for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
+        const unsigned cv = i % CV, blk = i / CV;
+        const unsigned c = cv * 8;
+        const int bj = (int)(blk % (unsigned)(Wg + 1));
+        const unsigned t = blk / (unsigned)(Wg + 1);
+        const int bi = (int)(t % (unsigned)(Hg + 1));
+        const unsigned n = t / (unsigned)(Hg + 1);
+        const int ra = max(bi - 1, 0), rb = min(bi, Hg - 1), ca = max(bj - 1, 0), cb = min(bj, Wg - 1);
+        const T* an = gact + (size_t)n * Hg * Wg * a_cs + c;
+        const T* fn = gfeat + (size_t)n * Hg * Wg * f_cs + c;
+        const int off[4] = {ra * Wg + ca, ra * Wg + cb, rb * Wg + ca, rb * Wg + cb};
+        uint4 qa[4], qf[4], ql[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            qa[k] = __ldg(reinterpret_cast<const uint4*>(an + (size_t)off[k] * a_cs));
+            qf[k] = __ldg(reinterpret_cast<const uint4*>(fn + (size_t)off[k] * f_cs));
+        }
+        size_t pix[4];
+        bool ok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int h = 2 * bi - 1 + (k >> 1), w = 2 * bj - 1 + (k & 1);
+            ok[k] = h >= 0 && h < H && w >= 0 && w < W;
+            pix[k] = ((size_t)n * H + min(max(h, 0), H - 1)) * W + min(max(w, 0), W - 1);
+            ql[k] = __ldg(reinterpret_cast<const uint4*>(local + pix[k] * l_cs + c));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!ok[k]) continue;
+            int h0, h1, w0, w1;
+            float lh, lw;
+            bilinear_src(2 * bi - 1 + (k >> 1), Hg, H, h0, h1, lh);   // (h0, h1) == (ra, rb) whenever lh != 0
+            bilinear_src(2 * bj - 1 + (k & 1), Wg, W, w0, w1, lw);
+            uint4 o;
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {   // one packed channel pair at a time keeps the temporaries small
+                float r[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    auto ch = [&](const uint4& q) -> float {
+                        const uint32_t w32 = reinterpret_cast<const uint32_t*>(&q)[j];
+                        return __uint_as_float(e ? (w32 & 0xffff0000u) : (w32 << 16));
+                    };
+                    const float sig = (1.f - lh) * ((1.f - lw) * hsig<T>(ch(qa[0])) + lw * hsig<T>(ch(qa[1]))) +
+                                      lh * ((1.f - lw) * hsig<T>(ch(qa[2])) + lw * hsig<T>(ch(qa[3])));
+                    const float gf = (1.f - lh) * ((1.f - lw) * ch(qf[0]) + lw * ch(qf[1])) + lh * ((1.f - lw) * ch(qf[2]) + lw * ch(qf[3]));
+                    r[e] = ch(ql[k]) * sig + gf;
+                }
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(r[0], r[1]);
+                ow[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(y + pix[k] * y_cs + c) = o;
+        }
+    }
+}
+}  // namespace mgdt
+
 extern "C" int mgdt_inject(const void* local, int l_cs, const void* gact, int a_cs, const void* gfeat, int f_cs,
                            void* y, int y_cs, int N, int H, int W, int Hg, int Wg, int C, int dtype, void* stream) {
     MGDT_CHECK(local && gact && gfeat && y, "inject: null pointer");
@@ -455,6 +592,17 @@ extern "C" int mgdt_inject(const void* local, int l_cs, const void* gact, int a_
         const bool vec = C % 8 == 0 && aligned8(local, l_cs, sizeof(T)) && aligned8(gact, a_cs, sizeof(T)) &&
                          aligned8(gfeat, f_cs, sizeof(T)) && aligned8(y, y_cs, sizeof(T));
         MGDT_VEC_SWITCH(vec, V, {
+            if (H == 2 * Hg && W == 2 * Wg && Hg > 1 && Wg > 1) {   // exact 2x upsampling: one thread per 2x2 output block
+                const unsigned total2 = (unsigned)((long long)N * (Hg + 1) * (Wg + 1) * (C / V));
+                if constexpr (sizeof(T) == 2 && V == 8)
+                    launch_k(inject2x_bf16_kernel, dim3(ew_grid(total2, 1)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)local, l_cs,
+                             (const T*)gact, a_cs, (const T*)gfeat, f_cs, (T*)y, y_cs, Hg, Wg, (unsigned)C, total2);
+                else
+                    launch_k(inject2x_kernel<T, V>, dim3(ew_grid(total2)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)local, l_cs,
+                             (const T*)gact, a_cs, (const T*)gfeat, f_cs, (T*)y, y_cs, Hg, Wg, (unsigned)C, total2);
+                MGDT_LAUNCH_CHECK("inject");
+                return 0;
+            }
             const unsigned total = (unsigned)((long long)N * H * W * (C / V));
             launch_k(inject_kernel<T, V>, dim3(ew_grid(total)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)local, l_cs, (const T*)gact, a_cs, (const T*)gfeat, f_cs, (T*)y, y_cs, H, W, Hg, Wg,
                 (unsigned)C, total);

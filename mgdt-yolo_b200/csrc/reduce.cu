@@ -334,6 +334,85 @@ extern "C" int mgdt_chan_stats_fin(const void* x, int x_cs, int N, int H, int W,
     return chan_stats_impl(x, x_cs, N, H, W, C, quads, out_sum, out_sumsq, ws, ws_bytes, counters, fin, dtype, stream);
 }
 
+// ------------------------------------------------------------------ consumer of conv-epilogue statistics
+namespace mgdt {
+__global__ void __launch_bounds__(CS_THREADS) stats_finish_kernel(double* __restrict__ acc, int R, int N, int H, int W, int C, int Q,
+                                                                  int sq, float* __restrict__ out_sum,
+                                                                  float* __restrict__ out_sumsq, StatsFin fin) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float sm[CS_THREADS * 8];
+    const int n = blockIdx.x, K = Q + sq;
+    const size_t rs = (size_t)N * K * C;
+    double* an = acc + (size_t)n * K * C;
+    const bool derive_tot = Q == 5 && ((H | W) & 1) == 0;   // the conv skipped the total plane: the windows partition the image
+    auto rd = [&](int i) -> double {   // copies summed in copy order, then reset for the next convolution
+        double v = 0.0;
+        for (int r0 = 0; r0 < R; r0 += 8) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = r0 + u < R ? __ldcg(&an[(size_t)(r0 + u) * rs + i]) : 0.0;   // loads first
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                v += t[u];
+                if (r0 + u < R) an[(size_t)(r0 + u) * rs + i] = 0.0;
+            }
+        }
+        return v;
+    };
+    for (int i = threadIdx.x; i < K * C; i += CS_THREADS) {
+        if (derive_tot && i < C) continue;
+        const double v = rd(i);
+        if (i < Q * C) out_sum[(size_t)n * Q * C + i] = (float)v;
+        else out_sumsq[(size_t)n * C + (i - Q * C)] = (float)v;
+    }
+    if (derive_tot) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += CS_THREADS) {
+            const float* q = out_sum + (size_t)n * Q * C + C + c;
+            out_sum[(size_t)n * Q * C + c] = (q[0] + q[C]) + (q[2 * C] + q[3 * C]);   // as mgdt_chan_stats does
+        }
+    }
+    if (!fin.kind) return;
+    __syncthreads();   // the bodies read this block's own global writes
+    if (fin.kind == 1)
+        mspa_gate_body(n, out_sum + (size_t)n * Q * C, H, W, C, fin.i0, fin.i1, fin.p0, fin.p1, fin.p2, fin.p3, fin.i2, fin.o0, sm);
+    else if (fin.kind == 2)
+        grn_scale_body(n, out_sumsq + (size_t)n * C, fin.p0, C, fin.o0, sm);
+    else if (fin.kind == 3)
+        gn_affine_body(n, out_sum + (size_t)n * Q * C, out_sumsq + (size_t)n * C, C, fin.i0, H * W, fin.f0, fin.p0, fin.p1,
+                       fin.o0, fin.o1);
+}
+}  // namespace mgdt
+
+extern "C" int mgdt_stats_finish(void* acc, int copies, int N, int H, int W, int C, int q, int sq, float* out_sum, float* out_sumsq,
+                                 const mgdt_stats_fin* f, void* stream) {
+    MGDT_CHECK(acc && copies > 0 && N > 0 && H > 0 && W > 0 && C > 0, "stats_finish: bad arguments");
+    MGDT_CHECK((q == 0 || q == 1 || q == 5) && (sq == 0 || sq == 1) && q + sq > 0, "stats_finish: bad plane selection q=%d sq=%d", q, sq);
+    MGDT_CHECK((q == 0 || out_sum) && (sq == 0 || out_sumsq), "stats_finish: missing output buffer");
+    StatsFin fin{};
+    if (f) {
+        fin.kind = f->kind; fin.p0 = f->p0; fin.p1 = f->p1; fin.p2 = f->p2; fin.p3 = f->p3;
+        fin.i0 = f->i0; fin.i1 = f->i1; fin.i2 = f->i2; fin.f0 = f->f0; fin.o0 = f->o0; fin.o1 = f->o1;
+    }
+    if (fin.kind == MGDT_FIN_GATE) {
+        MGDT_CHECK(q == 5 && fin.p0 && fin.p1 && fin.p2 && fin.p3 && fin.o0 && fin.i0 > 0 && C % fin.i0 == 0 && fin.i2 > 0,
+                   "stats_finish: bad SPR gate arguments");
+        const int ow = C / fin.i0;
+        MGDT_CHECK(fin.i0 * 5 * ow + fin.i0 * fin.i2 + fin.i0 * ow <= CS_THREADS * 8, "stats_finish: gate scratch does not fit (C=%d)", C);
+    } else if (fin.kind == MGDT_FIN_GRN) {
+        MGDT_CHECK(sq && fin.p0 && fin.o0, "stats_finish: bad GRN arguments");
+    } else if (fin.kind == MGDT_FIN_GN) {
+        MGDT_CHECK(q == 1 && sq && fin.p0 && fin.p1 && fin.o0 && fin.o1 && fin.i0 > 0 && C % fin.i0 == 0,
+                   "stats_finish: bad GroupNorm arguments");
+    } else {
+        MGDT_CHECK(fin.kind == 0, "stats_finish: unknown finaliser %d", fin.kind);
+    }
+    launch_k(stats_finish_kernel, dim3(N), dim3(CS_THREADS), 0, (cudaStream_t)stream, (double*)acc, copies, N, H, W, C, q, sq, out_sum, out_sumsq, fin);
+    MGDT_LAUNCH_CHECK("stats_finish");
+    return 0;
+}
+
 // ------------------------------------------------------------------ MSPA gate
 // One block per image, thread per (group g, channel c) pair for the MLP output.
 namespace mgdt {

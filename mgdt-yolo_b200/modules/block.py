@@ -148,7 +148,7 @@ class MSPA_C2f(KernelModule):
         def build():
             ws, bs = zip(*(fold_conv_bn(c.conv, getattr(c, "bn", None)) for c in branch))
             w = torch.stack([t.flatten(1).to(device).to(torch.bfloat16).float().t().contiguous() for t in ws])
-            return w.contiguous(), torch.stack([f32(b, device) for b in bs]).contiguous(), acts.copy().pop()
+            return ops.mspa_front_pack(w.contiguous()), torch.stack([f32(b, device) for b in bs]).contiguous(), acts.copy().pop()
 
         return self._packed("front", dtype, device, tensors, build)
 
@@ -174,9 +174,10 @@ class MSPA_C2f(KernelModule):
             sp = ops.affine_act(sp, other=last) if g > 1 else last  # sp + spx[-1] feeds bottleneck + its shortcut
         for j, m in enumerate(self.bottleneck):
             sp = m(sp, out=cat[:, (g - 1 + j) * iw:(g + j) * iw])
-        feat = self.convs[g - 1](cat)
-        co = feat.shape[1]
-        scale = ops.stats_gate(feat, *self.attention._pack(x.device), groups=g, softmax=True)   # stats + gate, one launch
+        mlp = self.attention._pack(x.device)
+        req = ops.gate_request(self.convs[g - 1].conv.out_channels, g, mlp[0].shape[0])
+        feat = self.convs[g - 1](cat, stat=req)   # SPR statistics accumulated in the conv's epilogue when it can
+        scale = ops.finish_gate(req, feat, *mlp, groups=g, softmax=True)
         return ops.affine_act(feat, a=scale)  # feats * softmax_g(gates), written back in group order
 
 
@@ -314,8 +315,9 @@ class ConvNeXtV2_Block(KernelModule):
         x = ops.as_act(x)
         p = self._pack(x.dtype, x.device)
         t = ops.dwconv7_ln(x, p["dw"], p["dwb"], p["lnw"], p["lnb"], self.norm.eps)
-        hid = ops.conv2d(t, p["w1"], p["b1"], 1, act="gelu")
-        scale = ops.stats_grn(hid, p["gamma"])   # sum of squares + GRN scale in one launch
+        req = ops.StatReq(0, True)
+        hid = ops.conv2d(t, p["w1"], p["b1"], 1, act="gelu", stat=req)   # sum of squares accumulated in the epilogue
+        scale = ops.finish_grn(req, hid, p["gamma"])
         return ops.conv2d(hid, p["w2"], p["b2"], 1, in_scale=scale, residual=x, out=out)
 
 

@@ -54,7 +54,7 @@ class Conv(KernelModule):
 
         return self._packed("conv", dtype, device, tensors, build)
 
-    def forward(self, x, out=None, residual=None, pre_add=None, in_scale=None):
+    def forward(self, x, out=None, residual=None, pre_add=None, in_scale=None, stat=None):
         self._check_mode(x)
         c = self.conv
         if c.groups != 1 or c.dilation != (1, 1) or c.kernel_size[0] != c.kernel_size[1] or c.stride[0] != c.stride[1]:
@@ -62,7 +62,7 @@ class Conv(KernelModule):
         x = ops.as_act(x)
         w, b = self._pack(x.dtype, x.device)
         return ops.conv2d(x, w, b, c.kernel_size[0], c.stride[0], c.padding[0], act_name(self.act), out=out,
-                          residual=residual, pre_add=pre_add, in_scale=in_scale)
+                          residual=residual, pre_add=pre_add, in_scale=in_scale, stat=stat)
 
     forward_fuse = forward  # after fuse() the reference swaps forward := forward_fuse (tasks.py:137)
 

@@ -56,8 +56,9 @@ class Conv_GN(KernelModule):
         x = ops.as_act(x)
         w, gw, gb = self._pack(x.dtype, x.device)
         c = self.conv
-        raw = ops.conv2d(x, w, None, c.kernel_size[0], c.stride[0], c.padding[0])
-        a, b = ops.stats_gn(raw, self.gn.num_groups, self.gn.eps, gw, gb)   # statistics + affine in one launch
+        req = ops.StatReq(1, True)
+        raw = ops.conv2d(x, w, None, c.kernel_size[0], c.stride[0], c.padding[0], stat=req)
+        a, b = ops.finish_gn(req, raw, self.gn.num_groups, self.gn.eps, gw, gb)   # GroupNorm statistics from the conv's epilogue
         return ops.affine_act(raw, a, b, act=act_name(self.act), out=out)
 
 

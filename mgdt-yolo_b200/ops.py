@@ -147,8 +147,36 @@ USE_UMMA = True  # tests flip this to compare the tcgen05 path with the CUDA-cor
 FUSE_MSPA_FRONT = True  # MSPA_C2f branch chain as one launch (bf16); tests flip this to compare with the unfused sequence
 
 
+FUSE_STATS = __import__('os').environ.get('MGDT_FUSE_STATS', '1') != '0'  # per-(n,c) statistics in the tcgen05 conv's epilogue; tests flip this to compare with mgdt_chan_stats
+
+
+class StatReq:
+    """Request that a convolution accumulates per-(n, c) statistics of its output in its epilogue: q = 0 / 1 / 5 sum
+    planes (none / total / total + adaptive 2x2 windows), sq = sum of squares.  After ops.conv2d returns, `fused` says
+    whether the kernel took it (tcgen05 path) -- if not, the caller runs the stand-alone statistics pass."""
+
+    def __init__(self, q, sq):
+        self.q, self.sq, self.acc, self.fused = q, 1 if sq else 0, None, False
+
+
+_STAT_ARENA = {}
+STAT_COPIES = int(__import__('os').environ.get('MGDT_STAT_COPIES', '4'))  # replicas of the accumulators (copy = tile % copies): spreads the atomics over L2 lines
+
+
+def _stat_arena(device, nelem):
+    """Zero fp64 accumulators for the fused statistics, one array per (device, stream): the convolution adds into it,
+    mgdt_stats_finish (the next launch on that stream) reads it and leaves it zero again.  Allocated outside any graph
+    capture pool on first use (warm-up passes always precede capture)."""
+    key = (device.index, stream_ptr())
+    t = _STAT_ARENA.get(key)
+    if t is None or t.numel() < nelem:
+        t = torch.zeros((max(nelem, 1 << 16),), dtype=torch.float64, device=device)
+        _STAT_ARENA[key] = t
+    return t
+
+
 def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scale=None, pix_scale=None,
-           residual=None, in_relu=False, cout=None, impl=0):
+           residual=None, in_relu=False, cout=None, impl=0, stat=None):
     """y = act(conv((x + pre_add) * in_scale[n,c] * pix_scale[n,h,w] |> relu?, w) + bias) + residual.
     `w` is a PackedConv (or a plain OHWI (Cout, k, k, Cin) tensor) in x's dtype; `out` may be a channel
     slice of a concat buffer."""
@@ -204,6 +232,15 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
                 bytes=es * (n * h * wd * cin * (2 if pre_add is not None else 1)
                             + n * ho * wo * cout * (2 if residual is not None else 1) + cout * cin * k * k)
                 + (n * h * wd * es if pix_scale is not None else 0))
+    if stat is not None:
+        stat.fused = False
+        if FUSE_STATS and x.dtype == torch.bfloat16 and a.w_umma:
+            stat.acc = _stat_arena(x.device, STAT_COPIES * n * (stat.q + stat.sq) * cout)
+            a.stat_acc, a.stat_q, a.stat_sq, a.stat_copies = stat.acc.data_ptr(), stat.q, stat.sq, STAT_COPIES
+            if lib().mgdt_conv2d_path(C.byref(a)) == 2:
+                stat.fused = True
+            else:
+                a.stat_acc, a.stat_q, a.stat_sq, a.stat_copies = None, 0, 0, 0
     if PROFILE is not None:  # attribute the launch to the kernel the library will actually run
         meta["kernel"] = {3: "conv_pointwise_kernel", 2: "conv_umma2_kernel"}.get(lib().mgdt_conv2d_path(C.byref(a)),
                                                                                   "conv_direct_kernel")
@@ -211,11 +248,21 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
     return out
 
 
+def mspa_front_pack(w32):
+    """fp32 [nstage, iw(ci), iw(co)] CUDA weights -> the bf16 B-fragment image mgdt_mspa_front reads."""
+    nstage, iw, _ = w32.shape
+    nbytes = lib().mgdt_mspa_front_packed_bytes(iw, nstage)
+    out = torch.empty((nbytes,), dtype=torch.uint8, device=w32.device)
+    with torch.cuda.device(w32.device):
+        check(lib().mgdt_mspa_front_pack(w32.contiguous().data_ptr(), nstage, iw, out.data_ptr(), stream_ptr()), "mspa_front_pack")
+    return out
+
+
 def mspa_front(x, w, bias, iw, act, ycat, ysp=None):
-    """MSPA_C2f branch chain in one launch (bf16): x (N, (nstage+1)*iw, H, W); w fp32 [nstage, iw(ci), iw(co)];
+    """MSPA_C2f branch chain in one launch (bf16): x (N, (nstage+1)*iw, H, W); w = mspa_front_pack(weights);
     bias fp32 [nstage, iw].  Writes sp_i into ycat[:, i*iw:(i+1)*iw] and returns sp_in = sp_last + spx[-1]."""
     xp, n, c, h, wd, xcs = view(x)
-    nstage = w.shape[0]
+    nstage = bias.shape[0]
     if c != (nstage + 1) * iw or x.dtype != torch.bfloat16:
         raise ValueError("mspa_front: x must be bf16 with (nstage+1)*iw channels")
     if ysp is None:
@@ -226,7 +273,7 @@ def mspa_front(x, w, bias, iw, act, ycat, ysp=None):
         raise ValueError("mspa_front: bad output shapes")
     es = x.element_size()
     meta = dict(shape=f"mspa_front iw{iw}x{nstage} {n}x{h}x{wd}", flops=2.0 * n * h * wd * nstage * iw * iw,
-                bytes=es * n * h * wd * (c + nstage * iw + iw) + 4 * w.numel(), kernel="mspa_front_kernel")
+                bytes=es * n * h * wd * (c + nstage * iw + iw) + w.numel(), kernel="mspa_front_kernel")
     _invoke("mgdt_mspa_front", meta, xp, xcs, w.data_ptr(), bias.data_ptr(), nstage, iw, ACTS[act], yp, ycs, sp, scs,
             n, h, wd, dtype_code(x.dtype), stream_ptr())
     return ysp
@@ -341,6 +388,59 @@ def stats_gn(x, groups, eps, gamma, beta):
     fin = StatsFin(kind=3, p0=gamma.data_ptr(), p1=beta.data_ptr(), p2=None, p3=None, i0=groups, i1=0, i2=0, f0=float(eps),
                    o0=a.data_ptr(), o1=b.data_ptr())
     chan_stats(x, sumsq=True, fin=fin)
+    return a, b
+
+
+def _stats_finish(req, y, fin, want_sum=True):
+    """mgdt_stats_finish on the accumulators a convolution filled for its output y -> (sum [N,q,C] | None, sumsq [N,C] | None)."""
+    _, n, c, h, w, _ = view(y)
+    s = torch.empty((n, req.q, c), dtype=torch.float32, device=y.device) if req.q else None
+    ss = torch.empty((n, c), dtype=torch.float32, device=y.device) if req.sq else None
+    _invoke("mgdt_stats_finish", dict(shape=f"stats_finish C{c} N{n} q{req.q}", bytes=8 * STAT_COPIES * n * (req.q + req.sq) * c, flops=0.0,
+                                      kernel="stats_finish_kernel"),
+            req.acc.data_ptr(), STAT_COPIES, n, h, w, c, req.q, req.sq, _p(s), _p(ss), None if fin is None else C.byref(fin), stream_ptr())
+    return s, ss
+
+
+def gate_request(c, groups, hidden):
+    """StatReq for the SPR gate of a C-channel map if the fused finaliser's scratch fits, else None."""
+    return StatReq(5, False) if _gate_fits(c, groups, hidden, True) else None
+
+
+def finish_gate(req, y, fc1_w, fc1_b, fc2_w, fc2_b, groups=4, softmax=True):
+    """SPR gate scale [N, C] of y: from the statistics its convolution accumulated (req.fused) or a stand-alone pass."""
+    if req is None or not req.fused:
+        return stats_gate(y, fc1_w, fc1_b, fc2_w, fc2_b, groups=groups, softmax=softmax)
+    from ._lib import StatsFin
+    n, c = y.shape[0], y.shape[1]
+    scale = torch.empty((n, c), dtype=torch.float32, device=y.device)
+    fin = StatsFin(kind=1, p0=fc1_w.data_ptr(), p1=fc1_b.data_ptr(), p2=fc2_w.data_ptr(), p3=fc2_b.data_ptr(), i0=groups,
+                   i1=1 if softmax else 0, i2=fc1_w.shape[0], f0=0.0, o0=scale.data_ptr(), o1=None)
+    _stats_finish(req, y, fin)
+    return scale
+
+
+def finish_grn(req, y, gamma):
+    if req is None or not req.fused:
+        return stats_grn(y, gamma)
+    from ._lib import StatsFin
+    n, c = y.shape[0], y.shape[1]
+    scale = torch.empty((n, c), dtype=torch.float32, device=y.device)
+    fin = StatsFin(kind=2, p0=gamma.data_ptr(), p1=None, p2=None, p3=None, i0=0, i1=0, i2=0, f0=0.0, o0=scale.data_ptr(), o1=None)
+    _stats_finish(req, y, fin)
+    return scale
+
+
+def finish_gn(req, y, groups, eps, gamma, beta):
+    if req is None or not req.fused:
+        return stats_gn(y, groups, eps, gamma, beta)
+    from ._lib import StatsFin
+    n, c = y.shape[0], y.shape[1]
+    a = torch.empty((n, c), dtype=torch.float32, device=y.device)
+    b = torch.empty((n, c), dtype=torch.float32, device=y.device)
+    fin = StatsFin(kind=3, p0=gamma.data_ptr(), p1=beta.data_ptr(), p2=None, p3=None, i0=groups, i1=0, i2=0, f0=float(eps),
+                   o0=a.data_ptr(), o1=b.data_ptr())
+    _stats_finish(req, y, fin)
     return a, b
 
 

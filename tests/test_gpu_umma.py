@@ -150,3 +150,46 @@ def test_mspa_front_fused_vs_unfused(iw, n):
     scale = float(outs[False].abs().max())
     err = float((outs[True] - outs[False]).abs().max()) / scale
     assert err <= 2 ** -7, f"iw={iw}: {err:.3e}"
+
+
+@pytest.mark.parametrize("kind,shape", [("mspa", (3, 128, 13, 17)), ("mspa", (2, 128, 20, 20)), ("mspa", (5, 256, 8, 8)),
+                                        ("convnext", (3, 96, 13, 17)), ("convnext", (2, 96, 40, 40)),
+                                        ("conv_gn", (3, 64, 13, 17)), ("conv_gn", (2, 64, 80, 80))])
+def test_fused_epilogue_stats_vs_chan_stats(kind, shape):
+    """Per-(n,c) statistics accumulated in the tcgen05 conv's epilogue (fp64 atomics + mgdt_stats_finish) against the
+    stand-alone mgdt_chan_stats pass, through the modules that use them: SPR gate (2x2 adaptive windows, odd sizes ->
+    overlapping windows, images that straddle 32-row groups), GRN (sum of squares), GroupNorm (sum + sum of squares).
+    Run three times: the accumulators must be left zero for the next use and the result must be reproducible."""
+    from mgdt_yolo_b200 import ops
+    from mgdt_yolo_b200.modules.block import ConvNeXtV2_Block, MSPA_C2f
+    from mgdt_yolo_b200.modules.head import Conv_GN
+    from mgdt_yolo_b200.synth import synth_state_dict
+    n, c, h, w = shape
+    torch.manual_seed(c + h)
+    m = {"mspa": lambda: MSPA_C2f(c, c, 1, True), "convnext": lambda: ConvNeXtV2_Block(c),
+         "conv_gn": lambda: Conv_GN(c, c, 3)}[kind]()
+    m.load_state_dict(synth_state_dict(m.state_dict(), seed=h))
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(h * w)
+    x = ops.as_act(torch.randn(n, c, h, w, generator=g).cuda().to(torch.bfloat16))
+    outs, launches = {}, {}
+    for rnd in range(3):
+        for fused in (True, False):
+            ops.FUSE_STATS = fused
+            try:
+                before = ops.lib().mgdt_launch_count()
+                with torch.no_grad():
+                    y = m(x).float()
+                torch.cuda.synchronize()
+                launches[fused] = ops.lib().mgdt_launch_count() - before
+            finally:
+                ops.FUSE_STATS = True
+            if rnd > 0 and fused:
+                assert torch.equal(y, outs[True]), "fused statistics are not reproducible / accumulators not reset"
+            outs[fused] = y
+    assert launches[True] == launches[False], launches   # chan_stats launch -> stats_finish launch
+    for t in ops._STAT_ARENA.values():
+        assert float(t.abs().max()) == 0.0
+    scale = float(outs[False].abs().max())
+    err = float((outs[True] - outs[False]).abs().max()) / scale
+    assert err <= 2 ** -7, f"{kind} {shape}: {err:.3e}"

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name)
-    assert L.mgdt_abi_version() == 1
+    assert L.mgdt_abi_version() == _lib.ABI_VERSION
 
 
 def test_sass_is_sm100a():
