@@ -821,6 +821,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         uint32_t ph = 0;   // phase of the stage's current use (flips each time the ring wraps)
         float xf_sc[8], xf_sc_new[8];   // LD_XFORM: input scales of the pending item / of the item being issued
         uint32_t xf_scn = 0xffffffffu, xf_scn_new = 0xffffffffu;
+        uint32_t stem_wa[9], stem_wb[9];   // LD_STEM_U8: prefetched source words
         bool xf_valid = false;   // LD_XFORM: the item whose raw copies are in flight and still to be transformed
         int xf_s = 0, xf_plane0 = 0;
         uint32_t xf_tile = 0, xf_tt = 0, xf_nimg = 0;
@@ -951,9 +952,9 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                         const size_t plane_sz = (size_t)p.stem_H * p.stem_W;
                         const uint8_t* src8 = reinterpret_cast<const uint8_t*>(p.stem_src);
                         const uint32_t rows = 128u * rn.MB;
-                        for (uint32_t pp = ptid; pp < rows / 2; pp += NP) {
-                            const uint32_t pos = 2 * pp, g = tile * rows + pos;
-                            uint32_t wa[9], wb[9];
+                        // the 18 source words of output-pixel pair pp of tile tl
+                        auto stem_load = [&](uint32_t tl, uint32_t pp, uint32_t (&wa)[9], uint32_t (&wb)[9]) {
+                            const uint32_t g = tl * rows + 2 * pp;
 #pragma unroll
                             for (int j = 0; j < 9; ++j) { wa[j] = 0u; wb[j] = 0u; }
                             if (g < p.M_total) {
@@ -974,6 +975,17 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                                     }
                                 }
                             }
+                        };
+                        // When one pass of the producers covers the tile (rows / 2 <= NP), the words of the NEXT tile are
+                        // requested as soon as this tile's have been converted, so that their latency (~1.5 us, the whole
+                        // per-tile time of the unpipelined loader) overlaps the wait for the ring slot and the barrier.
+                        const bool one_pass = rows / 2 <= (uint32_t)NP;
+                        if (one_pass && it == 0 && (uint32_t)ptid < rows / 2) stem_load(tile, ptid, stem_wa, stem_wb);
+                        for (uint32_t pp = ptid; pp < rows / 2; pp += NP) {
+                            const uint32_t pos = 2 * pp;
+                            uint32_t (&wa)[9] = stem_wa;
+                            uint32_t (&wb)[9] = stem_wb;
+                            if (!one_pass) stem_load(tile, pp, wa, wb);
 #pragma unroll
                             for (int px = 0; px < 2; ++px) {
                                 float f[32];
@@ -1000,6 +1012,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                                     *reinterpret_cast<uint4*>(sA + ((uint32_t)pll * rn.pstride16 + pos + px) * 16u) = o;
                                 }
                             }
+                            if (one_pass && tile + gridDim.x < tiles) stem_load(tile + gridDim.x, pp, wa, wb);
                         }
                     } else if (LOADER == LD_DCN && pl.PS % (p.dcn_cin / 8) == 0) {
                         // DCNv2 sampling, one (position, tap) item per thread iteration: offset / mask / bilinear weights
@@ -1009,19 +1022,35 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                         const int tap0 = plane0 / cgs, ntap = pl.PS / cgs;
                         const uint32_t rows = 128u * rn.MB;
                         const uint32_t items = rows * (uint32_t)ntap;
+                        // The thread's items are a dependent chain of global-load latencies (offsets -> corners -> store);
+                        // the offsets / mask of the NEXT item are requested while this one is sampled, and the corner loads
+                        // of two channel groups are in flight together: 2 instead of 1 + cgs latencies per item.
+                        auto dcn_raw = [&](uint32_t e, float& dy, float& dx, float& m) {
+                            const uint32_t tl = e / rows, pos = e - tl * rows;
+                            const int tap = tap0 + (int)tl;
+                            const uint32_t g = tile * rows + pos;
+                            dy = dx = m = 0.f;
+                            if (e < items && g < p.M_total) {
+                                const __nv_bfloat16* ofp = p.dcn_off + (size_t)g * p.off_cs + 2 * tap;
+                                dy = __bfloat162float(ofp[0]); dx = __bfloat162float(ofp[1]);
+                                m = __bfloat162float(p.dcn_mask[(size_t)g * p.mask_cs + tap]);
+                            }
+                        };
+                        float ndy, ndx, nm;
+                        dcn_raw(ptid, ndy, ndx, nm);
                         for (uint32_t e = ptid; e < items; e += NP) {
                             const uint32_t tl = e / rows, pos = e - tl * rows;   // consecutive threads -> consecutive pixels
                             const int tap = tap0 + (int)tl;
                             const uint32_t g = tile * rows + pos;
                             float wgt[4] = {0.f, 0.f, 0.f, 0.f};
                             const __nv_bfloat16* cp[4] = {p.x, p.x, p.x, p.x};
+                            const float dy = ndy, dx = ndx;
+                            float m = nm;
+                            dcn_raw(e + NP, ndy, ndx, nm);
                             if (g < p.M_total) {
                                 const uint32_t n = fdiv(g, p.d_HW);
                                 const uint32_t rem = g - n * (uint32_t)(p.H * p.W);
                                 const int hq = (int)fdiv(rem, p.d_W), wq = (int)rem - hq * p.W;
-                                const __nv_bfloat16* ofp = p.dcn_off + (size_t)g * p.off_cs + 2 * tap;
-                                const float dy = __bfloat162float(ofp[0]), dx = __bfloat162float(ofp[1]);
-                                float m = __bfloat162float(p.dcn_mask[(size_t)g * p.mask_cs + tap]);
                                 if (p.mask_logit) m = sigmoidf_(m);
                                 const float py = (float)(hq + tap / 3 - 1) + dy, px = (float)(wq + tap % 3 - 1) + dx;
                                 if (py > -1.f && py < (float)p.H && px > -1.f && px < (float)p.W) {
@@ -1042,28 +1071,35 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                                 }
                             }
                             unsigned char* dst = sA + ((uint32_t)((tap - tap0) * cgs) * rn.pstride16 + pos) * 16u;
-                            for (int cg = 0; cg < cgs; ++cg) {
-                                uint4 v[4];
+                            for (int cg0 = 0; cg0 < cgs; cg0 += 2) {
+                                uint4 v[2][4];
 #pragma unroll
-                                for (int c4 = 0; c4 < 4; ++c4) v[c4] = __ldg(reinterpret_cast<const uint4*>(cp[c4] + cg * 8));
-                                float f[8];
+                                for (int u = 0; u < 2; ++u)
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) f[j] = 0.f;
+                                    for (int c4 = 0; c4 < 4; ++c4)
+                                        v[u][c4] = __ldg(reinterpret_cast<const uint4*>(cp[c4] + min(cg0 + u, cgs - 1) * 8));
 #pragma unroll
-                                for (int c4 = 0; c4 < 4; ++c4) {
-                                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[c4]);
+                                for (int u = 0; u < 2; ++u) {
+                                    if (cg0 + u >= cgs) break;
+                                    float f[8];
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        const float2 t = __bfloat1622float2(h[j]);
-                                        f[2 * j] = fmaf(wgt[c4], t.x, f[2 * j]);
-                                        f[2 * j + 1] = fmaf(wgt[c4], t.y, f[2 * j + 1]);
+                                    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+#pragma unroll
+                                    for (int c4 = 0; c4 < 4; ++c4) {
+                                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u][c4]);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            const float2 t = __bfloat1622float2(h[j]);
+                                            f[2 * j] = fmaf(wgt[c4], t.x, f[2 * j]);
+                                            f[2 * j + 1] = fmaf(wgt[c4], t.y, f[2 * j + 1]);
+                                        }
                                     }
-                                }
-                                uint4 o;
-                                __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+                                    uint4 o;
+                                    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                                *reinterpret_cast<uint4*>(dst + (size_t)cg * rn.pstride16 * 16u) = o;
+                                    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                                    *reinterpret_cast<uint4*>(dst + (size_t)(cg0 + u) * rn.pstride16 * 16u) = o;
+                                }
                             }
                         }
                     } else {

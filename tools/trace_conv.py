@@ -14,6 +14,7 @@ cases = [("c32_3x3", 32, 32, 3, 1, 80, 80), ("c8_1x1", 8, 8, 1, 1, 160, 160), ("
          ("c64_256_noact", 64, 256, 1, 1, 80, 80), ("c64_256_relu", 64, 256, 1, 1, 80, 80),
          ("c96_384", 96, 384, 1, 1, 40, 40), ("c16_3x3", 16, 16, 3, 1, 80, 80), ("c32_64", 32, 64, 1, 1, 80, 80),
          ("c256_64", 256, 64, 1, 1, 80, 80), ("c16_32_s2", 16, 32, 3, 2, 320, 320), ("c384_96", 384, 96, 1, 1, 40, 40), ("c384_96_grn", 384, 96, 1, 1, 40, 40)]
+cases.append(("stem", 3, 16, 3, 2, 640, 640))
 sel = sys.argv[1:]
 if sel:
     cases = [c for c in cases if c[0] in sel]
@@ -23,6 +24,9 @@ for name, cin, cout, k, s, H, W in cases:
     m.load_state_dict(synth_state_dict(m.state_dict(), seed=3))
     m = m.cuda().eval()
     x = ops.as_act(torch.randn(B, cin, H, W, device="cuda").to(torch.bfloat16))
+    if name == "stem":   # fused uint8 preprocessing + layer-0 conv
+        x = torch.randint(0, 256, (B, cin, H, W), dtype=torch.uint8, device="cuda")
+        m.forward = m.forward_image
     with torch.no_grad():
         kw = {}
         if name.endswith("_grn"):   # GRN-scaled input + residual, as ConvNeXtV2_Block's pwconv2
