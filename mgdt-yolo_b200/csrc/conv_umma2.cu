@@ -287,6 +287,7 @@ struct P2 {
     // The accumulators are replicated st_R times (copy = tile % st_R, stride st_rs doubles) so that CTAs working on
     // neighbouring tiles of one image do not serialise on the same L2 lines; st_tot = 0 skips the total plane when the
     // windows partition the image (even Ho, Wo: mgdt_stats_finish derives it from the four window sums).
+    int pair_ok;                 // paired 16-column epilogue units allowed (debug: MGDT_CONV_PAIR=0 turns them off)
     double* st_acc;
     int st_Q, st_sq, st_h0e, st_h1b, st_w0e, st_w1b, st_R, st_tot;
     long long st_rs;
@@ -584,9 +585,10 @@ __device__ __forceinline__ void xform_stage_fixed(const P2& p, unsigned char* sA
 }
 
 // Epilogue arithmetic on NV accumulator columns of one output row: bias, activation, residual, bf16 pack.
+// opixB >= -1 with pairB: columns 16..31 belong to a SECOND output row (paired 16-column units, see the epilogue).
 template <int NV>
 __device__ __forceinline__ void epi_math(const P2& p, const uint32_t* r, const float* sBias, int cbase, int co0, int opix,
-                                         uint32_t* packed) {
+                                         uint32_t* packed, bool pairB = false, int opixB = -1) {
     float v[NV];
     unsigned long long a[NV / 2];
     const unsigned long long half2 = pk2(0.5f, 0.5f);
@@ -636,19 +638,21 @@ __device__ __forceinline__ void epi_math(const P2& p, const uint32_t* r, const f
 #undef MGDT_ACT_CASE
         default: break;
     }
-    if (p.residual && opix >= 0) {
-        const __nv_bfloat16* rp = p.residual + (size_t)opix * p.res_cs + co0;
+    if (p.residual && (opix >= 0 || (pairB && opixB >= 0))) {
 #pragma unroll
         for (int c8 = 0; c8 < NV; c8 += 8) {
-            if (co0 + c8 >= p.Cout) break;
-            if (co0 + c8 + 8 <= p.Cout && p.res_vec) {
-                const uint4 ra = __ldg(reinterpret_cast<const uint4*>(rp + c8));
+            const bool second = pairB && c8 >= 16;            // paired unit: columns 16.. are channels 0.. of row opixB
+            const int op = second ? opixB : opix, cc = second ? c8 - 16 : c8;
+            if (op < 0 || co0 + cc >= p.Cout) continue;
+            const __nv_bfloat16* rp = p.residual + (size_t)op * p.res_cs + co0 + cc;
+            if (co0 + cc + 8 <= p.Cout && p.res_vec) {
+                const uint4 ra = __ldg(reinterpret_cast<const uint4*>(rp));
                 const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&ra);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(ah[j]); v[c8 + 2 * j] += t.x; v[c8 + 2 * j + 1] += t.y; }
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) if (co0 + c8 + j < p.Cout) v[c8 + j] += __bfloat162float(rp[c8 + j]);
+                for (int j = 0; j < 8; ++j) if (co0 + cc + j < p.Cout) v[c8 + j] += __bfloat162float(rp[j]);
             }
         }
     }
@@ -750,8 +754,8 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     if (LOADER == LD_STEM_U8) {
         for (int i = tid; i < 256; i += U2_THREADS) sLut[i] = __bfloat16_as_ushort(__float2bfloat16_rn((float)i / 255.0f));
     }
-    for (int i = tid; i < pl.Nc; i += U2_THREADS) {
-        const int co = ns * pl.Nc + i;
+    for (int i = tid; i < (pl.Nc == 16 ? 32 : pl.Nc); i += U2_THREADS) {   // Nc = 16: duplicated for the paired units
+        const int co = ns * pl.Nc + (pl.Nc == 16 ? (i & 15) : i);
         sBias[i] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
     }
     for (int i = tid; i < pl.nmma_s; i += U2_THREADS) {
@@ -1224,11 +1228,19 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             mbar_wait(ACCFULL(a), aphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (trw && ti < 6) trace_mark(p, 10 + 8 * (int)ti);
-            int u = sub;                                           // units are numbered mb * ncch + cc
-            for (int mb = 0; mb < rn.MB; ++mb) {
-                if (u >= (mb + 1) * ncch) continue;                // no unit of this row block is ours
+            // 16-column tiles (Cout <= 16: the stem, the narrow 3x3 layers): the accumulators of row blocks mb and mb + 1
+            // are adjacent 16-column groups in TMEM, so ONE 32-column unit covers both -- columns 0..15 are channels
+            // 0..15 of row block mb, columns 16..31 the same channels of row block mb + 1.  The per-unit cost of this
+            // latency-bound loop is the same for 16 and 32 columns, so pairing halves the epilogue time of these layers.
+            const bool pair = !STATS && p.pair_ok && pl.Nc == 16 && (rn.MB & 1) == 0 && (p.residual == nullptr || p.Cout <= 8);   // (measured: a loss for 16-channel residual layers)
+            const int mbstep = pair ? 2 : 1;
+            int u = sub;                                           // units are numbered mg * ncch + cc
+            for (int mg = 0; mg * mbstep < rn.MB; ++mg) {
+                const int mb = mg * mbstep;
+                if (u >= (mg + 1) * ncch) continue;                // no unit of this row block (pair) is ours
                 const int opix = out_pixel2(p, tile, (uint32_t)(mb * 128 + quad * 32 + lane));
-                const bool any_row = __any_sync(0xffffffffu, opix >= 0);
+                const int opixB = pair ? out_pixel2(p, tile, (uint32_t)((mb + 1) * 128 + quad * 32 + lane)) : -1;
+                const bool any_row = __any_sync(0xffffffffu, opix >= 0 || opixB >= 0);
                 uint32_t skey = 0xffffffffu;   // fused statistics: (image << 4) | adaptive-pool window mask of this lane's row
                 if (STATS && opix >= 0) {
                     const uint32_t n = fdiv((uint32_t)opix, p.d_oHW);
@@ -1244,14 +1256,16 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                 __nv_bfloat16* yrow[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const int orow = __shfl_sync(0xffffffffu, opix, g * 8 + srow);
+                    const int orowA = __shfl_sync(0xffffffffu, opix, g * 8 + srow);
+                    const int orowB = __shfl_sync(0xffffffffu, opixB, g * 8 + srow);
+                    const int orow = (pair && schunk >= 2) ? orowB : orowA;   // paired unit: chunks 2, 3 are the second row block
                     yrow[g] = orow >= 0 ? p.y + (size_t)orow * p.y_cs : nullptr;
                 }
-                for (; u < (mb + 1) * ncch; u += NSUB) {
-                    const int cl = (u - mb * ncch) * 32;          // first column of the unit within this CTA's Nc
+                for (; u < (mg + 1) * ncch; u += NSUB) {
+                    const int cl = (u - mg * ncch) * 32;          // first column of the unit within this CTA's Nc
                     const int co0 = ns * pl.Nc + cl;
                     if (!any_row || co0 >= p.Cout) continue;
-                    const int nv = min(32, pl.Nc - cl);           // 32, or 16 for the last unit when Nc % 32 == 16
+                    const int nv = pair ? 32 : min(32, pl.Nc - cl);   // 32, or 16 for the last unit when Nc % 32 == 16
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
                                            (uint32_t)(a * rn.MB * pl.Nc + mb * pl.Nc + cl);
                     uint32_t r[32], pk[16];
@@ -1269,7 +1283,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                             : "r"(taddr));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                         if (tr) tc1 = clock64();
-                        epi_math<32>(p, r, sBias, cl, co0, opix, pk);
+                        epi_math<32>(p, r, sBias, cl, co0, opix, pk, pair, opixB);
                     } else {
                         asm volatile(
                             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -1289,7 +1303,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                                      "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
                     __syncwarp();
                     if (tr) tc2 = clock64();
-                    const int c8 = co0 + schunk * 8;              // first output channel of this lane's chunk
+                    const int c8 = co0 + (pair ? (schunk & 1) : schunk) * 8;   // first output channel of this lane's chunk
                     const bool chunk_on = schunk * 8 < nv && c8 < p.Cout;
                     const bool full8 = c8 + 8 <= p.Cout && p.y_vec;
 #pragma unroll
@@ -1410,6 +1424,7 @@ static int launch2(P2& p, cudaStream_t s) {
     }
     fill_divs(p);
     p.trace = g_trace;
+    { static int pr = -1; if (pr < 0) { const char* e = getenv("MGDT_CONV_PAIR"); pr = (e && e[0] == '0') ? 0 : 1; } p.pair_ok = pr; }
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MGDT_STATS_DEBUG"); dbg = e ? atoi(e) : 0; } if (dbg & 1) p.st_tot |= 256; if (dbg & 2) p.st_Q = 0, p.st_sq = 1, p.st_tot |= 256; }
     const long long tiles = p.rn.tiles;
     int ctas = (int)(tiles < 148 ? tiles : 148);

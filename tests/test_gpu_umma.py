@@ -18,6 +18,8 @@ SHAPES = [
     (64, 32, 3, 1, 1, 24, 20), (64, 27, 3, 1, 2, 12, 16), (16, 1, 3, 1, 2, 14, 10), (32, 32, 3, 1, 1, 80, 80),
     (16, 32, 3, 2, 2, 32, 40), (32, 64, 3, 2, 2, 20, 24), (64, 128, 3, 2, 2, 16, 12), (16, 32, 3, 2, 1, 21, 23),
     (8, 16, 3, 2, 2, 18, 14), (128, 256, 3, 2, 1, 8, 8),
+    # large enough for 256/512-row tiles: Cout <= 16 runs the PAIRED 16-column epilogue units (two row blocks per unit)
+    (8, 8, 3, 1, 5, 160, 160), (16, 16, 3, 1, 8, 120, 130), (64, 16, 1, 1, 8, 160, 100), (16, 8, 3, 1, 3, 200, 212),
 ]
 
 
@@ -193,3 +195,25 @@ def test_fused_epilogue_stats_vs_chan_stats(kind, shape):
     scale = float(outs[False].abs().max())
     err = float((outs[True] - outs[False]).abs().max()) / scale
     assert err <= 2 ** -7, f"{kind} {shape}: {err:.3e}"
+
+
+@pytest.mark.parametrize("cin,cout,k", [(16, 16, 3), (8, 8, 3), (32, 16, 1)])
+def test_umma_paired_units_with_residual(cin, cout, k):
+    """Paired 16-column epilogue units (Cout <= 16, multi-row-block tiles) with a residual and a channel-slice output:
+    the second half of a unit reads its residual / writes its rows from the NEXT row block."""
+    from mgdt_yolo_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout)
+    n, h, w = 8, 120, 130
+    x = ops.as_act(torch.randn(n, cin, h, w, generator=g).cuda().to(torch.bfloat16))
+    res = ops.as_act(torch.randn(n, cout, h, w, generator=g).cuda().to(torch.bfloat16))
+    wt = (torch.randn(cout, k, k, cin, generator=g) * (2.0 / (cin * k * k)) ** 0.5).cuda().to(torch.bfloat16)
+    pw = ops.PackedConv(wt, 1)
+    bias = torch.randn(cout, generator=g).cuda()
+    ybuf = ops.as_act(torch.zeros(n, cout + 16, h, w).cuda().to(torch.bfloat16))
+    y0 = ops.conv2d(x, pw, bias, k, 1, act="silu", impl=2, residual=res, out=ybuf[:, 8:8 + cout])
+    y1 = ops.conv2d(x, pw, bias, k, 1, act="silu", impl=1, residual=res)
+    torch.cuda.synchronize()
+    scale = float(y1.float().abs().max())
+    err = float((y0.float() - y1.float()).abs().max()) / scale
+    assert err <= 2 ** -7, f"{err:.3e}"
+    assert float(ybuf[:, :8].float().abs().max()) == 0.0 and float(ybuf[:, 8 + cout:].float().abs().max()) == 0.0
