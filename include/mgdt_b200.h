@@ -269,6 +269,22 @@ int mgdt_letterbox_u8(const void* src, int h0, int w0, int pitch, void* dst, int
 int mgdt_scale_boxes(float* dets, int row_stride, const int32_t* counts, int N, int max_rows, const float* params,
                      void* stream);
 
+/* Boxes.xywh / xyxyn / xywhn (yolo/engine/results.py:405-430; ops.xyxy2xywh, yolo/utils/ops.py:345-359): converts the
+ * xyxy columns of n rows of `boxes` (row_stride floats per row) into out[n][4].  mode bit 0: xyxy -> xywh (centre,
+ * size); bit 1: x / w, y / h.  Bit-exact with the reference's fp32 arithmetic. */
+int mgdt_box_convert(const float* boxes, int row_stride, int n, int mode, float w, float h, float* out, void* stream);
+
+/* DetectionValidator._process_batch (yolo/v8/detect/val.py:150-175) with metrics.box_iou (yolo/utils/metrics.py:52-72)
+ * for a whole batch in one launch.  dets[N][max_det][det_stride] rows (x1,y1,x2,y2,conf,cls,...) in native image space
+ * (after mgdt_scale_boxes), det_counts[N] valid rows (NULL = max_det); labels[N][max_lab][5] rows (cls,x1,y1,x2,y2) in
+ * the same space, lab_counts[N] (NULL = max_lab); iouv[niou] the IoU levels (torch.linspace(0.5, 0.95, 10), val.py:28).
+ * correct[N][max_det][niou] (uint8 0/1; rows past the count are 0): per level every detection keeps its highest-IoU
+ * class-matching label with IoU >= level, every label then keeps the lowest-index detection that chose it.  IoU ties
+ * between two labels of one detection keep the lower label index (the reference's argsort leaves them unspecified). */
+int mgdt_match_batch(const float* dets, int det_stride, const int32_t* det_counts, int max_det, const float* labels,
+                     const int32_t* lab_counts, int max_lab, const float* iouv, int niou, uint8_t* correct, int N,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

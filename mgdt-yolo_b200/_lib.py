@@ -50,6 +50,8 @@ SIGNATURES = {
     "mgdt_debug_set_trace": (None, [vp]),
     "mgdt_set_pdl": (None, [i32]),
     "mgdt_letterbox_u8": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_box_convert": (C.c_int, [vp, i32, i32, i32, f32, f32, vp, vp]),
+    "mgdt_match_batch": (C.c_int, [vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, i32, vp]),
     "mgdt_scale_boxes": (C.c_int, [vp, i32, vp, i32, i32, vp, vp]),
     "mgdt_conv2d_path": (C.c_int, [C.POINTER(ConvArgs)]),
     "mgdt_conv2d": (C.c_int, [C.POINTER(ConvArgs), vp]),

@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-DMGDT_WITH_UMMA"]
-PER_FILE = {"nms.cu": ["-fmad=false"], "imgproc.cu": ["-fmad=false"]}  # bit-exact IoU / resize arithmetic
+PER_FILE = {"nms.cu": ["-fmad=false"], "imgproc.cu": ["-fmad=false"], "metrics.cu": ["-fmad=false"]}  # bit-exact IoU / resize arithmetic
 
 
 def _sources():

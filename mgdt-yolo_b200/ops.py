@@ -639,3 +639,32 @@ def scale_boxes_packed(dets, counts, params):
     _invoke("mgdt_scale_boxes", dict(shape=f"scale_boxes N{n}", bytes=_nb(dets), flops=0.0), dets.data_ptr(), row, _p(counts),
             n, rows, params.data_ptr(), stream_ptr())
     return dets
+
+
+def box_convert(boxes, mode, w=1.0, h=1.0):
+    """xyxy columns of an fp32 CUDA (n, >=4) tensor -> (n, 4): mode bit 0 xyxy->xywh, bit 1 normalise by (w, h)."""
+    require_cuda(boxes, "boxes")
+    if boxes.dtype != torch.float32 or boxes.dim() != 2 or boxes.shape[1] < 4 or boxes.stride(1) != 1:
+        raise ValueError("box_convert: expects an fp32 (n, >=4) tensor with contiguous rows")
+    n = boxes.shape[0]
+    out = torch.empty((n, 4), dtype=torch.float32, device=boxes.device)
+    _invoke("mgdt_box_convert", dict(shape=f"box_convert n{n}", bytes=_nb(out) * 2, flops=0.0), boxes.data_ptr(),
+            int(boxes.stride(0)) if n > 1 else boxes.shape[1], n, mode, float(w), float(h), out.data_ptr(), stream_ptr())
+    return out
+
+
+def match_batch(dets, det_counts, labels, lab_counts, iouv):
+    """dets (N, max_det, >=6) fp32, labels (N, max_lab, 5) fp32 (cls, xyxy), counts int32 (N,) or None, iouv fp32 (niou,)
+    -> correct (N, max_det, niou) bool, all on device, no synchronisation."""
+    require_cuda(dets, "detections")
+    if dets.dtype != torch.float32 or not dets.is_contiguous() or dets.dim() != 3 or dets.shape[2] < 6:
+        raise ValueError("match_batch: dets must be a contiguous fp32 (N, max_det, >=6) tensor")
+    if labels.dtype != torch.float32 or not labels.is_contiguous() or labels.dim() != 3 or labels.shape[2] != 5:
+        raise ValueError("match_batch: labels must be a contiguous fp32 (N, max_lab, 5) tensor")
+    n, max_det, row = dets.shape
+    max_lab, niou = labels.shape[1], iouv.numel()
+    correct = torch.zeros((n, max_det, niou), dtype=torch.uint8, device=dets.device)
+    _invoke("mgdt_match_batch", dict(shape=f"match N{n} D{max_det} L{max_lab}", bytes=_nb(dets, labels, correct), flops=0.0),
+            dets.data_ptr(), row, _p(det_counts), max_det, labels.data_ptr(), _p(lab_counts), max_lab, iouv.data_ptr(), niou,
+            correct.data_ptr(), n, stream_ptr())
+    return correct.bool()

@@ -5,7 +5,8 @@ import torch
 
 from . import ops
 
-__all__ = ("non_max_suppression", "nms_packed", "scale_boxes", "clip_boxes", "scale_boxes_params")
+__all__ = ("non_max_suppression", "nms_packed", "scale_boxes", "clip_boxes", "scale_boxes_params", "process_batch",
+           "match_batch", "IOUV")
 
 nms_packed = ops.nms_packed
 
@@ -71,3 +72,25 @@ def clip_boxes(boxes, shape):
         return
     prm = torch.tensor([[1.0, 0.0, 0.0, float(shape[0]), float(shape[1])]], dtype=torch.float32, device=boxes.device)
     ops.scale_boxes_packed(boxes.unsqueeze(0), None, prm)
+
+
+def IOUV(device):
+    """iou vector for mAP@0.5:0.95 (yolo/v8/detect/val.py:28)."""
+    return torch.linspace(0.5, 0.95, 10).to(device)
+
+
+def process_batch(detections, labels, iouv=None):
+    """Drop-in for DetectionValidator._process_batch (yolo/v8/detect/val.py:150-175): detections (N, 6) xyxy conf cls,
+    labels (M, 5) cls xyxy, both fp32 CUDA tensors in native image space -> correct (N, niou) bool on the device."""
+    iouv = IOUV(detections.device) if iouv is None else iouv.to(device=detections.device, dtype=torch.float32)
+    if detections.shape[0] == 0:
+        return torch.zeros((0, iouv.numel()), dtype=torch.bool, device=detections.device)
+    lab = labels.to(torch.float32).contiguous().unsqueeze(0)
+    return ops.match_batch(detections.to(torch.float32).contiguous().unsqueeze(0), None, lab, None, iouv.contiguous())[0]
+
+
+def match_batch(dets, det_counts, labels, lab_counts, iouv=None):
+    """Whole-batch form on the packed NMS output (N, max_det, 6) + counts and packed labels (N, max_lab, 5) + counts:
+    one launch, no host synchronisation (the per-image loop of DetectionValidator.update_metrics, val.py:73-110)."""
+    iouv = IOUV(dets.device) if iouv is None else iouv
+    return ops.match_batch(dets, det_counts, labels, lab_counts, iouv.contiguous())

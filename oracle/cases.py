@@ -86,3 +86,39 @@ def synth_boxes(n, shape, seed):
 def module_inputs(name, shapes):
     from mgdt_yolo_b200.synth import synth_images
     return [synth_images(s[0], ch=s[1], h=s[2], w=s[3], seed=100 + i) * 2 - 0.5 for i, s in enumerate(shapes)]
+
+
+# validation matching (DetectionValidator._process_batch): name, detections, labels, classes, image (h, w)
+MATCH_CASES = [
+    ("coco_like", 300, 23, 4, (480, 640)),
+    ("crowded", 300, 160, 2, (640, 640)),
+    ("few", 7, 3, 1, (375, 500)),
+    ("one_label", 40, 1, 2, (640, 640)),
+    ("no_match", 25, 9, 80, (640, 640)),
+    ("single_det", 1, 12, 2, (320, 320)),
+]
+
+
+def synth_match(nd, nl, nc, shape, seed):
+    """Labels (cls, xyxy) and detections (xyxy, conf, cls): most detections are jittered copies of labels (several per
+    label, at every IoU level between 0.3 and 1), the rest are random boxes; no two labels coincide, so no IoU ties."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    h, w = shape
+    c = torch.rand(nl, 2, generator=g) * torch.tensor([w * 0.8, h * 0.8]) + torch.tensor([w * 0.1, h * 0.1])
+    wh = torch.rand(nl, 2, generator=g) * torch.tensor([w * 0.3, h * 0.3]) + 8
+    lab_box = torch.cat([c - wh / 2, c + wh / 2], 1)
+    lab_cls = torch.randint(0, nc, (nl, 1), generator=g).float()
+    labels = torch.cat([lab_cls, lab_box], 1)
+    src = torch.randint(0, nl, (nd,), generator=g)
+    jit = (torch.rand(nd, 4, generator=g) - 0.5) * torch.rand(nd, 1, generator=g) * 0.6
+    box = lab_box[src] + jit * torch.cat([wh[src], wh[src]], 1)
+    rnd = torch.rand(nd, generator=g) < 0.25
+    rb = synth_boxes(nd, shape, seed + 1)
+    box[rnd] = rb[rnd]
+    cls = lab_cls[src, 0].clone()
+    flip = torch.rand(nd, generator=g) < 0.15
+    cls[flip] = torch.randint(0, nc, (int(flip.sum()),), generator=g).float()
+    conf = torch.rand(nd, generator=g)
+    dets = torch.cat([box, conf[:, None], cls[:, None]], 1)
+    return dets[conf.argsort(descending=True)].contiguous(), labels.contiguous()

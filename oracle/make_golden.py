@@ -13,6 +13,7 @@ Fixture index (tests/golden/):
   modules.npz        one entry per module class on odd/ragged shapes
   nms.npz            reference non_max_suppression outputs for a parameter grid
   prepost.npz        LetterBox + BGR->RGB/CHW outputs (live cv2.resize) and ops.scale_boxes outputs
+  results.npz        Boxes.xywh/xyxyn/xywhn and DetectionValidator._process_batch outputs (validation matching)
 """
 from __future__ import annotations
 
@@ -132,11 +133,35 @@ def gen_prepost():
     print(path, os.path.getsize(path) // 1024, "KiB")
 
 
+def gen_results():
+    """Boxes views (results.py:405-430) and DetectionValidator._process_batch (v8/detect/val.py:150-175) of the live
+    reference on synthetic detections / labels."""
+    import types
+    ref_live.load()
+    from ultralytics.yolo.engine.results import Boxes
+    from ultralytics.yolo.v8.detect.val import DetectionValidator
+    from oracle.cases import MATCH_CASES, synth_match
+    dummy = types.SimpleNamespace(iouv=torch.linspace(0.5, 0.95, 10))
+    blob = {}
+    for ci, (name, nd, nl, nc, shape) in enumerate(MATCH_CASES):
+        dets, labels = synth_match(nd, nl, nc, shape, 500 + ci)
+        correct = DetectionValidator._process_batch(dummy, dets, labels)
+        blob[f"pb.{name}"] = correct.numpy()
+        b = Boxes(dets, shape)
+        blob[f"xywh.{name}"], blob[f"xyxyn.{name}"], blob[f"xywhn.{name}"] = b.xywh.numpy(), b.xyxyn.numpy(), b.xywhn.numpy()
+        print("match", name, tuple(correct.shape), "correct per level", correct.sum(0).tolist())
+    path = os.path.join(OUT, "results.npz")
+    np.savez_compressed(path, **blob)
+    print(path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    if "--only-prepost" not in sys.argv:
+    if "--only-prepost" not in sys.argv and "--only-results" not in sys.argv:
         gen_models()
         gen_modules()
         gen_nms()
-    gen_prepost()
+    if "--only-results" not in sys.argv:
+        gen_prepost()
+    gen_results()

@@ -131,3 +131,20 @@ def test_scale_boxes_bit_exact(ci, golden_dir):
     g = np.load(os.path.join(golden_dir, "prepost.npz"))
     out = O.scale_boxes(s1, synth_boxes(n, s1, 400 + ci), s0)
     assert torch.equal(out, torch.from_numpy(g[f"sb.{name}"]))
+
+
+def test_oracle_results_golden(golden_dir):
+    """oracle.process_batch / boxes_views against the live-reference fixtures (DetectionValidator._process_batch,
+    Boxes.xywh / xyxyn / xywhn)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import mgdt_oracle as O
+    from oracle.cases import MATCH_CASES, synth_match
+    g = np.load(os.path.join(golden_dir, "results.npz"))
+    for ci, (name, nd, nl, nc, shape) in enumerate(MATCH_CASES):
+        dets, labels = synth_match(nd, nl, nc, shape, 500 + ci)
+        assert np.array_equal(O.process_batch(dets, labels).numpy(), g[f"pb.{name}"]), name
+        xywh, xyxyn, xywhn = O.boxes_views(dets, shape)
+        assert np.array_equal(xywh.numpy(), g[f"xywh.{name}"]) and np.array_equal(xyxyn.numpy(), g[f"xyxyn.{name}"])
+        assert np.array_equal(xywhn.numpy(), g[f"xywhn.{name}"])
