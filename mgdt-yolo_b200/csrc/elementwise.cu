@@ -119,6 +119,70 @@ __global__ void __launch_bounds__(EW_THREADS) affine_act_kernel(const T* __restr
     }
 }
 
+// bf16, 8-channel chunks: four chunks per thread are requested (packed, 16 bytes each, + the `other` operand) before any
+// arithmetic, the per-(n,c) scales are fetched when a chunk is processed (L1 hits), <= 64 registers so that four
+// CTAs share an SM: ~2x the bytes in flight of the generic kernel, which was latency-bound at ~45 % of the HBM roofline.
+template <bool HAS_OTHER>
+__global__ void __launch_bounds__(EW_THREADS, 4) affine_act_bf16x4_kernel(const __nv_bfloat16* __restrict__ x, int x_cs,
+                                                                         const float* __restrict__ a, const float* __restrict__ b,
+                                                                         const __nv_bfloat16* __restrict__ other, int o_cs, int act,
+                                                                         __nv_bfloat16* __restrict__ y, int y_cs, unsigned HW,
+                                                                         unsigned C, unsigned total) {
+    pdl_trigger();
+    pdl_wait();
+    const unsigned CV = C / 8;
+    const unsigned stride = gridDim.x * EW_THREADS;
+    for (unsigned i0 = blockIdx.x * EW_THREADS + threadIdx.x; i0 < total; i0 += 4 * stride) {
+        uint4 xv[4], ov[HAS_OTHER ? 4 : 1];
+        unsigned pixs[4], cs_[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned i = min(i0 + u * stride, total - 1);
+            const unsigned pix = i / CV, cv = i - pix * CV;
+            pixs[u] = pix; cs_[u] = cv * 8;
+            xv[u] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)pix * x_cs + cv * 8));
+            if (HAS_OTHER) ov[u] = __ldg(reinterpret_cast<const uint4*>(other + (size_t)pix * o_cs + cv * 8));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u * stride >= total) break;
+            float f[8];
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&xv[u]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(w[j] << 16); f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+            if (a || b) {
+                const unsigned n = pixs[u] / HW;
+                if (a) {
+                    const float4* sp = reinterpret_cast<const float4*>(a + (size_t)n * C + cs_[u]);
+                    const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+                    f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w; f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+                }
+                if (b) {
+                    const float4* sp = reinterpret_cast<const float4*>(b + (size_t)n * C + cs_[u]);
+                    const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+                    f[0] += s0.x; f[1] += s0.y; f[2] += s0.z; f[3] += s0.w; f[4] += s1.x; f[5] += s1.y; f[6] += s1.z; f[7] += s1.w;
+                }
+            }
+            switch (act) {
+#define MGDT_ACT_CASE(A) case A: _Pragma("unroll") for (int j = 0; j < 8; ++j) f[j] = act_fast<A>(f[j]); break;
+                MGDT_ACT_CASE(MGDT_ACT_SILU)
+                MGDT_ACT_CASE(MGDT_ACT_RELU)
+                MGDT_ACT_CASE(MGDT_ACT_SIGMOID)
+                MGDT_ACT_CASE(MGDT_ACT_HSIGMOID)
+                MGDT_ACT_CASE(MGDT_ACT_GELU)
+#undef MGDT_ACT_CASE
+                default: break;
+            }
+            if (HAS_OTHER) {
+                const uint32_t* ow = reinterpret_cast<const uint32_t*>(&ov[HAS_OTHER ? u : 0]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { f[2 * j] += __uint_as_float(ow[j] << 16); f[2 * j + 1] += __uint_as_float(ow[j] & 0xffff0000u); }
+            }
+            VecIO<__nv_bfloat16, 8>::st(y + (size_t)pixs[u] * y_cs + cs_[u], f);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ resample
 __device__ __forceinline__ void bilinear_src(int o, int in, int out, int& i0, int& i1, float& l) {
     // F.interpolate(mode='bilinear', align_corners=False): src = (o + 0.5) * in/out - 0.5, clamped at 0
@@ -393,6 +457,14 @@ extern "C" int mgdt_affine_act(const void* x, int x_cs, const float* a, const fl
                          aligned8(other, other ? o_cs : 0, sizeof(T));
         MGDT_VEC_SWITCH(vec, V, {
             const unsigned total = (unsigned)((long long)N * H * W * (C / V));
+            if constexpr (sizeof(T) == 2 && V == 8) {
+                if (aligned8(a, 8, 4) && aligned8(b, 8, 4)) {
+                    if (other) launch_k(affine_act_bf16x4_kernel<true>, dim3(ew_grid((total + 3) / 4, 1)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, a, b, (const T*)other, o_cs, act, (T*)y, y_cs, (unsigned)(H * W), (unsigned)C, total);
+                    else launch_k(affine_act_bf16x4_kernel<false>, dim3(ew_grid((total + 3) / 4, 1)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, a, b, (const T*)other, o_cs, act, (T*)y, y_cs, (unsigned)(H * W), (unsigned)C, total);
+                    MGDT_LAUNCH_CHECK("affine_act");
+                    return 0;
+                }
+            }
             launch_k(affine_act_kernel<T, V>, dim3(ew_grid((total + 1) / 2, 1)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, a, b, (const T*)other, o_cs, act, (T*)y, y_cs, (unsigned)(H * W), (unsigned)C, total);
         });
     });

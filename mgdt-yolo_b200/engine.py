@@ -174,6 +174,14 @@ class Engine:
         cnt = s.host_counts.tolist()
         return [s.host_out[i, :cnt[i]].clone() for i in range(self.batch)]
 
+    def predict(self, ims, names=None, paths=None, auto=False, stride=32):
+        """DetectionPredictor's product for a list of BGR uint8 images (yolo/v8/detect/predict.py:12-30): one Results
+        per image with boxes in original-image pixels (submit_images -> collect -> results.build_results)."""
+        from .results import build_results
+        dets = self.collect(self.submit_images(ims, auto=auto, stride=stride))
+        names = names if names is not None else getattr(self.model, "names", None) or {i: str(i) for i in range(self.model.model[-1].nc)}
+        return build_results(dets, list(ims), paths, names)
+
     def __call__(self, images: torch.Tensor):
         """Convenience: images (B,C,H,W) uint8 or float on host or device -> list of (n_i,6) tensors."""
         if images.shape != self.slots[0].src.shape:

@@ -93,3 +93,7 @@ def test_engine_submit_images():
     for i in range(2):
         assert torch.equal(got[i], s.out[i, :cnt[i]].cpu())
         assert float(got[i][:, [0, 2]].max()) <= ims[i].shape[1] and float(got[i][:, [1, 3]].max()) <= ims[i].shape[0]
+    res = eng.predict(ims, paths=["a.jpg", "b.jpg"])                  # the same thing as Results objects
+    for i in range(2):
+        assert res[i].orig_shape == ims[i].shape[:2] and torch.equal(res[i].boxes.data, got[i])
+        assert torch.equal(res[i].boxes.xywh, O.boxes_views(got[i], ims[i].shape[:2])[0])
