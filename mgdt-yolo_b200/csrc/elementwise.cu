@@ -49,6 +49,12 @@ template <> struct VecIO<float, 8> {
     }
 };
 
+__device__ __forceinline__ void unpack_bf8(const uint4& v, float* f) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(w[j] << 16); f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+}
+
 static inline bool aligned8(const void* p, int cs, size_t esize) {
     return p == nullptr || ((((uintptr_t)p) % (8 * esize)) == 0 && (cs % 8) == 0);
 }
@@ -249,6 +255,89 @@ __global__ void __launch_bounds__(EW_THREADS) resample_kernel(const T* __restric
                 f[j] = (1.f - lh) * ((1.f - lw) * v00[j] + lw * v01[j]) + lh * ((1.f - lw) * v10[j] + lw * v11[j]);
         }
         VecIO<T, V>::st(y + (size_t)pix * y_cs + c, f);
+    }
+}
+
+// bf16 fast paths of the two resampling shapes the GD neck uses (same arithmetic and order as resample_kernel, so the
+// results are identical): exact K x K average pooling (Hi == K*Ho, Wi == K*Wo, K = 2 or 4) with all loads of a window
+// requested before the first add, and exact 2x bilinear upsampling with one thread per 2x2 output block (the four
+// source corners are shared by the block: 1 load per output instead of 4), as inject2x does.
+template <int K>
+__global__ void __launch_bounds__(EW_THREADS, 4) avgpool_exact_bf16_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, int Wi,
+                                                                          __nv_bfloat16* __restrict__ y, int y_cs, int Ho, int Wo,
+                                                                          unsigned C, unsigned total) {
+    pdl_trigger();
+    pdl_wait();
+    const unsigned CV = C / 8;
+    const int Hi = K * Ho;
+    for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
+        const unsigned cv = i % CV, pix = i / CV;
+        const int wo = (int)(pix % (unsigned)Wo);
+        const unsigned t = pix / (unsigned)Wo;
+        const int ho = (int)(t % (unsigned)Ho);
+        const unsigned n = t / (unsigned)Ho;
+        const __nv_bfloat16* xw = x + ((size_t)n * Hi * Wi + (size_t)(ho * K) * Wi + wo * K) * x_cs + cv * 8;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+#pragma unroll
+        for (int h0 = 0; h0 < K; h0 += 2) {   // two window rows (2K chunks) in flight at a time
+            uint4 v[2][K];
+#pragma unroll
+            for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+                for (int w = 0; w < K; ++w) v[dh][w] = __ldg(reinterpret_cast<const uint4*>(xw + (size_t)((h0 + dh) * Wi + w) * x_cs));
+#pragma unroll
+            for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+                for (int w = 0; w < K; ++w) {
+                    float g[8];
+                    unpack_bf8(v[dh][w], g);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += g[j];
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = f[j] / (float)(K * K);
+        VecIO<__nv_bfloat16, 8>::st(y + (size_t)pix * y_cs + cv * 8, f);
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS, 4) bilinear2x_bf16_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, int Hi, int Wi,
+                                                                       __nv_bfloat16* __restrict__ y, int y_cs, unsigned C,
+                                                                       unsigned total) {
+    pdl_trigger();
+    pdl_wait();
+    const int Ho = 2 * Hi, Wo = 2 * Wi;
+    const unsigned CV = C / 8;
+    for (unsigned i = blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += gridDim.x * EW_THREADS) {
+        const unsigned cv = i % CV, blk = i / CV;
+        const int bj = (int)(blk % (unsigned)(Wi + 1));
+        const unsigned t = blk / (unsigned)(Wi + 1);
+        const int bi = (int)(t % (unsigned)(Hi + 1));
+        const unsigned n = t / (unsigned)(Hi + 1);
+        const int ra = max(bi - 1, 0), rb = min(bi, Hi - 1), ca = max(bj - 1, 0), cb = min(bj, Wi - 1);
+        const __nv_bfloat16* xn = x + (size_t)n * Hi * Wi * x_cs + cv * 8;
+        const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(xn + (size_t)(ra * Wi + ca) * x_cs));
+        const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(xn + (size_t)(ra * Wi + cb) * x_cs));
+        const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(xn + (size_t)(rb * Wi + ca) * x_cs));
+        const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(xn + (size_t)(rb * Wi + cb) * x_cs));
+        float v00[8], v01[8], v10[8], v11[8];
+        unpack_bf8(q00, v00); unpack_bf8(q01, v01); unpack_bf8(q10, v10); unpack_bf8(q11, v11);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ho = 2 * bi - 1 + (k >> 1), wo = 2 * bj - 1 + (k & 1);
+            if (ho < 0 || ho >= Ho || wo < 0 || wo >= Wo) continue;
+            int h0, h1, w0, w1;
+            float lh, lw;
+            bilinear_src(ho, Hi, Ho, h0, h1, lh);   // (h0, h1) == (ra, rb) whenever lh != 0
+            bilinear_src(wo, Wi, Wo, w0, w1, lw);
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                f[j] = (1.f - lh) * ((1.f - lw) * v00[j] + lw * v01[j]) + lh * ((1.f - lw) * v10[j] + lw * v11[j]);
+            VecIO<__nv_bfloat16, 8>::st(y + (((size_t)n * Ho + ho) * Wo + wo) * y_cs + cv * 8, f);
+        }
     }
 }
 
@@ -483,6 +572,23 @@ extern "C" int mgdt_resample(const void* x, int x_cs, int Hi, int Wi, void* y, i
     MGDT_DTYPE_SWITCH(dtype, T, {
         const bool vec = C % 8 == 0 && aligned8(x, x_cs, sizeof(T)) && aligned8(y, y_cs, sizeof(T));
         MGDT_VEC_SWITCH(vec, V, {
+            if constexpr (sizeof(T) == 2 && V == 8) {
+                const bool pool2 = mode == MGDT_RS_AVGPOOL && Hi == 2 * Ho && Wi == 2 * Wo;
+                const bool pool4 = mode == MGDT_RS_AVGPOOL && Hi == 4 * Ho && Wi == 4 * Wo;
+                if (pool2 || pool4) {
+                    const unsigned tot = (unsigned)((long long)N * Ho * Wo * (C / 8));
+                    if (pool2) launch_k(avgpool_exact_bf16_kernel<2>, dim3(ew_grid(tot, 1)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, Wi, (T*)y, y_cs, Ho, Wo, (unsigned)C, tot);
+                    else launch_k(avgpool_exact_bf16_kernel<4>, dim3(ew_grid(tot, 1)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, Wi, (T*)y, y_cs, Ho, Wo, (unsigned)C, tot);
+                    MGDT_LAUNCH_CHECK("resample");
+                    return 0;
+                }
+                if (mode == MGDT_RS_BILINEAR && Ho == 2 * Hi && Wo == 2 * Wi && Hi > 1 && Wi > 1) {
+                    const unsigned tot = (unsigned)((long long)N * (Hi + 1) * (Wi + 1) * (C / 8));
+                    launch_k(bilinear2x_bf16_kernel, dim3(ew_grid(tot, 1)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, Hi, Wi, (T*)y, y_cs, (unsigned)C, tot);
+                    MGDT_LAUNCH_CHECK("resample");
+                    return 0;
+                }
+            }
             const unsigned total = (unsigned)((long long)N * Ho * Wo * (C / V));
             launch_k(resample_kernel<T, V>, dim3(ew_grid(total)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)x, x_cs, Hi, Wi, (T*)y, y_cs, Ho, Wo, (unsigned)C, mode, total);
         });
@@ -580,12 +686,6 @@ __global__ void __launch_bounds__(EW_THREADS) inject2x_kernel(const T* __restric
 }
 // bf16 form of inject2x_kernel: all twelve 16-byte loads of a 2x2 output block (8 corners + 4 local chunks) are issued
 // before any arithmetic and kept packed, so a thread has 192 bytes in flight and three CTAs fit on an SM.
-__device__ __forceinline__ void unpack_bf8(const uint4& v, float* f) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(w[j] << 16); f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
-}
-
 __global__ void __launch_bounds__(EW_THREADS, 3) inject2x_bf16_kernel(const __nv_bfloat16* __restrict__ local, int l_cs,
                                                                      const __nv_bfloat16* __restrict__ gact, int a_cs,
                                                                      const __nv_bfloat16* __restrict__ gfeat, int f_cs,
