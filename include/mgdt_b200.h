@@ -141,10 +141,13 @@ int mgdt_dwconv7_ln(const void* x, int x_cs, const void* w, const float* bias, c
  * here, so both may be channel slices of the raw spatial_conv_offset output (head.py:515-517).
  * w is [Cout][9][Cin] in dtype; w_umma (optional, bf16) is that matrix packed by mgdt_conv_umma_pack as
  * a 1x1 conv over 9*Cin channels: the tensor-core path builds the modulated bilinear im2col tile in
- * shared memory and runs it through tcgen05. */
+ * shared memory and runs it through tcgen05.  stat_acc / stat_q / stat_sq / stat_copies: fused output statistics as
+ * in mgdt_conv_args (NULL = none; the GroupNorm that follows DyDCNv2, block.py:430). */
 int mgdt_dcn3x3(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs,
                 int mask_is_logit, const void* w, const void* w_umma, int w_umma_f16, void* y, int y_cs, int N, int H, int W,
-                int Cin, int Cout, int dtype, void* stream);
+                int Cin, int Cout, int dtype, void* stat_acc, int stat_q, int stat_sq, int stat_copies, void* stream);
+/* 2 if mgdt_dcn3x3 would run the tcgen05 path for these arguments (the only one that takes stat_acc), else 1. */
+int mgdt_dcn3x3_path(const void* x, int x_cs, const void* w_umma, int N, int H, int W, int Cin, int Cout, int dtype);
 
 /* ---------------------------------------------------------------- reductions
  * Per-(n,c) sums over the image, optionally per adaptive 2x2 window as well.

@@ -63,7 +63,8 @@ SIGNATURES = {
     "mgdt_mspa_front_pack": (C.c_int, [vp, i32, i32, vp, vp]),
     "mgdt_mspa_front": (C.c_int, [vp, i32, vp, vp, i32, i32, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "mgdt_dwconv7_ln": (C.c_int, [vp, i32, vp, vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]),
-    "mgdt_dcn3x3": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_dcn3x3": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
+    "mgdt_dcn3x3_path": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32]),
     "mgdt_chan_stats_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
     "mgdt_chan_stats": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, i32, vp]),
     "mgdt_chan_stats_fin": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp, C.POINTER(StatsFin), i32, vp]),

@@ -455,20 +455,32 @@ extern "C" int mgdt_dwconv7_ln(const void* x, int x_cs, const void* w, const flo
 namespace mgdt {
 bool dcn_umma_supported(const void* x, int x_cs, const void* w_umma, int N, int H, int W, int Cin, int Cout);
 int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs, int mask_is_logit,
-             const void* w_umma, int w_f16, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
+             const void* w_umma, int w_f16, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, void* stat_acc, int stat_q,
+             int stat_sq, int stat_copies, cudaStream_t s);
 }
 #endif
 
+extern "C" int mgdt_dcn3x3_path(const void* x, int x_cs, const void* w_umma, int N, int H, int W, int Cin, int Cout, int dtype) {
+#ifdef MGDT_WITH_UMMA
+    if (dtype == MGDT_BF16 && dcn_umma_supported(x, x_cs, w_umma, N, H, W, Cin, Cout)) return 2;
+#endif
+    return 1;
+}
+
 extern "C" int mgdt_dcn3x3(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs,
                            int mask_is_logit, const void* w, const void* w_umma, int w_umma_f16, void* y, int y_cs, int N,
-                           int H, int W, int Cin, int Cout, int dtype, void* stream) {
+                           int H, int W, int Cin, int Cout, int dtype, void* stat_acc, int stat_q, int stat_sq, int stat_copies,
+                           void* stream) {
     MGDT_CHECK(x && offset && mask && w && y, "dcn3x3: null pointer");
     MGDT_CHECK(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && off_cs >= 18 && mask_cs >= 9, "dcn3x3: bad shape");
+    MGDT_CHECK(!stat_acc || ((stat_q == 0 || stat_q == 1 || stat_q == 5) && stat_q + (stat_sq ? 1 : 0) > 0 && ((uintptr_t)stat_acc & 7) == 0),
+               "dcn3x3: bad fused-statistics request");
 #ifdef MGDT_WITH_UMMA
     if (dtype == MGDT_BF16 && dcn_umma_supported(x, x_cs, w_umma, N, H, W, Cin, Cout))
         return dcn_umma(x, x_cs, offset, off_cs, mask, mask_cs, mask_is_logit, w_umma, w_umma_f16, y, y_cs, N, H, W, Cin, Cout,
-                        (cudaStream_t)stream);
+                        stat_acc, stat_q, stat_sq, stat_copies, (cudaStream_t)stream);
 #endif
+    if (stat_acc) return set_error(-ENOTSUP, "dcn3x3: fused statistics need the tcgen05 path (see mgdt_dcn3x3_path)");
     const size_t smem = sizeof(float) * DCN_PIX * (9 * Cin + 1);
     MGDT_CHECK(smem <= 200 * 1024, "dcn3x3: Cin=%d too large", Cin);
     const long long npix = (long long)N * H * W;

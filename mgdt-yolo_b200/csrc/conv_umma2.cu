@@ -1387,8 +1387,8 @@ static int launch2k(const P2& p, dim3 grid, cudaStream_t s) {
 
 // The statistics epilogue (STATS = 1) is instantiated only for the transform-free 1x1 / 3x3 stride-1 loaders -- the
 // producers of every map the model takes statistics of (MSPA convs[-1], ConvNeXt pwconv1, Conv_GN) -- so that all other
-// instantiations keep their code unchanged.
-template <int MODE, int LOADER> constexpr bool stats_variant() { return LOADER == LD_ASYNC && (MODE == 0 || MODE == 1); }
+// instantiations keep their code unchanged (+ the DCNv2 loader, whose output feeds a GroupNorm).
+template <int MODE, int LOADER> constexpr bool stats_variant() { return (LOADER == LD_ASYNC && (MODE == 0 || MODE == 1)) || LOADER == LD_DCN; }
 
 template <int MODE, int LOADER, int SPLIT>
 static int launch2t(const P2& p, dim3 grid, cudaStream_t s) {
@@ -1493,7 +1493,8 @@ bool dcn_umma_supported(const void* x, int x_cs, const void* w_umma, int N, int 
 }
 
 int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void* mask, int mask_cs, int mask_is_logit,
-             const void* w_umma, int w_f16, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, cudaStream_t s) {
+             const void* w_umma, int w_f16, void* y, int y_cs, int N, int H, int W, int Cin, int Cout, void* stat_acc, int stat_q,
+             int stat_sq, int stat_copies, cudaStream_t s) {
     P2 p;
     int Ho, Wo;
     if (!plan2_for(9 * Cin, Cout, 1, 1, N, H, W, p.pl, p.rn, Ho, Wo)) return set_error(-EINVAL, "dcn_umma: unsupported shape");
@@ -1508,7 +1509,11 @@ int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void
     p.dcn_off = (const __nv_bfloat16*)offset; p.dcn_mask = (const __nv_bfloat16*)mask;
     p.off_cs = off_cs; p.mask_cs = mask_cs; p.mask_logit = mask_is_logit; p.dcn_cin = Cin;
     p.stem_src = nullptr; p.stem_u8 = p.stem_C = p.stem_H = p.stem_W = 0;
-    p.st_acc = nullptr; p.st_Q = p.st_sq = p.st_h0e = p.st_h1b = p.st_w0e = p.st_w1b = p.st_tot = 0; p.st_R = 1; p.st_rs = 0;
+    p.st_acc = (double*)stat_acc; p.st_Q = stat_acc ? stat_q : 0; p.st_sq = (stat_acc && stat_sq) ? 1 : 0;
+    p.st_h0e = (H + 1) / 2; p.st_h1b = H / 2; p.st_w0e = (W + 1) / 2; p.st_w1b = W / 2;
+    p.st_R = stat_copies > 0 ? stat_copies : 1;
+    p.st_rs = (long long)N * (p.st_Q + p.st_sq) * Cout;
+    p.st_tot = (p.st_Q == 1 || (p.st_Q == 5 && ((H | W) & 1))) ? 1 : 0;
     return launch2(p, s);
 }
 

@@ -416,9 +416,9 @@ class DyDCNv2(KernelModule):
         x = ops.as_act(x)
         offset, mask = ops.as_act(offset, x.dtype), ops.as_act(mask, x.dtype)
         wp, gnw, gnb = self._pack(x.dtype, x.device)
-        y = ops.dcn3x3(x, offset, mask, wp, self.conv.weight.shape[0], mask_is_logit)
+        req = ops.StatReq(1, True) if self.with_norm else None
+        y = ops.dcn3x3(x, offset, mask, wp, self.conv.weight.shape[0], mask_is_logit, stat=req)
         if not self.with_norm:
             return y if act is None else ops.affine_act(y, act=act, out=out)
-        n, c, h, w = y.shape
-        a, b = ops.stats_gn(y, self.norm.num_groups, self.norm.eps, gnw, gnb)   # statistics + affine in one launch
+        a, b = ops.finish_gn(req, y, self.norm.num_groups, self.norm.eps, gnw, gnb)   # GroupNorm statistics from the conv's epilogue
         return ops.affine_act(y, a, b, act=act, out=out)

@@ -314,7 +314,7 @@ def dwconv7_ln(x, w49c, bias, ln_w, ln_b, eps=1e-6, out=None):
     return out
 
 
-def dcn3x3(x, offset, mask, w, cout, mask_is_logit, out=None):
+def dcn3x3(x, offset, mask, w, cout, mask_is_logit, out=None, stat=None):
     xp, n, cin, h, wd, xcs = view(x)
     op, on, oc, oh, ow, ocs = view(offset)
     mp, mn, mc, mh, mw, mcs = view(mask)
@@ -325,11 +325,19 @@ def dcn3x3(x, offset, mask, w, cout, mask_is_logit, out=None):
     if out is None:
         out = new_act(n, cout, h, wd, x.dtype, x.device)
     yp, *_, ycs = view(out)
+    umma_ptr = None if getattr(w, "umma", None) is None else w.umma.data_ptr()
+    st = (None, 0, 0, 0)
+    if stat is not None:
+        stat.fused = False
+        if FUSE_STATS and lib().mgdt_dcn3x3_path(xp, xcs, umma_ptr, n, h, wd, cin, cout, dtype_code(x.dtype)) == 2:
+            stat.acc = _stat_arena(x.device, STAT_COPIES * n * (stat.q + stat.sq) * cout)
+            st = (stat.acc.data_ptr(), stat.q, stat.sq, STAT_COPIES)
+            stat.fused = True
     _invoke("mgdt_dcn3x3", dict(shape=f"dcn {cin}->{cout} {n}x{h}x{wd}", bytes=_nb(x, offset, mask, out), flops=2.0 * 9 * cin * cout * n * h * wd,
                                 kernel="conv_umma2_kernel" if (getattr(w, "umma", None) is not None and x.dtype == torch.bfloat16) else "dcn3x3_kernel"), xp, xcs, op, ocs, mp, mcs, 1 if mask_is_logit else 0, w.data_ptr(),
             None if getattr(w, "umma", None) is None else w.umma.data_ptr(), 1 if getattr(w, "f16", False) else 0,
             yp, ycs, n, h, wd,
-                            cin, cout, dtype_code(x.dtype), stream_ptr())
+                            cin, cout, dtype_code(x.dtype), *st, stream_ptr())
     return out
 
 

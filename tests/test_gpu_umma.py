@@ -217,3 +217,35 @@ def test_umma_paired_units_with_residual(cin, cout, k):
     err = float((y0.float() - y1.float()).abs().max()) / scale
     assert err <= 2 ** -7, f"{err:.3e}"
     assert float(ybuf[:, :8].float().abs().max()) == 0.0 and float(ybuf[:, 8 + cout:].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape", [(3, 32, 13, 17), (2, 32, 40, 40)])
+def test_dcn_fused_groupnorm_stats(shape):
+    """DyDCNv2: GroupNorm sums accumulated in the DCN conv's epilogue against the stand-alone statistics pass."""
+    from mgdt_yolo_b200 import ops
+    from mgdt_yolo_b200.modules.block import DyDCNv2
+    from mgdt_yolo_b200.synth import synth_state_dict
+    n, c, h, w = shape
+    torch.manual_seed(h)
+    m = DyDCNv2(c, c)
+    m.load_state_dict(synth_state_dict(m.state_dict(), seed=w))
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(h * w)
+    x = ops.as_act(torch.randn(n, c, h, w, generator=g).cuda().to(torch.bfloat16))
+    off = ops.as_act((torch.randn(n, 18, h, w, generator=g) * 1.5).cuda().to(torch.bfloat16))
+    msk = ops.as_act(torch.rand(n, 9, h, w, generator=g).cuda().to(torch.bfloat16))
+    outs = {}
+    for rnd in range(2):
+        for fused in (True, False):
+            ops.FUSE_STATS = fused
+            try:
+                with torch.no_grad():
+                    y = m(x, off, msk, act="relu").float()
+                torch.cuda.synchronize()
+            finally:
+                ops.FUSE_STATS = True
+            if rnd and fused:
+                assert torch.equal(y, outs[True])
+            outs[fused] = y
+    err = float((outs[True] - outs[False]).abs().max()) / float(outs[False].abs().max())
+    assert err <= 2 ** -7, f"{err:.3e}"
