@@ -3,7 +3,7 @@
 //
 // Role: (1) the fp32 validation mode of the whole path (BASELINE.json north_star: "1e-4 in an
 // fp32 validation mode"); (2) the bf16 path for shapes the tcgen05 kernel does not take
-// (Cin = 3 stem, Cout in {1, 2, 27, ...}).  The tensor-core path lives in conv_umma.cu.
+// (Cin = 3 stem, Cout in {1, 2, 27, ...}).  The tensor-core path lives in conv_umma2.cu.
 //
 // Tiling: one CTA = BM output pixels x BN output channels, 256 threads, each thread a 4x4
 // register tile; K = taps x Cin is walked in chunks of BK=16 staged through shared memory.

@@ -1,6 +1,7 @@
 // Persistent, warp-specialised tcgen05 / TMEM implicit-GEMM convolution for sm_100a.
 //
-// Same GEMM mapping and shared-memory layouts as described in conv_umma.cu (pixels on M = 128,
+// Same GEMM mapping and shared-memory layouts as the first, non-persistent version (kept as conv_umma_v1.cu.txt for its
+// layout description; not compiled): pixels on M = 128,
 // channel planes [Cin/8][parity][P][16 B] in the no-swizzle K-major UMMA layout, taps as shifted
 // descriptors, stride 2 as four parity sub-images), restructured as ONE resident CTA per SM that
 // loops over output tiles with three overlapped roles:
@@ -707,9 +708,9 @@ __device__ __forceinline__ void epi_stats(double* acc, int Q, int sq, int want_t
         up2(add2(add2(qa[0], qa[1]), add2(qa[2], qa[3])), q0, q1);
         s0 += __shfl_xor_sync(full, s0, 16); s1 += __shfl_xor_sync(full, s1, 16);
         q0 += __shfl_xor_sync(full, q0, 16); q1 += __shfl_xor_sync(full, q1, 16);
-        if (col0 && !(want_tot & 256)) {
+        if (col0) {
             double* base = acc + ((size_t)(k >> 4) * K) * C + c;
-            if (want_tot & 1) { atomicAdd(base, (double)s0); if (col1) atomicAdd(base + 1, (double)s1); }
+            if (want_tot) { atomicAdd(base, (double)s0); if (col1) atomicAdd(base + 1, (double)s1); }
             if (Q == 5) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -1424,8 +1425,12 @@ static int launch2(P2& p, cudaStream_t s) {
     }
     fill_divs(p);
     p.trace = g_trace;
-    { static int pr = -1; if (pr < 0) { const char* e = getenv("MGDT_CONV_PAIR"); pr = (e && e[0] == '0') ? 0 : 1; } p.pair_ok = pr; }
-    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MGDT_STATS_DEBUG"); dbg = e ? atoi(e) : 0; } if (dbg & 1) p.st_tot |= 256; if (dbg & 2) p.st_Q = 0, p.st_sq = 1, p.st_tot |= 256; }
+    static int pair_env = -1;   // debug (MGDT_CONV_PAIR=0): paired 16-column epilogue units off, for A/B runs
+    if (pair_env < 0) {
+        const char* e = getenv("MGDT_CONV_PAIR");
+        pair_env = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.pair_ok = pair_env;
     const long long tiles = p.rn.tiles;
     int ctas = (int)(tiles < 148 ? tiles : 148);
     if (p.pl.nsplit > 1) ctas = (int)std::max(1LL, std::min(tiles, (long long)(148 / p.pl.nsplit)));
