@@ -1413,7 +1413,12 @@ static int launch2s(const P2& p, int split, dim3 grid, cudaStream_t s) {
 static int pick_split(const P2& p, bool xform) {
     (void)xform;
     const int units = p.rn.MB * ((p.pl.Nc + 31) / 32);
-    return units >= 8 ? 0 : units >= 6 ? 1 : 2;
+    // the statistics epilogue is ~40 % longer per unit: 1x1 layers that carry it want the epilogue-heavy split already
+    // at four units (32->32 @160^2: 62 -> 49 us, 80->64 @80^2: 41 -> 34 us with 3 / 16 warps)
+    if (p.st_acc && p.pl.mode == 0) return units >= 6 ? 1 : 0;
+    // wide-K layers (512->256) keep more producers even with eight units (23 -> 18 us)
+    if (units >= 8) return p.Cin >= 256 ? 1 : 0;
+    return units >= 6 ? 1 : 2;
 }
 
 static int launch2(P2& p, cudaStream_t s) {
