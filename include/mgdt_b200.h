@@ -94,6 +94,11 @@ typedef struct mgdt_conv_args {
      * separate mgdt_chan_stats pass over y. */
     void* stat_acc;
     int32_t stat_q, stat_sq, stat_copies;
+    /* Per-image weights (tcgen05 path, transform-free loader): w_umma points to N images packed back to back by
+     * mgdt_conv_umma_pack_scaled (image n = the weights with input channel ci scaled by in_scale[n][ci]); in_scale,
+     * pre_add, pix_scale and in_relu must then be unset.  The same product as in_scale on the activations
+     * (W (s_n o x) = (W diag(s_n)) x) without the loader's in-place transform; tiles are cut per image. */
+    int32_t w_per_image;
 } mgdt_conv_args;
 int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
 /* Which kernel mgdt_conv2d would run for these arguments: 3 = conv_pointwise_kernel (narrow 1x1 layers, CUDA cores,
@@ -107,6 +112,10 @@ int mgdt_conv2d_path(const mgdt_conv_args* a);
 size_t mgdt_conv_umma_packed_bytes(int Cin, int Cout, int k, int stride);
 int mgdt_conv_umma_pack(const void* w_ohwi, int w_dtype, int Cin, int Cout, int k, int stride, int out_f16, void* packed,
                         void* stream);
+/* N images of mgdt_conv_umma_packed_bytes each: image n = the bf16 image `packed_bf16` (from mgdt_conv_umma_pack) with
+ * every input channel ci scaled by in_scale[n][ci] (fp32 [N][Cin]) and rounded to bf16 again. */
+int mgdt_conv_umma_pack_scaled(const void* packed_bf16, int Cin, int Cout, int k, int stride, const float* in_scale, int N,
+                               void* out, void* stream);
 
 /* Fused input preprocessing + stem convolution on the tensor cores (bf16): 3x3 stride-2 pad-1 Conv+BN+act
  * (layer 0 of every config, models/v8/*.yaml) read straight from the NCHW uint8 (divided by 255,

@@ -28,7 +28,7 @@ class ConvArgs(C.Structure):
                 ("kh", i32), ("kw", i32), ("stride", i32), ("pad", i32),
                 ("x_cs", i32), ("y_cs", i32), ("add_cs", i32), ("ps_cs", i32), ("res_cs", i32),
                 ("act", i32), ("in_relu", i32), ("dtype", i32), ("impl", i32), ("w_umma", vp), ("w_umma_f16", i32),
-                ("stat_acc", vp), ("stat_q", i32), ("stat_sq", i32), ("stat_copies", i32)]
+                ("stat_acc", vp), ("stat_q", i32), ("stat_sq", i32), ("stat_copies", i32), ("w_per_image", i32)]
 
 
 class StatsFin(C.Structure):
@@ -57,6 +57,7 @@ SIGNATURES = {
     "mgdt_conv2d": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "mgdt_conv_umma_packed_bytes": (sz, [i32, i32, i32, i32]),
     "mgdt_conv_umma_pack": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "mgdt_conv_umma_pack_scaled": (C.c_int, [vp, i32, i32, i32, i32, vp, i32, vp, vp]),
     "mgdt_stem_conv": (C.c_int, [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_mspa_front_supported": (C.c_int, [i32, i32]),
     "mgdt_mspa_front_packed_bytes": (sz, [i32, i32]),

@@ -67,6 +67,7 @@ struct Plan2 {
 
 struct Run2 {
     int MB, S, NACC, P, Wq, halo, pstride16, tiles_per_img, tmem_cols;
+    int per_img;   // mode 0 tiled per image (tiles never straddle images): needed for per-image weights
     long long tiles;
     unsigned a_bytes, w_slice_bytes, stage_bytes, wres_bytes, smem_total;
 };
@@ -130,11 +131,17 @@ static Plan2 make_plan2(int Cin, int Cout, int k, int stride) {
     return p;
 }
 
-static bool try_run2(const Plan2& p, int MB, int N, int H, int W, int Ho, int Wo, Run2& r) {
+static bool try_run2(const Plan2& p, int MB, int N, int H, int W, int Ho, int Wo, Run2& r, bool per_img_w = false) {
     r.MB = MB;
     r.NACC = (2 * MB * p.Nc <= 512) ? 2 : 1;
+    r.per_img = 0;
     if (MB * p.Nc > 512) return false;
-    if (p.mode == 0) {
+    if (p.mode == 0 && per_img_w) {
+        r.Wq = W; r.halo = 0; r.P = 128 * MB;
+        r.per_img = 1;
+        r.tiles_per_img = (H * W + 128 * MB - 1) / (128 * MB);
+        r.tiles = (long long)r.tiles_per_img * N;
+    } else if (p.mode == 0) {
         r.Wq = W; r.halo = 0; r.P = 128 * MB;
         r.tiles_per_img = 1;
         r.tiles = ((long long)N * H * W + 128 * MB - 1) / (128 * MB);
@@ -161,6 +168,10 @@ static bool try_run2(const Plan2& p, int MB, int N, int H, int W, int Ho, int Wo
         r.wres_bytes = (unsigned)((size_t)p.nks * wall);
         r.w_slice_bytes = 0;
     }
+    if (per_img_w) {   // per-image weights change with the tile: every item carries its slice through the ring
+        r.wres_bytes = 0;
+        r.w_slice_bytes = wall;
+    }
     r.stage_bytes = r.a_bytes + r.w_slice_bytes;
     int S = U2_MAX_STAGES;
     while (S >= 2 && (size_t)r.wres_bytes + (size_t)S * r.stage_bytes + U2_TAIL > (size_t)U2_MAX_SMEM) --S;
@@ -173,12 +184,12 @@ static bool try_run2(const Plan2& p, int MB, int N, int H, int W, int Ho, int Wo
     return true;
 }
 
-static bool make_run2(const Plan2& p, int N, int H, int W, int Ho, int Wo, Run2& r) {
+static bool make_run2(const Plan2& p, int N, int H, int W, int Ho, int Wo, Run2& r, bool per_img_w = false) {
     const int mbs[3] = {4, 2, 1};
     bool found = false;
     for (int i = 0; i < 3; ++i) {
         Run2 t;
-        if (!try_run2(p, mbs[i], N, H, W, Ho, Wo, t)) continue;
+        if (!try_run2(p, mbs[i], N, H, W, Ho, Wo, t, per_img_w)) continue;
         if (t.NACC < 2 && mbs[i] > 1) continue;           // keep two accumulator buffers when a smaller tile allows it
         r = t;
         found = true;
@@ -186,7 +197,7 @@ static bool make_run2(const Plan2& p, int N, int H, int W, int Ho, int Wo, Run2&
     }
     if (!found) {
         Run2 t;
-        if (try_run2(p, 1, N, H, W, Ho, Wo, t)) { r = t; found = true; }
+        if (try_run2(p, 1, N, H, W, Ho, Wo, t, per_img_w)) { r = t; found = true; }
     }
     return found;
 }
@@ -199,6 +210,8 @@ template <> __device__ __forceinline__ __nv_bfloat16 cvt_w<float, __nv_bfloat16>
 template <> __device__ __forceinline__ __half cvt_w<float, __half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __half cvt_w<__nv_bfloat16, __half>(__nv_bfloat16 v) { return __float2half_rn(__bfloat162float(v)); }
 
+// in_scale != nullptr: `nimg` images are packed back to back, image n with its input channels scaled by
+// in_scale[n][ci] (per-image weights W diag(s_n): the GRN / TaskDecomposition input scale moved onto the weights).
 template <typename S, typename D>
 __global__ void umma2_pack_kernel(const S* __restrict__ w, D* __restrict__ out, Plan2 p, int Cin, int Cout, int k) {
     pdl_trigger();
@@ -288,6 +301,7 @@ struct P2 {
     // The accumulators are replicated st_R times (copy = tile % st_R, stride st_rs doubles) so that CTAs working on
     // neighbouring tiles of one image do not serialise on the same L2 lines; st_tot = 0 skips the total plane when the
     // windows partition the image (even Ho, Wo: mgdt_stats_finish derives it from the four window sums).
+    size_t w_img_elems;          // per-image weights: elements between consecutive images' packed weights (0 = shared)
     int pair_ok;                 // paired 16-column epilogue units allowed (debug: MGDT_CONV_PAIR=0 turns them off)
     double* st_acc;
     int st_Q, st_sq, st_h0e, st_h1b, st_w0e, st_w1b, st_R, st_tot;
@@ -298,6 +312,11 @@ struct P2 {
 
 // tile-relative output row m -> output pixel index, or -1 for junk / out-of-range rows
 __device__ __forceinline__ int out_pixel2(const P2& p, uint32_t tile, uint32_t m) {
+    if (p.pl.mode == 0 && p.rn.per_img) {
+        const uint32_t n = fdiv(tile, p.d_tpi);
+        const uint32_t q = (tile - n * p.rn.tiles_per_img) * (128u * p.rn.MB) + m;
+        return q < (uint32_t)(p.H * p.W) ? (int)(n * (uint32_t)(p.H * p.W) + q) : -1;
+    }
     if (p.pl.mode == 0) {
         const uint32_t pix = tile * (128u * p.rn.MB) + m;
         return pix < p.M_total ? (int)pix : -1;
@@ -462,7 +481,10 @@ template <int MODE>
 __device__ __forceinline__ int src_pixel(const P2& p, uint32_t tile, uint32_t tt, uint32_t n_img, uint32_t pos, uint32_t par,
                                          uint32_t& n) {
     n = n_img;
-    if (MODE == 0) {
+    if (MODE == 0 && p.rn.per_img) {
+        const uint32_t q = tt * (128u * p.rn.MB) + pos;
+        return q < (uint32_t)(p.H * p.W) ? (int)(n_img * (uint32_t)(p.H * p.W) + q) : -1;
+    } else if (MODE == 0) {
         const uint32_t g = tile * (128u * p.rn.MB) + pos;
         if (g >= p.M_total) return -1;
         n = fdiv(g, p.d_HW);
@@ -832,13 +854,13 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         uint32_t xf_tile = 0, xf_tt = 0, xf_nimg = 0;
         for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             uint32_t n_img = 0, tt = 0;
-            if (MODE != 0) { n_img = fdiv(tile, p.d_tpi); tt = tile - n_img * rn.tiles_per_img; }
+            if (MODE != 0 || rn.per_img) { n_img = fdiv(tile, p.d_tpi); tt = tile - n_img * rn.tiles_per_img; }
             for (int ks = 0; ks < nks; ++ks, ++it) {
                 mbar_wait(EMPTY(s), ph ^ 1);
                 unsigned char* sA = sStage + (size_t)s * rn.stage_bytes;
                 const uint32_t sA32 = s_u32(sA);
                 if (rn.w_slice_bytes) {
-                    const uint4* src = reinterpret_cast<const uint4*>(p.w + ((size_t)ns * nks + ks) * w_slice_elems);
+                    const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)n_img * p.w_img_elems + ((size_t)ns * nks + ks) * w_slice_elems);
                     const uint32_t dst = sA32 + rn.a_bytes;
                     const int n16 = (int)(rn.w_slice_bytes / 16);
                     for (int i = ptid; i < n16; i += NP) cp_async16(dst + 16u * i, src + i, 16u);
@@ -867,13 +889,15 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                         const uint32_t dpl = sA32 + (uint32_t)pll_fix * rn.pstride16 * 16u;
                         const uint32_t Pn = (uint32_t)rn.P;
                         if (MODE == 0) {
-                            const uint32_t g0 = tile * (128u * rn.MB);
+                            // linear pixel tiles, or (per-image weights) tiles that restart at every image
+                            const uint32_t g0 = rn.per_img ? n_img * (uint32_t)(p.H * p.W) + tt * (128u * rn.MB) : tile * (128u * rn.MB);
+                            const uint32_t gend = rn.per_img ? (n_img + 1u) * (uint32_t)(p.H * p.W) : p.M_total;
                             for (uint32_t pos0 = pos_fix; pos0 < Pn; pos0 += 4 * pstep) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
                                     const uint32_t pos = pos0 + u * pstep;
                                     const uint32_t g = g0 + pos;
-                                    const bool ok = g < p.M_total;
+                                    const bool ok = g < gend;
                                     if (pos < Pn) cp_async16(dpl + pos * 16u, ok ? xpl + (size_t)g * p.x_cs : p.x, ok ? 16u : 0u);
                                 }
                             }
@@ -1350,14 +1374,15 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------- host side
-static bool plan2_for(int Cin, int Cout, int k, int stride, int N, int H, int W, Plan2& pl, Run2& rn, int& Ho, int& Wo) {
+static bool plan2_for(int Cin, int Cout, int k, int stride, int N, int H, int W, Plan2& pl, Run2& rn, int& Ho, int& Wo,
+                      bool per_img_w = false) {
     pl = make_plan2(Cin, Cout, k, stride);
     if (!pl.ok) return false;
     const int pad = k / 2;
     Ho = (H + 2 * pad - k) / stride + 1;
     Wo = (W + 2 * pad - k) / stride + 1;
     if ((long long)N * H * W >= (1LL << 30) || (long long)N * Ho * Wo >= (1LL << 30)) return false;
-    if (!make_run2(pl, N, H, W, Ho, Wo, rn)) return false;
+    if (!make_run2(pl, N, H, W, Ho, Wo, rn, per_img_w)) return false;
     return rn.tiles < (1LL << 30);
 }
 
@@ -1461,8 +1486,10 @@ bool conv2d_umma_supported(const mgdt_conv_args* a) {
     if (!a->w_umma || a->dtype != MGDT_BF16 || a->kh != a->kw || a->pad != a->kh / 2) return false;
     // fused statistics: transform-free stride-1 loaders only (see stats_variant)
     if (a->stat_acc && (a->stride != 1 || a->pre_add || a->in_scale || a->pix_scale || a->in_relu)) return false;
+    // per-image weights (w_umma = N packed images): transform-free loader only, nothing else scaled per (n, c)
+    if (a->w_per_image && (a->pre_add || a->in_scale || a->pix_scale || a->in_relu)) return false;
     Plan2 pl; Run2 rn; int Ho, Wo;
-    if (!plan2_for(a->Cin, a->Cout, a->kh, a->stride, a->N, a->H, a->W, pl, rn, Ho, Wo)) return false;
+    if (!plan2_for(a->Cin, a->Cout, a->kh, a->stride, a->N, a->H, a->W, pl, rn, Ho, Wo, a->w_per_image != 0)) return false;
     if (((uintptr_t)a->x & 15) || (a->x_cs & 7)) return false;
     if (a->pre_add && (((uintptr_t)a->pre_add & 15) || (a->add_cs & 7))) return false;
     if (a->in_scale && ((uintptr_t)a->in_scale & 15)) return false;
@@ -1473,8 +1500,9 @@ bool conv2d_umma_supported(const mgdt_conv_args* a) {
 int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
     P2 p;
     int Ho, Wo;
-    if (!plan2_for(a->Cin, a->Cout, a->kh, a->stride, a->N, a->H, a->W, p.pl, p.rn, Ho, Wo))
+    if (!plan2_for(a->Cin, a->Cout, a->kh, a->stride, a->N, a->H, a->W, p.pl, p.rn, Ho, Wo, a->w_per_image != 0))
         return set_error(-EINVAL, "conv2d_umma: unsupported shape");
+    p.w_img_elems = a->w_per_image ? (size_t)p.pl.nsplit * p.pl.nks * p.pl.nmma_s * 2 * p.pl.Nc * 8 : 0;
     p.x = (const __nv_bfloat16*)a->x; p.w = (const __nv_bfloat16*)a->w_umma;
     p.pre_add = (const __nv_bfloat16*)a->pre_add; p.pix_scale = (const __nv_bfloat16*)a->pix_scale;
     p.residual = (const __nv_bfloat16*)a->residual; p.bias = a->bias; p.in_scale = a->in_scale;
@@ -1516,6 +1544,7 @@ int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void
     p.y_vec = (((uintptr_t)y & 15) == 0 && (y_cs & 7) == 0) ? 1 : 0;
     p.res_vec = 0;
     p.M_total = (unsigned)((long long)N * H * W);
+    p.w_img_elems = 0;
     p.dcn_off = (const __nv_bfloat16*)offset; p.dcn_mask = (const __nv_bfloat16*)mask;
     p.off_cs = off_cs; p.mask_cs = mask_cs; p.mask_logit = mask_is_logit; p.dcn_cin = Cin;
     p.stem_src = nullptr; p.stem_u8 = p.stem_C = p.stem_H = p.stem_W = 0;
@@ -1549,6 +1578,7 @@ int stem_umma(const void* src, int src_is_u8, const void* w_umma, int w_f16, con
     p.res_vec = 0;
     p.M_total = (unsigned)((long long)N * Ho * Wo);
     p.dcn_off = nullptr; p.dcn_mask = nullptr; p.off_cs = p.mask_cs = p.mask_logit = p.dcn_cin = 0;
+    p.w_img_elems = 0;
     p.stem_src = src; p.stem_u8 = src_is_u8; p.stem_C = C; p.stem_H = H; p.stem_W = W;
     p.st_acc = nullptr; p.st_Q = p.st_sq = p.st_h0e = p.st_h1b = p.st_w0e = p.st_w1b = p.st_tot = 0; p.st_R = 1; p.st_rs = 0;
     return launch2(p, s);
@@ -1593,5 +1623,50 @@ extern "C" int mgdt_conv_umma_pack(const void* w_ohwi, int w_dtype, int Cin, int
     else
         launch_k(umma2_pack_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(g), dim3(256), 0, s, (const __nv_bfloat16*)w_ohwi, (__nv_bfloat16*)packed, pl, Cin, Cout, k);
     MGDT_LAUNCH_CHECK("umma_pack");
+    return 0;
+}
+
+namespace mgdt {
+// Per-image scaled copies of a packed bf16 weight image: out[img][chunk] = packed[chunk] * in_scale[img][ci .. ci + 7].
+// One thread per 16-byte chunk (8 consecutive input channels of one (tap, plane, output column)).
+__global__ void umma2_scale_packed_kernel(const uint4* __restrict__ packed, uint4* __restrict__ out, Plan2 p, int Cin,
+                                          const float* __restrict__ in_scale, unsigned per_img, unsigned total) {
+    pdl_trigger();
+    pdl_wait();
+    const unsigned cps = (unsigned)p.nmma_s * 2u, Nc = (unsigned)p.Nc;
+    for (unsigned c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += gridDim.x * blockDim.x) {
+        const unsigned img = c0 / per_img, c = c0 - img * per_img;
+        const unsigned chunk = (c / Nc) % cps, ks = (c / (Nc * cps)) % (unsigned)p.nks;
+        uint4 v = __ldg(packed + c);
+        if (chunk < (unsigned)(p.taps * p.PS)) {
+            const unsigned plane = ks * (unsigned)p.PS + chunk % (unsigned)p.PS;
+            const float4* sp = reinterpret_cast<const float4*>(in_scale + (size_t)img * Cin + plane * 8u);
+            const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(w[j] << 16) * sc[2 * j],
+                                                               __uint_as_float(w[j] & 0xffff0000u) * sc[2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+        }
+        out[c0] = v;
+    }
+}
+}  // namespace mgdt
+
+extern "C" int mgdt_conv_umma_pack_scaled(const void* packed_bf16, int Cin, int Cout, int k, int stride, const float* in_scale,
+                                          int N, void* out, void* stream) {
+    MGDT_CHECK(packed_bf16 && out && in_scale && N > 0, "conv_umma_pack_scaled: bad arguments");
+    MGDT_CHECK((((uintptr_t)packed_bf16 | (uintptr_t)out | (uintptr_t)in_scale) & 15) == 0, "conv_umma_pack_scaled: pointers must be 16-byte aligned");
+    const Plan2 pl = make_plan2(Cin, Cout, k, stride);
+    MGDT_CHECK(pl.ok, "conv_umma_pack_scaled: shape %d->%d k%d s%d is not supported by the tcgen05 path", Cin, Cout, k, stride);
+    const long long per_img = (long long)pl.nsplit * pl.nks * pl.nmma_s * 2 * pl.Nc;   // 16-byte chunks
+    MGDT_CHECK(per_img * N < (1LL << 31), "conv_umma_pack_scaled: too large");
+    const int g = (int)std::min<long long>((per_img * N + 255) / 256, 148LL * 8);
+    launch_k(umma2_scale_packed_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, (const uint4*)packed_bf16, (uint4*)out, pl, Cin, in_scale,
+             (unsigned)per_img, (unsigned)(per_img * N));
+    MGDT_LAUNCH_CHECK("umma_pack_scaled");
     return 0;
 }

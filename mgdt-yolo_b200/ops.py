@@ -149,6 +149,7 @@ class PackedConv:
 # format -- so this stays off; the packer keeps the option for an all-fp16 mode.
 WEIGHT_F16 = False
 USE_UMMA = True  # tests flip this to compare the tcgen05 path with the CUDA-core path
+PER_IMAGE_WEIGHTS = __import__('os').environ.get('MGDT_PER_IMAGE_W', '1') != '0'  # per-(n,c) input scales folded into per-image weights
 FUSE_MSPA_FRONT = True  # MSPA_C2f branch chain as one launch (bf16); tests flip this to compare with the unfused sequence
 
 
@@ -187,9 +188,12 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
     slice of a concat buffer."""
     xp, n, cin, h, wd, xcs = view(x)
     w_umma, w_f16 = None, False
+    per_image = False
     if isinstance(w, PackedConv):
         if w.umma is not None and w.stride == s:
             w_umma, w_f16 = w.umma, w.f16
+            per_image = (PER_IMAGE_WEIGHTS and in_scale is not None and pre_add is None and pix_scale is None and not in_relu
+                         and impl != 1 and not w_f16 and x.dtype == torch.bfloat16)
         w = w.ohwi
     cout = cout if cout is not None else w.shape[0]
     p = k // 2 if p is None else p
@@ -232,6 +236,19 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
     a.impl = impl
     a.w_umma = None if (w_umma is None or impl == 1) else w_umma.data_ptr()
     a.w_umma_f16 = 1 if w_f16 else 0
+    if per_image:
+        # W (s_n o x) = (W diag(s_n)) x: if the tcgen05 path takes the layer with per-image weights (tiles cut per image,
+        # weight slices carried through the ring), pack one scaled weight image per sample and run the transform-free
+        # loader instead of scaling the activations inside the loader
+        a.in_scale, a.w_per_image = None, 1
+        if lib().mgdt_conv2d_path(C.byref(a)) == 2:
+            pw = torch.empty((n * w_umma.numel(),), dtype=torch.uint8, device=x.device)
+            _invoke("mgdt_conv_umma_pack_scaled", dict(shape=f"pack_scaled {cin}->{cout} N{n}", bytes=pw.numel() + 4 * n * cin, flops=0.0,
+                                                       kernel="umma2_scale_packed_kernel"),
+                    w_umma.data_ptr(), cin, cout, k, s, in_scale.data_ptr(), n, pw.data_ptr(), stream_ptr())
+            a.w_umma = pw.data_ptr()
+        else:
+            a.in_scale, a.w_per_image = in_scale.data_ptr(), 0
     es = x.element_size()
     meta = dict(shape=f"{cin}->{cout} k{k}s{s} {n}x{h}x{wd}", flops=2.0 * n * ho * wo * cout * cin * k * k,
                 bytes=es * (n * h * wd * cin * (2 if pre_add is not None else 1)

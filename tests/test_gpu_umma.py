@@ -249,3 +249,37 @@ def test_dcn_fused_groupnorm_stats(shape):
             outs[fused] = y
     err = float((outs[True] - outs[False]).abs().max()) / float(outs[False].abs().max())
     assert err <= 2 ** -7, f"{err:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(384, 96, 1, 3, 13, 17), (384, 96, 1, 4, 40, 40), (64, 32, 1, 3, 80, 80), (64, 32, 3, 2, 21, 19),
+                                   (32, 48, 1, 5, 8, 8)])
+def test_per_image_weights_vs_in_scale(shape):
+    """Per-(n, c) input scales folded into per-image weights (mgdt_conv_umma_pack_scaled + w_per_image, tiles cut per
+    image, weight slices through the ring) against the in-loader activation transform and an fp32 reference; images
+    whose pixel count is not a multiple of the tile, K-sliced layers, a residual and a channel-slice output."""
+    from mgdt_yolo_b200 import ops
+    cin, cout, k, n, h, w = shape
+    g = torch.Generator().manual_seed(cin + h)
+    x = ops.as_act(torch.randn(n, cin, h, w, generator=g).cuda().to(torch.bfloat16))
+    res = ops.as_act(torch.randn(n, cout, h, w, generator=g).cuda().to(torch.bfloat16))
+    wt32 = (torch.randn(cout, k, k, cin, generator=g) * (2.0 / (cin * k * k)) ** 0.5).cuda()
+    pw = ops.PackedConv(wt32.to(torch.bfloat16), 1, w32=wt32)
+    insc = (torch.rand(n, cin, generator=g) * 1.5 + 0.25).cuda().contiguous()
+    bias = torch.randn(cout, generator=g).cuda()
+    outs = {}
+    for per_image in (True, False):
+        ops.PER_IMAGE_WEIGHTS = per_image
+        try:
+            ybuf = ops.as_act(torch.zeros(n, cout + 16, h, w).cuda().to(torch.bfloat16))
+            ops.conv2d(x, pw, bias, k, 1, act="silu", in_scale=insc, residual=res, out=ybuf[:, 8:8 + cout])
+            torch.cuda.synchronize()
+        finally:
+            ops.PER_IMAGE_WEIGHTS = True
+        assert float(ybuf[:, :8].float().abs().max()) == 0.0 and float(ybuf[:, 8 + cout:].float().abs().max()) == 0.0
+        outs[per_image] = ybuf[:, 8:8 + cout].float()
+    ref = F.silu(F.conv2d(x.float() * insc.view(n, cin, 1, 1), wt32.permute(0, 3, 1, 2), bias, padding=k // 2)) + res.float()
+    scale = float(ref.abs().max())
+    for key, y in outs.items():
+        err = float((y - ref).abs().max()) / scale
+        assert err <= 1e-2, f"per_image={key}: {err:.3e}"
+    assert float((outs[True] - outs[False]).abs().max()) / scale <= 1e-2
