@@ -278,6 +278,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 struct P2 {
     const __nv_bfloat16 *x, *w, *pre_add, *pix_scale, *residual;
+    const __nv_bfloat16* row_scale;   // 1x1 layers: the per-pixel input scale applied to the accumulator row instead (stride ps_cs)
     const float *bias, *in_scale;
     __nv_bfloat16* y;
     int N, H, W, Cin, Cout, Ho, Wo;
@@ -615,13 +616,21 @@ __device__ __forceinline__ void epi_math(const P2& p, const uint32_t* r, const f
     float v[NV];
     unsigned long long a[NV / 2];
     const unsigned long long half2 = pk2(0.5f, 0.5f);
-    const unsigned long long sc2 = pk2(p.out_scale, p.out_scale);
+    // acc * scale + bias: scale = out_scale (1 except for the uint8 stem) times, for 1x1 layers with a per-PIXEL input scale,
+    // that pixel's scale (W (s x) = s (W x): the scale of cv3(cls_feat * cls_prob) is applied to the accumulator row)
+    float rs = p.out_scale, rsB = p.out_scale;
+    if (p.row_scale) {
+        if (opix >= 0) rs *= __bfloat162float(p.row_scale[(size_t)opix * p.ps_cs]);
+        if (pairB && opixB >= 0) rsB *= __bfloat162float(p.row_scale[(size_t)opixB * p.ps_cs]);
+    }
+    const unsigned long long sc2 = pk2(rs, rs), sc2B = pk2(rsB, rsB);
     const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(sBias + cbase);
 #pragma unroll
-    for (int j = 0; j < NV / 4; ++j) {   // acc * out_scale + bias (out_scale = 1 except for the uint8 stem)
+    for (int j = 0; j < NV / 4; ++j) {
         const ulonglong2 b = b2[j];
-        a[2 * j] = fma2(pk2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), sc2, b.x);
-        a[2 * j + 1] = fma2(pk2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), sc2, b.y);
+        const unsigned long long sc = (pairB && 4 * j >= 16) ? sc2B : sc2;
+        a[2 * j] = fma2(pk2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), sc, b.x);
+        a[2 * j + 1] = fma2(pk2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), sc, b.y);
     }
     if (p.act == MGDT_ACT_SILU || p.act == MGDT_ACT_SIGMOID) {
         // h = v/2, t = tanh(h) on the SFU: silu = h + h*t, sigmoid = 0.5 + 0.5*t
@@ -1507,6 +1516,11 @@ int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
     p.pre_add = (const __nv_bfloat16*)a->pre_add; p.pix_scale = (const __nv_bfloat16*)a->pix_scale;
     p.residual = (const __nv_bfloat16*)a->residual; p.bias = a->bias; p.in_scale = a->in_scale;
     p.y = (__nv_bfloat16*)a->y;
+    p.row_scale = nullptr;
+    if (p.pl.mode == 0 && p.pix_scale && !p.pre_add && !p.in_scale && !a->in_relu) {   // commutes with a 1x1 conv
+        p.row_scale = p.pix_scale;
+        p.pix_scale = nullptr;
+    }
     p.N = a->N; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout; p.Ho = Ho; p.Wo = Wo;
     p.x_cs = a->x_cs; p.y_cs = a->y_cs; p.add_cs = a->add_cs; p.ps_cs = a->ps_cs; p.res_cs = a->res_cs;
     p.act = a->act; p.in_relu = a->in_relu;
@@ -1537,7 +1551,7 @@ int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void
     int Ho, Wo;
     if (!plan2_for(9 * Cin, Cout, 1, 1, N, H, W, p.pl, p.rn, Ho, Wo)) return set_error(-EINVAL, "dcn_umma: unsupported shape");
     p.x = (const __nv_bfloat16*)x; p.w = (const __nv_bfloat16*)w_umma; p.pre_add = nullptr; p.pix_scale = nullptr;
-    p.residual = nullptr; p.bias = nullptr; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y;
+    p.residual = nullptr; p.bias = nullptr; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y; p.row_scale = nullptr;
     p.N = N; p.H = H; p.W = W; p.Cin = 9 * Cin; p.Cout = Cout; p.Ho = H; p.Wo = W;
     p.x_cs = x_cs; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = MGDT_ACT_NONE; p.in_relu = 0;
     p.w_f16 = w_f16; p.out_scale = 1.0f;
@@ -1567,7 +1581,7 @@ int stem_umma(const void* src, int src_is_u8, const void* w_umma, int w_f16, con
     int ho2, wo2;
     if (!plan2_for(Kp, Cout, 1, 1, N, Ho, Wo, p.pl, p.rn, ho2, wo2)) return set_error(-EINVAL, "stem_umma: unsupported shape");
     p.x = nullptr; p.w = (const __nv_bfloat16*)w_umma; p.pre_add = nullptr; p.pix_scale = nullptr; p.residual = nullptr;
-    p.bias = bias; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y;
+    p.bias = bias; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y; p.row_scale = nullptr;
     p.N = N; p.H = Ho; p.W = Wo; p.Cin = Kp; p.Cout = Cout; p.Ho = Ho; p.Wo = Wo;
     p.x_cs = 0; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = act; p.in_relu = 0;
     p.w_f16 = w_f16;

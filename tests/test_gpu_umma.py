@@ -283,3 +283,25 @@ def test_per_image_weights_vs_in_scale(shape):
         err = float((y - ref).abs().max()) / scale
         assert err <= 1e-2, f"per_image={key}: {err:.3e}"
     assert float((outs[True] - outs[False]).abs().max()) / scale <= 1e-2
+
+
+@pytest.mark.parametrize("cout,n,h,w", [(2, 2, 17, 19), (2, 8, 120, 130), (48, 3, 20, 24)])
+def test_pixel_scale_1x1_in_epilogue(cout, n, h, w):
+    """cv3(cls_feat * cls_prob) (head.py:528): for a 1x1 conv the per-pixel input scale is applied to the accumulator row
+    in the epilogue (W (s x) = s (W x)), also in the paired-unit form (Cout <= 16, large maps), against the CUDA-core
+    path that scales the input."""
+    from mgdt_yolo_b200 import ops
+    cin = 32
+    g = torch.Generator().manual_seed(cout + h)
+    x = ops.as_act(torch.randn(n, cin, h, w, generator=g).cuda().to(torch.bfloat16))
+    pix = ops.as_act(torch.rand(n, 1, h, w, generator=g).cuda().to(torch.bfloat16))
+    wt = (torch.randn(cout, 1, 1, cin, generator=g) * (2.0 / cin) ** 0.5).cuda().to(torch.bfloat16)
+    pw = ops.PackedConv(wt, 1)
+    bias = torch.randn(cout, generator=g).cuda()
+    y0 = ops.conv2d(x, pw, bias, 1, 1, pix_scale=pix, impl=2)
+    y1 = ops.conv2d(x, pw, bias, 1, 1, pix_scale=pix, impl=1)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float() * pix.float(), wt.float().permute(0, 3, 1, 2), bias)
+    scale = float(ref.abs().max())
+    assert float((y0.float() - ref).abs().max()) / scale <= 2 ** -7
+    assert float((y0.float() - y1.float()).abs().max()) / scale <= 2 ** -6
