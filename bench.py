@@ -40,6 +40,10 @@ WORKLOADS = {
     "mspa_c2f_gd_yolov8n": ("mspa_c2f_gd_yolov8n.yaml", 80, -18.701),
     "mspa_c2f_yolov8n": ("mspa_c2f_yolov8n.yaml", 80, -1.703),
     "yolov8n": ("yolov8n.yaml", 80, -33.456),
+    # other width scales (the TOODHead YAMLs fix the head width and exist at scale n only); the bias is
+    # the n-scale one, so the share of anchors that pass conf differs
+    "mspa_c2f_gd_yolov8s": ("mspa_c2f_gd_yolov8s.yaml", 80, -18.701),
+    "mspa_c2f_yolov8m": ("mspa_c2f_yolov8m.yaml", 80, -1.703),
 }
 CONF, IOU, MAX_DET = 0.25, 0.7, 300
 
