@@ -365,9 +365,36 @@ class InjectionMultiSum_Auto_pool(KernelModule):
         c0 = sum(self.global_inp[:self.flag])
         info = x_g[:, c0:c0 + self.global_inp[self.flag]]  # x_g.split(global_inp, 1)[flag] (block.py:378)
         local = self.local_embedding(x_l)
-        gact = self.global_act(info)
-        gfeat = self.global_embedding(info)
+        both = self._pack_global(info.dtype, info.device)
+        if both is not None:   # global_act and global_embedding read the same input: one conv with stacked output channels
+            w, b, oup = both
+            g = ops.conv2d(info, w, b, 1)
+            gact, gfeat = g[:, :oup], g[:, oup:]
+        else:
+            gact = self.global_act(info)
+            gfeat = self.global_embedding(info)
         return ops.inject(local, gact, gfeat)
+
+    def _pack_global(self, dtype, device):
+        """(PackedConv, bias, oup) of global_act and global_embedding stacked along the output channels (both are 1x1
+        Conv+BN without activation on the same input, block.py:381-383), or None if they differ in shape."""
+        ga, ge = self.global_act, self.global_embedding
+        if (act_name(ga.act) is not None or act_name(ge.act) is not None or ga.conv.kernel_size != (1, 1)
+                or ga.conv.weight.shape != ge.conv.weight.shape or ga.conv.groups != 1 or ge.conv.groups != 1):
+            return None
+        tensors = []
+        for c in (ga, ge):
+            bn = getattr(c, "bn", None)
+            tensors += [c.conv.weight] + ([c.conv.bias] if c.conv.bias is not None else [])
+            if bn is not None:
+                tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+        def build():
+            wa, ba = fold_conv_bn(ga.conv, getattr(ga, "bn", None))
+            we, be = fold_conv_bn(ge.conv, getattr(ge, "bn", None))
+            return ohwi(torch.cat([wa, we], 0), dtype, device, 1), f32(torch.cat([ba, be], 0), device), wa.shape[0]
+
+        return self._packed("global2", dtype, device, tensors, build)
 
 
 class _DeformWeights(nn.Module):
