@@ -20,6 +20,7 @@
 // each work item is (tile, K slice) and carries its own weight slice through the ring.
 #include "common.cuh"
 
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -36,7 +37,7 @@ constexpr int U2_MAX_SMEM = 226 * 1024;
 constexpr int U2_MAX_STAGES = 4;
 constexpr int U2_MLP = 8;          // 16-byte loads in flight per producer thread
 constexpr int U2_MAX_MMA = 160;   // K=16 instructions per (slice, 128-row block) the descriptor table holds
-constexpr int U2_TAIL = 128 + 2 * 8 * U2_MAX_MMA + 4 * 256 + 2 * 256 + U2_MAX_EPI_WARPS * 2048;  // barriers + TMEM slot, descriptor tables, bias[Nc], u8 LUT, epilogue staging
+constexpr int U2_TAIL = 128 + 2 * 8 * U2_MAX_MMA + 4 * 256 + 2 * 256 + U2_MAX_EPI_WARPS * 2048 + 512;  // barriers + TMEM slot, descriptor tables, bias[Nc], u8 LUT, epilogue staging (512-byte aligned)
 
 struct FastDiv {  // exact n / d for 0 <= n < 2^31
     uint32_t mul, shr, d;
@@ -303,6 +304,8 @@ struct P2 {
     // neighbouring tiles of one image do not serialise on the same L2 lines; st_tot = 0 skips the total plane when the
     // windows partition the image (even Ho, Wo: mgdt_stats_finish derives it from the four window sums).
     size_t w_img_elems;          // per-image weights: elements between consecutive images' packed weights (0 = shared)
+    alignas(64) CUtensorMap ymap;   // TMA store of 32-row x 32-channel output units (mode 0): 2D (channels, pixels) or, per-image tiles, 3D (channels, pixels of an image, image)
+    int tma_store;
     int pair_ok;                 // paired 16-column epilogue units allowed (debug: MGDT_CONV_PAIR=0 turns them off)
     double* st_acc;
     int st_Q, st_sq, st_h0e, st_h1b, st_w0e, st_w1b, st_R, st_tot;
@@ -1245,14 +1248,16 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         const int quad = warp & 3, sub = ew >> 2;
         constexpr int NSUB = NEW / 4;
         const int ncch = (pl.Nc + 31) / 32;
-        unsigned char* stg = sOut + ew * 2048;
+        // 2 KB staging tile per warp, 512-byte aligned: chunk c of row r at slot c ^ ((r >> 1) & 3) is then exactly the
+        // SWIZZLE_64B pattern of a TMA tensor map (address bits [4:5] ^= bits [7:8]), so the tile can be stored by TMA
+        const uint32_t stg32 = ((s_u32(sOut) + 511u) & ~511u) + (uint32_t)ew * 2048u;
         const int srow = lane >> 2, schunk = lane & 3;    // store phase: row within a group of 8, 16-byte chunk
-        const uint32_t st_wr = s_u32(stg) + lane * 64, sw_wr = (uint32_t)((lane >> 1) & 3);
+        const uint32_t st_wr = stg32 + lane * 64, sw_wr = (uint32_t)((lane >> 1) & 3);
         uint32_t st_rd[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int row = g * 8 + srow;
-            st_rd[g] = s_u32(stg) + row * 64 + ((schunk ^ ((row >> 1) & 3)) << 4);
+            st_rd[g] = stg32 + row * 64 + ((schunk ^ ((row >> 1) & 3)) << 4);
         }
         const bool trw = p.trace && ew == 0 && lane == 0;
         uint32_t ti = 0;
@@ -1330,13 +1335,39 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
 #pragma unroll
                         for (int j = 8; j < 16; ++j) pk[j] = 0u;
                     }
+                    const bool tma_on = MODE == 0 && p.tma_store && !pair;   // uniform per launch
+                    // a 16-column unit (the tail of a column split) keeps the LSU stores: the 32-channel box would spill
+                    // into the next split's channels (clipping only happens at Cout)
+                    const bool tma = tma_on && nv == 32;
+                    if (tma_on) {   // the previous unit's TMA store has read the staging tile
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                    }
                     // row `lane` -> staging: 64 bytes per row, 16-byte chunk c at slot c ^ ((row >> 1) & 3)
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_wr + ((c ^ sw_wr) << 4)), "r"(pk[4 * c]),
                                      "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+                    if (tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (tr) tc2 = clock64();
+                    if (tma) {
+                        // one TMA tensor store per unit: the engine reads the swizzled tile and writes 32 rows x 64 bytes
+                        // (clipped at Cout and at the end of the map / image), off the LSU path the producers' LDGSTS use
+                        if (lane == 0) {
+                            const uint32_t r0 = (uint32_t)(mb * 128 + quad * 32);
+                            if (rn.per_img) {
+                                const uint32_t n = fdiv(tile, p.d_tpi);
+                                const uint32_t q = (tile - n * rn.tiles_per_img) * (128u * rn.MB) + r0;
+                                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                                             ::"l"(&p.ymap), "r"(co0), "r"(q), "r"(n), "r"(stg32) : "memory");
+                            } else {
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                             ::"l"(&p.ymap), "r"(co0), "r"(tile * (128u * rn.MB) + r0), "r"(stg32) : "memory");
+                            }
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    } else {
                     const int c8 = co0 + (pair ? (schunk & 1) : schunk) * 8;   // first output channel of this lane's chunk
                     const bool chunk_on = schunk * 8 < nv && c8 < p.Cout;
                     const bool full8 = c8 + 8 <= p.Cout && p.y_vec;
@@ -1353,8 +1384,9 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                             }
                         }
                     }
+                    }
                     if (STATS)
-                        epi_stats(p.st_acc + (size_t)(tile % (uint32_t)p.st_R) * p.st_rs, p.st_Q, p.st_sq, p.st_tot, p.Cout, s_u32(stg), skey,
+                        epi_stats(p.st_acc + (size_t)(tile % (uint32_t)p.st_R) * p.st_rs, p.st_Q, p.st_sq, p.st_tot, p.Cout, stg32, skey,
                                   lane, nv, co0, p.Cout);
                     __syncwarp();
                     if (tr) {
@@ -1372,6 +1404,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             if (lane == 0) mbar_arrive_relaxed(ACCEMPTY(a));
             if (trw && ti < 6) trace_mark(p, 11 + 8 * (int)ti);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last TMA stores are complete before the CTA exits
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -1464,6 +1497,23 @@ static int launch2(P2& p, cudaStream_t s) {
     }
     fill_divs(p);
     p.trace = g_trace;
+    // TMA store map of the output (mode 0 layers with 16-byte aligned rows; the paired 16-column units keep the LSU path)
+    static int tma_env = -1;   // debug (MGDT_CONV_TMA_STORE=0): off, for A/B runs
+    if (tma_env < 0) {
+        const char* e = getenv("MGDT_CONV_TMA_STORE");
+        tma_env = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.tma_store = 0;
+    if (tma_env && p.pl.mode == 0 && p.y_vec && p.Cout >= 8) {
+        const unsigned long long HW = (unsigned long long)p.Ho * p.Wo;
+        cuuint64_t dims[3] = {(cuuint64_t)p.Cout, p.rn.per_img ? HW : (cuuint64_t)p.M_total, (cuuint64_t)p.N};
+        cuuint64_t strides[2] = {(cuuint64_t)p.y_cs * 2, HW * (cuuint64_t)p.y_cs * 2};
+        cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+        const CUresult r = cuTensorMapEncodeTiled(&p.ymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.rn.per_img ? 3 : 2, (void*)p.y, dims,
+                                                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        p.tma_store = r == CUDA_SUCCESS ? 1 : 0;
+    }
     static int pair_env = -1;   // debug (MGDT_CONV_PAIR=0): paired 16-column epilogue units off, for A/B runs
     if (pair_env < 0) {
         const char* e = getenv("MGDT_CONV_PAIR");

@@ -20,6 +20,8 @@ SHAPES = [
     (8, 16, 3, 2, 2, 18, 14), (128, 256, 3, 2, 1, 8, 8),
     # large enough for 256/512-row tiles: Cout <= 16 runs the PAIRED 16-column epilogue units (two row blocks per unit)
     (8, 8, 3, 1, 5, 160, 160), (16, 16, 3, 1, 8, 120, 130), (64, 16, 1, 1, 8, 160, 100), (16, 8, 3, 1, 3, 200, 212),
+    # column splits whose last unit has 16 columns (Cout 576 -> 4 x 144): that unit must not be stored as a 32-channel TMA box
+    (64, 576, 1, 1, 2, 12, 10), (96, 48, 1, 1, 3, 20, 24), (32, 27, 1, 1, 2, 30, 30),
 ]
 
 
