@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    r = subprocess.run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"], capture_output=True, text=True)
+    r = subprocess.run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp_file, "w") as fh:

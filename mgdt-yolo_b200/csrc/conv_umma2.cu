@@ -1509,10 +1509,28 @@ static int launch2(P2& p, cudaStream_t s) {
         cuuint64_t dims[3] = {(cuuint64_t)p.Cout, p.rn.per_img ? HW : (cuuint64_t)p.M_total, (cuuint64_t)p.N};
         cuuint64_t strides[2] = {(cuuint64_t)p.y_cs * 2, HW * (cuuint64_t)p.y_cs * 2};
         cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
-        const CUresult r = cuTensorMapEncodeTiled(&p.ymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.rn.per_img ? 3 : 2, (void*)p.y, dims,
-                                                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                                                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        p.tma_store = r == CUDA_SUCCESS ? 1 : 0;
+        // the driver entry point is resolved at run time (the library must load on machines without libcuda, where
+        // only the host-side checks run); without it the LSU store path is used
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        static bool looked_up = false;
+        if (!looked_up) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+                qres == cudaDriverEntryPointSuccess)
+                encode = (EncodeFn)fn;
+            (void)cudaGetLastError();
+            looked_up = true;
+        }
+        if (encode) {
+            const CUresult r = encode(&p.ymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.rn.per_img ? 3 : 2, (void*)p.y, dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            p.tma_store = r == CUDA_SUCCESS ? 1 : 0;
+        }
     }
     static int pair_env = -1;   // debug (MGDT_CONV_PAIR=0): paired 16-column epilogue units off, for A/B runs
     if (pair_env < 0) {
