@@ -83,3 +83,23 @@ def test_fuse_matches_reference_formula():
     assert not hasattr(c, "bn")
     assert torch.allclose(c.conv.weight, folded["conv.weight"], atol=1e-6)
     assert torch.allclose(c.conv.bias, folded["conv.bias"], atol=1e-6)
+
+
+def test_host_side_queries_of_the_new_entry_points():
+    """Pure host queries (no GPU): supported widths / packed sizes of the fused MSPA branch chain and the tcgen05 weight
+    images; argument validation that fails before any launch returns a negative code and a message."""
+    import ctypes as C
+    from mgdt_yolo_b200 import _lib
+    L = _lib.lib()
+    assert L.mgdt_mspa_front_supported(8, 3) == 1 and L.mgdt_mspa_front_supported(64, 3) == 1
+    assert L.mgdt_mspa_front_supported(96, 3) == 0 and L.mgdt_mspa_front_supported(16, 0) == 0
+    # [stage][n-tile][k-block][lane]{b0, b1}: 3 stages x (64/8) x (64/16) x 32 lanes x 8 bytes
+    assert L.mgdt_mspa_front_packed_bytes(64, 3) == 3 * 8 * 4 * 32 * 8
+    assert L.mgdt_mspa_front_packed_bytes(8, 3) == 3 * 1 * 1 * 32 * 8          # K padded to one 16-channel block
+    assert L.mgdt_mspa_front_packed_bytes(24, 3) == 0
+    assert L.mgdt_conv_umma_packed_bytes(384, 96, 1, 1) == 384 * 96 * 2        # K-sliced, no padding for this shape
+    assert L.mgdt_conv_umma_packed_bytes(7, 16, 1, 1) == 0                     # Cin % 8 != 0: not a tcgen05 shape
+    assert L.mgdt_box_convert(None, 6, 0, 1, 1.0, 1.0, None, None) == 0        # n = 0 is a no-op
+    assert L.mgdt_box_convert(None, 6, 4, 1, 1.0, 1.0, None, None) < 0 and b"null" in L.mgdt_last_error()
+    assert L.mgdt_match_batch(None, 6, None, 300, None, None, 8, None, 64, None, 2, None) < 0   # niou > 32
+    assert L.mgdt_stats_finish(None, 4, 1, 8, 8, 32, 1, 1, None, None, None, None) < 0
