@@ -17,3 +17,6 @@ python tools/ncu_conv.py c64_256 c32_3x3 c96_384 > gpurun_out/ncu_conv_plain_$R.
 ncu --set full --clock-control none --import-source on -k regex:conv_umma2 --launch-skip 0 -c 6 -f \
     -o gpurun_out/conv_umma2_full_$R python tools/ncu_conv.py c64_256 c32_3x3 c96_384 > gpurun_out/ncu_conv_full_$R.log 2>&1
 ls -la gpurun_out | tail -8
+# (4) full capture of the non-conv (memory-bound) kernels of the step -> python tools/ncu_membound.py ... profiles/membound_$R.md
+ncu --set full --clock-control none -k regex:"affine_act|inject2x|mspa_front|avgpool|bilinear2x|dwconv7|decode_staged|sppf_pool|resample_kernel|chan_stats|nms_scan" \
+    --launch-skip 120 -c 30 -f -o gpurun_out/membound_$R python bench.py --launch-list --no-graph --steps 1 --warmup 3 > gpurun_out/membound_ncu_$R.log 2>&1
