@@ -6,7 +6,7 @@ import torch
 from . import ops
 
 __all__ = ("non_max_suppression", "nms_packed", "scale_boxes", "clip_boxes", "scale_boxes_params", "process_batch",
-           "match_batch", "IOUV")
+           "match_batch", "update_metrics", "IOUV")
 
 nms_packed = ops.nms_packed
 
@@ -94,3 +94,56 @@ def match_batch(dets, det_counts, labels, lab_counts, iouv=None):
     one launch, no host synchronisation (the per-image loop of DetectionValidator.update_metrics, val.py:73-110)."""
     iouv = IOUV(dets.device) if iouv is None else iouv
     return ops.match_batch(dets, det_counts, labels, lab_counts, iouv.contiguous())
+
+
+def update_metrics(out, counts, batch, iouv=None, single_cls=False):
+    """DetectionValidator.update_metrics (yolo/v8/detect/val.py:73-110) for a whole batch on the packed NMS output.
+
+    out (N, max_det, 6) / counts (N,) are what nms_packed returns (letterboxed-image pixels); `batch` carries the
+    reference's keys: 'img' (only its shape is used), 'batch_idx' (M,), 'cls' (M, 1), 'bboxes' (M, 4) normalised xywh,
+    'ori_shape' [(h0, w0)], 'ratio_pad' [((gain, gain), (pad_w, pad_h))].  Predictions and labels are mapped to native
+    image space (mgdt_scale_boxes), matched at the IoU levels (mgdt_match_batch), and the per-image tuples the reference
+    appends to `self.stats` -- (correct (n, niou) bool, conf, pred_cls, target_cls) -- are returned (images without
+    predictions and without labels are skipped, as in the reference).  Two launches + one host read for the batch."""
+    dev = out.device
+    n, max_det, _ = out.shape
+    height, width = int(batch['img'].shape[2]), int(batch['img'].shape[3])
+    bidx = batch['batch_idx'].reshape(-1).cpu()
+    cls = batch['cls'].reshape(-1, 1).float().cpu()
+    bbox = batch['bboxes'].reshape(-1, 4).float().cpu()
+    prm = torch.tensor([scale_boxes_params((height, width), batch['ori_shape'][si], batch['ratio_pad'][si]) for si in range(n)],
+                       dtype=torch.float32, device=dev)
+    predn = out.clone()
+    if single_cls:
+        predn[:, :, 5] = 0
+    ops.scale_boxes_packed(predn, counts, prm)                       # native-space predictions (val.py:96-98)
+    per_img = [(bidx == si).nonzero().reshape(-1) for si in range(n)]
+    max_lab = max(1, max(int(i.numel()) for i in per_img))
+    tb = torch.zeros((n, max_lab, 4), dtype=torch.float32)
+    tc = torch.zeros((n, max_lab, 1), dtype=torch.float32)
+    for si, idx in enumerate(per_img):
+        if idx.numel():
+            b = bbox[idx]
+            xyxy = b.clone()                                         # ops.xywh2xyxy (yolo/utils/ops.py:372-377)
+            xyxy[..., 0] = b[..., 0] - b[..., 2] / 2
+            xyxy[..., 1] = b[..., 1] - b[..., 3] / 2
+            xyxy[..., 2] = b[..., 0] + b[..., 2] / 2
+            xyxy[..., 3] = b[..., 1] + b[..., 3] / 2
+            tb[si, :idx.numel()] = xyxy * torch.tensor((width, height, width, height), dtype=torch.float32)   # val.py:103-104
+            tc[si, :idx.numel()] = cls[idx]
+    lab_counts = torch.tensor([int(i.numel()) for i in per_img], dtype=torch.int32, device=dev)
+    tb = tb.to(dev)
+    ops.scale_boxes_packed(tb, lab_counts, prm)                      # native-space labels (val.py:105-106)
+    labels = torch.cat((tc.to(dev), tb), 2).contiguous()
+    correct = match_batch(predn, counts, labels, lab_counts, iouv)
+    cnt = counts.tolist()                                            # the single host sync
+    stats = []
+    for si in range(n):
+        npr, nl = cnt[si], int(per_img[si].numel())
+        tcls = cls[per_img[si], 0].to(dev)
+        if npr == 0:
+            if nl:
+                stats.append((correct[si, :0], torch.zeros(0, device=dev), torch.zeros(0, device=dev), tcls))
+            continue
+        stats.append((correct[si, :npr], out[si, :npr, 4], predn[si, :npr, 5], tcls))
+    return stats, predn

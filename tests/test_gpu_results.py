@@ -59,3 +59,60 @@ def test_boxes_views(ci, golden_dir):
     assert isinstance(r, Results) and len(r) == nd and r.orig_shape == tuple(shape)
     assert np.array_equal(r.cpu().numpy().boxes.xywh, g[f"xywh.{name}"])       # host copies use the reference's expressions
     assert len(r[:3]) == min(3, nd)
+
+
+def test_update_metrics_batch():
+    """update_metrics on the packed NMS output == the reference's per-image loop restated with the oracle
+    (scale_boxes on predictions and labels, xywh2xyxy * whwh, process_batch), bit-exact."""
+    from mgdt_yolo_b200.postprocess import update_metrics
+    from oracle.cases import synth_boxes
+    imgsz = (384, 640)
+    ori = [(480, 640), (375, 500), (720, 1280), (300, 400)]
+    n, max_det = len(ori), 60
+    g = torch.Generator().manual_seed(11)
+    ratio_pad, dets, det_n, lab_rows, bidx = [], torch.zeros(n, max_det, 6), [60, 17, 0, 9], [], []
+    for si, s0 in enumerate(ori):
+        gain = min(imgsz[0] / s0[0], imgsz[1] / s0[1])
+        pad = (round((imgsz[1] - s0[1] * gain) / 2 - 0.1), round((imgsz[0] - s0[0] * gain) / 2 - 0.1))
+        ratio_pad.append(((gain, gain), (float(pad[0]), float(pad[1]))))
+        nl = [7, 3, 4, 0][si]
+        c = torch.rand(nl, 2, generator=g) * 0.6 + 0.2
+        wh = torch.rand(nl, 2, generator=g) * 0.3 + 0.05
+        lab_rows.append(torch.cat([torch.randint(0, 2, (nl, 1), generator=g).float(), c, wh], 1))
+        bidx.append(torch.full((nl,), float(si)))
+        # detections: jittered copies of the labels (letterboxed pixels) + random boxes
+        if det_n[si]:
+            d = synth_boxes(det_n[si], imgsz, 30 + si)
+            if nl:
+                lb = lab_rows[-1]
+                px = torch.cat([lb[:, 1:3] - lb[:, 3:5] / 2, lb[:, 1:3] + lb[:, 3:5] / 2], 1) * torch.tensor([imgsz[1], imgsz[0]] * 2)
+                k = min(nl * 3, det_n[si])
+                d[:k] = px.repeat(3, 1)[:k] + (torch.rand(k, 4, generator=g) - 0.5) * 12
+            conf = torch.rand(det_n[si], generator=g).sort(descending=True).values
+            dets[si, :det_n[si]] = torch.cat([d, conf[:, None], torch.randint(0, 2, (det_n[si], 1), generator=g).float()], 1)
+    lab = torch.cat(lab_rows)
+    batch = dict(img=torch.empty(n, 3, *imgsz), batch_idx=torch.cat(bidx), cls=lab[:, :1], bboxes=lab[:, 1:], ori_shape=ori, ratio_pad=ratio_pad)
+    counts = torch.tensor(det_n, dtype=torch.int32)
+    stats, predn = update_metrics(dets.cuda(), counts.cuda(), batch)
+    k = 0
+    for si in range(n):
+        npr, lb = det_n[si], lab_rows[si]
+        if npr == 0 and lb.shape[0] == 0:
+            continue
+        correct, conf, pcls, tcls = stats[k]
+        k += 1
+        assert torch.equal(tcls.cpu(), lb[:, 0])
+        if npr == 0:
+            assert correct.shape == (0, 10)
+            continue
+        pn = O.scale_boxes(imgsz, dets[si, :npr].clone(), ori[si], ratio_pad=ratio_pad[si])
+        assert torch.equal(predn[si, :npr].cpu(), pn)
+        if lb.shape[0]:
+            tbox = O.xywh2xyxy(lb[:, 1:]) * torch.tensor((imgsz[1], imgsz[0], imgsz[1], imgsz[0]), dtype=torch.float32)
+            O.scale_boxes(imgsz, tbox, ori[si], ratio_pad=ratio_pad[si])
+            ref = O.process_batch(pn, torch.cat((lb[:, :1], tbox), 1))
+        else:
+            ref = torch.zeros(npr, 10, dtype=torch.bool)
+        assert torch.equal(correct.cpu(), ref), f"image {si}"
+        assert torch.equal(conf.cpu(), dets[si, :npr, 4]) and torch.equal(pcls.cpu(), dets[si, :npr, 5])
+    assert k == len(stats)
