@@ -7,6 +7,7 @@ and yields the raw pointer + channel stride the kernels take.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -149,11 +150,11 @@ class PackedConv:
 # format -- so this stays off; the packer keeps the option for an all-fp16 mode.
 WEIGHT_F16 = False
 USE_UMMA = True  # tests flip this to compare the tcgen05 path with the CUDA-core path
-PER_IMAGE_WEIGHTS = __import__('os').environ.get('MGDT_PER_IMAGE_W', '1') != '0'  # per-(n,c) input scales folded into per-image weights
+PER_IMAGE_WEIGHTS = os.environ.get('MGDT_PER_IMAGE_W', '1') != '0'  # per-(n,c) input scales folded into per-image weights
 FUSE_MSPA_FRONT = True  # MSPA_C2f branch chain as one launch (bf16); tests flip this to compare with the unfused sequence
 
 
-FUSE_STATS = __import__('os').environ.get('MGDT_FUSE_STATS', '1') != '0'  # per-(n,c) statistics in the tcgen05 conv's epilogue; tests flip this to compare with mgdt_chan_stats
+FUSE_STATS = os.environ.get('MGDT_FUSE_STATS', '1') != '0'  # per-(n,c) statistics in the tcgen05 conv's epilogue; tests flip this to compare with mgdt_chan_stats
 
 
 class StatReq:
@@ -166,7 +167,7 @@ class StatReq:
 
 
 _STAT_ARENA = {}
-STAT_COPIES = int(__import__('os').environ.get('MGDT_STAT_COPIES', '4'))  # replicas of the accumulators (copy = tile % copies): spreads the atomics over L2 lines
+STAT_COPIES = int(os.environ.get('MGDT_STAT_COPIES', '4'))  # replicas of the accumulators (copy = tile % copies): spreads the atomics over L2 lines
 
 
 def _stat_arena(device, nelem):
