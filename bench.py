@@ -12,11 +12,18 @@ JSON line (rank 0):
                 preprocess -> forward -> decode -> NMS -> D2H of the packed detections, all inside
                 the timed region (two batches in flight so copies overlap kernels)
   roofline      the dominant kernel (largest share of device time), algorithmic bytes / CUDA-event time
-  cpu_baseline  the oracle port (torch CPU fp32, all host threads) on a bounded sample, rank 0 / N=1
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, shipped by baseline/install_ref.py) on the box's host
+                cores, fp32, fused BN, all host threads, on a bounded sample (kind "reference"; the oracle port,
+                kind "port", only if the copy is absent), rank 0 / N=1
+  gpu_eager_baseline   the same reference model on the SAME B200 through torch eager (cuDNN / cuBLAS /
+                torchvision deform_conv2d + nms kernels, fp16 channels_last) -- the library bar -- with per-op
+                library timings for K1 (conv), K14 (DCNv2) and K17 (NMS) next to this repo's kernels
+  sustained     the device-resident loop repeated for >= 2 s (thermal / power steady state)
+  extra         batch sweep B = 1 ... 512 of the full config, the other three BASELINE configs at B = 32, NMS at the
+                validator setting (conf 0.001, multi_label)
 
-`--impl reference` times that CPU port alone (the reference is pure Python/PyTorch and cannot
-travel to the GPU box; oracle/mgdt_oracle.py is its restatement, pinned to the live reference by
-tests/test_oracle_golden.py).
+`--impl reference` times the reference's own CPU implementation alone, on this arm's config (same workload, images
+per step, steps and warm-up).
 """
 from __future__ import annotations
 
@@ -58,6 +65,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained run, the GPU eager baseline, the sweeps")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--slots", type=int, default=3, help="batches in flight (engine slots, one CUDA stream each; measured 2 / 3 / 4 -> 17.6k / 18.2k / 18.4k images/s, e2e 15.8k / 16.8k / 16.5k)")
     ap.add_argument("--profile-json", default="", help="write the per-launch table here")
@@ -137,48 +146,77 @@ def make_u8(batch, seed):
     return torch.randint(0, 256, (batch, 3, 640, 640), dtype=torch.uint8, generator=g)
 
 
-# ------------------------------------------------------------------------------------ CPU arm
-def cpu_reference(workload, sample_images, repeats):
-    """The reference's CPU path restated (oracle port): fused-BN fp32 forward + decode + NMS with all
-    host threads.  Returns (images/s, seconds, threads)."""
-    import torch
+# ------------------------------------------------------------------------------------ reference arms
+def synth_weights(workload, template):
     from mgdt_yolo_b200.synth import raise_cls_bias, synth_state_dict
-    from mgdt_yolo_b200.tasks import DetectionModel
-    from oracle import mgdt_oracle as O
-    cfg, nc, cls_bias = WORKLOADS[workload]
+    return raise_cls_bias(synth_state_dict(template, seed=1), WORKLOADS[workload][2])
+
+
+def build_reference(workload):
+    """The unmodified reference's DetectionModel (its own YAML, its own nn.Modules) with the benchmark's synthetic
+    weights, eval + fuse() as AutoBackend does (nn/autobackend.py:92-101).  None if the copy did not travel."""
+    from baseline import ref_loader
+    if not ref_loader.available():
+        return None
+    ref_loader.load()
+    cfg, nc, _ = WORKLOADS[workload]
+    m = ref_loader.build_model(cfg, nc=nc)
+    m.load_state_dict(synth_weights(workload, m.state_dict()))
+    return m.eval().fuse(verbose=False)
+
+
+def reference_nms(y):
+    from ultralytics.yolo.utils import ops as rops
+    return rops.non_max_suppression(y, CONF, IOU, max_det=MAX_DET, max_time_img=10.0)   # no wall-clock abort: every image is kept
+
+
+def cpu_reference(workload, batch, steps, warmup):
+    """The reference's CPU path: fp32 forward + decode + NMS of `batch` images per step with all host threads.
+    -> (images/s, seconds per step (median), threads, kind)."""
+    import torch
     threads = host_threads()
     torch.set_num_threads(threads)
-    tmpl = DetectionModel(cfg, nc=nc, verbose=False).state_dict()  # shapes only (CPU, no arithmetic)
-    sd = O.fold_bn(raise_cls_bias(synth_state_dict(tmpl, seed=1), cls_bias))  # AutoBackend fuses (autobackend.py:97)
-    x = make_u8(sample_images, 0).float() / 255
+    cfg, nc, cls_bias = WORKLOADS[workload]
+    x = make_u8(batch, 0).float() / 255
+    model = build_reference(workload)
     times = []
     with torch.inference_mode():
-        for it in range(repeats + 1):
+        if model is not None:
+            kind = "reference"
+            step = lambda: reference_nms(model(x))   # noqa: E731
+        else:   # the copy is absent: the oracle restatement (pinned to the live reference by tests/test_oracle_golden.py)
+            from mgdt_yolo_b200.tasks import DetectionModel
+            from oracle import mgdt_oracle as O
+            kind = "port"
+            sd = O.fold_bn(synth_weights(workload, DetectionModel(cfg, nc=nc, verbose=False).state_dict()))
+
+            def step():
+                y, _, _ = O.forward(cfg, sd, x, nc=nc, dcn="torchvision")
+                return O.non_max_suppression(y, CONF, IOU, max_det=MAX_DET, use_torchvision=True)
+        for it in range(warmup + steps):
             t0 = time.perf_counter()
-            y, _, _ = O.forward(cfg, sd, x, nc=nc, dcn="torchvision")
-            O.non_max_suppression(y, CONF, IOU, max_det=MAX_DET, use_torchvision=True)
-            dt = time.perf_counter() - t0
-            if it:  # first pass is the warm-up
-                times.append(dt)
+            step()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
     t = statistics.median(times)
-    return sample_images / t, t, threads
+    return batch / t, t, threads, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = 8
-    reps = max(1, min(args.steps, 5))
-    ips, t, threads = cpu_reference(args.workload, sample, reps)
+    ips, t, threads, kind = cpu_reference(args.workload, args.batch, args.steps, args.warmup)
+    what = ("the unmodified reference (baseline/_ref): DetectionModel.fuse() fp32 + ops.non_max_suppression on the host cores"
+            if kind == "reference" else "oracle port of the reference's CPU path (torch CPU fp32, fused BN, torchvision nms/deform_conv2d)")
     line = {
         "impl": "reference", "metric": "images/s @640x640 fwd+decode+NMS", "value": ips, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": reps, "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "images_per_step": sample, "imgsz": 640, "conf": CONF, "iou": IOU,
-                   "path": "oracle port of the reference's CPU path (torch CPU fp32, fused BN, torchvision nms/deform_conv2d)"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} images x {reps} passes (median), fwd+decode+NMS"},
+        "config": {"workload": args.workload, "images_per_gpu_per_step": args.batch, "imgsz": 640, "conf": CONF, "iou": IOU,
+                   "max_det": MAX_DET, "path": what},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind,
+                         "sample": f"{args.batch} images x {args.steps} steps (median step, {args.warmup} warm-up), fwd+decode+NMS"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -186,15 +224,188 @@ def run_reference(args):
     return 0
 
 
+def gpu_eager_reference(workload, batch, dev, steps=10, warmup=3):
+    """The library bar: the reference model itself on this B200 through torch eager -- cuDNN convolutions, cuBLAS
+    linears, torchvision's deform_conv2d and nms CUDA kernels -- fp16 (the reference's half mode, autobackend.py:99)
+    in channels_last, forward + decode + its own non_max_suppression.  Also per-op library timings."""
+    import torch
+    import torch.nn.functional as F
+    import torchvision
+    model = build_reference(workload)
+    if model is None:
+        return None
+    out = {"dtype": "fp16 channels_last", "path": "reference nn.Modules, torch eager (cuDNN / cuBLAS / torchvision CUDA ops)",
+           "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()}
+    model = model.to(dev).half().to(memory_format=torch.channels_last)
+    xs = [(make_u8(batch, 200 + i).to(dev).half() / 255).contiguous(memory_format=torch.channels_last) for i in range(3)]
+
+    def timed(fn, n=steps, w=warmup):
+        for _ in range(w):
+            fn(0)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    with torch.inference_mode():
+        ms_fwd = timed(lambda i: model(xs[i % 3]))
+        y = model(xs[0])[0]
+        ms_nms = timed(lambda i: reference_nms(y))
+        ms_all = timed(lambda i: reference_nms(model(xs[i % 3])))
+        out.update(value=batch / (ms_all * 1e-3), unit="images/s", images_per_step=batch, ms_per_step=ms_all,
+                   ms_forward_decode=ms_fwd, ms_nms=ms_nms)
+        # per-op library timings on the shapes of the full config (B = 32): K1 cuDNN conv (+ SiLU), K14 torchvision
+        # deform_conv2d, K17 the reference's non_max_suppression (torchvision.ops.nms inside a per-image python loop)
+        ops_ = []
+        for cin, cout, k, hw in ((32, 32, 3, 80), (64, 256, 1, 80), (96, 384, 1, 40), (16, 32, 3, 160)):
+            s2 = 2 if (cin, cout) == (16, 32) else 1
+            xin = torch.randn(batch, cin, hw * s2, hw * s2, device=dev, dtype=torch.half).contiguous(memory_format=torch.channels_last)
+            w = torch.randn(cout, cin, k, k, device=dev, dtype=torch.half).contiguous(memory_format=torch.channels_last)
+            b = torch.randn(cout, device=dev, dtype=torch.half)
+            ms = timed(lambda i: F.silu(F.conv2d(xin, w, b, s2, k // 2)), 20)
+            ops_.append({"op": "K1 cuDNN conv2d+bias, SiLU", "shape": f"{cin}->{cout} k{k}s{s2} {batch}x{hw * s2}x{hw * s2}", "lib_us": ms * 1e3})
+        xin = torch.randn(batch, 32, 80, 80, device=dev, dtype=torch.half)
+        off = torch.randn(batch, 18, 80, 80, device=dev, dtype=torch.half)
+        msk = torch.rand(batch, 9, 80, 80, device=dev, dtype=torch.half)
+        w = torch.randn(32, 32, 3, 3, device=dev, dtype=torch.half)
+        try:
+            ms = timed(lambda i: torchvision.ops.deform_conv2d(xin, off, w, None, 1, 1, 1, msk), 10)
+            ops_.append({"op": "K14 torchvision.ops.deform_conv2d", "shape": f"dcn 32->32 {batch}x80x80", "lib_us": ms * 1e3})
+        except Exception as e:   # noqa: BLE001
+            ops_.append({"op": "K14 torchvision.ops.deform_conv2d", "shape": f"dcn 32->32 {batch}x80x80", "error": str(e)[:80]})
+        ops_.append({"op": "K17 reference non_max_suppression (torchvision.ops.nms)", "shape": f"nms N{batch} nc{y.shape[1] - 4} A{y.shape[2]}",
+                     "lib_us": ms_nms * 1e3})
+        out["library_ops"] = ops_
+    del model, xs
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------ GPU arm
+def build_engine(workload, batch, dtype, dev, slots, use_graph=True, **nms):
+    from mgdt_yolo_b200.engine import Engine
+    from mgdt_yolo_b200.tasks import DetectionModel
+    cfg, nc, _ = WORKLOADS[workload]
+    model = DetectionModel(cfg, nc=nc, verbose=False)
+    model.load_state_dict(synth_weights(workload, model.state_dict()))
+    kw = dict(conf=CONF, iou=IOU, max_det=MAX_DET)
+    kw.update(nms)
+    return Engine(model, batch, 640, dtype, dev, slots=slots, use_graph=use_graph, **kw)
+
+
+def device_loop(eng, devin, steps, warmup, dev):
+    """`steps` device-resident batches alternating over the engine's slots -> (ms total, ms e2e is measured elsewhere)."""
+    import torch
+    nslot, R = len(eng.slots), len(devin)
+    main = torch.cuda.current_stream(dev)
+    for i in range(warmup):
+        eng.step_device(devin[i % R], slot=i % nslot)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for i in range(steps):
+        eng.step_device(devin[i % R], slot=i % nslot)
+    for sl in eng.slots:
+        main.wait_stream(sl.stream)
+    e1.record(main)
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1)
+
+
+def e2e_loop(eng, host, steps, warmup):
+    import torch
+    R = len(host)
+    for i in range(warmup):
+        eng.collect(eng.submit(host[i % R]))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pending = []
+    for i in range(steps):
+        pending.append(eng.submit(host[i % R]))
+        if len(pending) == len(eng.slots):
+            eng.collect(pending.pop(0))
+    while pending:
+        eng.collect(pending.pop(0))
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) * 1e3
+
+
+def extras(args, dev, dtype):
+    """Bounded side measurements of the default N = 1 run (each engine is built, timed and freed)."""
+    import torch
+    from mgdt_yolo_b200 import ops
+    out = {}
+    # (a) BASELINE.json configs[3]: batch sweep of the full config
+    sweep = []
+    for B in (1, 2, 4, 8, 16, 64, 128, 256, 512):
+        try:
+            slots = 3 if B <= 128 else 2
+            eng = build_engine(args.workload, B, dtype, dev, slots)
+            R = max(2, min(6, 160 // max(1, B * 3 * 640 * 640 // 1000000) + 1))
+            host = [make_u8(B, 300 + i).pin_memory() for i in range(R)]
+            devin = [h.to(dev) for h in host]
+            steps = max(6, min(60, 2048 // B))
+            ms = device_loop(eng, devin, steps, 3, dev)
+            ms2 = e2e_loop(eng, host, steps, 3)
+            sweep.append({"batch": B, "value": steps * B / (ms * 1e-3), "e2e": steps * B / (ms2 * 1e-3), "ms_per_step": ms / steps,
+                          "steps": steps, "launches_per_step": eng.launches_per_step})
+            del eng, host, devin
+            torch.cuda.empty_cache()
+        except Exception as e:   # noqa: BLE001
+            sweep.append({"batch": B, "error": str(e)[:120]})
+    out["batch_sweep"] = {"workload": args.workload, "unit": "images/s", "rows": sweep}
+    # (b) the other BASELINE configs at B = 32 (configs[1], configs[2], configs[0]'s graph on the GPU)
+    others = []
+    for wl in ("mspa_c2f_yolov8n", "mspa_c2f_gd_yolov8n", "yolov8n"):
+        try:
+            eng = build_engine(wl, 32, dtype, dev, 3)
+            host = [make_u8(32, 400 + i).pin_memory() for i in range(6)]
+            devin = [h.to(dev) for h in host]
+            ms = device_loop(eng, devin, 20, 3, dev)
+            ms2 = e2e_loop(eng, host, 20, 3)
+            others.append({"workload": wl, "batch": 32, "value": 20 * 32 / (ms * 1e-3), "e2e": 20 * 32 / (ms2 * 1e-3),
+                           "ms_per_step": ms / 20, "launches_per_step": eng.launches_per_step})
+            del eng, host, devin
+            torch.cuda.empty_cache()
+        except Exception as e:   # noqa: BLE001
+            others.append({"workload": wl, "error": str(e)[:120]})
+    out["other_configs"] = others
+    # (c) NMS alone on synthetic predictions (SURVEY 8(d)): the predictor setting and the validator setting
+    from mgdt_yolo_b200.synth import synth_predictions
+    nms_rows = []
+    for name, kw in (("predict conf0.25 single-label", dict(conf_thres=0.25, iou_thres=0.7)),
+                     ("validator conf0.001 multi_label", dict(conf_thres=0.001, iou_thres=0.7, multi_label=True))):
+        pred = synth_predictions(32, 2, 6400, seed=2).to(dev)
+        o, c = ops.nms_packed(pred, max_det=MAX_DET, **kw)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.nms_packed(pred, max_det=MAX_DET, out=o, counts=c, **kw)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 10
+        thr = kw["conf_thres"]
+        sc = pred[:, 4:]
+        ncand = int(((sc > thr).sum() if kw.get("multi_label") else (sc.amax(1) > thr).sum()).item())
+        per_img = ncand / 32
+        nms_rows.append({"setting": name, "batch": 32, "candidates_per_image": per_img, "ms": ms,
+                         "candidates_per_s": ncand / (ms * 1e-3), "iou_pairs_per_s": 32 * per_img * per_img / 2 / (ms * 1e-3),
+                         "kept": int(c.sum().item())})
+    out["nms"] = nms_rows
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from mgdt_yolo_b200 import ops
     from mgdt_yolo_b200._lib import lib
-    from mgdt_yolo_b200.engine import Engine
-    from mgdt_yolo_b200.synth import raise_cls_bias, synth_state_dict
-    from mgdt_yolo_b200.tasks import DetectionModel
+    from mgdt_yolo_b200.parallel import ShardedEngine, bind_rank_to_cores
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -209,11 +420,9 @@ def run_ours(args):
 
     cfg, nc, cls_bias = WORKLOADS[args.workload]
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    model = DetectionModel(cfg, nc=nc, verbose=False)
-    model.load_state_dict(raise_cls_bias(synth_state_dict(model.state_dict(), seed=1), cls_bias))
     B = args.batch
-    eng = Engine(model, B, 640, dtype, dev, conf=CONF, iou=IOU, max_det=MAX_DET, slots=args.slots,
-                 use_graph=not args.no_graph)
+    cores = bind_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world))) if world > 1 else None
+    eng = build_engine(args.workload, B, dtype, dev, args.slots, use_graph=not args.no_graph)
 
     # rotating inputs: 6 x 39 MB uint8 batches on the device (> 126 MB L2) and in pinned host memory
     R = 6
@@ -268,21 +477,51 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- (2) end to end from pinned host memory (H2D + D2H inside the timed region)
+    # ---- (1b) sustained: the same loop repeated for >= --sustain-seconds (power / thermal steady state; the driver's
+    # `steps` give a 25-40 ms timed region, shorter than the board's power controller reacts)
+    sustained = None
+    if not args.no_extras:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms_dev / args.steps, 1e-3)) + 1)
+        sampler2 = ClockSampler(local)
+        sampler2.start()
+        time.sleep(0.25)
+        barrier()
+        tw0 = time.time()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(main)
+        for i in range(n_sus):
+            eng.step_device(devin[i % R], slot=i % nslot)
+        for sl in eng.slots:
+            main.wait_stream(sl.stream)
+        s1.record(main)
+        barrier()
+        tw1 = time.time()
+        ms_sus = max_over_ranks(s0.elapsed_time(s1))
+        sustained = {"value": n_sus * B * world / (ms_sus * 1e-3), "unit": "images/s", "steps": n_sus, "seconds": ms_sus * 1e-3,
+                     "ms_per_step": ms_sus / n_sus, "clocks": sampler2.stop(tw0, tw1)}
+
+    # ---- (2) end to end from pinned host memory (H2D + D2H inside the timed region).  N > 1: through the sharding API
+    # (parallel.ShardedEngine: global batch -> this rank's slice -> packed results gathered on rank 0 in image order)
+    runner = ShardedEngine(eng, B * world) if world > 1 else eng
     for i in range(args.warmup):
-        eng.collect(eng.submit(host[i % R]))
+        runner.collect(runner.submit(host[i % R]))
     barrier()
     t0 = time.perf_counter()
     pending = []
+    n_out = 0
     for i in range(args.steps):
-        pending.append(eng.submit(host[i % R]))
+        pending.append(runner.submit(host[i % R]))
         if len(pending) == len(eng.slots):
-            eng.collect(pending.pop(0))
+            r_ = runner.collect(pending.pop(0))
+            n_out += len(r_) if r_ is not None else 0
     while pending:
-        eng.collect(pending.pop(0))
+        r_ = runner.collect(pending.pop(0))
+        n_out += len(r_) if r_ is not None else 0
     torch.cuda.synchronize()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
     barrier()
+    if rank == 0 and n_out != args.steps * B * world:
+        raise SystemExit(f"bench.py: the e2e leg returned {n_out} per-image results, expected {args.steps * B * world}")
 
     # ---- (3) per-launch profile of eager steps: CUDA events on the launching stream around every C-ABI call, PDL off
     # (so consecutive kernels do not overlap across the events) and the stream pre-loaded with a spin kernel so that
@@ -382,16 +621,36 @@ def run_ours(args):
                          "per-step activation traffic >> L2", "parallelism": f"dp{world} (batch sharded, no collective)"},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 640 * 640,
                 "d2h_bytes_per_step": B * (MAX_DET * 6 * 4 + 4), "ms_per_step": ms_e2e / args.steps,
-                "api": f"Engine.submit/collect, {nslot} batches in flight"},
+                "api": (f"ShardedEngine.submit/collect over {world} ranks (results gathered on rank 0 in image order), " if world > 1 else "")
+                       + f"Engine.submit/collect, {nslot} batches in flight", "host_cores_bound": cores},
         "gpu_launches": eng.launches_per_step * args.steps,
         "launches_per_step": eng.launches_per_step,
         "clocks": clocks,
         "roofline": roof,
     }
+    if sustained is not None:
+        line["sustained"] = sustained
+    if world == 1 and not args.no_extras:
+        try:
+            ge = gpu_eager_reference(args.workload, B, dev)
+            if ge is not None:
+                mine = {(r["name"], r["shape"]): r["ms"] / r["n"] * 1e3 for r in groups.values()}
+                for o in ge.get("library_ops", []):
+                    for (nm, shp), us in mine.items():
+                        if shp == o["shape"]:
+                            o["ours_us"] = us
+                ge["speedup_value_over_eager"] = line["value"] / ge["value"]
+                line["gpu_eager_baseline"] = ge
+        except Exception as e:   # noqa: BLE001
+            line["gpu_eager_baseline"] = {"error": str(e)[:200]}
+        try:
+            line["extra"] = extras(args, dev, dtype)
+        except Exception as e:   # noqa: BLE001
+            line["extra"] = {"error": str(e)[:200]}
     if world == 1 and not args.no_cpu_baseline:
-        ips, t, threads = cpu_reference(args.workload, 8, 3)
-        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                                "sample": "8 images x 3 passes (median) of the same workload, fwd+decode+NMS, torch CPU fp32"}
+        ips, t, threads, kind = cpu_reference(args.workload, 8, 3, 1)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": kind,
+                                "sample": "8 images x 3 steps (median, 1 warm-up) of the same workload, fwd+decode+NMS, torch CPU fp32"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

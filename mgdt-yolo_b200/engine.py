@@ -48,6 +48,12 @@ class Engine:
                                                                          device=self.device)
             self.slots = [self._make_slot() for _ in range(max(1, slots))]
         self._next = 0
+        # The captured graphs have the packed-weight pointers baked in: keep every pack alive for the engine's lifetime
+        # (a later repack by another dtype / a weight update must not free them) and remember the parameter versions
+        # the capture saw, so that a replay over changed weights raises instead of silently using stale ones.
+        self._pinned = [m.__dict__["_pk"].copy() for m in self.model.modules() if "_pk" in m.__dict__]
+        self._pinned.append((dict(ops._STAT_ARENA), dict(ops._TICKETS)))
+        self._wstate = [(t, t.data_ptr(), t._version) for t in list(self.model.parameters()) + list(self.model.buffers())]
 
     # ------------------------------------------------------------------ construction
     def _body(self, s):
@@ -115,9 +121,25 @@ class Engine:
         else:
             ops.preprocess(src, self.dtype, out=s.x)
 
+    def weights_changed(self) -> bool:
+        """True if a parameter / buffer was replaced or updated in place since the graphs were captured."""
+        return any(t.data_ptr() != p or t._version != v for t, p, v in self._wstate)
+
+    def _order_after_producer(self, s, src):
+        """The slot's private stream must not read `src` before the stream that produced it is done with it (a device
+        tensor the caller has just written on the current stream), and the allocator must not recycle `src` while the
+        slot still reads it."""
+        if src.is_cuda:
+            s.stream.wait_stream(torch.cuda.current_stream(self.device))
+            if src.data_ptr() != s.src.data_ptr():
+                src.record_stream(s.stream)
+
     def _run(self, s, src):
         """Enqueue preprocess/stem(src) + forward + decode + NMS on the slot's stream (no sync)."""
+        self._order_after_producer(s, src)
         with torch.cuda.stream(s.stream), torch.no_grad():
+            if not src.is_contiguous():
+                src = src.contiguous()      # on the slot's stream, after the wait above
             self._head(s, src)
             if s.graph is not None:
                 s.graph.replay()
@@ -125,8 +147,9 @@ class Engine:
                 self._body(s)
 
     def step_device(self, src: torch.Tensor, slot: int = 0):
-        """Inputs already resident in HBM: `src` is a (B,C,H,W) uint8/float32 device tensor.
-        Returns the slot (outputs in slot.out / slot.counts, on the device, not synchronised)."""
+        """Inputs already resident in HBM: `src` is a (B,C,H,W) uint8/float32 device tensor (ordered after the
+        caller's current stream).  Returns the slot (outputs in slot.out / slot.counts, on the device, not
+        synchronised).  The raw path: it does not re-check the weights (see weights_changed())."""
         s = self.slots[slot]
         self._run(s, src)
         return s
@@ -135,8 +158,12 @@ class Engine:
         """End-to-end: pinned host batch -> H2D -> pipeline -> D2H of the packed detections.
         Asynchronous; returns the slot, call `collect(slot)` for the result.  Consecutive submits
         alternate slots so the copies of one batch overlap the kernels of the other."""
+        if self.use_graph and self.weights_changed():
+            raise RuntimeError("Engine: model weights changed after the CUDA graphs were captured; build a new Engine")
         s = self.slots[self._next]
         self._next = (self._next + 1) % len(self.slots)
+        if host_src.is_cuda:
+            self._order_after_producer(s, host_src)
         with torch.cuda.stream(s.stream):
             s.src.copy_(host_src, non_blocking=True)
         self._run(s, s.src)
@@ -154,8 +181,14 @@ class Engine:
         from .preprocess import preprocess_images
         if len(ims) != self.batch:
             raise ValueError(f"Engine was built for batches of {self.batch} images, got {len(ims)}")
+        if self.use_graph and self.weights_changed():
+            raise RuntimeError("Engine: model weights changed after the CUDA graphs were captured; build a new Engine")
         s = self.slots[self._next]
         self._next = (self._next + 1) % len(self.slots)
+        s.stream.wait_stream(torch.cuda.current_stream(self.device))   # device images written on the caller's stream
+        for im in ims:
+            if isinstance(im, torch.Tensor) and im.is_cuda:
+                im.record_stream(s.stream)
         with torch.cuda.stream(s.stream), torch.no_grad():
             _, metas = preprocess_images(ims, (self.h, self.w), auto=auto, stride=stride, device=self.device, out=s.src)
             prm = torch.tensor([scale_boxes_params((self.h, self.w), m[0]) for m in metas], dtype=torch.float32)
@@ -188,8 +221,10 @@ class Engine:
             raise ValueError(f"Engine was built for input {tuple(self.slots[0].src.shape)}, got {tuple(images.shape)}")
         if images.dtype != self.input_dtype:
             raise TypeError(f"Engine was built for {self.input_dtype} input")
+        if self.use_graph and self.weights_changed():
+            raise RuntimeError("Engine: model weights changed after the CUDA graphs were captured; build a new Engine")
         if images.is_cuda:
-            s = self.step_device(images.contiguous())
+            s = self.step_device(images)
             s.stream.synchronize()
             cnt = s.counts.tolist()
             return [s.out[i, :cnt[i]].clone() for i in range(self.batch)]

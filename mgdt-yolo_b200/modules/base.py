@@ -17,15 +17,27 @@ class KernelModule(nn.Module):
     """nn.Module whose forward runs sm_100a kernels (eval mode, CUDA tensors only)."""
 
     def _packed(self, name, dtype, device, tensors, builder):
+        """Weights of this module in the kernels' layouts, built once per (name, dtype, device) and rebuilt when a
+        source parameter is replaced or updated in place (data_ptr / _version).  Packs for different dtypes / devices
+        coexist (an fp32 validation pass does not evict the bf16 pack a captured CUDA graph points at); a replaced
+        pack is parked in `_pk_old` until `release_stale_packs()` so that a graph captured over it never reads
+        freed memory (Engine additionally pins what it captured and refuses to replay over changed parameters)."""
         cache = self.__dict__.setdefault("_pk", {})
-        key = (dtype, device, tuple((t.data_ptr(), t._version) for t in tensors))
-        hit = cache.get(name)
-        if hit is not None and hit[0] == key:
+        key = (name, dtype, str(device))
+        ver = tuple((t.data_ptr(), t._version) for t in tensors)
+        hit = cache.get(key)
+        if hit is not None and hit[0] == ver:
             return hit[1]
         with torch.no_grad():
             val = builder()
-        cache[name] = (key, val)
+        if hit is not None:
+            self.__dict__.setdefault("_pk_old", []).append(hit[1])
+        cache[key] = (ver, val)
         return val
+
+    def release_stale_packs(self):
+        """Drop packs that were superseded by a weight update (call when no captured graph uses them any more)."""
+        self.__dict__.pop("_pk_old", None)
 
     def _check_mode(self, x):
         t = x[0] if isinstance(x, (list, tuple)) else x
@@ -38,6 +50,7 @@ class KernelModule(nn.Module):
     def __getstate__(self):  # packed caches hold device pointers; never pickle them
         d = dict(self.__dict__)
         d.pop("_pk", None)
+        d.pop("_pk_old", None)
         return d
 
 

@@ -167,6 +167,7 @@ class StatReq:
 
 
 _STAT_ARENA = {}
+_RETIRED = []   # outgrown arenas / ticket arrays, kept alive for CUDA graphs captured over them
 STAT_COPIES = int(os.environ.get('MGDT_STAT_COPIES', '4'))  # replicas of the accumulators (copy = tile % copies): spreads the atomics over L2 lines
 
 
@@ -177,6 +178,8 @@ def _stat_arena(device, nelem):
     key = (device.index, stream_ptr())
     t = _STAT_ARENA.get(key)
     if t is None or t.numel() < nelem:
+        if t is not None:
+            _RETIRED.append(t)   # a captured graph may still add into the smaller arena: never free it
         t = torch.zeros((max(nelem, 1 << 16),), dtype=torch.float64, device=device)
         _STAT_ARENA[key] = t
     return t
@@ -485,6 +488,8 @@ def _stats_tickets(device, n):
     key = (device.index, stream_ptr())
     t = _TICKETS.get(key)
     if t is None or t.numel() < n:
+        if t is not None:
+            _RETIRED.append(t)
         t = torch.zeros((max(n, 1024),), dtype=torch.int32, device=device)
         _TICKETS[key] = t
     return t

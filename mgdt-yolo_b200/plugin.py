@@ -27,6 +27,9 @@ MODULE_PATHS = {  # pickled checkpoints name classes by module path (trainer.py:
 }
 
 
+_REF_NMS = {}   # the reference's own non_max_suppression, remembered by install() for swap_nms()
+
+
 def install(ultralytics_pkg=None) -> dict:
     """Rebind the hot-path names inside an already imported reference package.  Returns the dict of
     replaced attributes {qualified name: original object} so `uninstall()` can restore them."""
@@ -57,6 +60,7 @@ def install(ultralytics_pkg=None) -> dict:
         eng_model.TASK_MAP["detect"] = entry
     ref_ops = sys.modules.get("ultralytics.yolo.utils.ops")
     if ref_ops is not None:                            # v8/detect/predict.py:14, v8/detect/val.py:65
+        _REF_NMS.setdefault("fn", ref_ops.non_max_suppression)
         rebind(ref_ops, "non_max_suppression", postprocess.non_max_suppression)
     return saved
 
@@ -70,3 +74,17 @@ def uninstall(saved: dict):
         mod = sys.modules.get(mod_name)
         if mod is not None and obj is not None:
             setattr(mod, name, obj)
+
+
+def swap_nms(ours: bool, saved=None):
+    """Toggle only the `ops.non_max_suppression` binding of an installed plugin (tests use it to run the untouched
+    reference model next to the B200 modules in one process).  Returns the binding that was replaced."""
+    ref_ops = sys.modules.get("ultralytics.yolo.utils.ops")
+    if ref_ops is None:
+        raise RuntimeError("swap_nms(): the reference package is not imported")
+    cur = ref_ops.non_max_suppression
+    if ours:
+        ref_ops.non_max_suppression = postprocess.non_max_suppression
+    else:
+        ref_ops.non_max_suppression = saved if saved is not None else _REF_NMS.get("fn", cur)
+    return cur

@@ -13,6 +13,7 @@ Fixture index (tests/golden/):
   modules.npz        one entry per module class on odd/ragged shapes
   nms.npz            reference non_max_suppression outputs for a parameter grid
   prepost.npz        LetterBox + BGR->RGB/CHW outputs (live cv2.resize) and ops.scale_boxes outputs
+  model640.npz       the four BASELINE configs at B=2, 640x640: decoded boxes / scores + per-layer statistics
   results.npz        Boxes.xywh/xyxyn/xywhn and DetectionValidator._process_batch outputs (validation matching)
 """
 from __future__ import annotations
@@ -63,6 +64,42 @@ def gen_models():
         path = os.path.join(OUT, f"model_{cfg[:-5]}.npz")
         np.savez_compressed(path, **blob)
         print(path, os.path.getsize(path) // 1024, "KiB")
+
+
+def gen_model640():
+    """The four BASELINE.json configs at the benchmarked size (B = 2, 640 x 640, seed 0), live reference, un-fused eval:
+    decoded boxes in full; class scores in full for the nc = 2 config, else their per-anchor max / argmax and every
+    16th anchor column; per-layer (mean |x|, max |x|) of every tensor-valued layer output."""
+    from tests.parity import BASELINE_CFGS
+    blob = {}
+    for cfg, nc in BASELINE_CFGS.items():
+        m = ref_live.build_model(cfg, nc=nc)
+        m.load_state_dict(synth_state_dict(m.state_dict(), seed=1))
+        m.eval()
+        name = cfg[:-5]
+        with torch.inference_mode():
+            x = synth_images(2, size=640, seed=0)
+            ys, cur = [], x
+            for layer in m.model:
+                if layer.f != -1:
+                    cur = ys[layer.f] if isinstance(layer.f, int) else [cur if j == -1 else ys[j] for j in layer.f]
+                cur = layer(cur)
+                ys.append(cur)
+            y = cur[0]
+        blob[f"{name}.boxes"] = y[:, :4].numpy()
+        sc = y[:, 4:]
+        if nc <= 4:
+            blob[f"{name}.scores"] = sc.numpy()
+        else:
+            blob[f"{name}.score_max"] = sc.max(1).values.numpy()
+            blob[f"{name}.score_argmax"] = sc.argmax(1).to(torch.int16).numpy()
+            blob[f"{name}.scores_16"] = sc[:, :, ::16].contiguous().numpy()
+        blob[f"{name}.layer_stats"] = np.array([[float(t.abs().mean()), float(t.abs().max())] if isinstance(t, torch.Tensor)
+                                                else [0.0, 0.0] for t in ys[:-1]], dtype=np.float64)
+        print("model640", cfg, tuple(y.shape))
+    path = os.path.join(OUT, "model640.npz")
+    np.savez_compressed(path, **blob)
+    print(path, os.path.getsize(path) // 1024, "KiB")
 
 
 def gen_modules():
@@ -158,8 +195,12 @@ def gen_results():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-640" in sys.argv:
+        gen_model640()
+        sys.exit(0)
     if "--only-prepost" not in sys.argv and "--only-results" not in sys.argv:
         gen_models()
+        gen_model640()
         gen_modules()
         gen_nms()
     if "--only-results" not in sys.argv:

@@ -148,3 +148,17 @@ def test_oracle_results_golden(golden_dir):
         xywh, xyxyn, xywhn = O.boxes_views(dets, shape)
         assert np.array_equal(xywh.numpy(), g[f"xywh.{name}"]) and np.array_equal(xyxyn.numpy(), g[f"xyxyn.{name}"])
         assert np.array_equal(xywhn.numpy(), g[f"xywhn.{name}"])
+
+
+@pytest.mark.parametrize("cfg", ["mspa_c2f_gd_tood_yolov8n.yaml", "mspa_c2f_gd_yolov8n.yaml", "mspa_c2f_yolov8n.yaml", "yolov8n.yaml"])
+def test_oracle_matches_live_reference_at_640(cfg):
+    """The benchmarked size: B = 2, 640 x 640, the four BASELINE.json configs -- the oracle restatement against the
+    live-reference fixture (boxes, scores, per-layer statistics), fp32 1e-4 relative (measured ~1e-6)."""
+    from mgdt_yolo_b200.synth import synth_images, synth_state_dict
+    from mgdt_yolo_b200.tasks import DetectionModel
+    from tests import parity
+    nc = parity.BASELINE_CFGS[cfg]
+    sd = synth_state_dict(DetectionModel(cfg, nc=nc, verbose=False).state_dict(), seed=1)
+    y, raw, layers = parity.oracle_640(cfg, sd, synth_images(2, size=640, seed=0), nc)
+    for k, (mx, l2) in parity.check_golden_640(cfg, y, layers).items():
+        assert mx <= 1e-4, f"{cfg} {k}: {mx:.3e}"
