@@ -234,10 +234,10 @@ def gpu_eager_reference(workload, batch, dev, steps=10, warmup=3):
     model = build_reference(workload)
     if model is None:
         return None
-    out = {"dtype": "fp16 channels_last", "path": "reference nn.Modules, torch eager (cuDNN / cuBLAS / torchvision CUDA ops)",
+    out = {"dtype": "fp16 (model NCHW as the reference runs it: its heads .view() the maps; per-op convs channels_last)", "path": "reference nn.Modules, torch eager (cuDNN / cuBLAS / torchvision CUDA ops)",
            "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()}
-    model = model.to(dev).half().to(memory_format=torch.channels_last)
-    xs = [(make_u8(batch, 200 + i).to(dev).half() / 255).contiguous(memory_format=torch.channels_last) for i in range(3)]
+    model = model.to(dev).half()
+    xs = [(make_u8(batch, 200 + i).to(dev).half() / 255).contiguous() for i in range(3)]
 
     def timed(fn, n=steps, w=warmup):
         for _ in range(w):

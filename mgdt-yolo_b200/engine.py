@@ -15,6 +15,7 @@ import torch
 
 from . import ops
 from ._lib import lib
+from .modules.base import _version
 
 __all__ = ("Engine",)
 
@@ -53,7 +54,7 @@ class Engine:
         # the capture saw, so that a replay over changed weights raises instead of silently using stale ones.
         self._pinned = [m.__dict__["_pk"].copy() for m in self.model.modules() if "_pk" in m.__dict__]
         self._pinned.append((dict(ops._STAT_ARENA), dict(ops._TICKETS)))
-        self._wstate = [(t, t.data_ptr(), t._version) for t in list(self.model.parameters()) + list(self.model.buffers())]
+        self._wstate = [(t, t.data_ptr(), _version(t)) for t in list(self.model.parameters()) + list(self.model.buffers())]
 
     # ------------------------------------------------------------------ construction
     def _body(self, s):
@@ -123,7 +124,7 @@ class Engine:
 
     def weights_changed(self) -> bool:
         """True if a parameter / buffer was replaced or updated in place since the graphs were captured."""
-        return any(t.data_ptr() != p or t._version != v for t, p, v in self._wstate)
+        return any(t.data_ptr() != p or _version(t) != v for t, p, v in self._wstate)
 
     def _order_after_producer(self, s, src):
         """The slot's private stream must not read `src` before the stream that produced it is done with it (a device

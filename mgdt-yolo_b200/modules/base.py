@@ -13,6 +13,13 @@ import torch.nn as nn
 from .. import ops
 
 
+def _version(t) -> int:
+    """In-place update counter of a tensor; inference tensors (parameters created / cast under torch.inference_mode,
+    as the reference's predictor and validator do, yolo/engine/model.py:222) do not track one and cannot be updated
+    in place either, so their storage pointer identifies them."""
+    return 0 if t.is_inference() else t._version
+
+
 class KernelModule(nn.Module):
     """nn.Module whose forward runs sm_100a kernels (eval mode, CUDA tensors only)."""
 
@@ -24,7 +31,7 @@ class KernelModule(nn.Module):
         freed memory (Engine additionally pins what it captured and refuses to replay over changed parameters)."""
         cache = self.__dict__.setdefault("_pk", {})
         key = (name, dtype, str(device))
-        ver = tuple((t.data_ptr(), t._version) for t in tensors)
+        ver = tuple((t.data_ptr(), _version(t)) for t in tensors)
         hit = cache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]

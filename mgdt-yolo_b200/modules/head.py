@@ -122,7 +122,7 @@ class _HeadBase(KernelModule):
         """self.stride as python floats, read back once per tensor (a .tolist() on a CUDA tensor is a
         sync and would invalidate a CUDA-graph capture)."""
         st = self.stride
-        key = (st.data_ptr(), st._version, str(st.device))
+        key = (st.data_ptr(), 0 if st.is_inference() else st._version, str(st.device))
         c = self.__dict__.get("_stride_cache")
         if c is None or c[0] != key:
             c = (key, [float(v) for v in st.tolist()])

@@ -20,6 +20,12 @@ for cfg in cfgs:
         worst = max(res.items(), key=lambda kv: kv[1][0])
         print(key, "worst max-rel", worst[0], f"{worst[1][0]:.3e}", " y", res["y"], flush=True)
         torch.cuda.empty_cache()
+for cfg in cfgs:   # the yardstick: the reference's own modules in bf16 (torch eager) against the same oracle
+    r = parity.reference_bf16_640(cfg, 32)
+    if r is not None:
+        out[f"{cfg}|reference-bf16-eager|B32"] = {k: [float(f"{v[0]:.4e}"), float(f"{v[1]:.4e}")] for k, v in r.items()}
+        print(cfg, "reference in bf16: y", r["y"], flush=True)
+    torch.cuda.empty_cache()
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", "parity640.json"), "w") as f:
     json.dump(out, f, indent=1)
