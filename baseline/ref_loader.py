@@ -110,6 +110,10 @@ def _install_stubs():
                 self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
 
             def forward(self, x, offset, mask):
+                if x.dtype == torch.bfloat16:   # torchvision has no bf16 deformable_im2col: compute in fp32, round the result
+                    b = None if self.bias is None else self.bias.float()
+                    return torchvision.ops.deform_conv2d(x.float(), offset.float(), self.weight.float(), b, self.stride,
+                                                         self.padding, self.dilation, mask.float()).to(x.dtype)
                 return torchvision.ops.deform_conv2d(x, offset, self.weight, self.bias, self.stride, self.padding,
                                                      self.dilation, mask)
 

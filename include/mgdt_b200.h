@@ -50,8 +50,16 @@ void mgdt_debug_set_trace(void* buf);
 /* Compiled-in facts for tests: returns 1 if the tcgen05/TMA conv path was built. */
 int mgdt_has_umma(void);
 /* Programmatic dependent launch (every kernel is launched with the programmatic-stream-serialization attribute and
- * orders itself with griddepcontrol.wait): 1 = on (default, or MGDT_PDL in the environment), 0 = plain launches. */
+ * orders itself with griddepcontrol.wait): 1 = on (default), 0 = plain launches. */
 void mgdt_set_pdl(int on);
+/* Library switches (A/B runs, debugging); the library itself reads no environment variables -- the Python layer
+ * forwards MGDT_<NAME> once at load time.  Returns 0, or -EINVAL for an unknown name.
+ *   "pdl"            1   programmatic dependent launch
+ *   "conv_tma_load"  1   TMA-fed kernel (cp.async.bulk.tensor loads) for transform-free 1x1 convolutions
+ *   "conv_tma_store" 1   TMA tensor stores of 1x1 epilogue units
+ *   "conv_pair"      1   paired 16-column epilogue units (Cout <= 16)
+ *   "conv_split"    -1   force the producer / epilogue warp split of the cp.async conv kernel (0 / 1 / 2) */
+int mgdt_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------- convolution
  * Replaces Conv.forward/forward_fuse (nn/modules/conv.py:36-42) with BatchNorm folded
@@ -102,7 +110,8 @@ typedef struct mgdt_conv_args {
 } mgdt_conv_args;
 int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
 /* Which kernel mgdt_conv2d would run for these arguments: 3 = conv_pointwise_kernel (narrow 1x1 layers, CUDA cores,
- * HBM-bound), 2 = conv_umma2_kernel (tcgen05), 1 = conv_direct_kernel (CUDA cores).  Used by the bench to attribute
+ * HBM-bound), 4 = conv1x1_tma_kernel (tcgen05, operand A fed by TMA: transform-free 1x1 layers), 2 = conv_umma2_kernel
+ * (tcgen05, cp.async-fed: 3x3, stride 2, fused input transforms), 1 = conv_direct_kernel (CUDA cores).  Used by the bench to attribute
  * launches to kernels. */
 int mgdt_conv2d_path(const mgdt_conv_args* a);
 
@@ -116,6 +125,12 @@ int mgdt_conv_umma_pack(const void* w_ohwi, int w_dtype, int Cin, int Cout, int 
  * every input channel ci scaled by in_scale[n][ci] (fp32 [N][Cin]) and rounded to bf16 again. */
 int mgdt_conv_umma_pack_scaled(const void* packed_bf16, int Cin, int Cout, int k, int stride, const float* in_scale, int N,
                                void* out, void* stream);
+/* Same with the output columns scaled in groups of group_cols: columns [g*group_cols, (g+1)*group_cols), g < ngroups, use
+ * in_scale[g][n][ci] (fp32 [ngroups][N][Cin]); columns past the last group stay unscaled.  Lets sibling 1x1 convs that
+ * read the same map run as ONE GEMM with per-image weights -- TOODHead's cls_decomp / reg_decomp reduction convs (each
+ * with its own layer attention) and cls_prob_conv1 (none), nn/modules/head.py:509-521. */
+int mgdt_conv_umma_pack_scaled_groups(const void* packed_bf16, int Cin, int Cout, int k, int stride, const float* in_scale,
+                                      int N, int ngroups, int group_cols, void* out, void* stream);
 
 /* Fused input preprocessing + stem convolution on the tensor cores (bf16): 3x3 stride-2 pad-1 Conv+BN+act
  * (layer 0 of every config, models/v8/*.yaml) read straight from the NCHW uint8 (divided by 255,

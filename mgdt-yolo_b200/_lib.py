@@ -49,6 +49,7 @@ SIGNATURES = {
     "mgdt_has_umma": (C.c_int, []),
     "mgdt_debug_set_trace": (None, [vp]),
     "mgdt_set_pdl": (None, [i32]),
+    "mgdt_set_option": (C.c_int, [C.c_char_p, i32]),
     "mgdt_letterbox_u8": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_box_convert": (C.c_int, [vp, i32, i32, i32, f32, f32, vp, vp]),
     "mgdt_match_batch": (C.c_int, [vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, i32, vp]),
@@ -58,6 +59,7 @@ SIGNATURES = {
     "mgdt_conv_umma_packed_bytes": (sz, [i32, i32, i32, i32]),
     "mgdt_conv_umma_pack": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "mgdt_conv_umma_pack_scaled": (C.c_int, [vp, i32, i32, i32, i32, vp, i32, vp, vp]),
+    "mgdt_conv_umma_pack_scaled_groups": (C.c_int, [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp]),
     "mgdt_stem_conv": (C.c_int, [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_mspa_front_supported": (C.c_int, [i32, i32]),
     "mgdt_mspa_front_packed_bytes": (sz, [i32, i32]),
@@ -101,6 +103,12 @@ def lib():
             fn.restype, fn.argtypes = res, args
         if L.mgdt_abi_version() != ABI_VERSION:
             raise RuntimeError("mgdt_yolo_b200: ABI version mismatch, rebuild the library")
+        # the library reads no environment variables: forward the documented MGDT_* switches once, here
+        for env, opt in (("MGDT_PDL", "pdl"), ("MGDT_CONV_TMA_LOAD", "conv_tma_load"), ("MGDT_CONV_TMA_STORE", "conv_tma_store"),
+                         ("MGDT_CONV_PAIR", "conv_pair"), ("MGDT_CONV_SPLIT", "conv_split")):
+            v = os.environ.get(env)
+            if v is not None and v.lstrip("-").isdigit():
+                L.mgdt_set_option(opt.encode(), int(v))
         _LIB = L
     return _LIB
 

@@ -2,20 +2,15 @@
 #include "common.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace mgdt {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
-int g_pdl = -1;
+int g_pdl = 1;
 
-int pdl_enabled() {
-    if (g_pdl < 0) {
-        const char* e = getenv("MGDT_PDL");
-        g_pdl = (e && e[0] == '0') ? 0 : 1;
-    }
-    return g_pdl;
-}
+int pdl_enabled() { return g_pdl != 0; }   // on unless mgdt_set_pdl(0) / mgdt_set_option("pdl", 0)
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -29,8 +24,10 @@ int conv2d_direct(const mgdt_conv_args* a, cudaStream_t s);
 bool conv2d_pointwise_supported(const mgdt_conv_args* a);
 int conv2d_pointwise(const mgdt_conv_args* a, cudaStream_t s);
 #ifdef MGDT_WITH_UMMA
+int conv_set_option(const char* name, int value);
 bool conv2d_umma_supported(const mgdt_conv_args* a);
 int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s);
+int conv2d_umma_path(const mgdt_conv_args* a);
 #endif
 
 }  // namespace mgdt
@@ -41,10 +38,18 @@ extern "C" int mgdt_abi_version(void) { return MGDT_ABI_VERSION; }
 extern "C" const char* mgdt_last_error(void) { return g_err; }
 extern "C" unsigned long long mgdt_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" void mgdt_set_pdl(int on) { g_pdl = on ? 1 : 0; }
+extern "C" int mgdt_set_option(const char* name, int value) {
+    MGDT_CHECK(name, "set_option: null name");
+    if (!strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return 0; }
+#ifdef MGDT_WITH_UMMA
+    if (conv_set_option(name, value)) return 0;
+#endif
+    return set_error(-EINVAL, "set_option: unknown option '%s'", name);
+}
 extern "C" int mgdt_conv2d_path(const mgdt_conv_args* a) {
     if (a && a->impl == 0 && !a->stat_acc && !a->w_per_image && conv2d_pointwise_supported(a)) return 3;
 #ifdef MGDT_WITH_UMMA
-    if (a && a->impl != 1 && conv2d_umma_supported(a)) return 2;
+    if (a && a->impl != 1 && conv2d_umma_supported(a)) return conv2d_umma_path(a);
 #endif
     return 1;
 }

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <stdlib.h>
+#include <string.h>
 
 namespace mgdt {
 
@@ -277,6 +278,16 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// run-time plan of the TMA-fed 1x1 kernel (conv_tma1x1.cuh)
+struct T1 {
+    int KB, nkb;          // channels per K block (= swizzle atom: 64 / 32 / 16), K blocks
+    int kb_stage, nst, S; // K blocks per ring stage, stages per tile, ring depth
+    int Nsub, nsub;       // columns per CTA, column sub-splits of a packed column block
+    int NACC, tmem_cols, w_ring, swz, ctas_per_sm, per_img, tiles_per_img, epiw;
+    unsigned a_kb_bytes, a_stage_bytes, w_stage_bytes, stage_bytes, w_bytes, smem_total;
+    long long tiles;
+};
+
 struct P2 {
     const __nv_bfloat16 *x, *w, *pre_add, *pix_scale, *residual;
     const __nv_bfloat16* row_scale;   // 1x1 layers: the per-pixel input scale applied to the accumulator row instead (stride ps_cs)
@@ -304,6 +315,8 @@ struct P2 {
     // neighbouring tiles of one image do not serialise on the same L2 lines; st_tot = 0 skips the total plane when the
     // windows partition the image (even Ho, Wo: mgdt_stats_finish derives it from the four window sums).
     size_t w_img_elems;          // per-image weights: elements between consecutive images' packed weights (0 = shared)
+    alignas(64) CUtensorMap xmap;   // TMA load of the activation as a 2D (channels, pixels) tensor (conv_tma1x1.cuh)
+    T1 t1;
     alignas(64) CUtensorMap ymap;   // TMA store of 32-row x 32-channel output units (mode 0): 2D (channels, pixels) or, per-image tiles, 3D (channels, pixels of an image, image)
     int tma_store;
     int pair_ok;                 // paired 16-column epilogue units allowed (debug: MGDT_CONV_PAIR=0 turns them off)
@@ -1442,7 +1455,14 @@ static void fill_divs(P2& p) {
 }
 
 static unsigned long long* g_trace = nullptr;
-static int g_force_split = -1;   // debug (MGDT_CONV_SPLIT=0/1/2): override the producer/epilogue warp split
+// Library options, set through the C ABI (mgdt_set_option; the Python layer forwards MGDT_* environment variables once
+// at load time): no getenv and no latched statics in the launch path.
+static int g_force_split = -1;     // "conv_split" 0/1/2: override the producer/epilogue warp split (-1 = cost model)
+static int g_tma_store = 1;        // "conv_tma_store": TMA tensor stores of 1x1 epilogue units
+static int g_pair = 1;             // "conv_pair": paired 16-column epilogue units
+static int g_use_tma_loads = 1;    // "conv_tma_load": TMA-fed kernel for transform-free 1x1 layers (conv_tma1x1.cuh)
+
+#include "conv_tma1x1.cuh"
 
 template <int MODE, int LOADER, int SPLIT, int STATS>
 static int launch2k(const P2& p, dim3 grid, cudaStream_t s) {
@@ -1489,42 +1509,16 @@ static int pick_split(const P2& p, bool xform) {
 }
 
 static int launch2(P2& p, cudaStream_t s) {
-    static bool env_read = false;
-    if (!env_read) {
-        const char* e = getenv("MGDT_CONV_SPLIT");
-        if (e && e[0] >= '0' && e[0] <= '2') g_force_split = e[0] - '0';
-        env_read = true;
-    }
     fill_divs(p);
     p.trace = g_trace;
     // TMA store map of the output (mode 0 layers with 16-byte aligned rows; the paired 16-column units keep the LSU path)
-    static int tma_env = -1;   // debug (MGDT_CONV_TMA_STORE=0): off, for A/B runs
-    if (tma_env < 0) {
-        const char* e = getenv("MGDT_CONV_TMA_STORE");
-        tma_env = (e && e[0] == '0') ? 0 : 1;
-    }
     p.tma_store = 0;
-    if (tma_env && p.pl.mode == 0 && p.y_vec && p.Cout >= 8) {
+    if (g_tma_store && p.pl.mode == 0 && p.y_vec && p.Cout >= 8) {
         const unsigned long long HW = (unsigned long long)p.Ho * p.Wo;
         cuuint64_t dims[3] = {(cuuint64_t)p.Cout, p.rn.per_img ? HW : (cuuint64_t)p.M_total, (cuuint64_t)p.N};
         cuuint64_t strides[2] = {(cuuint64_t)p.y_cs * 2, HW * (cuuint64_t)p.y_cs * 2};
         cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
-        // the driver entry point is resolved at run time (the library must load on machines without libcuda, where
-        // only the host-side checks run); without it the LSU store path is used
-        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static EncodeFn encode = nullptr;
-        static bool looked_up = false;
-        if (!looked_up) {
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
-                qres == cudaDriverEntryPointSuccess)
-                encode = (EncodeFn)fn;
-            (void)cudaGetLastError();
-            looked_up = true;
-        }
+        EncodeTiledFn encode = tensor_map_encoder();   // absent driver entry point: the LSU store path is used
         if (encode) {
             const CUresult r = encode(&p.ymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.rn.per_img ? 3 : 2, (void*)p.y, dims, strides, box, estr,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -1532,12 +1526,11 @@ static int launch2(P2& p, cudaStream_t s) {
             p.tma_store = r == CUDA_SUCCESS ? 1 : 0;
         }
     }
-    static int pair_env = -1;   // debug (MGDT_CONV_PAIR=0): paired 16-column epilogue units off, for A/B runs
-    if (pair_env < 0) {
-        const char* e = getenv("MGDT_CONV_PAIR");
-        pair_env = (e && e[0] == '0') ? 0 : 1;
+    p.pair_ok = g_pair;
+    if (p.pl.mode == 0) {   // transform-free 1x1 layers: the TMA-fed kernel
+        const int rc = try_launch_t1(p, s);
+        if (rc != 0) return rc < 0 ? rc : 0;
     }
-    p.pair_ok = pair_env;
     const long long tiles = p.rn.tiles;
     int ctas = (int)(tiles < 148 ? tiles : 148);
     if (p.pl.nsplit > 1) ctas = (int)std::max(1LL, std::min(tiles, (long long)(148 / p.pl.nsplit)));
@@ -1574,8 +1567,7 @@ bool conv2d_umma_supported(const mgdt_conv_args* a) {
     return true;
 }
 
-int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
-    P2 p;
+static int fill_p2(const mgdt_conv_args* a, P2& p) {
     int Ho, Wo;
     if (!plan2_for(a->Cin, a->Cout, a->kh, a->stride, a->N, a->H, a->W, p.pl, p.rn, Ho, Wo, a->w_per_image != 0))
         return set_error(-EINVAL, "conv2d_umma: unsupported shape");
@@ -1603,7 +1595,20 @@ int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
     p.st_R = a->stat_copies > 0 ? a->stat_copies : 1;
     p.st_rs = (long long)a->N * (p.st_Q + p.st_sq) * a->Cout;
     p.st_tot = (p.st_Q == 1 || (p.st_Q == 5 && ((Ho | Wo) & 1))) ? 1 : 0;
-    return launch2(p, s);
+    return 0;
+}
+
+int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
+    P2 p;
+    const int rc = fill_p2(a, p);
+    return rc < 0 ? rc : launch2(p, s);
+}
+
+// 2 = conv_umma2_kernel (cp.async-fed), 4 = conv1x1_tma_kernel (TMA-fed), for a layer conv2d_umma_supported() accepts
+int conv2d_umma_path(const mgdt_conv_args* a) {
+    P2 p;
+    if (fill_p2(a, p) < 0) return 2;
+    return (p.pl.mode == 0 && t1_eligible(p) && plan_t1(p, p.t1) && tensor_map_encoder()) ? 4 : 2;
 }
 
 bool dcn_umma_supported(const void* x, int x_cs, const void* w_umma, int N, int H, int W, int Cin, int Cout) {
@@ -1672,6 +1677,17 @@ using namespace mgdt;
 
 extern "C" void mgdt_debug_set_trace(void* buf) { mgdt::g_trace = (unsigned long long*)buf; }
 
+namespace mgdt {
+int conv_set_option(const char* name, int value) {
+    if (!strcmp(name, "conv_split")) g_force_split = (value >= 0 && value <= 2) ? value : -1;
+    else if (!strcmp(name, "conv_tma_store")) g_tma_store = value ? 1 : 0;
+    else if (!strcmp(name, "conv_pair")) g_pair = value ? 1 : 0;
+    else if (!strcmp(name, "conv_tma_load")) g_use_tma_loads = value ? 1 : 0;
+    else return 0;
+    return 1;
+}
+}  // namespace mgdt
+
 extern "C" int mgdt_stem_conv(const void* src, int src_is_u8, const void* w_umma, int w_umma_f16, const float* bias,
                               void* y, int y_cs, int N, int C, int H, int W, int Cout, int act, int dtype, void* stream) {
     MGDT_CHECK(src && w_umma && y, "stem_conv: null pointer");
@@ -1709,20 +1725,26 @@ extern "C" int mgdt_conv_umma_pack(const void* w_ohwi, int w_dtype, int Cin, int
 }
 
 namespace mgdt {
-// Per-image scaled copies of a packed bf16 weight image: out[img][chunk] = packed[chunk] * in_scale[img][ci .. ci + 7].
-// One thread per 16-byte chunk (8 consecutive input channels of one (tap, plane, output column)).
+// Per-image scaled copies of a packed bf16 weight image: out[img][chunk] = packed[chunk] * scale(img, column, ci .. ci + 7).
+// One thread per 16-byte chunk (8 consecutive input channels of one (tap, plane, output column)).  Output columns are
+// scaled in groups of `gcols`: group g < ngroups uses in_scale[g][img][ci], columns past the last group keep the
+// weights unscaled (siblings that read the same map fused into ONE GEMM: the two TaskDecomposition convs, each with
+// its own layer attention, and cls_prob_conv1 without any, nn/modules/head.py:509-521).
 __global__ void umma2_scale_packed_kernel(const uint4* __restrict__ packed, uint4* __restrict__ out, Plan2 p, int Cin,
-                                          const float* __restrict__ in_scale, unsigned per_img, unsigned total) {
+                                          const float* __restrict__ in_scale, unsigned per_img, unsigned total, int nimg,
+                                          int ngroups, int gcols) {
     pdl_trigger();
     pdl_wait();
     const unsigned cps = (unsigned)p.nmma_s * 2u, Nc = (unsigned)p.Nc;
     for (unsigned c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += gridDim.x * blockDim.x) {
         const unsigned img = c0 / per_img, c = c0 - img * per_img;
         const unsigned chunk = (c / Nc) % cps, ks = (c / (Nc * cps)) % (unsigned)p.nks;
+        const unsigned col = (c / (Nc * cps * (unsigned)p.nks)) * Nc + c % Nc;
+        const int g = (int)(col / (unsigned)gcols);
         uint4 v = __ldg(packed + c);
-        if (chunk < (unsigned)(p.taps * p.PS)) {
+        if (chunk < (unsigned)(p.taps * p.PS) && g < ngroups) {
             const unsigned plane = ks * (unsigned)p.PS + chunk % (unsigned)p.PS;
-            const float4* sp = reinterpret_cast<const float4*>(in_scale + (size_t)img * Cin + plane * 8u);
+            const float4* sp = reinterpret_cast<const float4*>(in_scale + ((size_t)g * nimg + img) * Cin + plane * 8u);
             const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
             const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
             uint32_t* w = reinterpret_cast<uint32_t*>(&v);
@@ -1738,17 +1760,23 @@ __global__ void umma2_scale_packed_kernel(const uint4* __restrict__ packed, uint
 }
 }  // namespace mgdt
 
-extern "C" int mgdt_conv_umma_pack_scaled(const void* packed_bf16, int Cin, int Cout, int k, int stride, const float* in_scale,
-                                          int N, void* out, void* stream) {
-    MGDT_CHECK(packed_bf16 && out && in_scale && N > 0, "conv_umma_pack_scaled: bad arguments");
+extern "C" int mgdt_conv_umma_pack_scaled_groups(const void* packed_bf16, int Cin, int Cout, int k, int stride, const float* in_scale,
+                                                 int N, int ngroups, int group_cols, void* out, void* stream) {
+    MGDT_CHECK(packed_bf16 && out && in_scale && N > 0 && ngroups > 0 && group_cols > 0, "conv_umma_pack_scaled: bad arguments");
     MGDT_CHECK((((uintptr_t)packed_bf16 | (uintptr_t)out | (uintptr_t)in_scale) & 15) == 0, "conv_umma_pack_scaled: pointers must be 16-byte aligned");
+    MGDT_CHECK(k == 1 || ngroups == 1, "conv_umma_pack_scaled: column groups are for 1x1 layers");
     const Plan2 pl = make_plan2(Cin, Cout, k, stride);
     MGDT_CHECK(pl.ok, "conv_umma_pack_scaled: shape %d->%d k%d s%d is not supported by the tcgen05 path", Cin, Cout, k, stride);
     const long long per_img = (long long)pl.nsplit * pl.nks * pl.nmma_s * 2 * pl.Nc;   // 16-byte chunks
     MGDT_CHECK(per_img * N < (1LL << 31), "conv_umma_pack_scaled: too large");
     const int g = (int)std::min<long long>((per_img * N + 255) / 256, 148LL * 8);
     launch_k(umma2_scale_packed_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, (const uint4*)packed_bf16, (uint4*)out, pl, Cin, in_scale,
-             (unsigned)per_img, (unsigned)(per_img * N));
+             (unsigned)per_img, (unsigned)(per_img * N), N, ngroups, group_cols);
     MGDT_LAUNCH_CHECK("umma_pack_scaled");
     return 0;
+}
+
+extern "C" int mgdt_conv_umma_pack_scaled(const void* packed_bf16, int Cin, int Cout, int k, int stride, const float* in_scale,
+                                          int N, void* out, void* stream) {
+    return mgdt_conv_umma_pack_scaled_groups(packed_bf16, Cin, Cout, k, stride, in_scale, N, 1, 1 << 30, out, stream);
 }

@@ -205,7 +205,7 @@ class TOODHead(_HeadBase):
 
     def _pack(self, dtype, device):
         plain = [self.spatial_conv_offset, self.cls_prob_conv1, self.cls_prob_conv2, self.cv2, self.cv3]
-        t = [c.weight for c in plain] + [c.bias for c in plain] + self.cls_decomp._tensors() + self.reg_decomp._tensors()
+        t = [c.weight for c in plain] + [c.bias for c in plain] + self.cls_decomp._tensors() + self.reg_decomp._tensors()  # noqa: E501
 
         def build():
             d = dict(zip(("off", "p1", "p2", "cv2", "cv3"), (_pack_plain(c, dtype, device) for c in plain)))
@@ -217,6 +217,12 @@ class TOODHead(_HeadBase):
             d["b2"] = stack(cd.la_conv2.bias, rd.la_conv2.bias)
             d["wcls"] = ohwi(cd.reduction_conv.conv.weight, dtype, device)
             d["wreg"] = ohwi(rd.reduction_conv.conv.weight, dtype, device)
+            # the three 1x1 convs that read `feat` (both reduction convs, applied without their bias, head.py:122-126,
+            # and cls_prob_conv1; all followed by ReLU) stacked along the output channels: ONE GEMM with per-image weights
+            wc, wr, wp = cd.reduction_conv.conv.weight, rd.reduction_conv.conv.weight, self.cls_prob_conv1.weight
+            if wc.shape == wr.shape and wc.shape[1] == wp.shape[1] and wc.shape[2:] == (1, 1) and wp.shape[2:] == (1, 1):
+                d["w3"] = ohwi(torch.cat([wc, wr, wp], 0), dtype, device)
+                d["b3"] = f32(torch.cat([torch.zeros(wc.shape[0] + wr.shape[0], device=wp.device), self.cls_prob_conv1.bias.detach().float()]), device)
             return d
 
         return self._packed("tood", dtype, device, t, build)
@@ -234,12 +240,18 @@ class TOODHead(_HeadBase):
             self.share_conv[1](feat[:, :h2], out=feat[:, h2:])
             s, _ = ops.chan_stats(feat)                                  # adaptive_avg_pool2d(feat, 1) (:509)
             att = ops.td_attn(s, h * w, p["w1"], p["b1"], p["w2"], p["b2"], 2)
-            cls_feat = ops.conv2d(feat, p["wcls"], None, 1, act="relu", in_scale=att[0])
-            reg_feat = ops.conv2d(feat, p["wreg"], None, 1, act="relu", in_scale=att[1])
+            fused = None
+            if "w3" in p and ops.FUSE_TOOD_SIBLINGS:
+                fused = ops.conv2d(feat, p["w3"], p["b3"], 1, act="relu", in_scale=att, scale_group_cols=h2)
+            if fused is not None:
+                cls_feat, reg_feat, prob = fused[:, :h2], fused[:, h2:2 * h2], fused[:, 2 * h2:]
+            else:
+                cls_feat = ops.conv2d(feat, p["wcls"], None, 1, act="relu", in_scale=att[0])
+                reg_feat = ops.conv2d(feat, p["wreg"], None, 1, act="relu", in_scale=att[1])
+                prob = ops.conv2d(feat, p["p1"][0], p["p1"][1], 1, act="relu")
             om = ops.conv2d(feat, p["off"][0], p["off"][1], 3)           # offsets 0..17, mask logits 18..26 (:514-517)
             reg = self.DyDCNV2(reg_feat, om[:, :self.offset_dim], om[:, self.offset_dim:], mask_is_logit=True,
                                act="relu")                               # GN, then the F.relu of :528
-            prob = ops.conv2d(feat, p["p1"][0], p["p1"][1], 1, act="relu")
             prob = ops.conv2d(prob, p["p2"][0], p["p2"][1], 3, act="sigmoid")
             raw = ops.new_act(n, self.no, h, w, xi.dtype, xi.device)
             ops.conv2d(reg, p["cv2"][0], p["cv2"][1], 1, out=raw[:, :rm4])

@@ -151,6 +151,7 @@ class PackedConv:
 WEIGHT_F16 = False
 USE_UMMA = True  # tests flip this to compare the tcgen05 path with the CUDA-core path
 PER_IMAGE_WEIGHTS = os.environ.get('MGDT_PER_IMAGE_W', '1') != '0'  # per-(n,c) input scales folded into per-image weights
+FUSE_TOOD_SIBLINGS = os.environ.get('MGDT_FUSE_TOOD', '1') != '0'  # cls_decomp / reg_decomp / cls_prob_conv1 as one per-image-weight GEMM
 FUSE_MSPA_FRONT = True  # MSPA_C2f branch chain as one launch (bf16); tests flip this to compare with the unfused sequence
 
 
@@ -186,10 +187,12 @@ def _stat_arena(device, nelem):
 
 
 def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scale=None, pix_scale=None,
-           residual=None, in_relu=False, cout=None, impl=0, stat=None):
+           residual=None, in_relu=False, cout=None, impl=0, stat=None, scale_group_cols=None):
     """y = act(conv((x + pre_add) * in_scale[n,c] * pix_scale[n,h,w] |> relu?, w) + bias) + residual.
     `w` is a PackedConv (or a plain OHWI (Cout, k, k, Cin) tensor) in x's dtype; `out` may be a channel
-    slice of a concat buffer."""
+    slice of a concat buffer.  With `scale_group_cols`, in_scale is [G, N, Cin] and output columns
+    [g*cols, (g+1)*cols) see the input scaled by in_scale[g] (columns past the last group: unscaled) -- sibling
+    convs fused into one GEMM; only the per-image-weight tcgen05 path implements it (returns None otherwise)."""
     xp, n, cin, h, wd, xcs = view(x)
     w_umma, w_f16 = None, False
     per_image = False
@@ -220,8 +223,13 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
         if (an, ac, ah, aw) != (n, cin, h, wd) or pre_add.dtype != x.dtype:
             raise ValueError("conv2d: pre_add must match x")
         a.pre_add, a.add_cs = ap, acs
+    ngroups = 1
     if in_scale is not None:
-        if in_scale.dtype != torch.float32 or in_scale.numel() != n * cin or not in_scale.is_contiguous():
+        if scale_group_cols is not None:
+            ngroups = in_scale.shape[0]
+            if not per_image or k != 1:
+                return None
+        if in_scale.dtype != torch.float32 or in_scale.numel() != ngroups * n * cin or not in_scale.is_contiguous():
             raise ValueError("conv2d: in_scale must be contiguous fp32 [N, Cin]")
         a.in_scale = in_scale.data_ptr()
     if pix_scale is not None:
@@ -245,12 +253,15 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
         # weight slices carried through the ring), pack one scaled weight image per sample and run the transform-free
         # loader instead of scaling the activations inside the loader
         a.in_scale, a.w_per_image = None, 1
-        if lib().mgdt_conv2d_path(C.byref(a)) == 2:
+        if lib().mgdt_conv2d_path(C.byref(a)) in (2, 4):
             pw = torch.empty((n * w_umma.numel(),), dtype=torch.uint8, device=x.device)
-            _invoke("mgdt_conv_umma_pack_scaled", dict(shape=f"pack_scaled {cin}->{cout} N{n}", bytes=pw.numel() + 4 * n * cin, flops=0.0,
-                                                       kernel="umma2_scale_packed_kernel"),
-                    w_umma.data_ptr(), cin, cout, k, s, in_scale.data_ptr(), n, pw.data_ptr(), stream_ptr())
+            _invoke("mgdt_conv_umma_pack_scaled_groups", dict(shape=f"pack_scaled {cin}->{cout} N{n}", bytes=pw.numel() + 4 * ngroups * n * cin,
+                                                              flops=0.0, kernel="umma2_scale_packed_kernel"),
+                    w_umma.data_ptr(), cin, cout, k, s, in_scale.data_ptr(), n, ngroups,
+                    scale_group_cols if scale_group_cols is not None else (1 << 30), pw.data_ptr(), stream_ptr())
             a.w_umma = pw.data_ptr()
+        elif scale_group_cols is not None:
+            return None
         else:
             a.in_scale, a.w_per_image = in_scale.data_ptr(), 0
     es = x.element_size()
@@ -263,12 +274,12 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
         if FUSE_STATS and x.dtype == torch.bfloat16 and a.w_umma:
             stat.acc = _stat_arena(x.device, STAT_COPIES * n * (stat.q + stat.sq) * cout)
             a.stat_acc, a.stat_q, a.stat_sq, a.stat_copies = stat.acc.data_ptr(), stat.q, stat.sq, STAT_COPIES
-            if lib().mgdt_conv2d_path(C.byref(a)) == 2:
+            if lib().mgdt_conv2d_path(C.byref(a)) in (2, 4):
                 stat.fused = True
             else:
                 a.stat_acc, a.stat_q, a.stat_sq, a.stat_copies = None, 0, 0, 0
     if PROFILE is not None:  # attribute the launch to the kernel the library will actually run
-        meta["kernel"] = {3: "conv_pointwise_kernel", 2: "conv_umma2_kernel"}.get(lib().mgdt_conv2d_path(C.byref(a)),
+        meta["kernel"] = {3: "conv_pointwise_kernel", 2: "conv_umma2_kernel", 4: "conv1x1_tma_kernel"}.get(lib().mgdt_conv2d_path(C.byref(a)),
                                                                                   "conv_direct_kernel")
     _invoke("mgdt_conv2d", meta, C.byref(a), stream_ptr())
     return out

@@ -22,6 +22,11 @@ SHAPES = [
     (8, 8, 3, 1, 5, 160, 160), (16, 16, 3, 1, 8, 120, 130), (64, 16, 1, 1, 8, 160, 100), (16, 8, 3, 1, 3, 200, 212),
     # column splits whose last unit has 16 columns (Cout 576 -> 4 x 144): that unit must not be stored as a 32-channel TMA box
     (64, 576, 1, 1, 2, 12, 10), (96, 48, 1, 1, 3, 20, 24), (32, 27, 1, 1, 2, 30, 30),
+    # the TMA-fed 1x1 kernel at sizes where every persistent CTA walks several 128-row tiles, the ring wraps, two CTAs
+    # share an SM and the last tile is partial; K blocks of 64 / 32 / 16 channels (SWIZZLE_128B / 64B / 32B)
+    (64, 256, 1, 1, 8, 80, 80), (96, 384, 1, 1, 8, 40, 40), (32, 32, 1, 1, 4, 160, 160), (160, 128, 1, 1, 4, 40, 40),
+    (80, 64, 1, 1, 4, 80, 80), (384, 96, 1, 1, 8, 40, 40), (512, 256, 1, 1, 8, 20, 20), (32, 512, 1, 1, 4, 40, 40),
+    (48, 40, 1, 1, 3, 33, 37), (16, 24, 1, 1, 5, 50, 61),
 ]
 
 
@@ -307,3 +312,30 @@ def test_pixel_scale_1x1_in_epilogue(cout, n, h, w):
     scale = float(ref.abs().max())
     assert float((y0.float() - ref).abs().max()) / scale <= 2 ** -7
     assert float((y0.float() - y1.float()).abs().max()) / scale <= 2 ** -6
+
+
+def test_tood_sibling_convs_as_one_gemm():
+    """cls_decomp / reg_decomp reduction convs (each with its own layer attention folded into per-image weights) and
+    cls_prob_conv1 (unscaled) as ONE per-image-weight GEMM (mgdt_conv_umma_pack_scaled_groups) against the three
+    separate launches: same operands, same bf16 rounding of the scaled weights -> same maps."""
+    from mgdt_yolo_b200 import ops
+    from mgdt_yolo_b200.modules import TOODHead
+    from mgdt_yolo_b200.synth import synth_state_dict
+    head = TOODHead(3, 64, (64,))
+    head.load_state_dict(synth_state_dict(head.state_dict(), seed=5))
+    head.stride = torch.tensor([8.0])
+    head = head.cuda().eval()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 64, 40, 56, generator=g).cuda().to(torch.bfloat16)
+    outs = {}
+    for flag in (True, False):
+        ops.FUSE_TOOD_SIBLINGS = flag
+        try:
+            with torch.no_grad():
+                y, raw = head([x.clone()])
+        finally:
+            ops.FUSE_TOOD_SIBLINGS = True
+        outs[flag] = (y.float(), raw[0].float())
+    for a, b in zip(outs[True], outs[False]):
+        err = float((a - b).abs().max()) / float(b.abs().max())
+        assert err <= 2 ** -7, f"fused sibling GEMM vs separate convs: {err:.3e}"

@@ -44,6 +44,9 @@ for name, cin, cout, k, s, H, W in cases:
     t = trace.view(-1, 64).cpu()
     act = t[:, 0] > 0
     t = t[act]
+    if len(t) == 0:
+        print(f"== {name}: event time {e0.elapsed_time(e1)*1000:.1f} us -- not the tcgen05 kernel (no trace)")
+        continue
     t0 = int(t[:, 0].min())
     rel = lambda col: [(int(v) - t0) / 1000 for v in col if v > 0]
     def stat(slot):
