@@ -56,6 +56,7 @@ void mgdt_set_pdl(int on);
  * forwards MGDT_<NAME> once at load time.  Returns 0, or -EINVAL for an unknown name.
  *   "pdl"            1   programmatic dependent launch
  *   "conv_tma_load"  1   TMA-fed kernel (cp.async.bulk.tensor loads) for transform-free 1x1 convolutions
+ *   "conv_tma_stats" 0   ... also for layers with fused output statistics (slower than the cp.async kernel's 16-warp epilogue)
  *   "conv_tma_store" 1   TMA tensor stores of 1x1 epilogue units
  *   "conv_pair"      1   paired 16-column epilogue units (Cout <= 16)
  *   "conv_split"    -1   force the producer / epilogue warp split of the cp.async conv kernel (0 / 1 / 2) */

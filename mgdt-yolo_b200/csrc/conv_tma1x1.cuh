@@ -23,7 +23,7 @@
 
 constexpr int T1_MAX_STAGES = 4;
 // barriers + TMEM slot (1 KB), bias (1 KB), two 2 KB staging tiles per epilogue warp (512-byte aligned)
-static constexpr unsigned t1_tail(int epiw) { return 1024u + 256u * 4u + (unsigned)epiw * 2u * 2048u + 512u; }
+static constexpr unsigned t1_tail(int epiw) { return 1024u + 256u * 4u + (unsigned)epiw * 2u * 2048u + 512u + (unsigned)epiw * 2u * 6u * 32u * 4u; }
 
 __device__ __forceinline__ uint64_t mk_desc_sw(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
     // K-major swizzled shared-memory matrix descriptor (version 1): LBO field = 1 (unused for swizzled K-major),
@@ -45,6 +45,76 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 
 // EPIW = 4: six warps, three CTAs per SM (narrow layers: one 32-column unit per TMEM quadrant and tile);
 // EPIW = 8: ten warps, two CTAs per SM, the two warps of a quadrant take the tile's column units alternately.
+// Fused output statistics, TMA kernel form.  Same per-unit reduction as epi_stats (lane l owns the column pair
+// 2 * (l & 15) over the 16 rows 2i + (l >> 4) of the staged unit, one shuffle combines the half-warps), but the results
+// are added to PER-WARP fp32 accumulators in shared memory (acc[unit slot][plane][32 columns], one owner lane per
+// address: no atomics) that are flushed to the global fp64 accumulators only when the image changes or the CTA ends
+// (t1_stats_flush).  With contiguous tile ranges per CTA that is once or twice per CTA instead of once per unit; the
+// flush order does not matter (fp64 atomics), the per-warp sums are formed in a fixed order: reproducible results.
+__device__ __forceinline__ void t1_stats_flush(const P2& p, float* wacc, int slots, int n_cur, int lane, int co_base, int slot_stride_cols) {
+    if (n_cur < 0) return;
+    const int K = p.st_Q + p.st_sq;
+    double* base = p.st_acc + (size_t)(blockIdx.x % (unsigned)p.st_R) * p.st_rs + (size_t)n_cur * K * p.Cout;
+    for (int sl = 0; sl < slots; ++sl) {
+        const int c = co_base + sl * slot_stride_cols + lane;
+        for (int k = 0; k < K; ++k) {
+            float* a = wacc + (sl * 6 + k) * 32 + lane;
+            const float v = *a;
+            *a = 0.f;
+            if (c < p.Cout && v != 0.f) atomicAdd(base + (size_t)k * p.Cout + c, (double)v);
+        }
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void t1_stats_unit(const P2& p, float* wacc, int slots, int& n_cur, int slot, uint32_t stg32, uint32_t skey,
+                                              int lane, int co_base, int slot_stride_cols) {
+    const uint32_t full = 0xffffffffu, INVALID = 0xffffffffu;
+    const uint32_t cp = (uint32_t)lane & 15u, half = (uint32_t)lane >> 4;
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t a = stg32 + (uint32_t)(2 * i) * 64u + half * 64u + (((cp >> 2) ^ ((uint32_t)i & 3u)) << 4) + (cp & 3u) * 4u;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[i]) : "r"(a));
+    }
+    const int Q = p.st_Q;
+    float* my = wacc + slot * 6 * 32 + 2 * (int)cp;
+    uint32_t rem = __ballot_sync(full, skey != INVALID);
+    while (rem) {
+        const uint32_t k = __shfl_sync(full, skey, __ffs((int)rem) - 1);
+        const uint32_t m = __ballot_sync(full, skey == k);
+        rem &= ~m;
+        if ((int)(k >> 4) != n_cur) {   // uniform: a new image starts -- publish the finished one first
+            t1_stats_flush(p, wacc, slots, n_cur, lane, co_base, slot_stride_cols);
+            n_cur = (int)(k >> 4);
+        }
+        const uint32_t mh = m >> half;
+        float2 sa[4], qa[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sa[u] = qa[u] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t tt = (m == full || (mh & (1u << (2 * i)))) ? w[i] : 0u;
+            const float2 v2 = make_float2(__uint_as_float(tt << 16), __uint_as_float(tt & 0xffff0000u));
+            sa[i & 3] = __fadd2_rn(v2, sa[i & 3]);
+            qa[i & 3] = __ffma2_rn(v2, v2, qa[i & 3]);
+        }
+        float2 s2 = __fadd2_rn(__fadd2_rn(sa[0], sa[1]), __fadd2_rn(sa[2], sa[3]));
+        float2 q2 = __fadd2_rn(__fadd2_rn(qa[0], qa[1]), __fadd2_rn(qa[2], qa[3]));
+        s2.x += __shfl_xor_sync(full, s2.x, 16); s2.y += __shfl_xor_sync(full, s2.y, 16);
+        q2.x += __shfl_xor_sync(full, q2.x, 16); q2.y += __shfl_xor_sync(full, q2.y, 16);
+        if (half == 0) {
+            if (p.st_tot) { float2* a = reinterpret_cast<float2*>(my); *a = __fadd2_rn(*a, s2); }
+            if (Q == 5) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (k & (1u << j)) { float2* a = reinterpret_cast<float2*>(my + (1 + j) * 32); *a = __fadd2_rn(*a, s2); }
+            }
+            if (p.st_sq) { float2* a = reinterpret_cast<float2*>(my + Q * 32); *a = __fadd2_rn(*a, q2); }
+        }
+        __syncwarp();
+    }
+}
+
 template <int STATS, int EPIW>
 __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma_kernel(const __grid_constant__ P2 p) {
     constexpr int T1_THREADS = 64 + 32 * EPIW, T1_EPI_WARPS = EPIW;
@@ -73,10 +143,15 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T1_MAX_STAGES + 5);
     float* sBias = reinterpret_cast<float*>(tail + 1024);
     const uint32_t sOut32 = (s_u32(tail + 1024 + 256 * 4) + 511u) & ~511u;
+    // per-warp statistics accumulators (STATS): [EPIW warps][2 unit slots][6 planes][32 columns] fp32, after the staging tiles
+    float* sStat = reinterpret_cast<float*>(tail + 1024 + 256 * 4 + 512 + (size_t)EPIW * 4096);
+    if (STATS) {
+        for (int i = tid; i < EPIW * 2 * 6 * 32; i += T1_THREADS) sStat[i] = 0.f;
+    }
 
     for (int i = tid; i < Nsub; i += T1_THREADS) {
         const int co = ns * pl.Nc + col0 + i;
-        sBias[i] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
+        sBias[i] = (p.bias && co < p.Cout) ? p.bias[co] * t1_bias_scale(p.act) : 0.f;
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)),
@@ -93,8 +168,13 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) { trace_mark(p, 0); trace_mark(p, 1); }
 
-    const uint32_t tiles = (uint32_t)t.tiles;
+    // contiguous tile range per CTA: consecutive tiles mostly belong to one image, so the fused statistics are
+    // accumulated per warp in shared memory and flushed to the global fp64 accumulators only when the image changes
+    const uint32_t tiles_all = (uint32_t)t.tiles;
+    const uint32_t tchunk = (tiles_all + gridDim.x - 1) / gridDim.x;
+    const uint32_t tile_lo = min(tiles_all, blockIdx.x * tchunk), tiles = min(tiles_all, tile_lo + tchunk);
     const uint32_t HW = (uint32_t)(p.H * p.W);
     const int nchunk_all = p.Cin / 8;                       // 16-byte K chunks of the packed weight image
     const uint32_t wchunk_bytes = (uint32_t)Nsub * 16u;     // one chunk of this CTA's columns in shared memory
@@ -125,7 +205,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
         pdl_wait();
         int s = 0;
         uint32_t ph = 0;
-        for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (uint32_t tile = tile_lo; tile < tiles; ++tile) {
             uint32_t n_img;
             const uint32_t pix0 = tile_pix0(tile, n_img);
             for (int st = 0; st < t.nst; ++st) {
@@ -142,6 +222,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
                         for (int c = 0; c < nk * cpk; ++c)
                             bulk_load(sWs + (uint32_t)c * wchunk_bytes, wsrc(n_img, kb0 * cpk + c), wchunk_bytes, FULL(s));
                     }
+                    if (p.trace && st == t.nst - 1) { const uint32_t tl = tile - tile_lo; if (tl < 6) trace_mark(p, 8 + 8 * (int)tl); }
                 }
                 __syncwarp();
                 if (++s == t.S) { s = 0; ph ^= 1; }
@@ -156,7 +237,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
         if (!t.w_ring) mbar_wait(WREADY, 0);
         int s = 0;
         uint32_t ph = 0, ti = 0;
-        for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+        for (uint32_t tile = tile_lo; tile < tiles; ++tile, ++ti) {
             const int a = t.NACC == 2 ? (int)(ti & 1) : 0;
             const uint32_t aphase = t.NACC == 2 ? ((ti >> 1) & 1) : (ti & 1);
             mbar_wait(ACCEMPTY(a), aphase ^ 1);
@@ -181,7 +262,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
                         }
                     }
                     umma_commit(EMPTY(s));
-                    if (st == t.nst - 1) umma_commit(ACCFULL(a));
+                    if (st == t.nst - 1) { umma_commit(ACCFULL(a)); if (p.trace && ti < 6) trace_mark(p, 9 + 8 * (int)ti); }
                 }
                 __syncwarp();
                 if (++s == t.S) { s = 0; ph ^= 1; }
@@ -198,7 +279,11 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
         const uint32_t sw_wr = (uint32_t)((lane >> 1) & 3);
         const bool tma_on = p.tma_store != 0;
         uint32_t ti = 0, ubuf = 0;
-        for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+        float* wacc = sStat + ew * (2 * 6 * 32);
+        int st_ncur = -1;                              // image whose partial sums the warp's accumulators hold
+        const int st_slots = (ncch - sub + NSUBW - 1) / NSUBW;   // units this warp handles per tile (<= 2)
+        const int st_co_base = ns * pl.Nc + col0 + sub * 32;
+        for (uint32_t tile = tile_lo; tile < tiles; ++tile, ++ti) {
             const int a = t.NACC == 2 ? (int)(ti & 1) : 0;
             const uint32_t aphase = t.NACC == 2 ? ((ti >> 1) & 1) : (ti & 1);
             uint32_t n_img;
@@ -233,6 +318,8 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
             }
             mbar_wait(ACCFULL(a), aphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool trw = p.trace && ew == 0 && lane == 0;
+            if (trw && ti < 6) trace_mark(p, 10 + 8 * (int)ti);
             for (int cc = sub; cc < ncch; cc += NSUBW) {
                 const int cl = cc * 32;
                 const int co0 = ns * pl.Nc + col0 + cl;
@@ -240,6 +327,9 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
                 const int nv = min(32, Nsub - cl);
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * Nsub + cl);
                 uint32_t r[32], pk[16];
+                const bool tr = trw && ti == 1;
+                long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
+                if (tr) tc0 = clock64();
                 if (nv == 32) {
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -250,7 +340,8 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
                           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    epi_math<32>(p, r, sBias, cl, co0, opix, pk);
+                    if (tr) tc1 = clock64();
+                    epi_fast_rt<32>(p, r, sBias, cl, co0, opix, pk);
                 } else {
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -258,7 +349,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    epi_math<16>(p, r, sBias, cl, co0, opix, pk);
+                    epi_fast_rt<16>(p, r, sBias, cl, co0, opix, pk);
 #pragma unroll
                     for (int j = 8; j < 16; ++j) pk[j] = 0u;
                 }
@@ -277,6 +368,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
                                  "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
                 if (tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
+                if (tr) tc2 = clock64();
                 if (tma) {
                     if (lane == 0) {
                         const uint32_t r0 = (uint32_t)(quad * 32);
@@ -310,19 +402,26 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
                         }
                     }
                 }
-                if (STATS)
-                    epi_stats(p.st_acc + (size_t)(tile % (uint32_t)p.st_R) * p.st_rs, p.st_Q, p.st_sq, p.st_tot, p.Cout, stg32, skey,
-                              lane, nv, co0, p.Cout);
+                if (STATS) t1_stats_unit(p, wacc, st_slots, st_ncur, (cc - sub) / NSUBW, stg32, skey, lane, st_co_base, NSUBW * 32);
                 __syncwarp();
+                if (tr) {
+                    tc3 = clock64();
+                    unsigned long long* tp = p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + 56;
+                    tp[0] += 1; tp[1] += (unsigned long long)(tc1 - tc0); tp[2] += (unsigned long long)(tc2 - tc1);
+                    tp[3] += (unsigned long long)(tc3 - tc2);
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_relaxed(ACCEMPTY(a));
+            if (trw && ti < 6) trace_mark(p, 11 + 8 * (int)ti);
         }
+        if (STATS) t1_stats_flush(p, wacc, st_slots, st_ncur, lane, st_co_base, NSUBW * 32);
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all TMA stores complete before exit
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (tid == 0) trace_mark(p, 3);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)t.tmem_cols)
                      : "memory");
@@ -346,6 +445,7 @@ static bool plan_t1(const P2& p, T1& t) {
     if (pl.Nc > 128 && (pl.Nc / 2) % 32 == 0) { t.Nsub = pl.Nc / 2; t.nsub = 2; }
     if (t.Nsub % 16 != 0 || t.Nsub > 256) return false;
     t.epiw = (t.Nsub + 31) / 32 >= 2 ? 8 : 4;
+    if (p.st_acc && ((t.Nsub + 31) / 32 + t.epiw / 4 - 1) / (t.epiw / 4) > 2) return false;   // two statistics slots per warp
     const int want_ctas = t.epiw == 8 ? 2 : 3;
     // accumulator buffers: two when `want_ctas` CTAs still fit the SM's 512 TMEM columns, else one (the CTAs of an SM
     // interleave their MMA and epilogue phases instead)
@@ -421,7 +521,7 @@ static int launch_t1k(const P2& p, dim3 grid, cudaStream_t s) {
 
 // Try the TMA kernel for this (already filled) mode-0 layer: 1 = launched, 0 = not eligible, < 0 = error.
 static bool t1_eligible(const P2& p) {
-    return g_use_tma_loads && !p.stem_src && !p.dcn_off && !p.pre_add && !p.in_scale && !p.pix_scale && !p.in_relu;
+    return g_use_tma_loads && (g_tma_stats || !p.st_acc) && !p.stem_src && !p.dcn_off && !p.pre_add && !p.in_scale && !p.pix_scale && !p.in_relu;
 }
 
 static int try_launch_t1(P2& p, cudaStream_t s) {

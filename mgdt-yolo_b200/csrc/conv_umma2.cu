@@ -711,6 +711,98 @@ __device__ __forceinline__ void epi_math(const P2& p, const uint32_t* r, const f
     }
 }
 
+// Epilogue arithmetic of one unit (NV accumulator columns of one output row per lane), specialised on the activation so
+// that the executed path is a straight run of packed fp32x2 instructions (FFMA2 / FMUL2 on adjacent register pairs,
+// no repacking moves, no runtime switch inside the loop): SiLU is 2 FFMA2 + 2 MUFU.TANH + 1 F2FP per output PAIR.
+//   h = acc * sc + hb   with (sc, hb) = (1/2, bias/2) for SiLU / sigmoid / GELU (the half of x the tanh forms need),
+//                       (1, bias) otherwise; a per-pixel row scale (cv3(cls_feat * cls_prob)) multiplies sc
+// sB holds the bias pre-multiplied accordingly (t1_bias_scale).
+__host__ __device__ constexpr float t1_bias_scale(int act) {
+    return (act == MGDT_ACT_SILU || act == MGDT_ACT_SIGMOID || act == MGDT_ACT_GELU) ? 0.5f : 1.0f;
+}
+// pairB (paired 16-column units of conv_umma2_kernel): columns 16..31 are channels 0..15 of a SECOND output row opixB.
+template <int ACT, int NV>
+__device__ __forceinline__ void epi_fast(const P2& p, const uint32_t* r, const float* sB, int cbase, int co0, int opix,
+                                         uint32_t* packed, bool pairB = false, int opixB = -1) {
+    float s = t1_bias_scale(ACT) * p.out_scale;
+    if (p.row_scale && opix >= 0) s *= __bfloat162float(p.row_scale[(size_t)opix * p.ps_cs]);
+    const float2 sc = make_float2(s, s);
+    const float2* b2 = reinterpret_cast<const float2*>(sB + cbase);
+    float2 y[NV / 2];
+#pragma unroll
+    for (int j = 0; j < NV / 2; ++j) {
+        const float2 acc = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        const float2 h = __ffma2_rn(acc, sc, b2[j]);
+        if (ACT == MGDT_ACT_SILU) {
+            const float2 t = make_float2(tanh_fast(h.x), tanh_fast(h.y));
+            y[j] = __ffma2_rn(h, t, h);                                    // x * sigmoid(x) = h + h * tanh(h), h = x / 2
+        } else if (ACT == MGDT_ACT_SIGMOID) {
+            const float2 t = make_float2(tanh_fast(h.x), tanh_fast(h.y));
+            y[j] = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+        } else if (ACT == MGDT_ACT_GELU) {
+            // erf(z) ~= tanh(z * (A + B z^2 + C z^4)), z = x / sqrt(2) = h * sqrt(2), |z| clamped to 5 (common.cuh: act_fast)
+            float2 z = __fmul2_rn(h, make_float2(1.41421356237309504880f, 1.41421356237309504880f));
+            z.x = fminf(fmaxf(z.x, -5.0f), 5.0f);
+            z.y = fminf(fmaxf(z.y, -5.0f), 5.0f);
+            const float2 u = __fmul2_rn(z, z);
+            const float2 q = __ffma2_rn(__ffma2_rn(make_float2(MGDT_ERF_C, MGDT_ERF_C), u, make_float2(MGDT_ERF_B, MGDT_ERF_B)), u,
+                                        make_float2(MGDT_ERF_A, MGDT_ERF_A));
+            const float2 w = __fmul2_rn(z, q);
+            const float2 t = make_float2(tanh_fast(w.x), tanh_fast(w.y));
+            y[j] = __ffma2_rn(h, t, h);
+        } else if (ACT == MGDT_ACT_RELU) {
+            y[j] = make_float2(fmaxf(h.x, 0.f), fmaxf(h.y, 0.f));
+        } else if (ACT == MGDT_ACT_HSIGMOID) {
+            y[j] = make_float2(__saturatef(fmaf(h.x, 1.0f / 6.0f, 0.5f)), __saturatef(fmaf(h.y, 1.0f / 6.0f, 0.5f)));
+        } else {
+            y[j] = h;
+        }
+    }
+    if (p.residual && (opix >= 0 || (pairB && opixB >= 0))) {
+#pragma unroll
+        for (int c8 = 0; c8 < NV; c8 += 8) {
+            const bool second = pairB && c8 >= 16;            // paired unit: columns 16.. are channels 0.. of row opixB
+            const int op = second ? opixB : opix, cc = second ? c8 - 16 : c8;
+            if (op < 0 || co0 + cc >= p.Cout) continue;
+            const __nv_bfloat16* rp = p.residual + (size_t)op * p.res_cs + co0 + cc;
+            if (co0 + cc + 8 <= p.Cout && p.res_vec) {
+                const uint4 ra = __ldg(reinterpret_cast<const uint4*>(rp));
+                const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&ra);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 tt = __bfloat1622float2(ah[j]);
+                    y[c8 / 2 + j].x += tt.x;
+                    y[c8 / 2 + j].y += tt.y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (co0 + cc + j < p.Cout) {
+                        const float add = __bfloat162float(rp[j]);
+                        if (j & 1) y[(c8 + j) / 2].y += add; else y[(c8 + j) / 2].x += add;
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NV / 2; ++j) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(y[j].x, y[j].y);
+        packed[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+}
+template <int NV>
+__device__ __forceinline__ void epi_fast_rt(const P2& p, const uint32_t* r, const float* sB, int cbase, int co0, int opix,
+                                            uint32_t* packed, bool pairB = false, int opixB = -1) {
+    switch (p.act) {   // uniform per launch
+        case MGDT_ACT_SILU: epi_fast<MGDT_ACT_SILU, NV>(p, r, sB, cbase, co0, opix, packed, pairB, opixB); break;
+        case MGDT_ACT_RELU: epi_fast<MGDT_ACT_RELU, NV>(p, r, sB, cbase, co0, opix, packed, pairB, opixB); break;
+        case MGDT_ACT_GELU: epi_fast<MGDT_ACT_GELU, NV>(p, r, sB, cbase, co0, opix, packed, pairB, opixB); break;
+        case MGDT_ACT_SIGMOID: epi_fast<MGDT_ACT_SIGMOID, NV>(p, r, sB, cbase, co0, opix, packed, pairB, opixB); break;
+        case MGDT_ACT_HSIGMOID: epi_fast<MGDT_ACT_HSIGMOID, NV>(p, r, sB, cbase, co0, opix, packed, pairB, opixB); break;
+        default: epi_fast<MGDT_ACT_NONE, NV>(p, r, sB, cbase, co0, opix, packed, pairB, opixB); break;
+    }
+}
+
 // Fused output statistics: the calling epilogue warp has just staged a 32-row x 32-column bf16 unit in its swizzled
 // shared-memory tile (row r at r*64, 16-byte chunk c at slot c ^ ((r >> 1) & 3)).  Lane l owns the column PAIR
 // (2*(l & 15), +1) over the 16 rows r = 2*i + (l >> 4) (an even and an odd row per instruction: all 32 banks, no
@@ -1284,7 +1376,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             // are adjacent 16-column groups in TMEM, so ONE 32-column unit covers both -- columns 0..15 are channels
             // 0..15 of row block mb, columns 16..31 the same channels of row block mb + 1.  The per-unit cost of this
             // latency-bound loop is the same for 16 and 32 columns, so pairing halves the epilogue time of these layers.
-            const bool pair = !STATS && p.pair_ok && pl.Nc == 16 && (rn.MB & 1) == 0 && (p.residual == nullptr || p.Cout <= 8);   // (measured: a loss for 16-channel residual layers)
+            const bool pair = !STATS && p.pair_ok && pl.Nc == 16 && (rn.MB & 1) == 0 && (p.residual == nullptr || p.Cout <= 8) && p.row_scale == nullptr;   // (measured: a loss for 16-channel residual layers)
             const int mbstep = pair ? 2 : 1;
             int u = sub;                                           // units are numbered mg * ncch + cc
             for (int mg = 0; mg * mbstep < rn.MB; ++mg) {
@@ -1461,6 +1553,7 @@ static int g_force_split = -1;     // "conv_split" 0/1/2: override the producer/
 static int g_tma_store = 1;        // "conv_tma_store": TMA tensor stores of 1x1 epilogue units
 static int g_pair = 1;             // "conv_pair": paired 16-column epilogue units
 static int g_use_tma_loads = 1;    // "conv_tma_load": TMA-fed kernel for transform-free 1x1 layers (conv_tma1x1.cuh)
+static int g_tma_stats = 0;        // "conv_tma_stats": also for layers with fused output statistics (measured slower than the 16-epilogue-warp split of conv_umma2_kernel: 96->384 GELU + sum of squares 41 -> 55 us)
 
 #include "conv_tma1x1.cuh"
 
@@ -1683,6 +1776,7 @@ int conv_set_option(const char* name, int value) {
     else if (!strcmp(name, "conv_tma_store")) g_tma_store = value ? 1 : 0;
     else if (!strcmp(name, "conv_pair")) g_pair = value ? 1 : 0;
     else if (!strcmp(name, "conv_tma_load")) g_use_tma_loads = value ? 1 : 0;
+    else if (!strcmp(name, "conv_tma_stats")) g_tma_stats = value ? 1 : 0;
     else return 0;
     return 1;
 }

@@ -151,7 +151,7 @@ class PackedConv:
 WEIGHT_F16 = False
 USE_UMMA = True  # tests flip this to compare the tcgen05 path with the CUDA-core path
 PER_IMAGE_WEIGHTS = os.environ.get('MGDT_PER_IMAGE_W', '1') != '0'  # per-(n,c) input scales folded into per-image weights
-FUSE_TOOD_SIBLINGS = os.environ.get('MGDT_FUSE_TOOD', '1') != '0'  # cls_decomp / reg_decomp / cls_prob_conv1 as one per-image-weight GEMM
+FUSE_TOOD_SIBLINGS = os.environ.get('MGDT_FUSE_TOOD', '0') != '0'  # cls_decomp / reg_decomp / cls_prob_conv1 as one per-image-weight GEMM; measured SLOWER in an in-box A/B (19.5k -> 19.1k images/s: the DCN sampler then reads reg_feat as a slice of an 80-channel map, 108 -> 142 us), so off by default
 FUSE_MSPA_FRONT = True  # MSPA_C2f branch chain as one launch (bf16); tests flip this to compare with the unfused sequence
 
 

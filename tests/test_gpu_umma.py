@@ -164,7 +164,7 @@ def test_mspa_front_fused_vs_unfused(iw, n):
 @pytest.mark.parametrize("kind,shape", [("mspa", (3, 128, 13, 17)), ("mspa", (2, 128, 20, 20)), ("mspa", (5, 256, 8, 8)),
                                         ("convnext", (3, 96, 13, 17)), ("convnext", (2, 96, 40, 40)),
                                         ("conv_gn", (3, 64, 13, 17)), ("conv_gn", (2, 64, 80, 80))])
-def test_fused_epilogue_stats_vs_chan_stats(kind, shape):
+def _fused_epilogue_stats_case(kind, shape):
     """Per-(n,c) statistics accumulated in the tcgen05 conv's epilogue (fp64 atomics + mgdt_stats_finish) against the
     stand-alone mgdt_chan_stats pass, through the modules that use them: SPR gate (2x2 adaptive windows, odd sizes ->
     overlapping windows, images that straddle 32-row groups), GRN (sum of squares), GroupNorm (sum + sum of squares).
@@ -202,6 +202,23 @@ def test_fused_epilogue_stats_vs_chan_stats(kind, shape):
     scale = float(outs[False].abs().max())
     err = float((outs[True] - outs[False]).abs().max()) / scale
     assert err <= 2 ** -7, f"{kind} {shape}: {err:.3e}"
+
+
+def test_fused_epilogue_stats_vs_chan_stats(kind, shape):
+    _fused_epilogue_stats_case(kind, shape)
+
+
+@pytest.mark.parametrize("kind,shape", [("mspa", (2, 32, 20, 28)), ("mspa", (3, 128, 37, 41)), ("convnext", (2, 96, 40, 40)),
+                                        ("convnext", (5, 96, 23, 17))])
+def test_fused_stats_in_tma_kernel(kind, shape):
+    """The same check with the 1x1 statistics layers routed to the TMA-fed kernel (option conv_tma_stats; off by default
+    because it measured slower): per-warp shared-memory accumulators flushed when the image changes."""
+    from mgdt_yolo_b200._lib import lib
+    lib().mgdt_set_option(b"conv_tma_stats", 1)
+    try:
+        _fused_epilogue_stats_case(kind, shape)
+    finally:
+        lib().mgdt_set_option(b"conv_tma_stats", 0)
 
 
 @pytest.mark.parametrize("cin,cout,k", [(16, 16, 3), (8, 8, 3), (32, 16, 1)])
@@ -334,7 +351,7 @@ def test_tood_sibling_convs_as_one_gemm():
             with torch.no_grad():
                 y, raw = head([x.clone()])
         finally:
-            ops.FUSE_TOOD_SIBLINGS = True
+            ops.FUSE_TOOD_SIBLINGS = False
         outs[flag] = (y.float(), raw[0].float())
     for a, b in zip(outs[True], outs[False]):
         err = float((a - b).abs().max()) / float(b.abs().max())

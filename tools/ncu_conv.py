@@ -20,12 +20,15 @@ cases = [  # cin, cout, k, s, H, W, act
     ("c16_32_s2", 16, 32, 3, 2, 320, 320),
     ("c96_384", 96, 384, 1, 1, 40, 40),
     ("c64_256", 64, 256, 1, 1, 80, 80),
+    ("c256_64", 256, 64, 1, 1, 80, 80),
+    ("c32_64", 32, 64, 1, 1, 80, 80),
+    ("c64_256_noact", 64, 256, 1, 1, 80, 80),
 ]
 sel = sys.argv[1:] or [c[0] for c in cases]
 for name, cin, cout, k, s, H, W in cases:
     if name not in sel:
         continue
-    m = Conv(cin, cout, k, s)
+    m = Conv(cin, cout, k, s, act=not name.endswith('_noact'))
     m.load_state_dict(synth_state_dict(m.state_dict(), seed=3))
     m = m.cuda().eval()
     with torch.no_grad():

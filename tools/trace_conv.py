@@ -14,13 +14,15 @@ cases = [("c32_3x3", 32, 32, 3, 1, 80, 80), ("c8_1x1", 8, 8, 1, 1, 160, 160), ("
          ("c64_256_noact", 64, 256, 1, 1, 80, 80), ("c64_256_relu", 64, 256, 1, 1, 80, 80),
          ("c96_384", 96, 384, 1, 1, 40, 40), ("c16_3x3", 16, 16, 3, 1, 80, 80), ("c32_64", 32, 64, 1, 1, 80, 80),
          ("c256_64", 256, 64, 1, 1, 80, 80), ("c16_32_s2", 16, 32, 3, 2, 320, 320), ("c384_96", 384, 96, 1, 1, 40, 40), ("c384_96_grn", 384, 96, 1, 1, 40, 40)]
+cases += [("c96_384_gelu", 96, 384, 1, 1, 40, 40), ("c96_384_gelu_sq", 96, 384, 1, 1, 40, 40), ("c96_384_silu_sq", 96, 384, 1, 1, 40, 40),
+          ("c32_32_q5", 32, 32, 1, 1, 160, 160), ("c32_32_160", 32, 32, 1, 1, 160, 160)]
 cases.append(("stem", 3, 16, 3, 2, 640, 640))
 sel = sys.argv[1:]
 if sel:
     cases = [c for c in cases if c[0] in sel]
-trace = torch.zeros(148 * 2 * 64, dtype=torch.int64, device="cuda")
+trace = torch.zeros(148 * 16 * 64, dtype=torch.int64, device="cuda")
 for name, cin, cout, k, s, H, W in cases:
-    m = Conv(cin, cout, k, s, act=(False if 'noact' in name else nn.ReLU() if 'relu' in name else True))
+    m = Conv(cin, cout, k, s, act=(False if 'noact' in name else nn.ReLU() if 'relu' in name else nn.GELU() if 'gelu' in name else True))
     m.load_state_dict(synth_state_dict(m.state_dict(), seed=3))
     m = m.cuda().eval()
     x = ops.as_act(torch.randn(B, cin, H, W, device="cuda").to(torch.bfloat16))
@@ -32,6 +34,10 @@ for name, cin, cout, k, s, H, W in cases:
         if name.endswith("_grn"):   # GRN-scaled input + residual, as ConvNeXtV2_Block's pwconv2
             kw = dict(in_scale=(torch.rand(B, cin, device="cuda") + 0.5).contiguous(),
                       residual=ops.as_act(torch.randn(B, cout, H, W, device="cuda").to(torch.bfloat16)))
+        if name.endswith("_sq"):
+            kw = dict(stat=ops.StatReq(0, True))
+        if name.endswith("_q5"):
+            kw = dict(stat=ops.StatReq(5, False))
         for _ in range(3):
             m(x, **kw)
         torch.cuda.synchronize()
