@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGDT_ABI_VERSION 2
+#define MGDT_ABI_VERSION 3
 
 enum { MGDT_F32 = 0, MGDT_BF16 = 1 };
 enum { MGDT_ACT_NONE = 0, MGDT_ACT_SILU = 1, MGDT_ACT_RELU = 2, MGDT_ACT_SIGMOID = 3, MGDT_ACT_HSIGMOID = 4,
@@ -57,6 +57,8 @@ void mgdt_set_pdl(int on);
  *   "pdl"            1   programmatic dependent launch
  *   "conv_tma_load"  1   TMA-fed kernel (cp.async.bulk.tensor loads) for transform-free 1x1 convolutions
  *   "conv_tma_stats" 0   ... also for layers with fused output statistics (slower than the cp.async kernel's 16-warp epilogue)
+ *   "conv_ksplit"    0   K = 16 steps of a tile rotate over 2 / 4 partial TMEM accumulators summed by the epilogue (an
+ *                        experiment: measured no gain, tcgen05.mma accumulation chains are not the bound)
  *   "conv_tma_store" 1   TMA tensor stores of 1x1 epilogue units
  *   "conv_pair"      1   paired 16-column epilogue units (Cout <= 16)
  *   "conv_split"    -1   force the producer / epilogue warp split of the cp.async conv kernel (0 / 1 / 2) */
@@ -108,6 +110,11 @@ typedef struct mgdt_conv_args {
      * pre_add, pix_scale and in_relu must then be unset.  The same product as in_scale on the activations
      * (W (s_n o x) = (W diag(s_n)) x) without the loader's in-place transform; tiles are cut per image. */
     int32_t w_per_image;
+    /* act applies to output channels < act_cols only (0 = all); the rest get no activation.  Lets two 1x1 convs on the
+     * same input run as one launch although only one of them is followed by an activation (InjectionMultiSum's
+     * global_act -> h_sigmoid next to global_embedding, block.py:381-393).  Must be a multiple of 32; implemented by the
+     * TMA-fed 1x1 kernel (mgdt_conv2d_path == 4), -ENOTSUP elsewhere. */
+    int32_t act_cols;
 } mgdt_conv_args;
 int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
 /* Which kernel mgdt_conv2d would run for these arguments: 3 = conv_pointwise_kernel (narrow 1x1 layers, CUDA cores,
@@ -254,6 +261,10 @@ int mgdt_sppf_pool(const void* x, int x_cs, void* y1, void* y2, void* y3, int y_
  * of (act, feat) without h_sigmoid. */
 int mgdt_inject(const void* local, int l_cs, const void* gact, int a_cs, const void* gfeat, int f_cs, void* y, int y_cs,
                 int N, int H, int W, int Hg, int Wg, int C, int dtype, void* stream);
+/* Same; gact_is_hsig = 1: `gact` already holds h_sigmoid(global_act), applied by the producing convolution's epilogue
+ * (mgdt_conv_args.act = HSIGMOID with act_cols): bf16 exact-2x upsampling only, -ENOTSUP otherwise. */
+int mgdt_inject2(const void* local, int l_cs, const void* gact, int a_cs, const void* gfeat, int f_cs, void* y, int y_cs,
+                 int N, int H, int W, int Hg, int Wg, int C, int gact_is_hsig, int dtype, void* stream);
 
 /* uint8 NCHW -> NHWC float/bf16, scaled by 1/255 (BasePredictor.preprocess,
  * yolo/engine/predictor.py:115-130).  Also float NCHW -> NHWC (scale 1). */

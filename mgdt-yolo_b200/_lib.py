@@ -13,7 +13,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmgdt_b200.so")
 
-ABI_VERSION = 2  # include/mgdt_b200.h MGDT_ABI_VERSION
+ABI_VERSION = 3  # include/mgdt_b200.h MGDT_ABI_VERSION
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_RELU, ACT_SIGMOID, ACT_HSIGMOID, ACT_GELU = range(6)
 RS_COPY, RS_AVGPOOL, RS_BILINEAR, RS_NEAREST = range(4)
@@ -28,7 +28,7 @@ class ConvArgs(C.Structure):
                 ("kh", i32), ("kw", i32), ("stride", i32), ("pad", i32),
                 ("x_cs", i32), ("y_cs", i32), ("add_cs", i32), ("ps_cs", i32), ("res_cs", i32),
                 ("act", i32), ("in_relu", i32), ("dtype", i32), ("impl", i32), ("w_umma", vp), ("w_umma_f16", i32),
-                ("stat_acc", vp), ("stat_q", i32), ("stat_sq", i32), ("stat_copies", i32), ("w_per_image", i32)]
+                ("stat_acc", vp), ("stat_q", i32), ("stat_sq", i32), ("stat_copies", i32), ("w_per_image", i32), ("act_cols", i32)]
 
 
 class StatsFin(C.Structure):
@@ -80,6 +80,7 @@ SIGNATURES = {
     "mgdt_resample": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_sppf_pool": (C.c_int, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_inject": (C.c_int, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_inject2": (C.c_int, [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_preprocess": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_decode": (C.c_int, [C.POINTER(DecodeLevel), i32, i32, i32, i32, i32, vp, i32, vp]),
     "mgdt_nms_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
@@ -104,7 +105,7 @@ def lib():
         if L.mgdt_abi_version() != ABI_VERSION:
             raise RuntimeError("mgdt_yolo_b200: ABI version mismatch, rebuild the library")
         # the library reads no environment variables: forward the documented MGDT_* switches once, here
-        for env, opt in (("MGDT_PDL", "pdl"), ("MGDT_CONV_TMA_LOAD", "conv_tma_load"), ("MGDT_CONV_TMA_STORE", "conv_tma_store"), ("MGDT_CONV_TMA_STATS", "conv_tma_stats"),
+        for env, opt in (("MGDT_PDL", "pdl"), ("MGDT_CONV_TMA_LOAD", "conv_tma_load"), ("MGDT_CONV_TMA_STORE", "conv_tma_store"), ("MGDT_CONV_TMA_STATS", "conv_tma_stats"), ("MGDT_CONV_KSPLIT", "conv_ksplit"),
                          ("MGDT_CONV_PAIR", "conv_pair"), ("MGDT_CONV_SPLIT", "conv_split")):
             v = os.environ.get(env)
             if v is not None and v.lstrip("-").isdigit():

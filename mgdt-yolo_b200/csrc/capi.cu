@@ -47,7 +47,7 @@ extern "C" int mgdt_set_option(const char* name, int value) {
     return set_error(-EINVAL, "set_option: unknown option '%s'", name);
 }
 extern "C" int mgdt_conv2d_path(const mgdt_conv_args* a) {
-    if (a && a->impl == 0 && !a->stat_acc && !a->w_per_image && conv2d_pointwise_supported(a)) return 3;
+    if (a && a->impl == 0 && !a->stat_acc && !a->w_per_image && !a->act_cols && conv2d_pointwise_supported(a)) return 3;
 #ifdef MGDT_WITH_UMMA
     if (a && a->impl != 1 && conv2d_umma_supported(a)) return conv2d_umma_path(a);
 #endif
@@ -75,12 +75,13 @@ extern "C" int mgdt_conv2d(const mgdt_conv_args* a, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     MGDT_CHECK(!a->stat_acc || ((a->stat_q == 0 || a->stat_q == 1 || a->stat_q == 5) && a->stat_q + (a->stat_sq ? 1 : 0) > 0 &&
                                 ((uintptr_t)a->stat_acc & 7) == 0), "conv2d: bad fused-statistics request");
-    if (a->impl == 0 && !a->stat_acc && !a->w_per_image && conv2d_pointwise_supported(a)) return conv2d_pointwise(a, s);   // narrow 1x1 layers: HBM-bound SIMT
+    if (a->impl == 0 && !a->stat_acc && !a->w_per_image && !a->act_cols && conv2d_pointwise_supported(a)) return conv2d_pointwise(a, s);   // narrow 1x1 layers: HBM-bound SIMT
 #ifdef MGDT_WITH_UMMA
     if (a->impl != 1 && conv2d_umma_supported(a)) return conv2d_umma(a, s);
 #endif
     if (a->stat_acc) return set_error(-ENOTSUP, "conv2d: fused statistics need the tcgen05 path (see mgdt_conv2d_path)");
     if (a->w_per_image) return set_error(-ENOTSUP, "conv2d: per-image weights need the tcgen05 path (see mgdt_conv2d_path)");
+    if (a->act_cols) return set_error(-ENOTSUP, "conv2d: act_cols needs the TMA-fed 1x1 kernel (see mgdt_conv2d_path)");
 #ifdef MGDT_WITH_UMMA
     MGDT_CHECK(a->impl != 2, "conv2d: tcgen05 path does not support this shape");
 #else

@@ -248,17 +248,18 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
                     const int kb0 = st * t.kb_stage, nk = min(t.kb_stage, t.nkb - kb0);
                     const uint32_t sA = sStage32 + (uint32_t)s * t.stage_bytes;
                     const uint32_t wb = t.w_ring ? sA + t.a_stage_bytes : sW32 + (uint32_t)(kb0 * (t.KB / 8)) * wchunk_bytes;
-                    const uint32_t d0 = tmem_base + (uint32_t)(a * Nsub);
+                    const uint32_t d0 = tmem_base + (uint32_t)(a * t.KS * Nsub);
                     const int steps = t.KB / 16;
                     for (int j = 0; j < nk; ++j) {
                         for (int e = 0; e < steps; ++e) {
                             const uint64_t adesc = mk_desc_sw(sA + (uint32_t)j * t.a_kb_bytes + (uint32_t)e * 32u, sbo, lay);
                             const uint64_t bdesc = mk_desc(wb + (uint32_t)((j * steps + e) * 2) * wchunk_bytes, wchunk_bytes, 128u);
-                            const uint32_t acc = (st > 0 || j > 0 || e > 0) ? 1u : 0u;
+                            const int g = (kb0 + j) * steps + e;               // K = 16 step of this tile
+                            const uint32_t acc = g >= t.KS ? 1u : 0u;          // the first step of every partial accumulator overwrites
                             asm volatile(
                                 "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-                                ::"r"(d0), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
+                                ::"r"(d0 + (uint32_t)((g & (t.KS - 1)) * Nsub)), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
                         }
                     }
                     umma_commit(EMPTY(s));
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
                 const int co0 = ns * pl.Nc + col0 + cl;
                 if (!any_row || co0 >= p.Cout) continue;
                 const int nv = min(32, Nsub - cl);
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * Nsub + cl);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * t.KS * Nsub + cl);
                 uint32_t r[32], pk[16];
                 const bool tr = trw && ti == 1;
                 long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
@@ -340,8 +341,12 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
                           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    for (int h = 1; h < t.KS; ++h) {
+                        tmem_ld_add16(taddr + (uint32_t)(h * Nsub), r);
+                        tmem_ld_add16(taddr + (uint32_t)(h * Nsub + 16), r + 16);
+                    }
                     if (tr) tc1 = clock64();
-                    epi_fast_rt<32>(p, r, sBias, cl, co0, opix, pk);
+                    epi_fast_rt<32>(p, r, sBias, cl, co0, opix, pk, false, -1, (p.act_cols && co0 >= p.act_cols) ? MGDT_ACT_NONE : p.act);
                 } else {
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -349,7 +354,8 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    epi_fast_rt<16>(p, r, sBias, cl, co0, opix, pk);
+                    for (int h = 1; h < t.KS; ++h) tmem_ld_add16(taddr + (uint32_t)(h * Nsub), r);
+                    epi_fast_rt<16>(p, r, sBias, cl, co0, opix, pk, false, -1, (p.act_cols && co0 >= p.act_cols) ? MGDT_ACT_NONE : p.act);
 #pragma unroll
                     for (int j = 8; j < 16; ++j) pk[j] = 0u;
                 }
@@ -457,6 +463,17 @@ static bool plan_t1(const P2& p, T1& t) {
         cols = 32;
         while (cols < t.Nsub) cols <<= 1;
     }
+    // K-split partial accumulators (see try_run2): a tile here is one 128-row block, so its K = 16 steps form a single
+    // dependent chain (~310 cycles each) unless they rotate over KS accumulators; wide-K layers (256 -> 64: 16 steps)
+    // would otherwise spend 5,000 cycles per tile waiting on themselves
+    t.KS = 1;
+    const int ksteps = p.Cin / 16;
+    if (g_ksplit)
+        for (int ks = 4; ks >= 2; ks >>= 1) {
+            int c2 = 32;
+            while (c2 < t.NACC * ks * t.Nsub) c2 <<= 1;
+            if (c2 * want_ctas <= 512 && ks * 2 <= ksteps) { t.KS = ks; cols = c2; break; }
+        }
     t.tmem_cols = cols;
     t.per_img = p.w_img_elems ? 1 : 0;
     const long long HW = (long long)p.H * p.W;
@@ -521,6 +538,7 @@ static int launch_t1k(const P2& p, dim3 grid, cudaStream_t s) {
 
 // Try the TMA kernel for this (already filled) mode-0 layer: 1 = launched, 0 = not eligible, < 0 = error.
 static bool t1_eligible(const P2& p) {
+    if (p.act_cols && t1_bias_scale(p.act) != 1.0f) return false;   // the bias is pre-scaled per launch, not per column range
     return g_use_tma_loads && (g_tma_stats || !p.st_acc) && !p.stem_src && !p.dcn_off && !p.pre_add && !p.in_scale && !p.pix_scale && !p.in_relu;
 }
 

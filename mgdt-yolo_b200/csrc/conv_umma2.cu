@@ -57,6 +57,8 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
     return (uint32_t)(((unsigned long long)n * f.mul) >> f.shr);
 }
 
+static int g_ksplit = 0;   // option "conv_ksplit": K-split partial accumulators (see try_run2 / plan_t1); measured: no gain (the MMA phase is not bound by accumulator dependencies), so off
+
 struct Plan2 {
     int mode;      // 0: 1x1 s1 (also DCN), 1: 3x3 s1, 2: 3x3 s2
     int planes, npar, taps;
@@ -69,6 +71,7 @@ struct Plan2 {
 
 struct Run2 {
     int MB, S, NACC, P, Wq, halo, pstride16, tiles_per_img, tmem_cols;
+    int KS;        // independent partial accumulators per row block (K-split): consecutive MMAs of a row block rotate over them
     int per_img;   // mode 0 tiled per image (tiles never straddle images): needed for per-image weights
     long long tiles;
     unsigned a_bytes, w_slice_bytes, stage_bytes, wres_bytes, smem_total;
@@ -180,8 +183,17 @@ static bool try_run2(const Plan2& p, int MB, int N, int H, int W, int Ho, int Wo
     if (S < 2) return false;
     r.S = S;
     r.smem_total = r.wres_bytes + S * r.stage_bytes + U2_TAIL;
+    // The MMAs of a tile are issued by up to four warps (Roles::NMW: one thread issues only one tcgen05.mma per ~154
+    // cycles), each owning whole accumulation chains.  A chain = (row block, partial accumulator): the K = 16 steps of a
+    // row block rotate over KS partial accumulators (summed by the epilogue) so that even a one-row-block tile has four
+    // independent chains, MB * KS >= 4.
+    r.KS = 1;
+    const long long nmma_total = (long long)p.nmma_s * p.nks;
+    if (g_ksplit)
+        for (int ks = 4; ks >= 2; ks >>= 1)
+            if (MB * (ks / 2) < 4 && r.NACC * ks * MB * p.Nc <= 512 && ks * 2 <= nmma_total) { r.KS = ks; break; }
     int cols = 32;
-    while (cols < r.NACC * MB * p.Nc) cols <<= 1;
+    while (cols < r.NACC * r.KS * MB * p.Nc) cols <<= 1;
     r.tmem_cols = cols;
     return true;
 }
@@ -283,7 +295,7 @@ struct T1 {
     int KB, nkb;          // channels per K block (= swizzle atom: 64 / 32 / 16), K blocks
     int kb_stage, nst, S; // K blocks per ring stage, stages per tile, ring depth
     int Nsub, nsub;       // columns per CTA, column sub-splits of a packed column block
-    int NACC, tmem_cols, w_ring, swz, ctas_per_sm, per_img, tiles_per_img, epiw;
+    int NACC, KS, tmem_cols, w_ring, swz, ctas_per_sm, per_img, tiles_per_img, epiw;
     unsigned a_kb_bytes, a_stage_bytes, w_stage_bytes, stage_bytes, w_bytes, smem_total;
     long long tiles;
 };
@@ -295,6 +307,7 @@ struct P2 {
     __nv_bfloat16* y;
     int N, H, W, Cin, Cout, Ho, Wo;
     int x_cs, y_cs, add_cs, ps_cs, res_cs, act, in_relu;
+    int act_cols;                // activation on output channels < act_cols only (0 = all); TMA kernel
     int y_vec, res_vec;
     int w_f16;                   // weights packed as fp16 (B operand format F16), activations stay bf16
     float out_scale;             // accumulator scale applied with the bias (1/255 for the uint8 stem, else 1)
@@ -460,10 +473,16 @@ template <int LOADER, int SPLIT> struct Roles {
     // kernel (measured; tools/ubench/cpasync.cu gives 50-115 cycles for a bare loop), so the producer/epilogue split
     // is chosen per layer by the host cost model (SPLIT 0/1/2 = 3/16, 7/12, 11/8 producer/epilogue warps).  DCN
     // sampling and the stem's byte gather are instruction-bound and take most of the CTA.
+    // MMA warps.  tools/ubench/umma_rate.cu: one thread issues a tcgen05.mma every ~150-300 cycles (the latency-bound
+    // instruction sequence around each UTCHMMA), four threads together one per 40-75 cycles whatever N <= 64, the
+    // layout or the alignment -- so the tensor core is NOT the limit of the small-N layers.  Spreading the chains of a
+    // tile over 2 / 4 issuing warps (NMW = 4 with 8 / 4 producer warps) was measured in this kernel and did not help:
+    // the 3x3 32->32 tile went from 2.9 to 4.0 us (trace_conv.py), 19.5k -> 17.7k images/s, so NMW stays 1.
+    static constexpr int NMW = 1;
     static constexpr int NPW = (LOADER == LD_ASYNC || LOADER == LD_XFORM) ? (SPLIT == 0 ? 3 : SPLIT == 1 ? 7 : 11)
                                : LOADER == LD_DCN ? 15 : 11;
-    static constexpr int MMAW = NPW;                          // the MMA warp
-    static constexpr int EPI0 = NPW + 1;                      // first epilogue warp (a multiple of 4: quadrant = warp % 4)
+    static constexpr int MMAW = NPW;                          // first MMA warp
+    static constexpr int EPI0 = NPW + NMW;                    // first epilogue warp (a multiple of 4: quadrant = warp % 4)
     static constexpr int NEW = U2_WARPS - EPI0;               // epilogue warps (16 or 12), NEW / 4 per lane quadrant
     static constexpr int NP = NPW * 32;                       // producer threads = arrival count of full[] / wready
 };
@@ -792,8 +811,8 @@ __device__ __forceinline__ void epi_fast(const P2& p, const uint32_t* r, const f
 }
 template <int NV>
 __device__ __forceinline__ void epi_fast_rt(const P2& p, const uint32_t* r, const float* sB, int cbase, int co0, int opix,
-                                            uint32_t* packed, bool pairB = false, int opixB = -1) {
-    switch (p.act) {   // uniform per launch
+                                            uint32_t* packed, bool pairB = false, int opixB = -1, int act = -1) {
+    switch (act < 0 ? p.act : act) {   // uniform per unit
         case MGDT_ACT_SILU: epi_fast<MGDT_ACT_SILU, NV>(p, r, sB, cbase, co0, opix, packed, pairB, opixB); break;
         case MGDT_ACT_RELU: epi_fast<MGDT_ACT_RELU, NV>(p, r, sB, cbase, co0, opix, packed, pairB, opixB); break;
         case MGDT_ACT_GELU: epi_fast<MGDT_ACT_GELU, NV>(p, r, sB, cbase, co0, opix, packed, pairB, opixB); break;
@@ -863,6 +882,19 @@ __device__ __forceinline__ void epi_stats(double* acc, int Q, int sq, int want_t
     }
 }
 
+// r16[0..15] += the 16 accumulator columns at taddr (this lane's row): the partial accumulators of a K-split tile
+__device__ __forceinline__ void tmem_ld_add16(uint32_t taddr, uint32_t* r16) {
+    uint32_t t[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]),
+          "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r16[j] = __float_as_uint(__uint_as_float(r16[j]) + __uint_as_float(t[j]));
+}
+
 template <int MODE, int LOADER, int SPLIT, int STATS>
 __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_constant__ P2 p) {
     pdl_trigger();
@@ -872,7 +904,8 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ns = blockIdx.y;
     constexpr int NPW = Roles<LOADER, SPLIT>::NPW, NEW = Roles<LOADER, SPLIT>::NEW, NP = Roles<LOADER, SPLIT>::NP;
-    constexpr int MMAW = Roles<LOADER, SPLIT>::MMAW, EPI0 = Roles<LOADER, SPLIT>::EPI0;
+    constexpr int MMAW = Roles<LOADER, SPLIT>::MMAW, EPI0 = Roles<LOADER, SPLIT>::EPI0, NMW = Roles<LOADER, SPLIT>::NMW;
+    static_assert(EPI0 % 4 == 0, "epilogue warps must start at a multiple of four");
 
     if (tid == 0) trace_mark(p, 0);
     unsigned char* sWres = smem;
@@ -920,8 +953,8 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int s = 0; s < rn.S; ++s) { mbar_init(FULL(s), NP); mbar_init(EMPTY(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(ACCFULL(a), 1); mbar_init(ACCEMPTY(a), NEW); }
+        for (int s = 0; s < rn.S; ++s) { mbar_init(FULL(s), NP); mbar_init(EMPTY(s), NMW); }
+        for (int a = 0; a < 2; ++a) { mbar_init(ACCFULL(a), NMW); mbar_init(ACCEMPTY(a), NEW); }
         mbar_init(WREADY, NP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1291,8 +1324,9 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(FULL(xf_s));
         }
-    } else if (warp == MMAW) {
-        // =============================================================== MMA issuer
+    } else if (warp < EPI0) {
+        // =============================================================== MMA issuers (warps MMAW .. MMAW + NMW - 1)
+        const int mw = warp - MMAW;   // this warp owns the chains (row block mb, partial accumulator h) with (mb * KS + h) % NMW == mw
         // The whole warp walks the pipeline (uniform control flow); the tcgen05 instructions are issued by the one
         // lane elect.sync picks, which lets ptxas emit them without a per-lane waterfall loop.
         // instruction descriptor: D = f32, A = bf16, B = bf16 or f16, both K-major, N = Nc, M = 128
@@ -1313,7 +1347,8 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                 if (elect_one()) {
                     const uint32_t a0 = s_u32(sStage + (size_t)s * rn.stage_bytes);
                     const uint32_t w0 = rn.w_slice_bytes ? a0 + rn.a_bytes : s_u32(sWres) + (uint32_t)ks * (uint32_t)(w_slice_elems * 2);
-                    const uint32_t d0 = tmem_base + (uint32_t)(a * rn.MB * pl.Nc);
+                    const uint32_t d0 = tmem_base + (uint32_t)(a * rn.KS * rn.MB * pl.Nc);
+                    const int kmask = rn.KS - 1;
                     const uint64_t abase = (uint64_t)(a0 >> 4), wbase = (uint64_t)(w0 >> 4);
                     // descriptors are fetched four at a time ahead of the instructions that use them
                     for (int i0 = 0; i0 < pl.nmma_s; i0 += 4) {
@@ -1324,20 +1359,23 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                         for (int u = 0; u < 4; ++u) {
                             if (i0 + u < pl.nmma_s) {
                                 const uint64_t bdesc = dsc[u].y + wbase;
-                                const uint32_t acc = (ks > 0 || i0 + u > 0) ? 1u : 0u;
+                                const int g = ks * pl.nmma_s + i0 + u;             // K = 16 step of this tile
+                                const uint32_t acc = g >= rn.KS ? 1u : 0u;         // the first step of every partial accumulator overwrites
+                                const uint32_t dh = d0 + (uint32_t)((g & kmask) * rn.MB * pl.Nc);
                                 for (int mb = 0; mb < rn.MB; ++mb) {
+                                    if (NMW > 1 && ((mb * rn.KS + (g & kmask)) & (NMW - 1)) != mw) continue;
                                     const uint64_t adesc = dsc[u].x + abase + (uint64_t)(mb * 128);   // 2048 B per row block
                                     asm volatile(
                                         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-                                        ::"r"(d0 + (uint32_t)(mb * pl.Nc)), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
+                                        ::"r"(dh + (uint32_t)(mb * pl.Nc)), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
                                 }
                             }
                         }
                     }
                     umma_commit(EMPTY(s));                       // smem stage may be refilled once these MMAs retire
                     if (ks == nks - 1) umma_commit(ACCFULL(a));  // accumulators complete
-                    if (it < 6) trace_mark(p, 9 + 8 * (int)it);
+                    if (mw == 0 && it < 6) trace_mark(p, 9 + 8 * (int)it);
                 }
                 __syncwarp();
                 if (++s == rn.S) { s = 0; ph ^= 1; }
@@ -1411,7 +1449,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                     if (!any_row || co0 >= p.Cout) continue;
                     const int nv = pair ? 32 : min(32, pl.Nc - cl);   // 32, or 16 for the last unit when Nc % 32 == 16
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                           (uint32_t)(a * rn.MB * pl.Nc + mb * pl.Nc + cl);
+                                           (uint32_t)(a * rn.KS * rn.MB * pl.Nc + mb * pl.Nc + cl);
                     uint32_t r[32], pk[16];
                     const bool tr = trw && ti == 1;
                     long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
@@ -1426,6 +1464,10 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                             : "r"(taddr));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        for (int h = 1; h < rn.KS; ++h) {
+                            tmem_ld_add16(taddr + (uint32_t)(h * rn.MB * pl.Nc), r);
+                            tmem_ld_add16(taddr + (uint32_t)(h * rn.MB * pl.Nc + 16), r + 16);
+                        }
                         if (tr) tc1 = clock64();
                         epi_math<32>(p, r, sBias, cl, co0, opix, pk, pair, opixB);
                     } else {
@@ -1435,6 +1477,7 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                             : "r"(taddr));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        for (int h = 1; h < rn.KS; ++h) tmem_ld_add16(taddr + (uint32_t)(h * rn.MB * pl.Nc), r);
                         if (tr) tc1 = clock64();
                         epi_math<16>(p, r, sBias, cl, co0, opix, pk);
 #pragma unroll
@@ -1624,6 +1667,7 @@ static int launch2(P2& p, cudaStream_t s) {
         const int rc = try_launch_t1(p, s);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
+    if (p.act_cols) return set_error(-ENOTSUP, "conv2d: act_cols needs the TMA-fed 1x1 kernel (see mgdt_conv2d_path)");
     const long long tiles = p.rn.tiles;
     int ctas = (int)(tiles < 148 ? tiles : 148);
     if (p.pl.nsplit > 1) ctas = (int)std::max(1LL, std::min(tiles, (long long)(148 / p.pl.nsplit)));
@@ -1651,6 +1695,7 @@ bool conv2d_umma_supported(const mgdt_conv_args* a) {
     if (a->stat_acc && (a->stride != 1 || a->pre_add || a->in_scale || a->pix_scale || a->in_relu)) return false;
     // per-image weights (w_umma = N packed images): transform-free loader only, nothing else scaled per (n, c)
     if (a->w_per_image && (a->pre_add || a->in_scale || a->pix_scale || a->in_relu)) return false;
+    if (a->act_cols && (a->act_cols % 32 != 0 || a->kh != 1 || a->stride != 1 || a->stat_acc)) return false;
     Plan2 pl; Run2 rn; int Ho, Wo;
     if (!plan2_for(a->Cin, a->Cout, a->kh, a->stride, a->N, a->H, a->W, pl, rn, Ho, Wo, a->w_per_image != 0)) return false;
     if (((uintptr_t)a->x & 15) || (a->x_cs & 7)) return false;
@@ -1676,7 +1721,7 @@ static int fill_p2(const mgdt_conv_args* a, P2& p) {
     }
     p.N = a->N; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.Cout = a->Cout; p.Ho = Ho; p.Wo = Wo;
     p.x_cs = a->x_cs; p.y_cs = a->y_cs; p.add_cs = a->add_cs; p.ps_cs = a->ps_cs; p.res_cs = a->res_cs;
-    p.act = a->act; p.in_relu = a->in_relu;
+    p.act = a->act; p.in_relu = a->in_relu; p.act_cols = a->act_cols;
     p.w_f16 = a->w_umma_f16; p.out_scale = 1.0f;
     p.y_vec = (((uintptr_t)a->y & 15) == 0 && (a->y_cs & 7) == 0) ? 1 : 0;
     p.res_vec = (a->residual && ((uintptr_t)a->residual & 15) == 0 && (a->res_cs & 7) == 0) ? 1 : 0;
@@ -1719,7 +1764,7 @@ int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void
     p.x = (const __nv_bfloat16*)x; p.w = (const __nv_bfloat16*)w_umma; p.pre_add = nullptr; p.pix_scale = nullptr;
     p.residual = nullptr; p.bias = nullptr; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y; p.row_scale = nullptr;
     p.N = N; p.H = H; p.W = W; p.Cin = 9 * Cin; p.Cout = Cout; p.Ho = H; p.Wo = W;
-    p.x_cs = x_cs; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = MGDT_ACT_NONE; p.in_relu = 0;
+    p.x_cs = x_cs; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = MGDT_ACT_NONE; p.in_relu = 0; p.act_cols = 0;
     p.w_f16 = w_f16; p.out_scale = 1.0f;
     p.y_vec = (((uintptr_t)y & 15) == 0 && (y_cs & 7) == 0) ? 1 : 0;
     p.res_vec = 0;
@@ -1749,7 +1794,7 @@ int stem_umma(const void* src, int src_is_u8, const void* w_umma, int w_f16, con
     p.x = nullptr; p.w = (const __nv_bfloat16*)w_umma; p.pre_add = nullptr; p.pix_scale = nullptr; p.residual = nullptr;
     p.bias = bias; p.in_scale = nullptr; p.y = (__nv_bfloat16*)y; p.row_scale = nullptr;
     p.N = N; p.H = Ho; p.W = Wo; p.Cin = Kp; p.Cout = Cout; p.Ho = Ho; p.Wo = Wo;
-    p.x_cs = 0; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = act; p.in_relu = 0;
+    p.x_cs = 0; p.y_cs = y_cs; p.add_cs = p.ps_cs = p.res_cs = 0; p.act = act; p.in_relu = 0; p.act_cols = 0;
     p.w_f16 = w_f16;
     // the fast uint8 loader stages exact integers and leaves the /255 to the epilogue
     const bool u8_fast = src_is_u8 && C == 3 && p.pl.PS == 4 && W % 4 == 0 && ((uintptr_t)src & 3) == 0;
@@ -1777,6 +1822,7 @@ int conv_set_option(const char* name, int value) {
     else if (!strcmp(name, "conv_pair")) g_pair = value ? 1 : 0;
     else if (!strcmp(name, "conv_tma_load")) g_use_tma_loads = value ? 1 : 0;
     else if (!strcmp(name, "conv_tma_stats")) g_tma_stats = value ? 1 : 0;
+    else if (!strcmp(name, "conv_ksplit")) g_ksplit = value ? 1 : 0;
     else return 0;
     return 1;
 }

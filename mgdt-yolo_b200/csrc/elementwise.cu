@@ -685,12 +685,21 @@ __global__ void __launch_bounds__(EW_THREADS) inject2x_kernel(const T* __restric
     }
 }
 // bf16 form of inject2x_kernel: all twelve 16-byte loads of a 2x2 output block (8 corners + 4 local chunks) are issued
-// before any arithmetic and kept packed, so a thread has 192 bytes in flight and three CTAs fit on an SM.
+// before any arithmetic and kept packed, so a thread has 192 bytes in flight and three CTAs fit on an SM.  The
+// arithmetic runs on channel PAIRS with packed fp32x2 instructions (the kernel was ALU-bound: ~40 scalar instructions
+// per output element, 81 us for 228 MB): the four bilinear weights of an output pixel are shared by its channels, so
+// sig and gfeat are one FMUL2 + three FFMA2 each.  pre_hsig: gact already holds h_sigmoid(global_act) -- applied in the
+// producing conv's epilogue, BEFORE the interpolation exactly as the reference does (block.py:393).
+__device__ __forceinline__ float2 bf2_unpack(uint32_t w32) { return make_float2(__uint_as_float(w32 << 16), __uint_as_float(w32 & 0xffff0000u)); }
+__device__ __forceinline__ float2 hsig2(float2 v) {
+    const float2 t = __ffma2_rn(v, make_float2(1.0f / 6.0f, 1.0f / 6.0f), make_float2(0.5f, 0.5f));
+    return make_float2(__saturatef(t.x), __saturatef(t.y));
+}
 __global__ void __launch_bounds__(EW_THREADS, 3) inject2x_bf16_kernel(const __nv_bfloat16* __restrict__ local, int l_cs,
                                                                      const __nv_bfloat16* __restrict__ gact, int a_cs,
                                                                      const __nv_bfloat16* __restrict__ gfeat, int f_cs,
                                                                      __nv_bfloat16* __restrict__ y, int y_cs, int Hg, int Wg,
-                                                                     unsigned C, unsigned total) {
+                                                                     unsigned C, unsigned total, int pre_hsig) {
     pdl_trigger();
     pdl_wait();
     using T = __nv_bfloat16;
@@ -722,6 +731,16 @@ __global__ void __launch_bounds__(EW_THREADS, 3) inject2x_bf16_kernel(const __nv
             pix[k] = ((size_t)n * H + min(max(h, 0), H - 1)) * W + min(max(w, 0), W - 1);
             ql[k] = __ldg(reinterpret_cast<const uint4*>(local + pix[k] * l_cs + c));
         }
+        // the gate's corner values as fp32 pairs, h-sigmoided once per corner (not once per output pixel)
+        float2 ga[4][4], gf[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 av = bf2_unpack(reinterpret_cast<const uint32_t*>(&qa[q])[j]);
+                ga[q][j] = pre_hsig ? av : hsig2(av);
+                gf[q][j] = bf2_unpack(reinterpret_cast<const uint32_t*>(&qf[q])[j]);
+            }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (!ok[k]) continue;
@@ -729,23 +748,16 @@ __global__ void __launch_bounds__(EW_THREADS, 3) inject2x_bf16_kernel(const __nv
             float lh, lw;
             bilinear_src(2 * bi - 1 + (k >> 1), Hg, H, h0, h1, lh);   // (h0, h1) == (ra, rb) whenever lh != 0
             bilinear_src(2 * bj - 1 + (k & 1), Wg, W, w0, w1, lw);
+            const float w00 = (1.f - lh) * (1.f - lw), w01 = (1.f - lh) * lw, w10 = lh * (1.f - lw), w11 = lh * lw;
+            const float2 v00 = make_float2(w00, w00), v01 = make_float2(w01, w01), v10 = make_float2(w10, w10), v11 = make_float2(w11, w11);
             uint4 o;
             uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {   // one packed channel pair at a time keeps the temporaries small
-                float r[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    auto ch = [&](const uint4& q) -> float {
-                        const uint32_t w32 = reinterpret_cast<const uint32_t*>(&q)[j];
-                        return __uint_as_float(e ? (w32 & 0xffff0000u) : (w32 << 16));
-                    };
-                    const float sig = (1.f - lh) * ((1.f - lw) * hsig<T>(ch(qa[0])) + lw * hsig<T>(ch(qa[1]))) +
-                                      lh * ((1.f - lw) * hsig<T>(ch(qa[2])) + lw * hsig<T>(ch(qa[3])));
-                    const float gf = (1.f - lh) * ((1.f - lw) * ch(qf[0]) + lw * ch(qf[1])) + lh * ((1.f - lw) * ch(qf[2]) + lw * ch(qf[3]));
-                    r[e] = ch(ql[k]) * sig + gf;
-                }
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(r[0], r[1]);
+            for (int j = 0; j < 4; ++j) {
+                const float2 sig = __ffma2_rn(v11, ga[3][j], __ffma2_rn(v10, ga[2][j], __ffma2_rn(v01, ga[1][j], __fmul2_rn(v00, ga[0][j]))));
+                const float2 g = __ffma2_rn(v11, gf[3][j], __ffma2_rn(v10, gf[2][j], __ffma2_rn(v01, gf[1][j], __fmul2_rn(v00, gf[0][j]))));
+                const float2 r = __ffma2_rn(bf2_unpack(reinterpret_cast<const uint32_t*>(&ql[k])[j]), sig, g);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(r.x, r.y);
                 ow[j] = *reinterpret_cast<const uint32_t*>(&h2);
             }
             *reinterpret_cast<uint4*>(y + pix[k] * y_cs + c) = o;
@@ -756,6 +768,11 @@ __global__ void __launch_bounds__(EW_THREADS, 3) inject2x_bf16_kernel(const __nv
 
 extern "C" int mgdt_inject(const void* local, int l_cs, const void* gact, int a_cs, const void* gfeat, int f_cs,
                            void* y, int y_cs, int N, int H, int W, int Hg, int Wg, int C, int dtype, void* stream) {
+    return mgdt_inject2(local, l_cs, gact, a_cs, gfeat, f_cs, y, y_cs, N, H, W, Hg, Wg, C, 0, dtype, stream);
+}
+
+extern "C" int mgdt_inject2(const void* local, int l_cs, const void* gact, int a_cs, const void* gfeat, int f_cs,
+                            void* y, int y_cs, int N, int H, int W, int Hg, int Wg, int C, int gact_is_hsig, int dtype, void* stream) {
     MGDT_CHECK(local && gact && gfeat && y, "inject: null pointer");
     MGDT_CHECK(N > 0 && H > 0 && W > 0 && Hg > 0 && Wg > 0 && C > 0, "inject: bad shape");
     MGDT_CHECK((long long)N * H * W * C < (1LL << 31) && (long long)N * Hg * Wg * C < (1LL << 31),
@@ -768,13 +785,16 @@ extern "C" int mgdt_inject(const void* local, int l_cs, const void* gact, int a_
                 const unsigned total2 = (unsigned)((long long)N * (Hg + 1) * (Wg + 1) * (C / V));
                 if constexpr (sizeof(T) == 2 && V == 8)
                     launch_k(inject2x_bf16_kernel, dim3(ew_grid(total2, 1)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)local, l_cs,
-                             (const T*)gact, a_cs, (const T*)gfeat, f_cs, (T*)y, y_cs, Hg, Wg, (unsigned)C, total2);
+                             (const T*)gact, a_cs, (const T*)gfeat, f_cs, (T*)y, y_cs, Hg, Wg, (unsigned)C, total2, gact_is_hsig);
+                else if (gact_is_hsig)
+                    return set_error(-ENOTSUP, "inject: a pre-activated gate is implemented for the bf16 exact-2x kernel only");
                 else
                     launch_k(inject2x_kernel<T, V>, dim3(ew_grid(total2)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)local, l_cs,
                              (const T*)gact, a_cs, (const T*)gfeat, f_cs, (T*)y, y_cs, Hg, Wg, (unsigned)C, total2);
                 MGDT_LAUNCH_CHECK("inject");
                 return 0;
             }
+            if (gact_is_hsig) return set_error(-ENOTSUP, "inject: a pre-activated gate is implemented for the bf16 exact-2x kernel only");
             const unsigned total = (unsigned)((long long)N * H * W * (C / V));
             launch_k(inject_kernel<T, V>, dim3(ew_grid(total)), dim3(EW_THREADS), 0, (cudaStream_t)stream, (const T*)local, l_cs, (const T*)gact, a_cs, (const T*)gfeat, f_cs, (T*)y, y_cs, H, W, Hg, Wg,
                 (unsigned)C, total);

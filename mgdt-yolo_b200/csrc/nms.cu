@@ -5,7 +5,14 @@
 //   2. nms_compact  deterministic compaction -> 64-bit keys  (~score_bits << 32 | anchor*nc + class)
 //                   ascending key order == score descending, ties by candidate index (stable sort)
 //   3. nms_rank     rank-by-counting sort of the keys (all SMs; keys are unique) -> sorted keys,
-//                   truncated to max_nms
+//                   truncated to max_nms.  O(n^2) per image: used while an image can have at most NMS_DIRECT_CAP
+//                   candidates (the predictor setting: single label, conf 0.25).
+//   3'. bucketed sort for large candidate sets (the validator setting conf 0.001 + multi_label: A*nc candidates):
+//                   nms_compact also histograms the keys over 16384 buckets (the top 16 bits of the inverted score:
+//                   sign / exponent / 7 mantissa bits, monotone in the key), nms_bscan turns the histogram into
+//                   bucket offsets, nms_scatter groups the keys by bucket, nms_brank ranks every key among the
+//                   members of ITS bucket only: O(n * bucket size) instead of O(n^2) -- 12,800 candidates spread
+//                   over ~1,300 occupied buckets.  Same sorted output, bit for bit (keys are unique).
 //   4. nms_scan     one CTA per image: greedy suppression over the sorted candidates in chunks of
 //                   NMS_CHUNK; each chunk is first tested against the boxes kept so far, then
 //                   resolved internally with a 64-bit IoU bitmask and a find-first-set walk.
@@ -21,6 +28,8 @@ namespace mgdt {
 constexpr int NMS_T = 256;
 constexpr int NMS_CHUNK = 512;       // candidates per scan step == threads of nms_scan
 constexpr int NMS_WORDS = NMS_CHUNK / 32;
+constexpr int NMS_BUCKETS = 16384;   // (key >> 48) - 0xC000 for scores in [0, 2): 2 exponent-range bits + 7 mantissa bits
+constexpr int NMS_DIRECT_CAP = 8192; // images that can hold more candidates than this take the bucketed sort
 
 struct NmsP {
     const float* pred; int N, nc, A; float conf, iou; int multi, agnostic, max_det, max_nms; float max_wh;
@@ -31,7 +40,15 @@ struct NmsP {
     unsigned long long* keys;        // [N][cap]
     unsigned long long* sorted;      // [N][max_nms_eff]
     int sorted_cap;
+    int* hist;                       // bucketed sort: [N][NMS_BUCKETS + 1] counts -> exclusive offsets (+ total)
+    int* cursor;                     // [N][NMS_BUCKETS] scatter cursors (zero on entry)
+    unsigned long long* grouped;     // [N][cap] keys grouped by bucket
 };
+
+__device__ __forceinline__ int key_bucket(unsigned long long key) {
+    const int b = (int)(key >> 48) - 0xC000;   // ascending bucket == ascending key == descending score
+    return b < 0 ? 0 : b;                      // scores >= 2 share bucket 0 (still monotone)
+}
 
 __device__ __forceinline__ bool class_ok(const NmsP& p, int j) {
     if (!p.classes) return true;
@@ -111,7 +128,74 @@ __global__ void __launch_bounds__(NMS_T) nms_compact(NmsP p) {
     int woff = 0;
     for (int i = 0; i < wid; ++i) woff += wpre[i];
     const int off = base_s + woff + incl - c;
-    if (c > 0) anchor_candidates(p, n, a, p.keys + (long long)n * p.cap + off);
+    if (c > 0) {
+        unsigned long long* dst = p.keys + (long long)n * p.cap + off;
+        anchor_candidates(p, n, a, dst);
+        if (p.hist)
+            for (int j = 0; j < c; ++j) atomicAdd(p.hist + (long long)n * (NMS_BUCKETS + 1) + key_bucket(dst[j]), 1);
+    }
+}
+
+// bucket counts -> exclusive offsets (in place), one CTA per image; hist[n][NMS_BUCKETS] receives the total
+__global__ void __launch_bounds__(1024) nms_bscan(NmsP p) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ int wsum[32];
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int* h = p.hist + (long long)n * (NMS_BUCKETS + 1);
+    constexpr int PER = NMS_BUCKETS / 1024;
+    int v[PER], s = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { v[j] = h[tid * PER + j]; s += v[j]; }
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    int run = wsum[wid] + incl - s;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { h[tid * PER + j] = run; run += v[j]; }
+    if (tid == 1023) h[NMS_BUCKETS] = run;
+}
+
+__global__ void __launch_bounds__(NMS_T) nms_scatter(NmsP p) {
+    pdl_trigger();
+    pdl_wait();
+    const int n = blockIdx.y, i = blockIdx.x * NMS_T + threadIdx.x;
+    if (i >= p.ncand[n]) return;
+    const unsigned long long key = p.keys[(long long)n * p.cap + i];
+    const int b = key_bucket(key);
+    const int pos = p.hist[(long long)n * (NMS_BUCKETS + 1) + b] + atomicAdd(p.cursor + (long long)n * NMS_BUCKETS + b, 1);
+    p.grouped[(long long)n * p.cap + pos] = key;
+}
+
+// rank of every key = offset of its bucket + number of smaller keys in the bucket
+__global__ void __launch_bounds__(NMS_T) nms_brank(NmsP p) {
+    pdl_trigger();
+    pdl_wait();
+    const int n = blockIdx.y, i = blockIdx.x * NMS_T + threadIdx.x;
+    if (i >= p.ncand[n]) return;
+    const unsigned long long* g = p.grouped + (long long)n * p.cap;
+    const unsigned long long mine = g[i];
+    const int b = key_bucket(mine);
+    const int* h = p.hist + (long long)n * (NMS_BUCKETS + 1);
+    const int lo = h[b], hi = h[b + 1];
+    int rank = lo;
+    for (int j = lo; j < hi; ++j) rank += (g[j] < mine) ? 1 : 0;
+    if (rank < p.sorted_cap) p.sorted[(long long)n * p.sorted_cap + rank] = mine;
 }
 
 __global__ void __launch_bounds__(NMS_T) nms_rank(NmsP p) {
@@ -258,7 +342,7 @@ __global__ void __launch_bounds__(NMS_CHUNK) nms_scan(NmsP p, float* __restrict_
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-struct NmsLayout { size_t blockcnt, ncand, keys, sorted, total; int nchunks, cap, sorted_cap; };
+struct NmsLayout { size_t blockcnt, ncand, keys, sorted, hist, cursor, grouped, total; int nchunks, cap, sorted_cap, bucketed; };
 
 static NmsLayout nms_layout(int N, int nc, int A, int multi, int max_nms) {
     NmsLayout L;
@@ -270,6 +354,13 @@ static NmsLayout nms_layout(int N, int nc, int A, int multi, int max_nms) {
     L.ncand = off;    off = align_up(off + sizeof(int) * (size_t)N, 256);
     L.keys = off;     off = align_up(off + sizeof(unsigned long long) * (size_t)N * L.cap, 256);
     L.sorted = off;   off = align_up(off + sizeof(unsigned long long) * (size_t)N * L.sorted_cap, 256);
+    L.bucketed = L.cap > NMS_DIRECT_CAP ? 1 : 0;
+    L.hist = L.cursor = L.grouped = off;
+    if (L.bucketed) {   // hist and cursor are adjacent: one memset clears both
+        L.hist = off;    off = align_up(off + sizeof(int) * (size_t)N * (NMS_BUCKETS + 1), 256);
+        L.cursor = off;  off = align_up(off + sizeof(int) * (size_t)N * NMS_BUCKETS, 256);
+        L.grouped = off; off = align_up(off + sizeof(unsigned long long) * (size_t)N * L.cap, 256);
+    }
     L.total = off;
     return L;
 }
@@ -305,12 +396,26 @@ extern "C" int mgdt_nms(const float* pred, int N, int nc, int A, float conf_thre
     p.blockcnt = (int*)(base + L.blockcnt); p.ncand = (int*)(base + L.ncand);
     p.keys = (unsigned long long*)(base + L.keys); p.sorted = (unsigned long long*)(base + L.sorted);
     cudaStream_t s = (cudaStream_t)stream;
+    p.hist = nullptr; p.cursor = nullptr; p.grouped = nullptr;
+    if (L.bucketed) {
+        p.hist = (int*)(base + L.hist); p.cursor = (int*)(base + L.cursor); p.grouped = (unsigned long long*)(base + L.grouped);
+        if (cudaMemsetAsync(base + L.hist, 0, L.grouped - L.hist, s) != cudaSuccess) return set_error(-EIO, "nms: memset failed");
+    }
     launch_k(nms_count, dim3(dim3(L.nchunks, N)), dim3(NMS_T), 0, s, p);
     MGDT_LAUNCH_CHECK("nms_count");
     launch_k(nms_compact, dim3(dim3(L.nchunks, N)), dim3(NMS_T), 0, s, p);
     MGDT_LAUNCH_CHECK("nms_compact");
-    launch_k(nms_rank, dim3(dim3(cdiv(L.cap, NMS_T), N)), dim3(NMS_T), 0, s, p);
-    MGDT_LAUNCH_CHECK("nms_rank");
+    if (L.bucketed) {
+        launch_k(nms_bscan, dim3(N), dim3(1024), 0, s, p);
+        MGDT_LAUNCH_CHECK("nms_bscan");
+        launch_k(nms_scatter, dim3(dim3(cdiv(L.cap, NMS_T), N)), dim3(NMS_T), 0, s, p);
+        MGDT_LAUNCH_CHECK("nms_scatter");
+        launch_k(nms_brank, dim3(dim3(cdiv(L.cap, NMS_T), N)), dim3(NMS_T), 0, s, p);
+        MGDT_LAUNCH_CHECK("nms_brank");
+    } else {
+        launch_k(nms_rank, dim3(dim3(cdiv(L.cap, NMS_T), N)), dim3(NMS_T), 0, s, p);
+        MGDT_LAUNCH_CHECK("nms_rank");
+    }
     const size_t smem = (sizeof(Box) + sizeof(float)) * (size_t)(max_det + NMS_CHUNK) +
                         sizeof(unsigned) * (size_t)(NMS_CHUNK * NMS_WORDS + NMS_WORDS);
     if (smem + 4096 > 48 * 1024) {  // the 48 KB default covers static + dynamic shared memory together

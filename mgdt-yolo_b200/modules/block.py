@@ -366,14 +366,24 @@ class InjectionMultiSum_Auto_pool(KernelModule):
         info = x_g[:, c0:c0 + self.global_inp[self.flag]]  # x_g.split(global_inp, 1)[flag] (block.py:378)
         local = self.local_embedding(x_l)
         both = self._pack_global(info.dtype, info.device)
+        pre_hsig = False
         if both is not None:   # global_act and global_embedding read the same input: one conv with stacked output channels
             w, b, oup = both
-            g = ops.conv2d(info, w, b, 1)
+            n, _, h, wd = local.shape
+            g = None
+            if (info.dtype == torch.bfloat16 and oup % 32 == 0 and h == 2 * info.shape[2] and wd == 2 * info.shape[3]
+                    and info.shape[2] > 1 and info.shape[3] > 1 and oup % 8 == 0):
+                # h_sigmoid of the gate in the conv's epilogue (it precedes the interpolation, block.py:393): once per
+                # low-resolution element instead of four times per output element inside mgdt_inject
+                g = ops.conv2d(info, w, b, 1, act="hsigmoid", act_cols=oup)
+                pre_hsig = g is not None
+            if g is None:
+                g = ops.conv2d(info, w, b, 1)
             gact, gfeat = g[:, :oup], g[:, oup:]
         else:
             gact = self.global_act(info)
             gfeat = self.global_embedding(info)
-        return ops.inject(local, gact, gfeat)
+        return ops.inject(local, gact, gfeat, gact_is_hsig=pre_hsig)
 
     def _pack_global(self, dtype, device):
         """(PackedConv, bias, oup) of global_act and global_embedding stacked along the output channels (both are 1x1

@@ -187,12 +187,14 @@ def _stat_arena(device, nelem):
 
 
 def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scale=None, pix_scale=None,
-           residual=None, in_relu=False, cout=None, impl=0, stat=None, scale_group_cols=None):
+           residual=None, in_relu=False, cout=None, impl=0, stat=None, scale_group_cols=None, act_cols=0):
     """y = act(conv((x + pre_add) * in_scale[n,c] * pix_scale[n,h,w] |> relu?, w) + bias) + residual.
     `w` is a PackedConv (or a plain OHWI (Cout, k, k, Cin) tensor) in x's dtype; `out` may be a channel
     slice of a concat buffer.  With `scale_group_cols`, in_scale is [G, N, Cin] and output columns
     [g*cols, (g+1)*cols) see the input scaled by in_scale[g] (columns past the last group: unscaled) -- sibling
-    convs fused into one GEMM; only the per-image-weight tcgen05 path implements it (returns None otherwise)."""
+    convs fused into one GEMM; only the per-image-weight tcgen05 path implements it (returns None otherwise).
+    `act_cols` > 0: the activation applies to output channels < act_cols only (TMA-fed 1x1 kernel; returns None when
+    another kernel would take the layer)."""
     xp, n, cin, h, wd, xcs = view(x)
     w_umma, w_f16 = None, False
     per_image = False
@@ -248,6 +250,10 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
     a.impl = impl
     a.w_umma = None if (w_umma is None or impl == 1) else w_umma.data_ptr()
     a.w_umma_f16 = 1 if w_f16 else 0
+    if act_cols:
+        a.act_cols = act_cols
+        if lib().mgdt_conv2d_path(C.byref(a)) != 4:
+            return None
     if per_image:
         # W (s_n o x) = (W diag(s_n)) x: if the tcgen05 path takes the layer with per-image weights (tiles cut per image,
         # weight slices carried through the ring), pack one scaled weight image per sample and run the transform-free
@@ -578,7 +584,7 @@ def sppf_pool(x, y1, y2, y3, k=5):
     _invoke("mgdt_sppf_pool", dict(shape=f"sppf C{c} {n}x{h}x{w}", bytes=_nb(x) * 4, flops=0.0), xp, xcs, p1, p2, p3, ycs, n, h, w, c, k, dtype_code(x.dtype), stream_ptr())
 
 
-def inject(local, gact, gfeat, out=None):
+def inject(local, gact, gfeat, out=None, gact_is_hsig=False):
     lp, n, c, h, w, lcs = view(local)
     ap, an, ac, hg, wg, acs = view(gact)
     fp, fn, fc, fh, fw, fcs = view(gfeat)
@@ -587,8 +593,8 @@ def inject(local, gact, gfeat, out=None):
     if out is None:
         out = new_act(n, c, h, w, local.dtype, local.device)
     yp, *_, ycs = view(out)
-    _invoke("mgdt_inject", dict(shape=f"inject C{c} {n}x{h}x{w}", bytes=_nb(local, gact, gfeat, out), flops=0.0), lp, lcs, ap, acs, fp, fcs, yp, ycs, n, h, w, hg, wg, c, dtype_code(local.dtype),
-                            stream_ptr())
+    _invoke("mgdt_inject2", dict(shape=f"inject C{c} {n}x{h}x{w}", bytes=_nb(local, gact, gfeat, out), flops=0.0, kernel="inject_kernel"), lp, lcs, ap, acs, fp, fcs, yp, ycs,
+            n, h, w, hg, wg, c, 1 if gact_is_hsig else 0, dtype_code(local.dtype), stream_ptr())
     return out
 
 

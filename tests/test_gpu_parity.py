@@ -191,3 +191,22 @@ def test_other_width_scales_vs_oracle(cfg):
     assert float((y32.float().cpu() - y_ref).abs().max()) / scale <= 1e-4
     l2 = float((y16.float().cpu() - y_ref).norm() / y_ref.norm())
     assert l2 <= 1e-2, f"{cfg}: bf16 relative L2 {l2:.3e}"
+
+
+@pytest.mark.parametrize("nc,anchors,batch,kw", [
+    (80, 8400, 2, dict(conf_thres=0.001, iou_thres=0.7, multi_label=True)),           # 672,000 pairs/img -> max_nms truncation
+    (2, 6400, 32, dict(conf_thres=0.001, iou_thres=0.7, multi_label=True)),           # the validator setting at B = 32
+    (2, 6400, 4, dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=1000)),  # long scan: several 512-chunks
+])
+def test_nms_validator_setting_vs_oracle(nc, anchors, batch, kw):
+    """DetectionValidator.postprocess (yolo/v8/detect/val.py:63-71: conf 0.001, multi_label) -- every (box, class) pair
+    above conf is a candidate, A*nc of them: the bucketed sort path and the max_nms = 30000 cut (ops.py:244), against the
+    oracle's restatement of non_max_suppression on identical predictions: bit-exact keep sets."""
+    from mgdt_yolo_b200.postprocess import non_max_suppression
+    from mgdt_yolo_b200.synth import synth_predictions
+    from oracle import mgdt_oracle as O
+    pred = synth_predictions(batch, nc, anchors, seed=77)
+    got = non_max_suppression(pred.cuda(), **kw)
+    want = O.non_max_suppression(pred[:4], **kw)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and torch.equal(a.cpu(), b), f"keep set differs ({a.shape} vs {b.shape})"

@@ -161,9 +161,6 @@ def test_mspa_front_fused_vs_unfused(iw, n):
     assert err <= 2 ** -7, f"iw={iw}: {err:.3e}"
 
 
-@pytest.mark.parametrize("kind,shape", [("mspa", (3, 128, 13, 17)), ("mspa", (2, 128, 20, 20)), ("mspa", (5, 256, 8, 8)),
-                                        ("convnext", (3, 96, 13, 17)), ("convnext", (2, 96, 40, 40)),
-                                        ("conv_gn", (3, 64, 13, 17)), ("conv_gn", (2, 64, 80, 80))])
 def _fused_epilogue_stats_case(kind, shape):
     """Per-(n,c) statistics accumulated in the tcgen05 conv's epilogue (fp64 atomics + mgdt_stats_finish) against the
     stand-alone mgdt_chan_stats pass, through the modules that use them: SPR gate (2x2 adaptive windows, odd sizes ->
@@ -204,6 +201,9 @@ def _fused_epilogue_stats_case(kind, shape):
     assert err <= 2 ** -7, f"{kind} {shape}: {err:.3e}"
 
 
+@pytest.mark.parametrize("kind,shape", [("mspa", (3, 128, 13, 17)), ("mspa", (2, 128, 20, 20)), ("mspa", (5, 256, 8, 8)),
+                                        ("convnext", (3, 96, 13, 17)), ("convnext", (2, 96, 40, 40)),
+                                        ("conv_gn", (3, 64, 13, 17)), ("conv_gn", (2, 64, 80, 80))])
 def test_fused_epilogue_stats_vs_chan_stats(kind, shape):
     _fused_epilogue_stats_case(kind, shape)
 

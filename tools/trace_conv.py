@@ -16,6 +16,7 @@ cases = [("c32_3x3", 32, 32, 3, 1, 80, 80), ("c8_1x1", 8, 8, 1, 1, 160, 160), ("
          ("c256_64", 256, 64, 1, 1, 80, 80), ("c16_32_s2", 16, 32, 3, 2, 320, 320), ("c384_96", 384, 96, 1, 1, 40, 40), ("c384_96_grn", 384, 96, 1, 1, 40, 40)]
 cases += [("c96_384_gelu", 96, 384, 1, 1, 40, 40), ("c96_384_gelu_sq", 96, 384, 1, 1, 40, 40), ("c96_384_silu_sq", 96, 384, 1, 1, 40, 40),
           ("c32_32_q5", 32, 32, 1, 1, 160, 160), ("c32_32_160", 32, 32, 1, 1, 160, 160)]
+cases += [("c32_3x3_w78", 32, 32, 3, 1, 80, 78), ("c32_3x3_w86", 32, 32, 3, 1, 80, 86), ("c32_3x3_w62", 32, 32, 3, 1, 80, 62)]
 cases.append(("stem", 3, 16, 3, 2, 640, 640))
 sel = sys.argv[1:]
 if sel:
