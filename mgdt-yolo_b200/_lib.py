@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmgdt_b200.so")
+LIB_PATH = os.environ.get("MGDT_LIB") or os.path.join(HERE, "libmgdt_b200.so")   # MGDT_LIB: A/B runs of two builds in one session
 
 ABI_VERSION = 3  # include/mgdt_b200.h MGDT_ABI_VERSION
 F32, BF16 = 0, 1

@@ -35,8 +35,11 @@ def _stamp():
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra=(), out: str | None = None) -> str:
+    """`extra` nvcc flags + `out` build a variant library next to the default one (A/B experiments: MGDT_LIB=<out>)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if extra or out:
+        return _build_variant(nvcc, list(extra), out or LIB[:-3] + "_variant.so")
     stamp_file = os.path.join(OBJ, "stamp")
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
@@ -63,6 +66,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with open(stamp_file, "w") as fh:
         fh.write(stamp)
     return LIB
+
+
+def _build_variant(nvcc, extra, out):
+    objdir = OBJ + "_variant"
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        cmd = [nvcc, *ARCH, *COMMON, *PER_FILE.get(src, []), *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(compile_one, _sources()))
+    r = subprocess.run([nvcc, *ARCH, "-shared", "-o", out, *objs, "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return out
 
 
 if __name__ == "__main__":

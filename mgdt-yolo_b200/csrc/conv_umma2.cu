@@ -27,6 +27,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifndef MGDT_WAIT_HINT
+#define MGDT_WAIT_HINT 100000   // mbarrier.try_wait suspend-time hint (ns)
+#endif
+
 namespace mgdt {
 
 // 20 warps (five per SM sub-partition, so 96 registers per thread): producers | one MMA warp | epilogue; the split
@@ -276,7 +280,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         // warps do not steal issue slots from the producers while they wait
         asm volatile(
             "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)MGDT_WAIT_HINT) : "memory");
         if (ok) return;
         if (clock64() - t0 > 8000000000LL) __trap();
     }
@@ -478,8 +482,9 @@ template <int LOADER, int SPLIT> struct Roles {
     // layout or the alignment -- so the tensor core is NOT the limit of the small-N layers.  Spreading the chains of a
     // tile over 2 / 4 issuing warps (NMW = 4 with 8 / 4 producer warps) was measured in this kernel and did not help:
     // the 3x3 32->32 tile went from 2.9 to 4.0 us (trace_conv.py), 19.5k -> 17.7k images/s, so NMW stays 1.
-    static constexpr int NMW = 1;
-    static constexpr int NPW = (LOADER == LD_ASYNC || LOADER == LD_XFORM) ? (SPLIT == 0 ? 3 : SPLIT == 1 ? 7 : 11)
+    // SPLIT 3 (experiment, option conv_split = 3): 8 producer, 4 MMA-issuing, 8 epilogue warps.
+    static constexpr int NMW = ((LOADER == LD_ASYNC || LOADER == LD_XFORM) && SPLIT == 3) ? 4 : 1;
+    static constexpr int NPW = (LOADER == LD_ASYNC || LOADER == LD_XFORM) ? (SPLIT == 0 ? 3 : SPLIT == 1 ? 7 : SPLIT == 2 ? 11 : 8)
                                : LOADER == LD_DCN ? 15 : 11;
     static constexpr int MMAW = NPW;                          // first MMA warp
     static constexpr int EPI0 = NPW + NMW;                    // first epilogue warp (a multiple of 4: quadrant = warp % 4)
@@ -1627,6 +1632,7 @@ template <int MODE, int LOADER>
 static int launch2s(const P2& p, int split, dim3 grid, cudaStream_t s) {
     if (split == 0) return launch2t<MODE, LOADER, 0>(p, grid, s);
     if (split == 1) return launch2t<MODE, LOADER, 1>(p, grid, s);
+    if (split == 3 && LOADER == LD_ASYNC) return launch2t<MODE, LD_ASYNC, 3>(p, grid, s);
     return launch2t<MODE, LOADER, 2>(p, grid, s);
 }
 
@@ -1817,7 +1823,7 @@ extern "C" void mgdt_debug_set_trace(void* buf) { mgdt::g_trace = (unsigned long
 
 namespace mgdt {
 int conv_set_option(const char* name, int value) {
-    if (!strcmp(name, "conv_split")) g_force_split = (value >= 0 && value <= 2) ? value : -1;
+    if (!strcmp(name, "conv_split")) g_force_split = (value >= 0 && value <= 3) ? value : -1;
     else if (!strcmp(name, "conv_tma_store")) g_tma_store = value ? 1 : 0;
     else if (!strcmp(name, "conv_pair")) g_pair = value ? 1 : 0;
     else if (!strcmp(name, "conv_tma_load")) g_use_tma_loads = value ? 1 : 0;
