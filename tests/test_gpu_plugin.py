@@ -95,8 +95,10 @@ def test_predict_through_reference_predictor(arms):
         assert frac >= min(0.9, frac_ref - 0.15), (f"half arm: {frac:.3f} of the top reference detections matched at IoU > 0.8 "
                                                    f"(the reference's own fp16 mode: {frac_ref:.3f})")
     # (3) the CUDA-graph Engine (device LetterBox, fused uint8 stem) on the same images
-    eng = Engine(R.make_yolo().model, len(ims), 640, torch.bfloat16, "cuda:0", conf=0.25, iou=0.7, slots=1)
-    d_eng = [r.boxes.data.float().cpu() for r in eng.predict(ims, auto=False)]   # fixed 640 x 640 letterbox (the engine's static shape)
+    # the predictor letterboxes 480 x 640 sources with auto=True, i.e. to 480 x 640 without padding; the engine's static
+    # shape is set to the same rectangle (a 640 x 640 engine pads, and the global-context layers then see other statistics)
+    eng = Engine(R.make_yolo().model, len(ims), (480, 640), torch.bfloat16, "cuda:0", conf=0.25, iou=0.7, slots=1)
+    d_eng = [r.boxes.data.float().cpu() for r in eng.predict(ims, auto=False)]
     for a, b, c in zip(d_eng, d_ref, d_ref16):
         frac, frac_ref = _matched_fraction(b, a, thr=0.8), _matched_fraction(b, c, thr=0.8)
         assert frac >= min(0.9, frac_ref - 0.15), (f"engine arm: {frac:.3f} of the top reference detections matched at IoU > 0.8 "
