@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const T1& t = p.t1;
     const Plan2& pl = p.pl;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: uniform role branches, uniform-datapath descriptor arithmetic
     const int ns = (int)blockIdx.y / t.nsub, hs = (int)blockIdx.y - ns * t.nsub;   // packed column block, sub-split
     const int col0 = hs * t.Nsub;                                                  // first column within the block
     const int Nsub = t.Nsub;
@@ -237,6 +238,11 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
         if (!t.w_ring) mbar_wait(WREADY, 0);
         int s = 0;
         uint32_t ph = 0, ti = 0;
+        // whole warp in uniform control flow, descriptors on the uniform datapath, only the tcgen05 instructions under the
+        // elect.sync predicate (see conv_umma2_kernel's MMA role / tools/ubench/umma_issue.cu)
+        const bool lead = elect_one();
+        const uint64_t adesc_t = mk_desc_sw(0u, sbo, lay), bdesc_t = mk_desc(0u, wchunk_bytes, 128u);
+        const int steps = t.KB / 16;
         for (uint32_t tile = tile_lo; tile < tiles; ++tile, ++ti) {
             const int a = t.NACC == 2 ? (int)(ti & 1) : 0;
             const uint32_t aphase = t.NACC == 2 ? ((ti >> 1) & 1) : (ti & 1);
@@ -244,24 +250,24 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, EPIW == 4 ? 3 : 2) conv1x1_tma
             for (int st = 0; st < t.nst; ++st) {
                 mbar_wait(FULL(s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const int kb0 = st * t.kb_stage, nk = min(t.kb_stage, t.nkb - kb0);
-                    const uint32_t sA = sStage32 + (uint32_t)s * t.stage_bytes;
-                    const uint32_t wb = t.w_ring ? sA + t.a_stage_bytes : sW32 + (uint32_t)(kb0 * (t.KB / 8)) * wchunk_bytes;
-                    const uint32_t d0 = tmem_base + (uint32_t)(a * t.KS * Nsub);
-                    const int steps = t.KB / 16;
-                    for (int j = 0; j < nk; ++j) {
-                        for (int e = 0; e < steps; ++e) {
-                            const uint64_t adesc = mk_desc_sw(sA + (uint32_t)j * t.a_kb_bytes + (uint32_t)e * 32u, sbo, lay);
-                            const uint64_t bdesc = mk_desc(wb + (uint32_t)((j * steps + e) * 2) * wchunk_bytes, wchunk_bytes, 128u);
-                            const int g = (kb0 + j) * steps + e;               // K = 16 step of this tile
-                            const uint32_t acc = g >= t.KS ? 1u : 0u;          // the first step of every partial accumulator overwrites
+                const int kb0 = st * t.kb_stage, nk = min(t.kb_stage, t.nkb - kb0);
+                const uint32_t sA = sStage32 + (uint32_t)s * t.stage_bytes;
+                const uint32_t wb = t.w_ring ? sA + t.a_stage_bytes : sW32 + (uint32_t)(kb0 * (t.KB / 8)) * wchunk_bytes;
+                const uint32_t d0 = tmem_base + (uint32_t)(a * t.KS * Nsub);
+                uint64_t bdesc = bdesc_t + (uint64_t)(wb >> 4);
+                for (int j = 0; j < nk; ++j) {
+                    uint64_t adesc = adesc_t + (uint64_t)((sA + (uint32_t)j * t.a_kb_bytes) >> 4);
+                    for (int e = 0; e < steps; ++e, adesc += 2, bdesc += (uint64_t)(2u * (wchunk_bytes >> 4))) {   // 32 B of K per step
+                        const int g = (kb0 + j) * steps + e;               // K = 16 step of this tile
+                        const uint32_t acc = g >= t.KS ? 1u : 0u;          // the first step of every partial accumulator overwrites
+                        if (lead)
                             asm volatile(
                                 "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                                 ::"r"(d0 + (uint32_t)((g & (t.KS - 1)) * Nsub)), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
-                        }
                     }
+                }
+                if (lead) {
                     umma_commit(EMPTY(s));
                     if (st == t.nst - 1) { umma_commit(ACCFULL(a)); if (p.trace && ti < 6) trace_mark(p, 9 + 8 * (int)ti); }
                 }

@@ -61,6 +61,7 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
     return (uint32_t)(((unsigned long long)n * f.mul) >> f.shr);
 }
 
+static int g_force_mb = 0;  // option "conv_mb": force the row blocks per tile (1 / 2 / 4) where the plan allows it (experiments)
 static int g_ksplit = 0;   // option "conv_ksplit": K-split partial accumulators (see try_run2 / plan_t1); measured: no gain (the MMA phase is not bound by accumulator dependencies), so off
 
 struct Plan2 {
@@ -205,13 +206,19 @@ static bool try_run2(const Plan2& p, int MB, int N, int H, int W, int Ho, int Wo
 static bool make_run2(const Plan2& p, int N, int H, int W, int Ho, int Wo, Run2& r, bool per_img_w = false) {
     const int mbs[3] = {4, 2, 1};
     bool found = false;
+    if (g_force_mb) {
+        Run2 t;
+        if (try_run2(p, g_force_mb, N, H, W, Ho, Wo, t, per_img_w)) { r = t; return true; }
+    }
     for (int i = 0; i < 3; ++i) {
         Run2 t;
         if (!try_run2(p, mbs[i], N, H, W, Ho, Wo, t, per_img_w)) continue;
         if (t.NACC < 2 && mbs[i] > 1) continue;           // keep two accumulator buffers when a smaller tile allows it
         r = t;
         found = true;
-        if (t.tiles * p.nsplit >= 3 * 148) break;          // enough tiles for every persistent CTA to pipeline
+        // (with the uniform-datapath MMA issue a K = 16 step costs ~150 cycles + ~40 per row block, so four row blocks per
+        // tile win as soon as most SMs get a tile: forced MB = 4 measured +2 % images/s over the old ">= 3 x 148 tiles" rule)
+        if (t.tiles * p.nsplit >= 120) break;
     }
     if (!found) {
         Run2 t;
@@ -232,7 +239,10 @@ template <> __device__ __forceinline__ __half cvt_w<__nv_bfloat16, __half>(__nv_
 // in_scale[n][ci] (per-image weights W diag(s_n): the GRN / TaskDecomposition input scale moved onto the weights).
 template <typename S, typename D>
 __global__ void umma2_pack_kernel(const S* __restrict__ w, D* __restrict__ out, Plan2 p, int Cin, int Cout, int k) {
-    pdl_trigger();
+    // NO pdl_trigger(): the convolution kernels copy their resident weights BEFORE griddepcontrol.wait (they are constants
+    // of the layer), so the kernel that follows a pack in the stream must not be scheduled before this grid has completed
+    // (without a trigger the dependent launch happens at grid completion).  Found as NaNs on the first forward of a model
+    // (lazy pack -> conv back to back) once the conv's set-up got faster.
     pdl_wait();
     const int cps = p.nmma_s * 2;
     const long long total = (long long)p.nsplit * p.nks * cps * p.Nc * 8;
@@ -342,7 +352,13 @@ struct P2 {
     long long st_rs;
     FastDiv d_oHW, d_oW;
     unsigned long long* trace;   // debug: per-CTA phase timestamps (mgdt_debug_set_trace), normally NULL
+    // A-operand descriptor of every K = 16 instruction of a (slice, 128-row block), relative to the stage base (tile
+    // independent, filled by the host: fill_adesc).  Read from the constant bank with a uniform index, so the MMA warp's
+    // descriptor arithmetic stays in uniform registers (no LDS + R2UR chain in front of every UTCHMMA).
+    unsigned long long adesc[U2_MAX_MMA];
 };
+
+static_assert(sizeof(P2) <= 4096, "kernel parameter space");
 
 // tile-relative output row m -> output pixel index, or -1 for junk / out-of-range rows
 __device__ __forceinline__ int out_pixel2(const P2& p, uint32_t tile, uint32_t m) {
@@ -906,7 +922,10 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     extern __shared__ __align__(128) unsigned char smem[];
     const Plan2& pl = p.pl;
     const Run2& rn = p.rn;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp index through a shuffle: provably warp-uniform, so the role dispatch below is a uniform branch and ptxas keeps
+    // the MMA warp's loop state and descriptor arithmetic on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int ns = blockIdx.y;
     constexpr int NPW = Roles<LOADER, SPLIT>::NPW, NEW = Roles<LOADER, SPLIT>::NEW, NP = Roles<LOADER, SPLIT>::NP;
     constexpr int MMAW = Roles<LOADER, SPLIT>::MMAW, EPI0 = Roles<LOADER, SPLIT>::EPI0, NMW = Roles<LOADER, SPLIT>::NMW;
@@ -936,22 +955,6 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
         const int co = ns * pl.Nc + (pl.Nc == 16 ? (i & 15) : i);
         sBias[i] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
     }
-    for (int i = tid; i < pl.nmma_s; i += U2_THREADS) {
-        const int c0 = 2 * i, c1 = 2 * i + 1;
-        auto off = [&](int c) -> uint32_t {
-            const int t = c / pl.PS, pll = c - t * pl.PS;
-            int shift;
-            if (MODE == 0) shift = 0;
-            else if (MODE == 1) shift = rn.halo + (pl.tap_dy[t] - 1) * rn.Wq + (pl.tap_dx[t] - 1);
-            else shift = (pl.tap_dy[t] >> 1) * rn.Wq + (pl.tap_dx[t] >> 1);
-            return ((uint32_t)pll * rn.pstride16 + (uint32_t)pl.tap_par[t] * rn.P + shift) * 16u;
-        };
-        const uint32_t o0 = off(c0);
-        const uint32_t lbo = (c1 < pl.taps * pl.PS) ? (off(c1) - o0) : 16u;  // dummy chunk: its weights are zero
-        const uint32_t b_lbo = (uint32_t)pl.Nc * 16;
-        desc_t[i] = make_ulonglong2(mk_desc(o0, lbo, 128u), mk_desc((uint32_t)c0 * b_lbo, b_lbo, 128u));
-    }
-
     if (warp == MMAW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)),
                      "r"((uint32_t)rn.tmem_cols) : "memory");
@@ -1332,14 +1335,21 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
     } else if (warp < EPI0) {
         // =============================================================== MMA issuers (warps MMAW .. MMAW + NMW - 1)
         const int mw = warp - MMAW;   // this warp owns the chains (row block mb, partial accumulator h) with (mb * KS + h) % NMW == mw
-        // The whole warp walks the pipeline (uniform control flow); the tcgen05 instructions are issued by the one
-        // lane elect.sync picks, which lets ptxas emit them without a per-lane waterfall loop.
+        // The whole warp walks the pipeline in uniform control flow and computes the (warp-uniform) descriptors; only the
+        // tcgen05 instructions themselves sit under the elect.sync predicate.  tools/ubench/umma_issue.cu: with the
+        // descriptor arithmetic in per-thread registers (a table in shared memory, the loop inside `if (elect)`) every
+        // K = 16 step costs ~150 cycles of LDS / R2UR latency before its first UTCHMMA (213 cycles per instruction at two
+        // row blocks); on the uniform datapath a four-row-block step issues at ~58 cycles per instruction.
         // instruction descriptor: D = f32, A = bf16, B = bf16 or f16, both K-major, N = Nc, M = 128
         const uint32_t idesc = (1u << 4) | (1u << 7) | ((p.w_f16 ? 0u : 1u) << 10) | ((uint32_t)(pl.Nc >> 3) << 17) | ((128u >> 4) << 24);
+        const bool lead = elect_one();
         if (rn.wres_bytes) mbar_wait(WREADY, 0);
         uint32_t it = 0, ti = 0;
         int s = 0;
         uint32_t ph = 0;
+        const uint32_t stage0 = s_u32(sStage), wres0 = s_u32(sWres);
+        const uint64_t bdesc_t = mk_desc(0u, (uint32_t)pl.Nc * 16u, 128u);   // B: chunk c at c * Nc * 16 bytes, LBO = Nc * 16
+        const int kmask = rn.KS - 1;
         for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
             const int a = rn.NACC == 2 ? (int)(ti & 1) : 0;
             const uint32_t aphase = rn.NACC == 2 ? ((ti >> 1) & 1) : (ti & 1);
@@ -1349,35 +1359,32 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                 // the stage was written through the generic proxy (cp.async / st.shared by the producers)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint32_t a0 = s_u32(sStage + (size_t)s * rn.stage_bytes);
-                    const uint32_t w0 = rn.w_slice_bytes ? a0 + rn.a_bytes : s_u32(sWres) + (uint32_t)ks * (uint32_t)(w_slice_elems * 2);
-                    const uint32_t d0 = tmem_base + (uint32_t)(a * rn.KS * rn.MB * pl.Nc);
-                    const int kmask = rn.KS - 1;
-                    const uint64_t abase = (uint64_t)(a0 >> 4), wbase = (uint64_t)(w0 >> 4);
-                    // descriptors are fetched four at a time ahead of the instructions that use them
-                    for (int i0 = 0; i0 < pl.nmma_s; i0 += 4) {
-                        ulonglong2 dsc[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) dsc[u] = desc_t[min(i0 + u, pl.nmma_s - 1)];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (i0 + u < pl.nmma_s) {
-                                const uint64_t bdesc = dsc[u].y + wbase;
-                                const int g = ks * pl.nmma_s + i0 + u;             // K = 16 step of this tile
-                                const uint32_t acc = g >= rn.KS ? 1u : 0u;         // the first step of every partial accumulator overwrites
-                                const uint32_t dh = d0 + (uint32_t)((g & kmask) * rn.MB * pl.Nc);
-                                for (int mb = 0; mb < rn.MB; ++mb) {
-                                    if (NMW > 1 && ((mb * rn.KS + (g & kmask)) & (NMW - 1)) != mw) continue;
-                                    const uint64_t adesc = dsc[u].x + abase + (uint64_t)(mb * 128);   // 2048 B per row block
-                                    asm volatile(
-                                        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-                                        ::"r"(dh + (uint32_t)(mb * pl.Nc)), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
-                                }
-                            }
+                const uint32_t a0 = stage0 + (uint32_t)s * rn.stage_bytes;
+                const uint32_t w0 = rn.w_slice_bytes ? a0 + rn.a_bytes : wres0 + (uint32_t)ks * (uint32_t)(w_slice_elems * 2);
+                const uint32_t d0 = tmem_base + (uint32_t)(a * rn.KS * rn.MB * pl.Nc);
+                const uint64_t abase = (uint64_t)(a0 >> 4);
+                uint64_t bdesc = bdesc_t + (uint64_t)(w0 >> 4);
+                for (int i = 0; i < pl.nmma_s; ++i, bdesc += (uint64_t)(2 * pl.Nc)) {
+                    const uint64_t ad0 = p.adesc[i] + abase;
+                    const int g = ks * pl.nmma_s + i;                  // K = 16 step of this tile
+                    const uint32_t acc = g >= rn.KS ? 1u : 0u;         // the first step of every partial accumulator overwrites
+                    const uint32_t dh = d0 + (uint32_t)((g & kmask) * rn.MB * pl.Nc);
+                    auto issue = [&](int mb) {   // 2048 B of A and Nc accumulator columns per row block
+                        if (lead)
+                            asm volatile(
+                                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                                ::"r"(dh + (uint32_t)(mb * pl.Nc)), "l"(ad0 + (uint64_t)(mb * 128)), "l"(bdesc), "r"(idesc), "r"(acc));
+                    };
+                    if (NMW == 1 && rn.MB == 4) { issue(0); issue(1); issue(2); issue(3); }        // straight-line code for the common tiles
+                    else if (NMW == 1 && rn.MB == 2) { issue(0); issue(1); }
+                    else
+                        for (int mb = 0; mb < rn.MB; ++mb) {
+                            if (NMW > 1 && ((mb * rn.KS + (g & kmask)) & (NMW - 1)) != mw) continue;
+                            issue(mb);
                         }
-                    }
+                }
+                if (lead) {
                     umma_commit(EMPTY(s));                       // smem stage may be refilled once these MMAs retire
                     if (ks == nks - 1) umma_commit(ACCFULL(a));  // accumulators complete
                     if (mw == 0 && it < 6) trace_mark(p, 9 + 8 * (int)it);
@@ -1594,6 +1601,27 @@ static void fill_divs(P2& p) {
     p.d_oW = make_fastdiv((uint32_t)p.Wo);
 }
 
+// A descriptors of the K = 16 steps of a (slice, 128-row block): chunk c = (tap t, plane-in-slice pll); an instruction
+// takes chunks 2i and 2i + 1 (LBO = their distance: the next plane, or -- Cin = 8 -- the next tap)
+static void fill_adesc(P2& p) {
+    const Plan2& pl = p.pl;
+    const Run2& rn = p.rn;
+    auto off = [&](int c) -> uint32_t {
+        const int t = c / pl.PS, pll = c - t * pl.PS;
+        int shift;
+        if (pl.mode == 0) shift = 0;
+        else if (pl.mode == 1) shift = rn.halo + (pl.tap_dy[t] - 1) * rn.Wq + (pl.tap_dx[t] - 1);
+        else shift = (pl.tap_dy[t] >> 1) * rn.Wq + (pl.tap_dx[t] >> 1);
+        return ((uint32_t)pll * rn.pstride16 + (uint32_t)pl.tap_par[t] * rn.P + shift) * 16u;
+    };
+    for (int i = 0; i < pl.nmma_s && i < U2_MAX_MMA; ++i) {
+        const int c0 = 2 * i, c1 = 2 * i + 1;
+        const uint32_t o0 = off(c0);
+        const uint32_t lbo = (c1 < pl.taps * pl.PS) ? (off(c1) - o0) : 16u;  // dummy chunk: its weights are zero
+        p.adesc[i] = (uint64_t)((o0 >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);
+    }
+}
+
 static unsigned long long* g_trace = nullptr;
 // Library options, set through the C ABI (mgdt_set_option; the Python layer forwards MGDT_* environment variables once
 // at load time): no getenv and no latched statics in the launch path.
@@ -1652,6 +1680,7 @@ static int pick_split(const P2& p, bool xform) {
 
 static int launch2(P2& p, cudaStream_t s) {
     fill_divs(p);
+    fill_adesc(p);
     p.trace = g_trace;
     // TMA store map of the output (mode 0 layers with 16-byte aligned rows; the paired 16-column units keep the LSU path)
     p.tma_store = 0;
@@ -1823,7 +1852,8 @@ extern "C" void mgdt_debug_set_trace(void* buf) { mgdt::g_trace = (unsigned long
 
 namespace mgdt {
 int conv_set_option(const char* name, int value) {
-    if (!strcmp(name, "conv_split")) g_force_split = (value >= 0 && value <= 3) ? value : -1;
+    if (!strcmp(name, "conv_mb")) g_force_mb = (value == 1 || value == 2 || value == 4) ? value : 0;
+    else if (!strcmp(name, "conv_split")) g_force_split = (value >= 0 && value <= 3) ? value : -1;
     else if (!strcmp(name, "conv_tma_store")) g_tma_store = value ? 1 : 0;
     else if (!strcmp(name, "conv_pair")) g_pair = value ? 1 : 0;
     else if (!strcmp(name, "conv_tma_load")) g_use_tma_loads = value ? 1 : 0;

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(mf_threads<IW>()) mspa_front_kernel(MfP p) {
 
 // fp32 [nstage][ci][co] -> bf16 B fragments [nstage][nt][kb][lane]{b0, b1}: b_r = {W[kb*16 + 2t + 8r][nt*8 + g], W[.. + 1][..]}
 __global__ void mspa_front_pack_kernel(const float* __restrict__ w, uint2* __restrict__ out, int nstage, int iw) {
-    pdl_trigger();
+    // no pdl_trigger(): the consumer stages the packed weights before its griddepcontrol.wait (see umma2_pack_kernel)
     pdl_wait();
     const int KB = (iw + 15) / 16, NTL = iw / 8;
     const int total = nstage * NTL * KB * 32;

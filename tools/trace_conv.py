@@ -18,6 +18,7 @@ cases += [("c96_384_gelu", 96, 384, 1, 1, 40, 40), ("c96_384_gelu_sq", 96, 384, 
           ("c32_32_q5", 32, 32, 1, 1, 160, 160), ("c32_32_160", 32, 32, 1, 1, 160, 160)]
 cases += [("c32_3x3_w78", 32, 32, 3, 1, 80, 78), ("c32_3x3_w86", 32, 32, 3, 1, 80, 86), ("c32_3x3_w62", 32, 32, 3, 1, 80, 62)]
 cases.append(("stem", 3, 16, 3, 2, 640, 640))
+cases += [("c8_3x3", 8, 8, 3, 1, 160, 160), ("c64_32_3x3", 64, 32, 3, 1, 80, 80), ("c32_3x3_40", 32, 32, 3, 1, 40, 40)]
 sel = sys.argv[1:]
 if sel:
     cases = [c for c in cases if c[0] in sel]
