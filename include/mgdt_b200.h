@@ -118,8 +118,9 @@ typedef struct mgdt_conv_args {
 } mgdt_conv_args;
 int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
 /* Which kernel mgdt_conv2d would run for these arguments: 3 = conv_pointwise_kernel (narrow 1x1 layers, CUDA cores,
- * HBM-bound), 4 = conv1x1_tma_kernel (tcgen05, operand A fed by TMA: transform-free 1x1 layers), 2 = conv_umma2_kernel
- * (tcgen05, cp.async-fed: 3x3, stride 2, fused input transforms), 1 = conv_direct_kernel (CUDA cores).  Used by the bench to attribute
+ * HBM-bound), 4 = conv1x1_tma_kernel (tcgen05, operand A fed by TMA: transform-free 1x1 layers), 5 = conv3x3_tma_kernel
+ * (tcgen05, operand A fed by 4-D TMA boxes: transform-free 3x3 stride-1 layers with Cin <= 64), 2 = conv_umma2_kernel
+ * (tcgen05, cp.async-fed: wide 3x3, stride 2, fused input transforms / statistics), 1 = conv_direct_kernel (CUDA cores).  Used by the bench to attribute
  * launches to kernels. */
 int mgdt_conv2d_path(const mgdt_conv_args* a);
 

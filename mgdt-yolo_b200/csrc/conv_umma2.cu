@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -314,6 +315,15 @@ struct T1 {
     long long tiles;
 };
 
+// run-time plan of the TMA-fed 3x3 stride-1 kernel (conv_tma3x3.cuh)
+struct T3 {
+    int MB, R, Wq;            // row blocks per tile, image rows per tile, padded row pitch W + 2
+    int PB, pstride;          // positions the TMA box writes per plane ((R + 2) * Wq), plane stride in positions
+    int S, NACC, tmem_cols, ctas_per_sm, tiles_per_img, epiw;
+    unsigned tx_bytes, w_copy_bytes, w_bytes, stage_bytes, smem_total;
+    long long tiles;
+};
+
 struct P2 {
     const __nv_bfloat16 *x, *w, *pre_add, *pix_scale, *residual;
     const __nv_bfloat16* row_scale;   // 1x1 layers: the per-pixel input scale applied to the accumulator row instead (stride ps_cs)
@@ -344,6 +354,7 @@ struct P2 {
     size_t w_img_elems;          // per-image weights: elements between consecutive images' packed weights (0 = shared)
     alignas(64) CUtensorMap xmap;   // TMA load of the activation as a 2D (channels, pixels) tensor (conv_tma1x1.cuh)
     T1 t1;
+    T3 t3;
     alignas(64) CUtensorMap ymap;   // TMA store of 32-row x 32-channel output units (mode 0): 2D (channels, pixels) or, per-image tiles, 3D (channels, pixels of an image, image)
     int tma_store;
     int pair_ok;                 // paired 16-column epilogue units allowed (debug: MGDT_CONV_PAIR=0 turns them off)
@@ -1363,26 +1374,46 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                 const uint32_t w0 = rn.w_slice_bytes ? a0 + rn.a_bytes : wres0 + (uint32_t)ks * (uint32_t)(w_slice_elems * 2);
                 const uint32_t d0 = tmem_base + (uint32_t)(a * rn.KS * rn.MB * pl.Nc);
                 const uint64_t abase = (uint64_t)(a0 >> 4);
-                uint64_t bdesc = bdesc_t + (uint64_t)(w0 >> 4);
-                for (int i = 0; i < pl.nmma_s; ++i, bdesc += (uint64_t)(2 * pl.Nc)) {
-                    const uint64_t ad0 = p.adesc[i] + abase;
-                    const int g = ks * pl.nmma_s + i;                  // K = 16 step of this tile
-                    const uint32_t acc = g >= rn.KS ? 1u : 0u;         // the first step of every partial accumulator overwrites
-                    const uint32_t dh = d0 + (uint32_t)((g & kmask) * rn.MB * pl.Nc);
-                    auto issue = [&](int mb) {   // 2048 B of A and Nc accumulator columns per row block
-                        if (lead)
-                            asm volatile(
-                                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-                                ::"r"(dh + (uint32_t)(mb * pl.Nc)), "l"(ad0 + (uint64_t)(mb * 128)), "l"(bdesc), "r"(idesc), "r"(acc));
-                    };
-                    if (NMW == 1 && rn.MB == 4) { issue(0); issue(1); issue(2); issue(3); }        // straight-line code for the common tiles
-                    else if (NMW == 1 && rn.MB == 2) { issue(0); issue(1); }
-                    else
+                const uint64_t bdesc0 = bdesc_t + (uint64_t)(w0 >> 4);
+                // common case (one issuing warp, no K-split): one copy of the K loop per tile height, the MB instructions of
+                // a step under ONE branch on the elected lane
+                auto kloop = [&](auto mbc) {
+                    constexpr int MBK = decltype(mbc)::value;
+                    uint64_t bdesc = bdesc0;
+                    const uint32_t acc0 = ks ? 1u : 0u;
+#pragma unroll 2
+                    for (int i = 0; i < pl.nmma_s; ++i, bdesc += (uint64_t)(2 * pl.Nc)) {
+                        const uint64_t ad0 = p.adesc[i] + abase;
+                        const uint32_t acc = i ? 1u : acc0;            // the first step of the tile overwrites
+                        if (lead) {
+#pragma unroll
+                            for (int mb = 0; mb < MBK; ++mb)   // 2048 B of A and Nc accumulator columns per row block
+                                asm volatile(
+                                    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                                    ::"r"(d0 + (uint32_t)(mb * pl.Nc)), "l"(ad0 + (uint64_t)(mb * 128)), "l"(bdesc), "r"(idesc), "r"(acc));
+                        }
+                    }
+                };
+                if (NMW == 1 && rn.KS == 1 && rn.MB == 4) kloop(std::integral_constant<int, 4>());
+                else if (NMW == 1 && rn.KS == 1 && rn.MB == 2) kloop(std::integral_constant<int, 2>());
+                else if (NMW == 1 && rn.KS == 1 && rn.MB == 1) kloop(std::integral_constant<int, 1>());
+                else {
+                    uint64_t bdesc = bdesc0;
+                    for (int i = 0; i < pl.nmma_s; ++i, bdesc += (uint64_t)(2 * pl.Nc)) {
+                        const uint64_t ad0 = p.adesc[i] + abase;
+                        const int g = ks * pl.nmma_s + i;                  // K = 16 step of this tile
+                        const uint32_t acc = g >= rn.KS ? 1u : 0u;         // the first step of every partial accumulator overwrites
+                        const uint32_t dh = d0 + (uint32_t)((g & kmask) * rn.MB * pl.Nc);
                         for (int mb = 0; mb < rn.MB; ++mb) {
                             if (NMW > 1 && ((mb * rn.KS + (g & kmask)) & (NMW - 1)) != mw) continue;
-                            issue(mb);
+                            if (lead)
+                                asm volatile(
+                                    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                                    ::"r"(dh + (uint32_t)(mb * pl.Nc)), "l"(ad0 + (uint64_t)(mb * 128)), "l"(bdesc), "r"(idesc), "r"(acc));
                         }
+                    }
                 }
                 if (lead) {
                     umma_commit(EMPTY(s));                       // smem stage may be refilled once these MMAs retire
@@ -1632,6 +1663,7 @@ static int g_use_tma_loads = 1;    // "conv_tma_load": TMA-fed kernel for transf
 static int g_tma_stats = 0;        // "conv_tma_stats": also for layers with fused output statistics (measured slower than the 16-epilogue-warp split of conv_umma2_kernel: 96->384 GELU + sum of squares 41 -> 55 us)
 
 #include "conv_tma1x1.cuh"
+#include "conv_tma3x3.cuh"
 
 template <int MODE, int LOADER, int SPLIT, int STATS>
 static int launch2k(const P2& p, dim3 grid, cudaStream_t s) {
@@ -1700,6 +1732,10 @@ static int launch2(P2& p, cudaStream_t s) {
     p.pair_ok = g_pair;
     if (p.pl.mode == 0) {   // transform-free 1x1 layers: the TMA-fed kernel
         const int rc = try_launch_t1(p, s);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
+    if (p.pl.mode == 1) {   // transform-free 3x3 stride-1 layers with Cin <= 64: the TMA-fed kernel
+        const int rc = try_launch_t3(p, s);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
     if (p.act_cols) return set_error(-ENOTSUP, "conv2d: act_cols needs the TMA-fed 1x1 kernel (see mgdt_conv2d_path)");
@@ -1781,7 +1817,9 @@ int conv2d_umma(const mgdt_conv_args* a, cudaStream_t s) {
 int conv2d_umma_path(const mgdt_conv_args* a) {
     P2 p;
     if (fill_p2(a, p) < 0) return 2;
-    return (p.pl.mode == 0 && t1_eligible(p) && plan_t1(p, p.t1) && tensor_map_encoder()) ? 4 : 2;
+    if (p.pl.mode == 0 && t1_eligible(p) && plan_t1(p, p.t1) && tensor_map_encoder()) return 4;
+    if (p.pl.mode == 1 && t3_eligible(p) && plan_t3(p, p.t3) && tensor_map_encoder()) return 5;
+    return 2;
 }
 
 bool dcn_umma_supported(const void* x, int x_cs, const void* w_umma, int N, int H, int W, int Cin, int Cout) {
@@ -1857,6 +1895,7 @@ int conv_set_option(const char* name, int value) {
     else if (!strcmp(name, "conv_tma_store")) g_tma_store = value ? 1 : 0;
     else if (!strcmp(name, "conv_pair")) g_pair = value ? 1 : 0;
     else if (!strcmp(name, "conv_tma_load")) g_use_tma_loads = value ? 1 : 0;
+    else if (!strcmp(name, "conv_tma3x3")) g_use_tma3 = value ? 1 : 0;
     else if (!strcmp(name, "conv_tma_stats")) g_tma_stats = value ? 1 : 0;
     else if (!strcmp(name, "conv_ksplit")) g_ksplit = value ? 1 : 0;
     else return 0;

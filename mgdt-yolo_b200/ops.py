@@ -259,7 +259,7 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
         # weight slices carried through the ring), pack one scaled weight image per sample and run the transform-free
         # loader instead of scaling the activations inside the loader
         a.in_scale, a.w_per_image = None, 1
-        if lib().mgdt_conv2d_path(C.byref(a)) in (2, 4):
+        if lib().mgdt_conv2d_path(C.byref(a)) in (2, 4, 5):
             pw = torch.empty((n * w_umma.numel(),), dtype=torch.uint8, device=x.device)
             _invoke("mgdt_conv_umma_pack_scaled_groups", dict(shape=f"pack_scaled {cin}->{cout} N{n}", bytes=pw.numel() + 4 * ngroups * n * cin,
                                                               flops=0.0, kernel="umma2_scale_packed_kernel"),
@@ -280,12 +280,12 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
         if FUSE_STATS and x.dtype == torch.bfloat16 and a.w_umma:
             stat.acc = _stat_arena(x.device, STAT_COPIES * n * (stat.q + stat.sq) * cout)
             a.stat_acc, a.stat_q, a.stat_sq, a.stat_copies = stat.acc.data_ptr(), stat.q, stat.sq, STAT_COPIES
-            if lib().mgdt_conv2d_path(C.byref(a)) in (2, 4):
+            if lib().mgdt_conv2d_path(C.byref(a)) in (2, 4, 5):
                 stat.fused = True
             else:
                 a.stat_acc, a.stat_q, a.stat_sq, a.stat_copies = None, 0, 0, 0
     if PROFILE is not None:  # attribute the launch to the kernel the library will actually run
-        meta["kernel"] = {3: "conv_pointwise_kernel", 2: "conv_umma2_kernel", 4: "conv1x1_tma_kernel"}.get(lib().mgdt_conv2d_path(C.byref(a)),
+        meta["kernel"] = {3: "conv_pointwise_kernel", 2: "conv_umma2_kernel", 4: "conv1x1_tma_kernel", 5: "conv3x3_tma_kernel"}.get(lib().mgdt_conv2d_path(C.byref(a)),
                                                                                   "conv_direct_kernel")
     _invoke("mgdt_conv2d", meta, C.byref(a), stream_ptr())
     return out
