@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGDT_ABI_VERSION 3
+#define MGDT_ABI_VERSION 4
 
 enum { MGDT_F32 = 0, MGDT_BF16 = 1 };
 enum { MGDT_ACT_NONE = 0, MGDT_ACT_SILU = 1, MGDT_ACT_RELU = 2, MGDT_ACT_SIGMOID = 3, MGDT_ACT_HSIGMOID = 4,
@@ -324,6 +324,39 @@ int mgdt_box_convert(const float* boxes, int row_stride, int n, int mode, float 
 int mgdt_match_batch(const float* dets, int det_stride, const int32_t* det_counts, int max_det, const float* labels,
                      const int32_t* lab_counts, int max_lab, const float* iouv, int niou, uint8_t* correct, int N,
                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Row f3: training criterion and optimizer-side element-wise work (csrc/train.cu).
+ *
+ * mgdt_v8_loss replaces v8DetectionLoss.__call__ (yolo/utils/loss.py:159-208) after the concatenation of the head's
+ * train-mode outputs: bbox_decode (loss.py:150-157), HeuristicPositiveSampleAssigner_v1 / TaskAlignedAssigner
+ * (yolo/utils/tal.py:56-142, 144-353; CIoU overlaps of yolo/utils/metrics.py:75-128, top-k, select_highest_overlaps on
+ * the alignment metric, normalised target scores), BCE + CIoU + DFL (loss.py:60-92) -- and their gradient.
+ *   pred      (B, no, A) fp32, no = 4 * reg_max + nc: the DFL logits (side-major) then the class logits
+ *   anchors   (A, 2) fp32 anchor centres in grid units, strides (A) fp32   (make_anchors, tal.py:484-500)
+ *   gt        (B, G, 5) fp32 rows (class, x1, y1, x2, y2) in pixels, all-zero rows = padding (loss.py:131-148); G may be 0
+ *   alpha     0.5 * (100 - calls / 161) / 100 (tal.py:110, 266), beta 8, topk 10 as the reference constructs it
+ *   loss4     out: box, cls, dfl (each already multiplied by its gain; the reference returns their sum * B) and
+ *             target_scores_sum
+ *   grad_pred out or NULL: d(sum(loss3) * B) / d(pred), same layout as pred
+ *   out_tscore / out_idx / out_tbox / out_label: optional assigner outputs, (B, A) fp32 target score of the assigned
+ *             class, (B, A) int32 gt index or -1, (B, A, 4) fp32 target box in pixels, (B, A) int32 label or -1
+ *   ws        device scratch of mgdt_v8_loss_ws_bytes(B, A, G) bytes */
+size_t mgdt_v8_loss_ws_bytes(int B, int A, int G);
+int mgdt_v8_loss(const float* pred, const float* anchors, const float* strides, const float* gt, int B, int A, int G, int nc,
+                 int reg_max, float alpha, float beta, int topk, float box_gain, float cls_gain, float dfl_gain, float* loss4,
+                 float* grad_pred, float* out_tscore, int32_t* out_idx, float* out_tbox, int32_t* out_label, void* ws, size_t ws_bytes,
+                 void* stream);
+/* ModelEMA.update (yolo/utils/torch_utils.py:347-358) over one flat fp32 buffer: ema = ema * decay + (1 - decay) * model. */
+int mgdt_ema_update(float* ema, const float* model, size_t n, float decay, void* stream);
+/* Sum of squares of a flat fp32 buffer into *out (fp64; zeroed first): the gradient norm of clip_grad_norm_. */
+int mgdt_sumsq(const float* x, size_t n, double* out, void* stream);
+/* DetectionTrainer.optimizer_step (yolo/engine/trainer.py:462-470) over one flat bucket: clip_grad_norm_(max_norm) from
+ * *gnorm_sq (NULL = no clipping), then torch.optim.SGD(momentum, nesterov) with the three parameter groups of
+ * build_optimizer (trainer.py:614-650): group[i] = 0 weights (decay), 1 normalisation weights, 2 biases; lr3 / wd3 are
+ * HOST arrays of three floats.  grad_scale multiplies the gradients first (1 / world_size after a summing all-reduce). */
+int mgdt_sgd_step(float* prm, const float* grad, float* mom, const unsigned char* group, size_t n, const float* lr3, const float* wd3,
+                  float momentum, int nesterov, int first_step, const double* gnorm_sq, float max_norm, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MGDT_LIB") or os.path.join(HERE, "libmgdt_b200.so")   # MGDT_LIB: A/B runs of two builds in one session
 
-ABI_VERSION = 3  # include/mgdt_b200.h MGDT_ABI_VERSION
+ABI_VERSION = 4  # include/mgdt_b200.h MGDT_ABI_VERSION
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_RELU, ACT_SIGMOID, ACT_HSIGMOID, ACT_GELU = range(6)
 RS_COPY, RS_AVGPOOL, RS_BILINEAR, RS_NEAREST = range(4)
@@ -85,6 +85,11 @@ SIGNATURES = {
     "mgdt_decode": (C.c_int, [C.POINTER(DecodeLevel), i32, i32, i32, i32, i32, vp, i32, vp]),
     "mgdt_nms_ws_bytes": (sz, [i32, i32, i32, i32, i32]),
     "mgdt_nms": (C.c_int, [vp, i32, i32, i32, f32, f32, i32, i32, i32, i32, f32, vp, i32, vp, vp, vp, sz, vp]),
+    "mgdt_v8_loss_ws_bytes": (sz, [i32, i32, i32]),
+    "mgdt_v8_loss": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, f32, f32, f32, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "mgdt_ema_update": (C.c_int, [vp, vp, sz, f32, vp]),
+    "mgdt_sumsq": (C.c_int, [vp, sz, vp, vp]),
+    "mgdt_sgd_step": (C.c_int, [vp, vp, vp, vp, sz, C.POINTER(C.c_float), C.POINTER(C.c_float), f32, i32, i32, vp, f32, f32, vp]),
 }
 
 _LIB = None

@@ -21,7 +21,15 @@ def _version(t) -> int:
 
 
 class KernelModule(nn.Module):
-    """nn.Module whose forward runs sm_100a kernels (eval mode, CUDA tensors only)."""
+    """nn.Module whose forward runs sm_100a kernels (eval mode, CUDA tensors only).  In train mode the call is routed
+    to the differentiable torch-operator forward of train_forward.py (batch-statistics BatchNorm, autograd backward):
+    the training step's B200-native parts are the criterion and the optimizer side (train.py, csrc/train.cu)."""
+
+    def __call__(self, *args, **kwargs):
+        if self.training:
+            from .. import train_forward
+            return train_forward.run(self, *args, **kwargs)
+        return super().__call__(*args, **kwargs)
 
     def _packed(self, name, dtype, device, tensors, builder):
         """Weights of this module in the kernels' layouts, built once per (name, dtype, device) and rebuilt when a
@@ -49,10 +57,9 @@ class KernelModule(nn.Module):
     def _check_mode(self, x):
         t = x[0] if isinstance(x, (list, tuple)) else x
         ops.require_cuda(t, f"{type(self).__name__} input")
-        if self.training:
-            raise NotImplementedError(
-                f"{type(self).__name__}: the B200 path implements the inference forward (call .eval()); the "
-                "training step is outside the accelerated hot path (DESIGN.md, out of scope).")
+        if self.training:   # unreachable through __call__; a direct .forward() in train mode
+            raise RuntimeError(f"{type(self).__name__}.forward is the inference kernel path; call the module (train mode "
+                               "dispatches to train_forward.py) or switch to .eval()")
 
     def __getstate__(self):  # packed caches hold device pointers; never pickle them
         d = dict(self.__dict__)

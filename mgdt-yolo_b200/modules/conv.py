@@ -150,6 +150,8 @@ class Upsample(nn.Upsample):
     defer = False  # set by DetectionModel when the only consumer is the next Concat
 
     def forward(self, x):
+        if self.training:
+            return nn.Upsample.forward(self, x)
         ops.require_cuda(x, "Upsample input")
         if self.mode not in ("nearest", "bilinear") or self.scale_factor is None:
             raise NotImplementedError("Upsample: nearest/bilinear with scale_factor only")

@@ -162,27 +162,39 @@ def _downscale(model):
 
 
 class BaseModel(nn.Module):
-    """tasks.py:28-216 restricted to inference."""
+    """tasks.py:28-216."""
 
     def forward(self, x, *args, **kwargs):
-        if isinstance(x, dict):
-            raise NotImplementedError("training (loss) is outside the B200 hot path; see DESIGN.md 'out of scope'")
+        if isinstance(x, dict):          # training / validation-loss call of the trainer (tasks.py:42-44)
+            return self.loss(x, *args, **kwargs)
         return self.predict(x, *args, **kwargs)
+
+    def loss(self, batch, preds=None):
+        """tasks.py:204-216: criterion(preds or forward(batch['img']), batch)."""
+        if not hasattr(self, "criterion"):
+            self.criterion = self.init_criterion()
+        preds = self.forward(batch["img"]) if preds is None else preds
+        return self.criterion(preds, batch)
 
     def predict(self, x, profile=False, visualize=False, augment=False):
         return self._predict_once(x, profile, visualize)
 
     def _predict_once(self, x, profile=False, visualize=False):
         """tasks.py:65-87.  `profile`/`visualize` are accepted for signature parity and ignored."""
+        if self.training:      # differentiable torch-operator forward (train_forward.py); any device
+            return self._walk(x)
         ops.require_cuda(x, "model input")
         with torch.cuda.device(x.device):
-            y = []
-            for m in self.model:
-                if m.f != -1:
-                    x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
-                x = m(x)
-                y.append(x if m.i in self.save else None)
-            return x
+            return self._walk(x)
+
+    def _walk(self, x):
+        y = []
+        for m in self.model:
+            if m.f != -1:
+                x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
+            x = m(x)
+            y.append(x if m.i in self.save else None)
+        return x
 
     def stem_fusable(self):
         m0 = self.model[0]
@@ -269,4 +281,6 @@ class DetectionModel(BaseModel):
                 layer.defer = True
 
     def init_criterion(self):
-        raise NotImplementedError("training loss is outside the B200 hot path")
+        """tasks.py:293-294: v8DetectionLoss(self) -- here the fused CUDA criterion (train.py, csrc/train.cu)."""
+        from .train import v8DetectionLoss
+        return v8DetectionLoss(self)
