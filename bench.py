@@ -19,6 +19,9 @@ JSON line (rank 0):
                 torchvision deform_conv2d + nms kernels, fp16 channels_last) -- the library bar -- with per-op
                 library timings for K1 (conv), K14 (DCNv2) and K17 (NMS) next to this repo's kernels
   sustained     the device-resident loop repeated for >= 2 s (thermal / power steady state)
+  training      BASELINE configs[4]: training step of the full config, 16 images per GPU, bf16 autocast forward / backward,
+                fused CUDA criterion, one flat-bucket NCCL all-reduce (N > 1), fused clip + SGD + EMA; plus the criterion
+                alone against the reference's on the same GPU
   extra         batch sweep B = 1 ... 512 of the full config, the other three BASELINE configs at B = 32, NMS at the
                 validator setting (conf 0.001, multi_label)
 
@@ -400,6 +403,69 @@ def extras(args, dev, dtype):
     return out
 
 
+def training_leg(dev, world, rank, barrier, max_over_ranks, steps=5, warmup=2, batch=16):
+    """BASELINE.json configs[4] / SURVEY 8(d) #5: training step of the full MGDT config, 16 images per GPU at 640 x 640,
+    bf16 autocast forward / backward (train-mode modules: torch operators), the fused CUDA criterion, ONE flat-bucket
+    gradient all-reduce over NCCL, fused clip + SGD + EMA.  Every rank takes part; timed on the device, max over ranks."""
+    import torch
+    from mgdt_yolo_b200.tasks import DetectionModel
+    from mgdt_yolo_b200.train import FlatBucket, synth_targets, train_step, v8DetectionLoss
+    wl = "mspa_c2f_gd_tood_yolov8n"
+    cfg, nc, _ = WORKLOADS[wl]
+    m = DetectionModel(cfg, nc=nc, verbose=False)
+    m.load_state_dict(synth_weights(wl, m.state_dict()))
+    m = m.to(dev)
+    fb = FlatBucket(m, lr=0.01)
+    b = synth_targets(batch, 20, nc, seed=rank, device=dev)
+    b["img"] = make_u8(batch, 500 + rank).to(dev)
+    for _ in range(warmup):
+        train_step(m, fb, b)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, items = train_step(m, fb, b)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    out = {"workload": wl, "images_per_gpu_per_step": batch, "imgsz": 640, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "value": steps * batch * world / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / steps, "dtype": "bf16 autocast",
+           "allreduce": {"backend": "nccl" if world > 1 else None, "calls_per_step": 1 if world > 1 else 0, "bytes": fb.n * 4},
+           "params": fb.n, "loss_last": float(loss), "forward_backward": "torch operators (train_forward.py)",
+           "native": ["mgdt_v8_loss", "mgdt_sumsq", "mgdt_sgd_step", "mgdt_ema_update"]}
+    if rank == 0:
+        # the criterion alone at this step's shapes: the fused CUDA call vs the reference's own v8DetectionLoss on this GPU
+        from oracle.train_cases import model_stub
+        f = torch.randn(batch, nc + 64, 80, 80, device=dev)
+        f[:, :64] *= 1.5
+
+        def timed(crit, n=10):
+            x = f.clone().requires_grad_(True)
+            for _ in range(2):
+                crit([x], b)[0].backward()
+            torch.cuda.synchronize(dev)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(n):
+                crit([x], b)[0].backward()
+            a1.record()
+            torch.cuda.synchronize(dev)
+            return a0.elapsed_time(a1) / n
+        stub = model_stub(nc, 16, [(80, 80, 8.0)], dev)
+        out["criterion_ms"] = {"ours_fwd_bwd": timed(v8DetectionLoss(stub))}
+        try:
+            from baseline import ref_loader
+            if ref_loader.available():
+                ref_loader.load()
+                from ultralytics.yolo.utils import loss as L
+                out["criterion_ms"]["reference_fwd_bwd"] = timed(L.v8DetectionLoss(stub))
+        except Exception as e:   # noqa: BLE001
+            out["criterion_ms"]["reference_error"] = str(e)[:120]
+    del m, fb, b
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -523,6 +589,18 @@ def run_ours(args):
     if rank == 0 and n_out != args.steps * B * world:
         raise SystemExit(f"bench.py: the e2e leg returned {n_out} per-image results, expected {args.steps * B * world}")
 
+    # ---- (2b) BASELINE configs[4]: the training step (all ranks: its gradient all-reduce is the one collective of the repo)
+    training = None
+    if not args.no_extras:
+        ok = torch.ones(1, device=dev)
+        try:
+            training = training_leg(dev, world, rank, barrier, max_over_ranks)
+        except Exception as e:   # noqa: BLE001
+            if world > 1:
+                raise            # a rank that drops out of the collective would hang the others
+            training = {"error": str(e)[:200]}
+        del ok
+
     # ---- (3) per-launch profile of eager steps: CUDA events on the launching stream around every C-ABI call, PDL off
     # (so consecutive kernels do not overlap across the events) and the stream pre-loaded with a spin kernel so that
     # the launches are queued ahead of the GPU (the events then bracket kernel execution, not CPU launch gaps)
@@ -630,6 +708,8 @@ def run_ours(args):
     }
     if sustained is not None:
         line["sustained"] = sustained
+    if training is not None:
+        line["training"] = training
     if world == 1 and not args.no_extras:
         try:
             ge = gpu_eager_reference(args.workload, B, dev)
