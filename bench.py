@@ -455,7 +455,9 @@ def training_leg(dev, world, rank, barrier, max_over_ranks, steps=5, warmup=2, b
         out["criterion_ms"] = {"ours_fwd_bwd": timed(v8DetectionLoss(stub))}
         try:
             from baseline import ref_loader
-            if ref_loader.available():
+            # N = 1 only: importing the reference under an initialised process group runs a rank-0-only dist.barrier()
+            # (yolo/utils/__init__.py SettingsManager -> torch_distributed_zero_first), which would unpair the ranks
+            if world == 1 and ref_loader.available():
                 ref_loader.load()
                 from ultralytics.yolo.utils import loss as L
                 out["criterion_ms"]["reference_fwd_bwd"] = timed(L.v8DetectionLoss(stub))
@@ -481,7 +483,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that drops out must not park the others for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=int(os.environ.get("MGDT_BENCH_NCCL_TIMEOUT", "120"))))
     lib()  # fail loudly now if the extension is missing
 
     cfg, nc, cls_bias = WORKLOADS[args.workload]
