@@ -660,12 +660,18 @@ def run_ours(args):
     else:
         roof = {"bound": "hbm", "achieved": b_launch / t_launch / 1e9, "peak": hbm, "unit": "GB/s"}
     traffic = None
-    try:  # measured DRAM bytes per launch of that kernel from the committed ncu capture (profiles/traffic_r01.json)
-        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
-            tj = json.load(f)
-        if tj.get("kernel") == top["kernel"] and tj.get("batch") == B and tj.get("workload") == args.workload:
-            traffic = tj["dram_bytes_per_launch"]
-    except Exception:
+    try:  # measured DRAM bytes per launch of that kernel from the committed ncu capture (profiles/traffic_rNN.json)
+        for fn in ("traffic_r02.json", "traffic_r01.json"):
+            path = os.path.join(ROOT, "profiles", fn)
+            if not os.path.isfile(path):
+                continue
+            with open(path) as f:
+                tj = json.load(f)
+            tj = tj.get("kernels", {}).get(top["kernel"], tj)
+            if tj.get("kernel") == top["kernel"] and tj.get("workload") == args.workload and tj.get("batch") == B:
+                traffic = tj["dram_bytes_per_launch"]
+                break
+    except Exception:   # noqa: BLE001
         traffic = None
     roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=top["kernel"],
                 launches_per_step=top["n"], us_per_launch=t_launch * 1e6, share_of_step=top["ms"] / total_ms,

@@ -56,11 +56,12 @@ with open(os.path.join(P, f"launches_{R}.md"), "w") as f:
     f.write("\n## launches in order\n\n| # | kernel | grid | block | us |\n|---:|---|---|---|---:|\n")
     for i, r in enumerate(step):
         f.write(f"| {i} | `{short(r[4])}` | {r[8]} | {r[7]} | {float(r[14]) / 1000.0:.1f} |\n")
-print("launch list:", len(step), "launches", f"{tot:.1f} us; conv_umma2 share {100 * fam['conv_umma2_kernel'][0] / tot:.1f}%")
+conv_fams = [k for k in fam if k.startswith("conv")]
+print("launch list:", len(step), "launches", f"{tot:.1f} us;", ", ".join(f"{k} {100 * fam[k][0] / tot:.1f}%" for k in conv_fams))
 
 # ---- (2) traffic
 out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"), os.path.join(G, f"traffic_{R}.csv"),
-                      "conv_umma2_kernel", str(CONV_PER_STEP), "32", "mspa_c2f_gd_tood_yolov8n"], capture_output=True, text=True)
+                      "ALL" if R != "r01" else "conv_umma2_kernel", str(CONV_PER_STEP), "32", "mspa_c2f_gd_tood_yolov8n"], capture_output=True, text=True)
 open(os.path.join(P, f"traffic_{R}.json"), "w").write(out.stdout)
 print(out.stdout)
 
@@ -82,8 +83,13 @@ TC_WANT = ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "sm__mem_tensor_cycl
 tc_cols = [(h, i) for i, h in enumerate(hdr) if h in TC_WANT]
 cases = ["c32_3x3 (32->32 3x3 @80^2, B=32)", "c32_3x3 (2nd launch, warm)", "c96_384 (96->384 1x1 @40^2)", "c96_384 (2nd launch, warm)",
          "c64_256 (64->256 1x1 @80^2)", "c64_256 (2nd launch, warm)"]
+if R != "r01":
+    cases = ["c32_3x3 (32->32 3x3 @80^2, B=32: conv3x3_tma_kernel)", "c32_3x3 (2nd launch, warm)",
+             "c16_32_s2 (16->32 3x3 stride 2 @320^2: conv_umma2_kernel)", "c16_32_s2 (2nd launch, warm)",
+             "c96_384 (96->384 1x1 @40^2: conv1x1_tma_kernel without statistics)", "c96_384 (2nd launch, warm)",
+             "c64_256 (64->256 1x1 @80^2: conv1x1_tma_kernel)", "c64_256 (2nd launch, warm)"]
 with open(os.path.join(P, f"conv_umma2_full_{R}.md"), "w") as f:
-    f.write(f"# `ncu --set full --clock-control none --import-source on` of conv_umma2_kernel -- tools/ncu_conv.py c64_256 c32_3x3 c96_384\n\n"
+    f.write(f"# `ncu --set full --clock-control none --import-source on` of the tcgen05 conv kernels -- tools/ncu_conv.py ({', '.join(c.split()[0] for c in cases[::2])})\n\n"
             "Two launches per shape (the second is warm).  Raw report: gpurun_out/ (scratch, not committed).\n\n")
     for k, r in enumerate(rr[2:]):
         f.write(f"## launch {k}: {cases[k] if k < len(cases) else ''}\n\n| metric | value | unit |\n|---|---:|---|\n")
@@ -94,7 +100,9 @@ with open(os.path.join(P, f"conv_umma2_full_{R}.md"), "w") as f:
                 f.write(f"| {h} | {r[i][:40]} | {units[i]} |\n")
         f.write("\n")
     # stall summary of the warm c64_256 and c32_3x3 launches
-    for kid, label in ((2, "c32_3x3, warm launch"), (6, "c64_256, warm launch")):
+    for kid, label in (((2, "c32_3x3, warm launch"), (6, "c64_256, warm launch")) if R == "r01" else
+                       ((2, "c32_3x3 (conv3x3_tma_kernel), warm launch"), (4, "c16_32_s2 (conv_umma2_kernel), warm launch"),
+                        (8, "c64_256 (conv1x1_tma_kernel), warm launch"))):
         src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-id", f":::{kid}"],
                              capture_output=True, text=True).stdout
         sr = list(csv.reader(io.StringIO(src)))

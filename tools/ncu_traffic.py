@@ -11,6 +11,21 @@ import json
 import sys
 
 path, kernel, n, batch, workload = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
+if kernel == "ALL":   # one entry per conv kernel function: {"kernels": {name: {...}}}; n = launches of ALL of them in one step
+    import re
+    import subprocess
+    allrows = [r for r in csv.reader(open(path)) if len(r) > 14 and r[0].isdigit()]
+    ids_all = sorted({int(r[0]) for r in allrows})[-n:]
+    names = {}
+    for r in allrows:
+        if int(r[0]) in ids_all:
+            names.setdefault(re.sub(r"<.*", "", r[4].replace("void ", "").replace("mgdt::", "")), set()).add(int(r[0]))
+    out = {}
+    for k, ids in names.items():
+        sub = subprocess.run([sys.executable, __file__, path, k, str(len(ids)), str(batch), workload], capture_output=True, text=True)
+        out[k] = json.loads(sub.stdout)
+    print(json.dumps({"kernels": out}, indent=1))
+    sys.exit(0)
 rows = [r for r in csv.reader(open(path)) if len(r) > 14 and r[0].isdigit() and kernel in r[4]]
 by_id = {}
 for r in rows:
