@@ -153,3 +153,38 @@ def test_train_steps_full_config_then_inference():
     with torch.no_grad():
         y, raw = m(batch["img"].to(torch.bfloat16))
     assert y.shape == (4, 6, 16 * 20) and torch.isfinite(y.float()).all()
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference copy (baseline/_ref) not present")
+def test_model_loss_and_gradients_match_reference_model():
+    """`model(batch)` as the trainer calls it (trainer.py:329-334): the drop-in DetectionModel (train-mode modules + the fused
+    CUDA criterion) against the reference's DetectionModel + its own v8DetectionLoss on the same GPU, fp32, TF32 off."""
+    import types
+    from mgdt_yolo_b200.synth import synth_images, synth_state_dict
+    from mgdt_yolo_b200.tasks import DetectionModel
+    from mgdt_yolo_b200.train import synth_targets
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = "mspa_c2f_gd_tood_yolov8n.yaml"
+    ref = ref_loader.build_model(cfg, nc=2)
+    sd = synth_state_dict(ref.state_dict(), seed=1)
+    ref.load_state_dict(sd)
+    ours = DetectionModel(cfg, nc=2, verbose=False)
+    ours.load_state_dict(sd)
+    hyp = types.SimpleNamespace(box=7.5, cls=0.5, dfl=1.5)
+    ref, ours = ref.cuda().train(), ours.cuda().train()
+    ref.args, ours.args = hyp, hyp
+    batch = synth_targets(4, 10, 2, seed=3)
+    batch["img"] = synth_images(4, h=128, w=160, seed=2).cuda()
+    lr, ir = ref(dict(batch))
+    lo, io = ours(dict(batch))
+    assert _rel(lo, lr) <= 1e-4 and _rel(io, ir) <= 1e-4, (io.tolist(), ir.tolist())
+    lr.backward()
+    lo.backward()
+    pr, po = dict(ref.named_parameters()), dict(ours.named_parameters())
+    gmax = max(float(p.grad.abs().max()) for p in pr.values() if p.grad is not None)
+    for k, p in pr.items():
+        if p.grad is None:
+            assert po[k].grad is None or float(po[k].grad.abs().max()) == 0.0, k
+        else:   # atomics in cuDNN / deform_conv2d backward: compare on the scale of the largest gradient
+            assert float((po[k].grad - p.grad).abs().max()) <= 2e-3 * max(float(p.grad.abs().max()), 1e-3 * gmax), k
