@@ -1,5 +1,6 @@
 // TMA-fed tcgen05 / TMEM kernel for the transform-free 3x3 stride-1 convolutions with Cin <= 64 (mode 1 of conv_umma2.cu).
-// Included by conv_umma2.cu inside namespace mgdt, after conv_tma1x1.cuh (shares its helpers and the epilogue arithmetic).
+// Included by conv_umma2.cu inside namespace mgdt, after conv_tma1x1.cuh (shares its helpers, the epilogue arithmetic and the
+// fused output statistics of conv_umma2_kernel: STATS = 1 for the Conv_GN layers of the TOOD head).
 //
 // A operand: the same no-swizzle K-major channel planes [Cin/8][positions][16 B] as conv_umma2_kernel, positions = linear
 // indices of the zero-padded image (row pitch Wq = W + 2), so a tap (dy, dx) is the plane read through a descriptor whose
@@ -27,7 +28,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 
 static constexpr unsigned t3_tail(int epiw) { return 1024u + 256u * 4u + (unsigned)epiw * 2048u + 512u; }
 
-template <int EPIW>
+template <int EPIW, int STATS>
 __global__ void __launch_bounds__(64 + 32 * EPIW, 2) conv3x3_tma_kernel(const __grid_constant__ P2 p) {
     constexpr int T3_THREADS = 64 + 32 * EPIW;
     pdl_trigger();
@@ -183,6 +184,16 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 2) conv3x3_tma_kernel(const __
                 const int opix = (r < (uint32_t)t.R && x < (uint32_t)p.W && y0 + r < (uint32_t)p.H)
                                      ? (int)((n_img * (uint32_t)p.H + y0 + r) * (uint32_t)p.W + x) : -1;
                 const bool any_row = __any_sync(0xffffffffu, opix >= 0);
+                uint32_t skey = 0xffffffffu;   // fused statistics: (image << 4) | adaptive-pool window mask of this lane's row
+                if (STATS && opix >= 0) {
+                    uint32_t mask = 0;
+                    if (p.st_Q == 5) {
+                        const int h = (int)(y0 + r), w = (int)x;
+                        const uint32_t top = h < p.st_h0e, bot = h >= p.st_h1b, lef = w < p.st_w0e, rig = w >= p.st_w1b;
+                        mask = (top & lef) | ((top & rig) << 1) | ((bot & lef) << 2) | ((bot & rig) << 3);
+                    }
+                    skey = (n_img << 4) | mask;
+                }
                 __nv_bfloat16* yrow[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -248,6 +259,9 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 2) conv3x3_tma_kernel(const __
                             }
                         }
                     }
+                    if (STATS)   // per-(image, channel) sums of the staged (bf16-rounded) unit, fp64 atomics (see epi_stats)
+                        epi_stats(p.st_acc + (size_t)(tile % (uint32_t)p.st_R) * p.st_rs, p.st_Q, p.st_sq, p.st_tot, p.Cout, stg32, skey, lane, nv,
+                                  co0, p.Cout);
                     __syncwarp();
                     if (tr) {
                         tc3 = clock64();
@@ -334,17 +348,17 @@ static void fill_adesc3(P2& p) {
     }
 }
 
-template <int EPIW>
+template <int EPIW, int STATS>
 static int launch_t3k(const P2& p, dim3 grid, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tma_kernel<EPIW>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tma_kernel<EPIW, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_MAX_SMEM);
     if (e != cudaSuccess) return set_error(-EIO, "conv3x3_tma: smem attr: %s", cudaGetErrorString(e));
-    launch_k(conv3x3_tma_kernel<EPIW>, grid, dim3(64 + 32 * EPIW), p.t3.smem_total, s, p);
+    launch_k(conv3x3_tma_kernel<EPIW, STATS>, grid, dim3(64 + 32 * EPIW), p.t3.smem_total, s, p);
     MGDT_LAUNCH_CHECK("conv3x3_tma");
     return 0;
 }
 
 static bool t3_eligible(const P2& p) {
-    return g_use_tma3 && p.pl.mode == 1 && !p.st_acc && !p.stem_src && !p.dcn_off && !p.pre_add && !p.in_scale && !p.pix_scale &&
+    return g_use_tma3 && p.pl.mode == 1 && !p.stem_src && !p.dcn_off && !p.pre_add && !p.in_scale && !p.pix_scale &&
            !p.in_relu && !p.row_scale && !p.act_cols && !p.w_img_elems && p.Cout <= 256;
 }
 
@@ -366,6 +380,7 @@ static int try_launch_t3(P2& p, cudaStream_t s) {
     fill_adesc3(p);
     const long long cx = std::min<long long>(t.tiles, 148LL * t.ctas_per_sm);
     const dim3 grid((unsigned)cx, 1);
-    const int rc = t.epiw == 8 ? launch_t3k<8>(p, grid, s) : launch_t3k<4>(p, grid, s);
+    const int rc = t.epiw == 8 ? (p.st_acc ? launch_t3k<8, 1>(p, grid, s) : launch_t3k<8, 0>(p, grid, s))
+                               : (p.st_acc ? launch_t3k<4, 1>(p, grid, s) : launch_t3k<4, 0>(p, grid, s));
     return rc < 0 ? rc : 1;
 }

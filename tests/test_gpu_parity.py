@@ -171,9 +171,10 @@ def test_full_size_properties():
         assert torch.equal(again[:, 4], again[:, 4].sort(descending=True).values)
 
 
-@pytest.mark.parametrize("cfg", ["mspa_c2f_gd_yolov8s.yaml", "mspa_c2f_yolov8s.yaml", "mspa_c2f_yolov8m.yaml", "yolov8s.yaml"])
+@pytest.mark.parametrize("cfg", ["mspa_c2f_gd_yolov8s.yaml", "mspa_c2f_yolov8s.yaml", "mspa_c2f_yolov8m.yaml", "yolov8s.yaml",
+                                 "mspa_c2f_yolov8l.yaml", "mspa_c2f_gd_yolov8x.yaml", "yolov8x.yaml"])
 def test_other_width_scales_vs_oracle(cfg):
-    """the other width scales of models/v8/*.yaml (`scales:` s / m: wider channels, MSPA branch widths 16-96,
+    """the other width scales of models/v8/*.yaml (`scales:` s / m / l / x: wider channels, MSPA branch widths 16-160,
     deeper C2f) build from the same YAMLs and agree with the CPU oracle on identical synthetic weights (no golden fixture:
     the oracle itself is pinned by the n-scale fixtures).  The TOODHead configs exist at scale n only: their YAMLs fix the
     head width (hidc = 64 / 128) while the neck output scales, so the reference itself cannot build them at s / m.  fp32 validation mode 1e-4; bf16 decode output 1e-2 (relative L2)."""
