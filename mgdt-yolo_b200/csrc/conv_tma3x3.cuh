@@ -19,7 +19,15 @@
 //   warp 1    MMA       K = 16 steps x MB row blocks, A descriptors from the kernel parameters (p.adesc), uniform datapath
 //   warps 2+  epilogue  tcgen05.ld -> bias / activation / residual / bf16 -> swizzled staging tile -> 16-byte stores
 //
-// Output row m of a tile (n, ty):  r = m / Wq, x = m % Wq, y = ty * R + r;  valid iff r < R, x < W, y < H.
+// Output row m of a tile (n, ty):  r = m / Wq, x = m % Wq, y = ty * R + r;  valid iff r < R, x < Wo, y < Ho.
+//
+// Stride 2 (same kernel, t.s2): the padded input is split into its four row / column parity sub-images while loading
+// (space-to-depth, as conv_umma2_kernel's mode 2), after which every tap is again a pure shift of one sub-plane.  TMA does
+// the split: the NHWC tensor is described as (channels of a COLUMN PAIR, W / 2, H, N) -- the column parity becomes a
+// channel offset, so no element stride is needed along x (the widest layer has 2 * 161 > 256 columns) -- with element
+// stride 2 along y.  Sub-image (ph, pw) of the tile's rows is the box {8, Wq = Wo + 1, R + 1 rows, 1} at
+// (plane * 8 + (pw ? 0 : x_cs), pw ? 0 : -1, 2 * y0 + ph - 1, n): input column 2c + pw - 1 is the second pixel of pair
+// c - 1 (pw = 0) or the first pixel of pair c (pw = 1).
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -59,11 +67,11 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 2) conv3x3_tma_kernel(const __
     // rows -- for junk rows, and by the zero-weight dummy chunk of Cin = 8 layers for valid ones: keep them zero
     // (NaN bit patterns times zero weights would poison valid accumulators).
     {
-        const uint32_t slack16 = (uint32_t)(t.pstride - t.PB);
-        const uint32_t per_stage = (uint32_t)pl.planes * slack16;
+        const uint32_t slack16 = (uint32_t)(t.Ppar - t.PB);
+        const uint32_t per_stage = (uint32_t)(pl.planes * t.npar) * slack16;
         for (uint32_t i = tid; slack16 && i < (uint32_t)t.S * per_stage; i += T3_THREADS) {
-            const uint32_t s = i / per_stage, r = i - s * per_stage, pll = r / slack16, q = r - pll * slack16;
-            *reinterpret_cast<uint4*>(base + t.w_bytes + (size_t)s * t.stage_bytes + ((size_t)pll * t.pstride + t.PB + q) * 16) = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t s = i / per_stage, r = i - s * per_stage, sub = r / slack16, q = r - sub * slack16;   // sub = plane * npar + parity
+            *reinterpret_cast<uint4*>(base + t.w_bytes + (size_t)s * t.stage_bytes + ((size_t)sub * t.Ppar + t.PB + q) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
     }
     if (warp == 1) {
@@ -103,8 +111,18 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 2) conv3x3_tma_kernel(const __
             if (elect_one()) {
                 const uint32_t sA = sStage32 + (uint32_t)s * t.stage_bytes;
                 mbar_expect_tx(FULL(s), t.tx_bytes);
-                for (int pll = 0; pll < pl.planes; ++pll)
-                    tma_load_4d(sA + (uint32_t)pll * (uint32_t)t.pstride * 16u, &p.xmap, pll * 8, -1, (int)(ty * (uint32_t)t.R) - 1, (int)n_img, FULL(s));
+                if (!t.s2) {
+                    for (int pll = 0; pll < pl.planes; ++pll)
+                        tma_load_4d(sA + (uint32_t)pll * (uint32_t)t.pstride * 16u, &p.xmap, pll * 8, -1, (int)(ty * (uint32_t)t.R) - 1, (int)n_img, FULL(s));
+                } else {
+                    const int yb = 2 * (int)(ty * (uint32_t)t.R) - 1;
+                    for (int pll = 0; pll < pl.planes; ++pll)
+                        for (int par = 0; par < 4; ++par) {
+                            const int ph = par >> 1, pw = par & 1;
+                            tma_load_4d(sA + ((uint32_t)pll * (uint32_t)t.pstride + (uint32_t)par * (uint32_t)t.Ppar) * 16u, &p.xmap,
+                                        pll * 8 + (pw ? 0 : t.xoff2), pw ? 0 : -1, yb + ph, (int)n_img, FULL(s));
+                        }
+                }
                 if (p.trace && tl < 6) trace_mark(p, 8 + 8 * (int)tl);
             }
             __syncwarp();
@@ -181,8 +199,8 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 2) conv3x3_tma_kernel(const __
                 // output pixel of this lane's row
                 const uint32_t m = (uint32_t)(mb * 128 + quad * 32 + lane);
                 const uint32_t r = fdiv(m, p.d_Wq), x = m - r * (uint32_t)t.Wq;
-                const int opix = (r < (uint32_t)t.R && x < (uint32_t)p.W && y0 + r < (uint32_t)p.H)
-                                     ? (int)((n_img * (uint32_t)p.H + y0 + r) * (uint32_t)p.W + x) : -1;
+                const int opix = (r < (uint32_t)t.R && x < (uint32_t)t.Wo && y0 + r < (uint32_t)t.Ho)
+                                     ? (int)((n_img * (uint32_t)t.Ho + y0 + r) * (uint32_t)t.Wo + x) : -1;
                 const bool any_row = __any_sync(0xffffffffu, opix >= 0);
                 uint32_t skey = 0xffffffffu;   // fused statistics: (image << 4) | adaptive-pool window mask of this lane's row
                 if (STATS && opix >= 0) {
@@ -287,27 +305,33 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, 2) conv3x3_tma_kernel(const __
 }
 
 // ---------------------------------------------------------------------------------- host side
-static int g_use_tma3 = 1;   // option "conv_tma3x3": TMA-fed kernel for transform-free 3x3 stride-1 layers
+static int g_use_tma3 = 1;      // option "conv_tma3x3": TMA-fed kernel for transform-free 3x3 layers
+static int g_use_tma3_s2 = 1;   // option "conv_tma3x3_s2": ... also for stride 2
 
 static bool plan_t3(const P2& p, T3& best) {
     const Plan2& pl = p.pl;
-    if (pl.mode != 1 || pl.nks != 1 || pl.nsplit != 1 || pl.PS != pl.planes || pl.planes > 8) return false;
-    const int Wq = p.W + 2;
-    if (Wq > 256 || p.H < 1) return false;
+    const bool s2 = pl.mode == 2;
+    if ((pl.mode != 1 && !s2) || pl.nks != 1 || pl.nsplit != 1 || pl.PS != pl.planes) return false;
+    if (pl.planes * (s2 ? 4 : 1) > 32) return false;
+    if (s2 && ((p.W & 1) || (p.H & 1))) return false;                    // column pairs; even H keeps Ho = H / 2
+    const int Wq = s2 ? p.Wo + 1 : p.W + 2, Ho = p.Ho, Wo = p.Wo;
+    if (Wq > 256 || Ho < 1) return false;
     const unsigned w_copy = (unsigned)pl.nmma_s * 2u * (unsigned)pl.Nc * 16u;
     int best_score = -1;
     for (int mb : {4, 2, 1}) {
-        int R = std::min(128 * mb / Wq, p.H);
-        if (R < 1 || R + 2 > 256) continue;
+        int R = std::min(128 * mb / Wq, Ho);
+        if (R < 1 || 2 * (R + 2) > 256) continue;
         if (mb > 1 && (long long)R * Wq * 10 < 128LL * mb * 7) continue;   // less than 70 % of the tile's rows are pixels
         for (int epiw : {8, 4}) {
             T3 c{};
-            c.MB = mb; c.R = R; c.Wq = Wq; c.epiw = epiw;
-            c.PB = (R + 2) * Wq;
-            c.pstride = (std::max(c.PB, 128 * mb + 2 * Wq + 3) + 7) / 8 * 8;
-            c.tiles_per_img = (p.H + R - 1) / R;
+            c.MB = mb; c.R = R; c.Wq = Wq; c.epiw = epiw; c.s2 = s2 ? 1 : 0; c.npar = s2 ? 4 : 1; c.Ho = Ho; c.Wo = Wo; c.xoff2 = p.x_cs;
+            c.PB = (s2 ? R + 1 : R + 2) * Wq;
+            const int reach = 128 * mb + (s2 ? Wq + 2 : 2 * Wq + 3);      // furthest position a tap of the tile's last row reads
+            c.Ppar = (std::max(c.PB, reach) + 7) / 8 * 8;
+            c.pstride = c.npar * c.Ppar;
+            c.tiles_per_img = (Ho + R - 1) / R;
             c.tiles = (long long)c.tiles_per_img * p.N;
-            c.tx_bytes = (unsigned)pl.planes * (unsigned)c.PB * 16u;
+            c.tx_bytes = (unsigned)(pl.planes * c.npar) * (unsigned)c.PB * 16u;
             c.w_copy_bytes = w_copy;
             c.w_bytes = (w_copy + 1023u) / 1024u * 1024u;
             c.stage_bytes = ((unsigned)pl.planes * (unsigned)c.pstride * 16u + 1023u) / 1024u * 1024u;
@@ -338,6 +362,9 @@ static void fill_adesc3(P2& p) {
     const T3& t = p.t3;
     auto off = [&](int c) -> uint32_t {
         const int tp = c / pl.PS, pll = c - tp * pl.PS;
+        if (t.s2)   // parity sub-plane of the tap, shifted by (dy >> 1, dx >> 1)
+            return ((uint32_t)pll * (uint32_t)t.pstride + (uint32_t)pl.tap_par[tp] * (uint32_t)t.Ppar +
+                    (uint32_t)((pl.tap_dy[tp] >> 1) * t.Wq + (pl.tap_dx[tp] >> 1))) * 16u;
         return ((uint32_t)pll * (uint32_t)t.pstride + (uint32_t)(pl.tap_dy[tp] * t.Wq + pl.tap_dx[tp])) * 16u;
     };
     for (int i = 0; i < pl.nmma_s && i < U2_MAX_MMA; ++i) {
@@ -358,7 +385,7 @@ static int launch_t3k(const P2& p, dim3 grid, cudaStream_t s) {
 }
 
 static bool t3_eligible(const P2& p) {
-    return g_use_tma3 && p.pl.mode == 1 && !p.stem_src && !p.dcn_off && !p.pre_add && !p.in_scale && !p.pix_scale &&
+    return g_use_tma3 && (p.pl.mode == 1 || (p.pl.mode == 2 && g_use_tma3_s2)) && !p.stem_src && !p.dcn_off && !p.pre_add && !p.in_scale && !p.pix_scale &&
            !p.in_relu && !p.row_scale && !p.act_cols && !p.w_img_elems && p.Cout <= 256;
 }
 
@@ -372,6 +399,11 @@ static int try_launch_t3(P2& p, cudaStream_t s) {
     cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
     cuuint64_t strides[3] = {(cuuint64_t)p.x_cs * 2, (cuuint64_t)p.W * p.x_cs * 2, (cuuint64_t)p.H * p.W * p.x_cs * 2};
     cuuint32_t box[4] = {8, (cuuint32_t)t.Wq, (cuuint32_t)(t.R + 2), 1}, estr[4] = {1, 1, 1, 1};
+    if (t.s2) {   // column pairs as channels, element stride 2 along y: R + 1 rows of one row parity per box
+        dims[0] = (cuuint64_t)p.x_cs + (cuuint64_t)p.Cin; dims[1] = (cuuint64_t)(p.W / 2);
+        strides[0] = (cuuint64_t)p.x_cs * 4;
+        box[2] = (cuuint32_t)(2 * (t.R + 1)); estr[2] = 2;
+    }
     if (encode(&p.xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)p.x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return 0;

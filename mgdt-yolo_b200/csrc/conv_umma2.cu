@@ -318,7 +318,9 @@ struct T1 {
 // run-time plan of the TMA-fed 3x3 stride-1 kernel (conv_tma3x3.cuh)
 struct T3 {
     int MB, R, Wq;            // row blocks per tile, image rows per tile, padded row pitch W + 2
-    int PB, pstride;          // positions the TMA box writes per plane ((R + 2) * Wq), plane stride in positions
+    int PB, pstride;          // positions one TMA box writes ((R + 2) * Wq; stride 2: (R + 1) * Wq per parity sub-plane), plane stride in positions
+    int s2, npar, Ppar;       // stride-2 layer: four parity sub-planes of Ppar positions per plane (stride 1: npar = 1, Ppar = pstride)
+    int Ho, Wo, xoff2;        // output size; stride 2: channel coordinate of the SECOND pixel of a column pair (= x_cs)
     int S, NACC, tmem_cols, ctas_per_sm, tiles_per_img, epiw;
     unsigned tx_bytes, w_copy_bytes, w_bytes, stage_bytes, smem_total;
     long long tiles;
@@ -1734,7 +1736,7 @@ static int launch2(P2& p, cudaStream_t s) {
         const int rc = try_launch_t1(p, s);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
-    if (p.pl.mode == 1) {   // transform-free 3x3 stride-1 layers with Cin <= 64: the TMA-fed kernel
+    if (p.pl.mode == 1 || p.pl.mode == 2) {   // transform-free 3x3 layers whose whole K extent fits one stage: the TMA-fed kernel
         const int rc = try_launch_t3(p, s);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
@@ -1818,7 +1820,7 @@ int conv2d_umma_path(const mgdt_conv_args* a) {
     P2 p;
     if (fill_p2(a, p) < 0) return 2;
     if (p.pl.mode == 0 && t1_eligible(p) && plan_t1(p, p.t1) && tensor_map_encoder()) return 4;
-    if (p.pl.mode == 1 && t3_eligible(p) && plan_t3(p, p.t3) && tensor_map_encoder()) return 5;
+    if ((p.pl.mode == 1 || p.pl.mode == 2) && t3_eligible(p) && plan_t3(p, p.t3) && tensor_map_encoder()) return 5;
     return 2;
 }
 
@@ -1896,6 +1898,7 @@ int conv_set_option(const char* name, int value) {
     else if (!strcmp(name, "conv_pair")) g_pair = value ? 1 : 0;
     else if (!strcmp(name, "conv_tma_load")) g_use_tma_loads = value ? 1 : 0;
     else if (!strcmp(name, "conv_tma3x3")) g_use_tma3 = value ? 1 : 0;
+    else if (!strcmp(name, "conv_tma3x3_s2")) g_use_tma3_s2 = value ? 1 : 0;
     else if (!strcmp(name, "conv_tma_stats")) g_tma_stats = value ? 1 : 0;
     else if (!strcmp(name, "conv_ksplit")) g_ksplit = value ? 1 : 0;
     else return 0;
