@@ -297,6 +297,8 @@ def build_engine(workload, batch, dtype, dev, slots, use_graph=True, **nms):
     model.load_state_dict(synth_weights(workload, model.state_dict()))
     kw = dict(conf=CONF, iou=IOU, max_det=MAX_DET)
     kw.update(nms)
+    if os.environ.get("MGDT_COPY_SPLIT"):
+        kw["copy_split"] = int(os.environ["MGDT_COPY_SPLIT"])   # A/B: concurrent H2D chunk copies per batch
     return Engine(model, batch, 640, dtype, dev, slots=slots, use_graph=use_graph, **kw)
 
 

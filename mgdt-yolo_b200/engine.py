@@ -28,7 +28,7 @@ class _Slot:
 class Engine:
     def __init__(self, model, batch: int, imgsz=640, dtype=torch.bfloat16, device=None, conf=0.25, iou=0.7,
                  max_det=300, multi_label=False, agnostic=False, classes=None, max_nms=30000, max_wh=7680.0,
-                 input_dtype=torch.uint8, slots: int = 2, use_graph: bool = True):
+                 input_dtype=torch.uint8, slots: int = 2, use_graph: bool = True, copy_split: int = 1):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if self.device.type != "cuda":
             raise RuntimeError("Engine: a CUDA (B200) device is required; there is no CPU fallback")
@@ -49,6 +49,14 @@ class Engine:
                                                                          device=self.device)
             self.slots = [self._make_slot() for _ in range(max(1, slots))]
         self._next = 0
+        # Host -> device input copies: one cudaMemcpyAsync moves ~16.5 GB/s on this platform, three concurrent ones ~29 GB/s
+        # (tools/dbg/h2d_bw.py), i.e. 1.37 ms per 39 MB batch of 32 -- as long as the compute.  `copy_split` > 1 splits a
+        # batch over that many copy streams; with three slots in flight the slots' own copies already overlap and the split
+        # measured slightly slower (e2e 19.8k -> 19.1k images/s), so it is off by default: the end-to-end rate sits at
+        # ~85 % of the platform's pinned host -> device ceiling (23.4k images/s of 1.2 MB each).
+        self.copy_split = max(1, min(int(copy_split), batch))
+        with torch.cuda.device(self.device):
+            self._copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.copy_split)] if self.copy_split > 1 else []
         # The captured graphs have the packed-weight pointers baked in: keep every pack alive for the engine's lifetime
         # (a later repack by another dtype / a weight update must not free them) and remember the parameter versions
         # the capture saw, so that a replay over changed weights raises instead of silently using stale ones.
@@ -165,8 +173,19 @@ class Engine:
         self._next = (self._next + 1) % len(self.slots)
         if host_src.is_cuda:
             self._order_after_producer(s, host_src)
-        with torch.cuda.stream(s.stream):
-            s.src.copy_(host_src, non_blocking=True)
+        if not host_src.is_cuda and self._copy_streams and host_src.is_pinned():
+            # the slot's previous batch has been collected (its kernels no longer read s.src); the copy streams only
+            # have to follow whatever the slot's stream still has queued
+            ev0 = torch.cuda.Event()
+            ev0.record(s.stream)
+            for cs, dst, src in zip(self._copy_streams, s.src.chunk(self.copy_split), host_src.chunk(self.copy_split)):
+                cs.wait_event(ev0)
+                with torch.cuda.stream(cs):
+                    dst.copy_(src, non_blocking=True)
+                s.stream.wait_stream(cs)
+        else:
+            with torch.cuda.stream(s.stream):
+                s.src.copy_(host_src, non_blocking=True)
         self._run(s, s.src)
         with torch.cuda.stream(s.stream):
             s.host_out.copy_(s.out, non_blocking=True)
