@@ -718,6 +718,23 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof,
     }
+    if world == 1:
+        # the platform's pinned host -> device rate with as many copies in flight as the e2e leg has batches: the
+        # ceiling of an end-to-end images/s that moves 1.2 MB per image over PCIe
+        try:
+            cs = [torch.cuda.Stream(device=dev) for _ in range(nslot)]
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            reps = 4 * nslot
+            for i in range(reps):
+                with torch.cuda.stream(cs[i % nslot]):
+                    devin[i % R].copy_(host[i % R], non_blocking=True)
+            torch.cuda.synchronize(dev)
+            gbs = reps * B * 3 * 640 * 640 / (time.perf_counter() - t0) / 1e9
+            line["e2e"].update(h2d_gbs_measured=gbs, h2d_ceiling_images_per_s=gbs * 1e9 / (3 * 640 * 640),
+                               frac_of_h2d_ceiling=line["e2e"]["value"] / (gbs * 1e9 / (3 * 640 * 640)))
+        except Exception:   # noqa: BLE001
+            pass
     if sustained is not None:
         line["sustained"] = sustained
     if training is not None:
