@@ -679,7 +679,11 @@ def run_ours(args):
                 launches_per_step=top["n"], us_per_launch=t_launch * 1e6, share_of_step=top["ms"] / total_ms,
                 algorithmic_bytes=b_launch, flops=f_launch, peak_source=peak_src,
                 arithmetic_intensity=ai, tensor_frac_of_sustained=f_launch / t_launch / 1e12 / tf_sus,
-                note="totals over all launches of the kernel in one step / their summed CUDA-event durations")
+                note="totals over all launches of the kernel in one step / their summed CUDA-event durations",
+                # the other kernels of the step, same definition (share of the serialised step, algorithmic GB/s / measured peak)
+                other_kernels=[{"kernel": g["kernel"], "launches_per_step": g["n"], "share_of_step": g["ms"] / total_ms,
+                                "us_per_launch": g["ms"] / g["n"] * 1e3, "hbm_frac": g["bytes"] / (g["ms"] * 1e-3) / 1e9 / hbm}
+                               for g in sorted(kernels.values(), key=lambda g: -g["ms"]) if g is not top][:8])
 
     if args.profile_json:
         os.makedirs(os.path.dirname(os.path.abspath(args.profile_json)), exist_ok=True)
