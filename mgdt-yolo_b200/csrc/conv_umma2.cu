@@ -343,6 +343,7 @@ struct P2 {
     FastDiv d_ps, d_P, d_Wq, d_HW, d_tpi, d_W, d_cgs;
     const __nv_bfloat16 *dcn_off, *dcn_mask;   // DCNv2 staging: virtual 9*dcn_cin-channel input
     int off_cs, mask_cs, mask_logit, dcn_cin;
+    int dcn_wide;                // DCN sampler: pixels are 32-byte aligned, so a corner's two channel groups come in ONE 256-bit load
     // fused preprocess + stem: 3x3 stride-2 conv read straight from the NCHW uint8 / float source image
     const void* stem_src;
     int stem_u8, stem_C, stem_H, stem_W;
@@ -1273,11 +1274,23 @@ __global__ void __launch_bounds__(U2_THREADS, 1) conv_umma2_kernel(const __grid_
                             unsigned char* dst = sA + ((uint32_t)((tap - tap0) * cgs) * rn.pstride16 + pos) * 16u;
                             for (int cg0 = 0; cg0 < cgs; cg0 += 2) {
                                 uint4 v[2][4];
-#pragma unroll
-                                for (int u = 0; u < 2; ++u)
+                                if (p.dcn_wide && cg0 + 1 < cgs) {
+                                    // LDG.E.256: both channel groups of a corner are one 32-byte sector -- two 16-byte loads
+                                    // request that sector twice, and this gather is bound by L1 sector throughput (ncu: 29
+                                    // sectors per request, l1tex 72 % of peak)
 #pragma unroll
                                     for (int c4 = 0; c4 < 4; ++c4)
-                                        v[u][c4] = __ldg(reinterpret_cast<const uint4*>(cp[c4] + min(cg0 + u, cgs - 1) * 8));
+                                        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                                     : "=r"(v[0][c4].x), "=r"(v[0][c4].y), "=r"(v[0][c4].z), "=r"(v[0][c4].w),
+                                                       "=r"(v[1][c4].x), "=r"(v[1][c4].y), "=r"(v[1][c4].z), "=r"(v[1][c4].w)
+                                                     : "l"(cp[c4] + cg0 * 8));
+                                } else {
+#pragma unroll
+                                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                                        for (int c4 = 0; c4 < 4; ++c4)
+                                            v[u][c4] = __ldg(reinterpret_cast<const uint4*>(cp[c4] + min(cg0 + u, cgs - 1) * 8));
+                                }
 #pragma unroll
                                 for (int u = 0; u < 2; ++u) {
                                     if (cg0 + u >= cgs) break;
@@ -1799,7 +1812,7 @@ static int fill_p2(const mgdt_conv_args* a, P2& p) {
     p.y_vec = (((uintptr_t)a->y & 15) == 0 && (a->y_cs & 7) == 0) ? 1 : 0;
     p.res_vec = (a->residual && ((uintptr_t)a->residual & 15) == 0 && (a->res_cs & 7) == 0) ? 1 : 0;
     p.M_total = (unsigned)((long long)a->N * a->H * a->W);
-    p.dcn_off = nullptr; p.dcn_mask = nullptr; p.off_cs = p.mask_cs = p.mask_logit = p.dcn_cin = 0;
+    p.dcn_off = nullptr; p.dcn_mask = nullptr; p.off_cs = p.mask_cs = p.mask_logit = p.dcn_cin = 0; p.dcn_wide = 0;
     p.stem_src = nullptr; p.stem_u8 = p.stem_C = p.stem_H = p.stem_W = 0;
     p.st_acc = (double*)a->stat_acc; p.st_Q = a->stat_q; p.st_sq = a->stat_sq ? 1 : 0;
     p.st_h0e = (Ho + 1) / 2; p.st_h1b = Ho / 2; p.st_w0e = (Wo + 1) / 2; p.st_w1b = Wo / 2;
@@ -1847,6 +1860,7 @@ int dcn_umma(const void* x, int x_cs, const void* offset, int off_cs, const void
     p.w_img_elems = 0;
     p.dcn_off = (const __nv_bfloat16*)offset; p.dcn_mask = (const __nv_bfloat16*)mask;
     p.off_cs = off_cs; p.mask_cs = mask_cs; p.mask_logit = mask_is_logit; p.dcn_cin = Cin;
+    p.dcn_wide = ((((uintptr_t)x) & 31) == 0 && (x_cs & 15) == 0 && (Cin & 15) == 0) ? 1 : 0;
     p.stem_src = nullptr; p.stem_u8 = p.stem_C = p.stem_H = p.stem_W = 0;
     p.st_acc = (double*)stat_acc; p.st_Q = stat_acc ? stat_q : 0; p.st_sq = (stat_acc && stat_sq) ? 1 : 0;
     p.st_h0e = (H + 1) / 2; p.st_h1b = H / 2; p.st_w0e = (W + 1) / 2; p.st_w1b = W / 2;
@@ -1877,7 +1891,7 @@ int stem_umma(const void* src, int src_is_u8, const void* w_umma, int w_f16, con
     p.y_vec = (((uintptr_t)y & 15) == 0 && (y_cs & 7) == 0) ? 1 : 0;
     p.res_vec = 0;
     p.M_total = (unsigned)((long long)N * Ho * Wo);
-    p.dcn_off = nullptr; p.dcn_mask = nullptr; p.off_cs = p.mask_cs = p.mask_logit = p.dcn_cin = 0;
+    p.dcn_off = nullptr; p.dcn_mask = nullptr; p.off_cs = p.mask_cs = p.mask_logit = p.dcn_cin = 0; p.dcn_wide = 0;
     p.w_img_elems = 0;
     p.stem_src = src; p.stem_u8 = src_is_u8; p.stem_C = C; p.stem_H = H; p.stem_W = W;
     p.st_acc = nullptr; p.st_Q = p.st_sq = p.st_h0e = p.st_h1b = p.st_w0e = p.st_w1b = p.st_tot = 0; p.st_R = 1; p.st_rs = 0;
