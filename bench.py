@@ -56,6 +56,7 @@ WORKLOADS = {
     "mspa_c2f_yolov8m": ("mspa_c2f_yolov8m.yaml", 80, -1.703),
 }
 CONF, IOU, MAX_DET = 0.25, 0.7, 300
+E2E_DEPTH = int(os.environ.get("MGDT_E2E_DEPTH", "2"))   # submissions in flight per engine slot in the e2e legs (1 or 2)
 
 
 def parse():
@@ -331,7 +332,7 @@ def e2e_loop(eng, host, steps, warmup):
     pending = []
     for i in range(steps):
         pending.append(eng.submit(host[i % R]))
-        if len(pending) == len(eng.slots):
+        if len(pending) == E2E_DEPTH * len(eng.slots):   # two submissions in flight per slot (the next input is copied while the current batch computes)
             eng.collect(pending.pop(0))
     while pending:
         eng.collect(pending.pop(0))
@@ -583,7 +584,7 @@ def run_ours(args):
     n_out = 0
     for i in range(args.steps):
         pending.append(runner.submit(host[i % R]))
-        if len(pending) == len(eng.slots):
+        if len(pending) == (E2E_DEPTH if world == 1 else 1) * len(eng.slots):
             r_ = runner.collect(pending.pop(0))
             n_out += len(r_) if r_ is not None else 0
     while pending:
@@ -716,7 +717,7 @@ def run_ours(args):
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 640 * 640,
                 "d2h_bytes_per_step": B * (MAX_DET * 6 * 4 + 4), "ms_per_step": ms_e2e / args.steps,
                 "api": (f"ShardedEngine.submit/collect over {world} ranks (results gathered on rank 0 in image order), " if world > 1 else "")
-                       + f"Engine.submit/collect, {nslot} batches in flight", "host_cores_bound": cores},
+                       + f"Engine.submit/collect, {nslot} slots x {E2E_DEPTH if world == 1 else 1} submissions in flight", "host_cores_bound": cores},
         "gpu_launches": eng.launches_per_step * args.steps,
         "launches_per_step": eng.launches_per_step,
         "clocks": clocks,

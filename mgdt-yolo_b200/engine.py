@@ -21,8 +21,21 @@ __all__ = ("Engine",)
 
 
 class _Slot:
-    """One in-flight batch: device input, graph, outputs, pinned host mirrors, stream."""
+    """One pipeline: device input, graph, outputs, pinned host mirrors, stream."""
     pass
+
+
+class _Ticket:
+    """One submitted batch: the slot that computes it and which of the slot's two input / host-result buffers it uses.
+    Quacks like the slot for code that reads `.out`, `.counts`, `.done`, `.stream` (parallel.ShardedEngine)."""
+
+    def __init__(self, slot, k):
+        self.slot, self.k = slot, k
+        self.done = slot.dones[k]
+        self.host_out, self.host_counts = slot.host_outs[k], slot.host_countss[k]
+
+    def __getattr__(self, name):
+        return getattr(self.slot, name)
 
 
 class Engine:
@@ -90,9 +103,18 @@ class Engine:
         s.out = torch.zeros((B, self.max_det, 6), dtype=torch.float32, device=self.device)
         s.counts = torch.zeros((B,), dtype=torch.int32, device=self.device)
         s.ws = None
-        s.host_out = torch.empty((B, self.max_det, 6), dtype=torch.float32).pin_memory()
-        s.host_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
-        s.done = torch.cuda.Event()
+        # Two submissions may be in flight per slot: while batch i computes, the input of the slot's NEXT batch is already
+        # being copied into the other input buffer on the slot's copy stream (the source buffer is only read by the stem,
+        # the first launch), and the packed results of batch i sit in their own pinned mirror until collected.
+        s.srcs = [s.src, torch.zeros_like(s.src)]
+        s.src_free = [None, None]                      # event: the stem that last read srcs[k] has run
+        s.copy_stream = torch.cuda.Stream(device=self.device)
+        s.host_outs = [torch.empty((B, self.max_det, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+        s.host_countss = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        s.dones = [torch.cuda.Event(), torch.cuda.Event()]
+        s.outstanding = [False, False]                 # ticket k submitted and not collected yet
+        s.turn = 0
+        s.host_out, s.host_counts, s.done = s.host_outs[0], s.host_countss[0], s.dones[0]
         s.graph = None
         with torch.no_grad():
             # warm-up (packs weights, sizes the NMS workspace) on the slot's stream, then capture
@@ -143,13 +165,16 @@ class Engine:
             if src.data_ptr() != s.src.data_ptr():
                 src.record_stream(s.stream)
 
-    def _run(self, s, src):
-        """Enqueue preprocess/stem(src) + forward + decode + NMS on the slot's stream (no sync)."""
+    def _run(self, s, src, head_done=None):
+        """Enqueue preprocess/stem(src) + forward + decode + NMS on the slot's stream (no sync).  `head_done`: event to
+        record once the first launch (the only reader of `src`) is enqueued."""
         self._order_after_producer(s, src)
         with torch.cuda.stream(s.stream), torch.no_grad():
             if not src.is_contiguous():
                 src = src.contiguous()      # on the slot's stream, after the wait above
             self._head(s, src)
+            if head_done is not None:
+                head_done.record(s.stream)
             if s.graph is not None:
                 s.graph.replay()
             else:
@@ -165,33 +190,47 @@ class Engine:
 
     def submit(self, host_src: torch.Tensor):
         """End-to-end: pinned host batch -> H2D -> pipeline -> D2H of the packed detections.
-        Asynchronous; returns the slot, call `collect(slot)` for the result.  Consecutive submits
-        alternate slots so the copies of one batch overlap the kernels of the other."""
+        Asynchronous; returns a ticket, call `collect(ticket)` for the result.  Consecutive submits rotate over the slots
+        so the copies of one batch overlap the kernels of the others, and every slot takes TWO submissions in flight
+        (2 x slots in total): the input of a slot's next batch is copied while its current batch computes."""
         if self.use_graph and self.weights_changed():
             raise RuntimeError("Engine: model weights changed after the CUDA graphs were captured; build a new Engine")
         s = self.slots[self._next]
         self._next = (self._next + 1) % len(self.slots)
+        k = s.turn & 1
+        if s.outstanding[k]:
+            raise RuntimeError("Engine.submit: more than two uncollected batches on one slot; collect() the oldest first")
+        s.turn += 1
+        s.outstanding[k] = True
+        src = s.srcs[k]
         if host_src.is_cuda:
             self._order_after_producer(s, host_src)
-        if not host_src.is_cuda and self._copy_streams and host_src.is_pinned():
-            # the slot's previous batch has been collected (its kernels no longer read s.src); the copy streams only
-            # have to follow whatever the slot's stream still has queued
-            ev0 = torch.cuda.Event()
-            ev0.record(s.stream)
-            for cs, dst, src in zip(self._copy_streams, s.src.chunk(self.copy_split), host_src.chunk(self.copy_split)):
-                cs.wait_event(ev0)
-                with torch.cuda.stream(cs):
-                    dst.copy_(src, non_blocking=True)
-                s.stream.wait_stream(cs)
-        else:
             with torch.cuda.stream(s.stream):
-                s.src.copy_(host_src, non_blocking=True)
-        self._run(s, s.src)
+                src.copy_(host_src, non_blocking=True)
+        else:
+            cs = s.copy_stream
+            if s.src_free[k] is not None:
+                cs.wait_event(s.src_free[k])           # the stem of the batch that last used this buffer has read it
+            with torch.cuda.stream(cs):
+                if self._copy_streams and host_src.is_pinned():
+                    ev0 = torch.cuda.Event()
+                    ev0.record(cs)
+                    for c2, dst, part in zip(self._copy_streams, src.chunk(self.copy_split), host_src.chunk(self.copy_split)):
+                        c2.wait_event(ev0)
+                        with torch.cuda.stream(c2):
+                            dst.copy_(part, non_blocking=True)
+                        cs.wait_stream(c2)
+                else:
+                    src.copy_(host_src, non_blocking=True)
+            s.stream.wait_stream(cs)
+        if s.src_free[k] is None:
+            s.src_free[k] = torch.cuda.Event()
+        self._run(s, src, head_done=s.src_free[k])
         with torch.cuda.stream(s.stream):
-            s.host_out.copy_(s.out, non_blocking=True)
-            s.host_counts.copy_(s.counts, non_blocking=True)
-            s.done.record(s.stream)
-        return s
+            s.host_outs[k].copy_(s.out, non_blocking=True)
+            s.host_countss[k].copy_(s.counts, non_blocking=True)
+            s.dones[k].record(s.stream)
+        return _Ticket(s, k)
 
     def submit_images(self, ims, auto=False, stride=32):
         """The reference's predictor path for a list of (h, w, 3) BGR uint8 images (numpy or torch, host or device):
@@ -205,6 +244,11 @@ class Engine:
             raise RuntimeError("Engine: model weights changed after the CUDA graphs were captured; build a new Engine")
         s = self.slots[self._next]
         self._next = (self._next + 1) % len(self.slots)
+        k = s.turn & 1
+        if s.outstanding[k]:
+            raise RuntimeError("Engine.submit_images: more than two uncollected batches on one slot; collect() the oldest first")
+        s.turn += 1
+        s.outstanding[k] = True
         s.stream.wait_stream(torch.cuda.current_stream(self.device))   # device images written on the caller's stream
         for im in ims:
             if isinstance(im, torch.Tensor) and im.is_cuda:
@@ -216,16 +260,20 @@ class Engine:
         self._run(s, s.src)
         with torch.cuda.stream(s.stream):
             ops.scale_boxes_packed(s.out, s.counts, s.scale_prm)
-            s.host_out.copy_(s.out, non_blocking=True)
-            s.host_counts.copy_(s.counts, non_blocking=True)
-            s.done.record(s.stream)
-        return s
+            s.host_outs[k].copy_(s.out, non_blocking=True)
+            s.host_countss[k].copy_(s.counts, non_blocking=True)
+            s.dones[k].record(s.stream)
+        return _Ticket(s, k)
 
-    def collect(self, s):
-        """Wait for a submitted batch; returns the reference's format: list of (n_i, 6) CPU tensors."""
-        s.done.synchronize()
-        cnt = s.host_counts.tolist()
-        return [s.host_out[i, :cnt[i]].clone() for i in range(self.batch)]
+    def collect(self, t):
+        """Wait for a submitted batch (its ticket); returns the reference's format: list of (n_i, 6) CPU tensors."""
+        if not isinstance(t, _Ticket):                 # a bare slot: its most recent submission
+            t = _Ticket(t, (t.turn - 1) & 1)
+        t.done.synchronize()
+        cnt = t.host_counts.tolist()
+        out = t.host_out.clone()                       # one copy out of the pinned mirror, then views per image
+        t.slot.outstanding[t.k] = False
+        return [out[i, :cnt[i]] for i in range(self.batch)]
 
     def predict(self, ims, names=None, paths=None, auto=False, stride=32):
         """DetectionPredictor's product for a list of BGR uint8 images (yolo/v8/detect/predict.py:12-30): one Results

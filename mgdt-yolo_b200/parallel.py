@@ -130,10 +130,14 @@ class ShardedEngine:
 
     def collect(self, slot):
         """-> on `dst`: list of B_global (n_i, 6) CPU tensors in image order; None on the other ranks."""
-        slot.done.synchronize()
         if self.world == 1:
             return self.engine.collect(slot)
+        slot.done.synchronize()
+        # the device-side packed results are gathered, so at most ONE submission per engine slot may be in flight here
+        # (the slot's next batch would overwrite them); the ticket is released for the engine's bookkeeping
         out, cnt = gather_packed(slot.out, slot.counts, self.group, self.dst)
+        if hasattr(slot, "k"):
+            slot.slot.outstanding[slot.k] = False
         if out is None:
             return None
         out, cnt = out.cpu(), cnt.tolist()
