@@ -488,7 +488,7 @@ def run_ours(args):
     if world > 1:
         import datetime
         # a rank that drops out must not park the others for NCCL's default 10 minutes
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=int(os.environ.get("MGDT_BENCH_NCCL_TIMEOUT", "120"))))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=int(os.environ.get("MGDT_BENCH_NCCL_TIMEOUT", "300"))))
     lib()  # fail loudly now if the extension is missing
 
     cfg, nc, cls_bias = WORKLOADS[args.workload]
