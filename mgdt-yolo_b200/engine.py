@@ -100,8 +100,12 @@ class Engine:
         s.src = torch.zeros((B, C, H, W), dtype=self.input_dtype, device=self.device)
         s.x = ops.new_act(B, C, H, W, self.dtype, self.device) if not self.fused_stem else None
         s.x0 = None
-        s.out = torch.zeros((B, self.max_det, 6), dtype=torch.float32, device=self.device)
-        s.counts = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        # packed detections and per-image counts share ONE allocation (counts = the last B words, viewed as int32): one
+        # device -> host copy per batch, one gather per batch in the sharded API
+        n_out = B * self.max_det * 6
+        s.blob = torch.zeros((n_out + B,), dtype=torch.float32, device=self.device)
+        s.out = s.blob[:n_out].view(B, self.max_det, 6)
+        s.counts = s.blob[n_out:].view(torch.int32)
         s.ws = None
         # Two submissions may be in flight per slot: while batch i computes, the input of the slot's NEXT batch is already
         # being copied into the other input buffer on the slot's copy stream (the source buffer is only read by the stem,
@@ -109,8 +113,9 @@ class Engine:
         s.srcs = [s.src, torch.zeros_like(s.src)]
         s.src_free = [None, None]                      # event: the stem that last read srcs[k] has run
         s.copy_stream = torch.cuda.Stream(device=self.device)
-        s.host_outs = [torch.empty((B, self.max_det, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
-        s.host_countss = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        s.host_blobs = [torch.empty((n_out + B,), dtype=torch.float32).pin_memory() for _ in range(2)]
+        s.host_outs = [h[:n_out].view(B, self.max_det, 6) for h in s.host_blobs]
+        s.host_countss = [h[n_out:].view(torch.int32) for h in s.host_blobs]
         s.dones = [torch.cuda.Event(), torch.cuda.Event()]
         s.outstanding = [False, False]                 # ticket k submitted and not collected yet
         s.turn = 0
@@ -227,8 +232,7 @@ class Engine:
             s.src_free[k] = torch.cuda.Event()
         self._run(s, src, head_done=s.src_free[k])
         with torch.cuda.stream(s.stream):
-            s.host_outs[k].copy_(s.out, non_blocking=True)
-            s.host_countss[k].copy_(s.counts, non_blocking=True)
+            s.host_blobs[k].copy_(s.blob, non_blocking=True)
             s.dones[k].record(s.stream)
         return _Ticket(s, k)
 
@@ -260,8 +264,7 @@ class Engine:
         self._run(s, s.src)
         with torch.cuda.stream(s.stream):
             ops.scale_boxes_packed(s.out, s.counts, s.scale_prm)
-            s.host_outs[k].copy_(s.out, non_blocking=True)
-            s.host_countss[k].copy_(s.counts, non_blocking=True)
+            s.host_blobs[k].copy_(s.blob, non_blocking=True)
             s.dones[k].record(s.stream)
         return _Ticket(s, k)
 

@@ -135,7 +135,18 @@ class ShardedEngine:
         slot.done.synchronize()
         # the device-side packed results are gathered, so at most ONE submission per engine slot may be in flight here
         # (the slot's next batch would overwrite them); the ticket is released for the engine's bookkeeping
-        out, cnt = gather_packed(slot.out, slot.counts, self.group, self.dst)
+        blob = getattr(slot, "blob", None)
+        if blob is not None:   # detections + counts in one allocation: ONE gather per batch
+            parts = [torch.empty_like(blob) for _ in range(self.world)] if self.rank == self.dst else None
+            dist.gather(blob, parts, dst=self.dst, group=self.group)
+            out = cnt = None
+            if parts is not None:
+                n_out = slot.out.numel()
+                host = torch.stack(parts).cpu()
+                out = host[:, :n_out].reshape(self.world * slot.out.shape[0], *slot.out.shape[1:])
+                cnt = host[:, n_out:].contiguous().view(torch.int32).reshape(-1)
+        else:
+            out, cnt = gather_packed(slot.out, slot.counts, self.group, self.dst)
         if hasattr(slot, "k"):
             slot.slot.outstanding[slot.k] = False
         if out is None:
