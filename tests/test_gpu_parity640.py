@@ -88,3 +88,22 @@ def test_engine_640(dtype, batch):
     assert sum(int(t.shape[0]) for t in want) > batch
     for a, b in zip(dets, want):
         assert torch.equal(a.cpu(), b), "NMS keep set differs from the oracle given identical scores and boxes"
+
+
+def test_engine_two_submissions_in_flight_per_slot():
+    """Engine.submit takes 2 x slots uncollected batches (double-buffered inputs and pinned result mirrors); results are
+    those of one-at-a-time processing, in ticket order; a further submit without a collect raises."""
+    from mgdt_yolo_b200.engine import Engine
+    m, _ = parity.build_model(FULL, nc=parity.BASELINE_CFGS[FULL], cls_bias=-1.238)
+    eng = Engine(m, 2, 640, torch.bfloat16, "cuda:0", conf=0.25, iou=0.7, slots=2)
+    g = torch.Generator().manual_seed(9)
+    batches = [torch.randint(0, 256, (2, 3, 640, 640), dtype=torch.uint8, generator=g).pin_memory() for _ in range(4)]
+    want = [eng(b) for b in batches]
+    tickets = [eng.submit(b) for b in batches]                # 4 = 2 slots x 2
+    with pytest.raises(RuntimeError):
+        eng.submit(batches[0])
+    got = [eng.collect(t) for t in tickets]
+    for a, b in zip(got, want):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+    again = eng.collect(eng.submit(batches[1]))
+    assert all(torch.equal(x, y) for x, y in zip(again, want[1]))
