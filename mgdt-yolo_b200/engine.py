@@ -201,10 +201,10 @@ class Engine:
         if self.use_graph and self.weights_changed():
             raise RuntimeError("Engine: model weights changed after the CUDA graphs were captured; build a new Engine")
         s = self.slots[self._next]
-        self._next = (self._next + 1) % len(self.slots)
         k = s.turn & 1
         if s.outstanding[k]:
             raise RuntimeError("Engine.submit: more than two uncollected batches on one slot; collect() the oldest first")
+        self._next = (self._next + 1) % len(self.slots)
         s.turn += 1
         s.outstanding[k] = True
         src = s.srcs[k]
@@ -247,10 +247,10 @@ class Engine:
         if self.use_graph and self.weights_changed():
             raise RuntimeError("Engine: model weights changed after the CUDA graphs were captured; build a new Engine")
         s = self.slots[self._next]
-        self._next = (self._next + 1) % len(self.slots)
         k = s.turn & 1
         if s.outstanding[k]:
             raise RuntimeError("Engine.submit_images: more than two uncollected batches on one slot; collect() the oldest first")
+        self._next = (self._next + 1) % len(self.slots)
         s.turn += 1
         s.outstanding[k] = True
         s.stream.wait_stream(torch.cuda.current_stream(self.device))   # device images written on the caller's stream
