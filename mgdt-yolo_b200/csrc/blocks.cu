@@ -387,6 +387,33 @@ __global__ void __launch_bounds__(128) decode_staged_kernel(DecodeLevels L, int 
     const int hq = la / Wl, wq = la - hq * Wl;
     const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(dec_sm + t * pitch);
     float d[4];
+    if (reg_max == 16) {
+        // the common head (TOODHead / stock Detect at reg_max 16): fully unrolled, bins read as 32-bit pairs from the
+        // staged row (the generic loop below costs ~2,400 instructions per anchor: ncu SM 50 % for 27 us).  Same
+        // operations in the same order as the loop: running max, then exp / sum / weighted sum in bin order.
+        const uint32_t* pw = dec_sm + t * pitch;
+#pragma unroll
+        for (int side = 0; side < 4; ++side) {
+            float v[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const uint32_t w = pw[side * 8 + k2];
+                v[2 * k2] = __uint_as_float(w << 16);
+                v[2 * k2 + 1] = __uint_as_float(w & 0xffff0000u);
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) mx = fmaxf(mx, v[k]);
+            float den = 0.f, num = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float e = __expf(v[k] - mx);
+                den += e;
+                num += e * (float)k;
+            }
+            d[side] = num / den;
+        }
+    } else
     for (int side = 0; side < 4; ++side) {
         if (reg_max > 1) {
             float mx = -INFINITY;
