@@ -445,6 +445,69 @@ __global__ void __launch_bounds__(128) decode_staged_kernel(DecodeLevels L, int 
     for (int j = 0; j < nc; ++j) yo[(4LL + j) * L.A] = sigmoidf_(__bfloat162float(pc[j]));
 }
 
+// reg_max = 16 heads with at most 8 classes and 16-byte aligned rows (the TOOD head of the full config: 66 channels at a
+// stride of 72): every thread reads ITS anchor's row with nine 16-byte loads straight into registers -- no staging, no
+// index division, no barrier -- and walks it fully unrolled.  Same operations in the same order as decode_kernel.
+__global__ void __launch_bounds__(128) decode_rows16_kernel(DecodeLevels L, int nc, int dist_only, float* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
+    const int a = blockIdx.x * 128 + threadIdx.x, n = blockIdx.y;
+    if (a >= L.A) return;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (i < L.nl && a >= L.a0[i]) l = i;
+    const int Wl = L.W[l], Hl = L.H[l], la = a - L.a0[l];
+    const int hq = la / Wl, wq = la - hq * Wl;
+    const uint4* row = reinterpret_cast<const uint4*>((const __nv_bfloat16*)L.raw[l] + ((long long)n * Hl * Wl + la) * L.cs[l]);
+    uint32_t w[36];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        const uint4 v = __ldg(row + c);
+        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+    }
+    float d[4];
+#pragma unroll
+    for (int side = 0; side < 4; ++side) {
+        float v[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+            v[2 * k2] = __uint_as_float(w[side * 8 + k2] << 16);
+            v[2 * k2 + 1] = __uint_as_float(w[side * 8 + k2] & 0xffff0000u);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) mx = fmaxf(mx, v[k]);
+        float den = 0.f, num = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float e = __expf(v[k] - mx);
+            den += e;
+            num += e * (float)k;
+        }
+        d[side] = num / den;
+    }
+    if (dist_only) {
+        float* yd = y + (long long)n * 4 * L.A + a;
+#pragma unroll
+        for (int side = 0; side < 4; ++side) yd[(long long)side * L.A] = d[side];
+        return;
+    }
+    const float ax = (float)wq + 0.5f, ay = (float)hq + 0.5f, st = L.stride[l];
+    const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+    float* yo = y + (long long)n * (4 + nc) * L.A + a;
+    yo[0] = (x1 + x2) / 2.f * st;
+    yo[(long long)L.A] = (y1 + y2) / 2.f * st;
+    yo[2LL * L.A] = (x2 - x1) * st;
+    yo[3LL * L.A] = (y2 - y1) * st;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < nc) {
+            const uint32_t ww = w[32 + (j >> 1)];
+            yo[(4LL + j) * L.A] = sigmoidf_(__uint_as_float((j & 1) ? (ww & 0xffff0000u) : (ww << 16)));
+        }
+}
+
 }  // namespace mgdt
 
 using namespace mgdt;
@@ -551,6 +614,15 @@ extern "C" int mgdt_decode(const mgdt_decode_level* levels, int nl, int N, int r
     for (int i = 0; i < nl && staged; ++i) {
         if ((levels[i].cs & 1) || ((uintptr_t)levels[i].raw & 3)) staged = false;
         if (i + 1 < nl && (levels[i].H * levels[i].W) % 128 != 0) staged = false;
+    }
+    // registers-only path (decode_rows16_kernel): reg_max 16, at most 8 classes, rows of >= 72 elements at 16-byte alignment
+    bool rows16 = dtype == MGDT_BF16 && reg_max == 16 && nc <= 8;
+    for (int i = 0; i < nl && rows16; ++i)
+        if (levels[i].cs < 72 || (levels[i].cs & 7) || ((uintptr_t)levels[i].raw & 15)) rows16 = false;
+    if (rows16) {
+        launch_k(decode_rows16_kernel, dim3(cdiv(L.A, 128), N), dim3(128), 0, (cudaStream_t)stream, L, nc, dist_only, y);
+        MGDT_LAUNCH_CHECK("decode_rows16");
+        return 0;
     }
     if (staged) {
         const int nw = (4 * reg_max + nc) / 2;
