@@ -103,3 +103,23 @@ def test_host_side_queries_of_the_new_entry_points():
     assert L.mgdt_box_convert(None, 6, 4, 1, 1.0, 1.0, None, None) < 0 and b"null" in L.mgdt_last_error()
     assert L.mgdt_match_batch(None, 6, None, 300, None, None, 8, None, 64, None, 2, None) < 0   # niou > 32
     assert L.mgdt_stats_finish(None, 4, 1, 8, 8, 32, 1, 1, None, None, None, None) < 0
+
+
+def test_export_fused_round_trip(tmp_path):
+    """Row f4: the fused-graph file rebuilds a BN-free DetectionModel with the folded weights of BaseModel.fuse."""
+    import torch
+    from mgdt_yolo_b200.export import export_fused, load_fused
+    from mgdt_yolo_b200.synth import synth_state_dict
+    from mgdt_yolo_b200.tasks import DetectionModel
+    m = DetectionModel("mspa_c2f_gd_tood_yolov8n.yaml", nc=2, verbose=False)
+    m.load_state_dict(synth_state_dict(m.state_dict(), seed=1))
+    meta = export_fused(m, str(tmp_path / "m.fused"))
+    assert meta["head"] == "TOODHead" and meta["nc"] == 2
+    assert not m.is_fused()                                   # the source model is untouched
+    f = load_fused(str(tmp_path / "m.fused"))
+    assert f.is_fused() and not any(isinstance(x, torch.nn.BatchNorm2d) for x in f.modules())
+    ref = DetectionModel("mspa_c2f_gd_tood_yolov8n.yaml", nc=2, verbose=False)
+    ref.load_state_dict(synth_state_dict(ref.state_dict(), seed=1))
+    ref.fuse(verbose=False)
+    a, b = ref.state_dict(), f.state_dict()
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
