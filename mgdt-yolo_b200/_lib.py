@@ -111,7 +111,7 @@ def lib():
             raise RuntimeError("mgdt_yolo_b200: ABI version mismatch, rebuild the library")
         # the library reads no environment variables: forward the documented MGDT_* switches once, here
         for env, opt in (("MGDT_PDL", "pdl"), ("MGDT_CONV_TMA_LOAD", "conv_tma_load"), ("MGDT_CONV_TMA_STORE", "conv_tma_store"), ("MGDT_CONV_TMA_STATS", "conv_tma_stats"), ("MGDT_CONV_KSPLIT", "conv_ksplit"),
-                         ("MGDT_CONV_PAIR", "conv_pair"), ("MGDT_CONV_SPLIT", "conv_split"), ("MGDT_CONV_MB", "conv_mb"), ("MGDT_CONV_TMA3X3", "conv_tma3x3"), ("MGDT_CONV_TMA3X3_S2", "conv_tma3x3_s2")):
+                         ("MGDT_CONV_PAIR", "conv_pair"), ("MGDT_CONV_SPLIT", "conv_split"), ("MGDT_CONV_MB", "conv_mb"), ("MGDT_CONV_TMA3X3", "conv_tma3x3"), ("MGDT_CONV_TMA3X3_S2", "conv_tma3x3_s2"), ("MGDT_DW_PAIRS", "dw_pairs")):
             v = os.environ.get(env)
             if v is not None and v.lstrip("-").isdigit():
                 L.mgdt_set_option(opt.encode(), int(v))

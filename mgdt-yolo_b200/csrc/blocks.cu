@@ -1,6 +1,7 @@
 // Block-specific kernels: ConvNeXtV2 depthwise 7x7 + LayerNorm, modulated deformable conv
 // (DCNv2), and the DFL / dist2bbox decode.
 #include "common.cuh"
+#include <string.h>
 
 namespace mgdt {
 
@@ -75,6 +76,11 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv7_ln_kernel(const T* __re
 // weights live in shared memory; warp r computes output row r (8 pixels, lanes over channels, CPL
 // channels per lane) re-using every staged input value for the up-to-7 outputs it contributes to, then
 // LayerNorm is a warp reduction per pixel.  ~200 instructions per pixel-lane instead of ~500 global loads.
+static int g_dw_pairs = 1;       // option "dw_pairs": channel-pair kernel for bf16 (dwconv7_ln_pairs)
+int blocks_set_option(const char* name, int value) {
+    if (!strcmp(name, "dw_pairs")) { g_dw_pairs = value ? 1 : 0; return 1; }
+    return 0;
+}
 constexpr int DT = 8;            // tile edge
 constexpr int DTI = DT + 6;      // input tile edge
 
@@ -214,6 +220,137 @@ __global__ void __launch_bounds__(256) dwconv7_ln_tiled(const T* __restrict__ x,
     }
 }
 
+// Channel-PAIR form of the tiled kernel (bf16, C % 8 == 0): ncu showed dwconv7_ln_tiled issue-bound (IPC 2.3, "not selected"
+// 30 %) at ~3,500 instructions per 8-pixel row -- one LDS.U16 + shift + FFMA per channel and tap.  Here a lane owns channel
+// pairs (2q, 2q + 1), q = l16 + 16 j: one LDS.32 fetches both values, two ALU instructions unpack them and one packed
+// FFMA2 (fma.rn.f32x2, bit-identical to two FFMAs) does both channels.  A half-warp holds all C channels of a pixel, so a
+// warp computes TWO output rows x four pixels; weights stay bf16 pairs in shared memory (48 KB per CTA: four CTAs / SM).
+// The tile's row pitch is padded by 16 words so that the two half-warps (rows r, r + 1) read disjoint banks.
+// Same accumulation order per output as dwconv7_ln_tiled (bias, then dy, ix ascending).
+template <int CPL>
+__global__ void __launch_bounds__(256) dwconv7_ln_pairs(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat16* __restrict__ w,
+                                                        const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                        const float* __restrict__ ln_b, float eps, __nv_bfloat16* __restrict__ y,
+                                                        int y_cs, int H, int W, int C, int tiles_x, int tiles_y) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char dsm[];
+    constexpr int CP = CPL * 32, CW = CP / 2;                    // padded channels, 32-bit words per pixel
+    constexpr int C8 = CPL * 4;                                  // 8-channel chunks per padded pixel
+    constexpr int ROWW = DTI * CW + 16;                          // words per tile row (padded)
+    uint32_t* sw = reinterpret_cast<uint32_t*>(dsm);             // [49][CW] bf16 pairs
+    uint32_t* sx = sw + 49 * CW;                                 // [DTI][ROWW]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int b = blockIdx.x;
+    const int tx = b % tiles_x; b /= tiles_x;
+    const int ty = b % tiles_y;
+    const int n = b / tiles_y;
+    const int h0 = ty * DT, w0 = tx * DT;
+    const __nv_bfloat16* xn = x + (size_t)n * H * W * x_cs;
+    {
+        const uint32_t sx32 = (uint32_t)__cvta_generic_to_shared(sx), sw32 = (uint32_t)__cvta_generic_to_shared(sw);
+        // (ncu: the index arithmetic of a flat chunk loop -- two divisions, 64-bit addressing per 16-byte chunk -- was half
+        // of the kernel's instructions.)  A thread keeps ONE (column, channel chunk) of the tile and walks its 14 rows:
+        // everything but the row test is computed once.
+        for (int t = tid; t < DTI * C8; t += 256) {
+            const int ix = t / C8, c8 = (t - ix * C8) * 8;
+            const int ww = w0 + ix - 3;
+            const bool colok = c8 < C && ww >= 0 && ww < W;
+            const __nv_bfloat16* src = xn + (ptrdiff_t)((h0 - 3) * W + ww) * x_cs + c8;
+            uint32_t dst = sx32 + (uint32_t)(ix * CW) * 4u + (uint32_t)c8 * 2u;
+            const ptrdiff_t rstep = (ptrdiff_t)W * x_cs;
+#pragma unroll
+            for (int iy = 0; iy < DTI; ++iy, src += rstep, dst += ROWW * 4u) {
+                const bool ok = colok && (unsigned)(h0 + iy - 3) < (unsigned)H;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src : xn), "r"(ok ? 16u : 0u) : "memory");
+            }
+        }
+        for (int i = tid; i < 49 * C8; i += 256) {
+            const int tap = i / C8, c8 = (i - tap * C8) * 8;
+            const bool ok = c8 < C;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sw32 + (uint32_t)(tap * CW) * 4u + (uint32_t)c8 * 2u),
+                         "l"(ok ? w + tap * C + c8 : w), "r"(ok ? 16u : 0u) : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncthreads();
+    const int half = lane >> 4, l16 = lane & 15;
+    const int r = 2 * (warp >> 1) + half;          // output row inside the tile
+    const int px0 = 4 * (warp & 1);                // first of this warp's four output pixels
+    float2 acc[4][CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const int c = 2 * (l16 + 16 * j);
+        const float2 bj = c < C ? make_float2(bias[c], bias[c + 1]) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) acc[px][j] = bj;
+    }
+    auto unpack = [](uint32_t v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); };
+#pragma unroll
+    for (int dy = 0; dy < 7; ++dy) {
+        float2 wk[7][CPL];
+#pragma unroll
+        for (int dx = 0; dx < 7; ++dx)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) wk[dx][j] = unpack(sw[(dy * 7 + dx) * CW + l16 + 16 * j]);
+        const uint32_t* row = sx + (size_t)(r + dy) * ROWW + px0 * CW;
+#pragma unroll
+        for (int ixl = 0; ixl < 10; ++ixl) {       // input columns px0 .. px0 + 9 of the tile
+            float2 v[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) v[j] = unpack(row[ixl * CW + l16 + 16 * j]);
+#pragma unroll
+            for (int dx = 0; dx < 7; ++dx) {
+                const int px = ixl - dx;
+                if (px >= 0 && px < 4) {
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) acc[px][j] = __ffma2_rn(v[j], wk[dx][j], acc[px][j]);
+                }
+            }
+        }
+    }
+    const int hq = h0 + r;
+    float2 lw[CPL], lb[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const int c = 2 * (l16 + 16 * j);
+        lw[j] = c < C ? make_float2(ln_w[c], ln_w[c + 1]) : make_float2(0.f, 0.f);
+        lb[j] = c < C ? make_float2(ln_b[c], ln_b[c + 1]) : make_float2(0.f, 0.f);
+    }
+    auto half_sum = [](float v) {                  // over the 16 lanes of this half-warp
+#pragma unroll
+        for (int o = 8; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+            if (2 * (l16 + 16 * j) < C) s += acc[px][j].x + acc[px][j].y;
+        const float mean = half_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+            if (2 * (l16 + 16 * j) < C) {
+                const float d0 = acc[px][j].x - mean, d1 = acc[px][j].y - mean;
+                q += d0 * d0 + d1 * d1;
+            }
+        const float rstd = rsqrtf(half_sum(q) / (float)C + eps);
+        const int wq = w0 + px0 + px;
+        if (hq < H && wq < W) {
+            __nv_bfloat16* yp = y + ((size_t)n * H * W + (size_t)hq * W + wq) * y_cs;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const int c = 2 * (l16 + 16 * j);
+                if (c < C)
+                    *reinterpret_cast<__nv_bfloat162*>(yp + c) = __floats2bfloat162_rn((acc[px][j].x - mean) * rstd * lw[j].x + lb[j].x,
+                                                                                       (acc[px][j].y - mean) * rstd * lw[j].y + lb[j].y);
+            }
+        }
+    }
+}
+
 template <typename T, int CPL>
 static int launch_dw_tiled(const void* x, int x_cs, const void* w, const float* bias, const float* ln_w,
                            const float* ln_b, float eps, void* y, int y_cs, int N, int H, int W, int C, cudaStream_t s) {
@@ -222,6 +359,16 @@ static int launch_dw_tiled(const void* x, int x_cs, const void* w, const float* 
     const bool vec = sizeof(T) == 2 && C % 8 == 0 && x_cs % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0;
     const size_t smem = sizeof(float) * 49 * CP + (vec ? 2 : sizeof(float)) * DTI * DTI * CP;
     cudaError_t e;
+    if constexpr (sizeof(T) == 2) {
+        if (vec && g_dw_pairs && (y_cs & 1) == 0 && ((uintptr_t)y & 3) == 0) {
+            const size_t smem2 = 4 * (size_t)(49 * (CP / 2) + DTI * (DTI * (CP / 2) + 16));
+            e = cudaFuncSetAttribute(dwconv7_ln_pairs<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return set_error(-EIO, "dwconv7_ln: smem attr: %s", cudaGetErrorString(e));
+            launch_k(dwconv7_ln_pairs<CPL>, dim3(tx * ty * N), dim3(256), smem2, s, (const __nv_bfloat16*)x, x_cs, (const __nv_bfloat16*)w, bias,
+                     ln_w, ln_b, eps, (__nv_bfloat16*)y, y_cs, H, W, C, tx, ty);
+            return 0;
+        }
+    }
     if (vec) {
         e = cudaFuncSetAttribute(dwconv7_ln_tiled<T, CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(-EIO, "dwconv7_ln: smem attr: %s", cudaGetErrorString(e));

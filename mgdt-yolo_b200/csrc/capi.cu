@@ -20,6 +20,7 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+int blocks_set_option(const char* name, int value);
 int conv2d_direct(const mgdt_conv_args* a, cudaStream_t s);
 bool conv2d_pointwise_supported(const mgdt_conv_args* a);
 int conv2d_pointwise(const mgdt_conv_args* a, cudaStream_t s);
@@ -41,6 +42,7 @@ extern "C" void mgdt_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 extern "C" int mgdt_set_option(const char* name, int value) {
     MGDT_CHECK(name, "set_option: null name");
     if (!strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return 0; }
+    if (blocks_set_option(name, value)) return 0;
 #ifdef MGDT_WITH_UMMA
     if (conv_set_option(name, value)) return 0;
 #endif
