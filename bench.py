@@ -88,15 +88,44 @@ def host_threads():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).
+
+    The driver's `steps` give a 25-40 ms timed region, shorter than one `nvidia-smi -lms` period (and nvidia-smi needs
+    ~1 s to print its first row), so the samples come from NVML in this process (`pynvml`, one query pair per ~2 ms on a
+    thread); `nvidia-smi -lms 100` is the fallback when NVML cannot be opened."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.002
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv, self.h, self.run = index, [], None, None, None, False
+        self.max_mhz = 0.0
+
+    def _nvml_open(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        self.nv = pynvml
 
     def start(self):
+        try:
+            self._nvml_open()
+            self.run = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
@@ -106,17 +135,21 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while self.run:
+            try:
+                clk = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.rows.append((time.time(), clk, tuple(n for n, b in names if bits & b)))
+            except Exception:
+                pass
+            time.sleep(self.PERIOD_S)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
-        for t, line in self.rows:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -124,15 +157,34 @@ class ClockSampler:
                 clk, cmax = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            mx = max(mx, cmax)
-            if t0 - 0.05 <= t <= t1 + 0.15:
-                sm.append(clk)
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        if not sm:  # region shorter than the sampling period: use the nearest samples
-            sm = [float(l.split(",")[1]) for _, l in self.rows[-3:] if l.count(",") >= 8] or [0.0]
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+            self.max_mhz = max(self.max_mhz, cmax)
+            rs = tuple(n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9])
+                       if v.lower().startswith("active"))
+            self.rows.append((time.time(), clk, rs))
+
+    def stop(self, t0, t1):
+        if self.nv is None and self.proc is None:
+            return None
+        if self.nv is not None:
+            self.run = False
+            self.t.join(timeout=1.0)
+            source = "nvml"
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
+            source = "nvidia-smi"
+        inside = [(clk, rs) for t, clk, rs in self.rows if t0 <= t <= t1]
+        if not inside:  # region shorter than the sampling period: the samples nearest to it
+            near = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:3]
+            inside = [(clk, rs) for _, clk, rs in near]
+            source += " (nearest samples: none fell inside the timed region)"
+        if not inside:
+            return None
+        reasons = set()
+        for _, rs in inside:
+            reasons.update(rs)
+        return {"sm_mhz": statistics.median(c for c, _ in inside), "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                "samples": len(inside), "source": source}
 
 
 def peaks():
@@ -720,7 +772,7 @@ def run_ours(args):
                        + f"Engine.submit/collect, {nslot} slots x {E2E_DEPTH if world == 1 else 1} submissions in flight", "host_cores_bound": cores},
         "gpu_launches": eng.launches_per_step * args.steps,
         "launches_per_step": eng.launches_per_step,
-        "clocks": clocks,
+        "clocks": clocks if clocks is not None else (dict(sustained["clocks"], source="sustained leg") if sustained and sustained.get("clocks") else None),
         "roofline": roof,
     }
     if world == 1:

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MGDT_ABI_VERSION 4
+#define MGDT_ABI_VERSION 5
 
 enum { MGDT_F32 = 0, MGDT_BF16 = 1 };
 enum { MGDT_ACT_NONE = 0, MGDT_ACT_SILU = 1, MGDT_ACT_RELU = 2, MGDT_ACT_SIGMOID = 3, MGDT_ACT_HSIGMOID = 4,
@@ -147,6 +147,18 @@ int mgdt_conv_umma_pack_scaled_groups(const void* packed_bf16, int Cin, int Cout
  * 1x1 conv over round_up(9*C, 16) channels (k = (dy*3+dx)*C + c, zero padded). */
 int mgdt_stem_conv(const void* src, int src_is_u8, const void* w_umma, int w_umma_f16, const float* bias, void* y, int y_cs,
                    int N, int C, int H, int W, int Cout, int act, int dtype, void* stream);
+
+/* The same layer for the predictor's own input -- uint8 NCHW, 3 channels (yolo/engine/predictor.py:115-130: /255 after
+ * the copy) -- on warp-level tensor-core MMAs (csrc/stem_mma.cu): raw byte rows staged in shared memory, bytes turned
+ * into exact fp16 integers in registers, fp16 weights scaled per output channel by a power of two, 1 / (255 * scale) on
+ * the fp32 accumulator.  w = BN-folded fp32 weights (Cout, kp), k = (ky * 3 + kx) * 3 + c, kp >= 27 the row pitch.
+ * Supported: C == 3, W % 16 == 0, Cout in {16, 32, 48, 64, 80}, y_cs % 8 == 0 (mgdt_stem_u8_supported); other shapes and
+ * float32 sources take mgdt_stem_conv.  packed: mgdt_stem_u8_packed_bytes(Cout) bytes, 16-byte aligned. */
+int mgdt_stem_u8_supported(int C, int H, int W, int Cout, int y_cs);
+size_t mgdt_stem_u8_packed_bytes(int Cout);
+int mgdt_stem_u8_pack(const float* w, int kp, int Cout, void* packed, void* stream);
+int mgdt_stem_u8(const void* src, const void* packed, const float* bias, void* y, int y_cs, int N, int H, int W, int Cout,
+                 int act, void* stream);
 
 /* MSPA_C2f hierarchy front (nn/modules/block.py:248-262) in ONE launch (bf16): the chain of pointwise Conv+BN+act
  * branches  sp_0 = convs[0](spx[0]);  sp_i = convs[i](sp_{i-1} + spx[i]), i < nstage;  sp_in = sp_{nstage-1} + spx[nstage]

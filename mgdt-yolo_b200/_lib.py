@@ -13,7 +13,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MGDT_LIB") or os.path.join(HERE, "libmgdt_b200.so")   # MGDT_LIB: A/B runs of two builds in one session
 
-ABI_VERSION = 4  # include/mgdt_b200.h MGDT_ABI_VERSION
+ABI_VERSION = 5  # include/mgdt_b200.h MGDT_ABI_VERSION
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_RELU, ACT_SIGMOID, ACT_HSIGMOID, ACT_GELU = range(6)
 RS_COPY, RS_AVGPOOL, RS_BILINEAR, RS_NEAREST = range(4)
@@ -61,6 +61,10 @@ SIGNATURES = {
     "mgdt_conv_umma_pack_scaled": (C.c_int, [vp, i32, i32, i32, i32, vp, i32, vp, vp]),
     "mgdt_conv_umma_pack_scaled_groups": (C.c_int, [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp]),
     "mgdt_stem_conv": (C.c_int, [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_stem_u8_supported": (C.c_int, [i32, i32, i32, i32, i32]),
+    "mgdt_stem_u8_packed_bytes": (sz, [i32]),
+    "mgdt_stem_u8_pack": (C.c_int, [vp, i32, i32, vp, vp]),
+    "mgdt_stem_u8": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_mspa_front_supported": (C.c_int, [i32, i32]),
     "mgdt_mspa_front_packed_bytes": (sz, [i32, i32]),
     "mgdt_mspa_front_pack": (C.c_int, [vp, i32, i32, vp, vp]),

@@ -86,7 +86,10 @@ class Conv(KernelModule):
             kp = (k.shape[1] + 15) // 16 * 16
             wp = torch.zeros((w.shape[0], 1, 1, kp), dtype=torch.float32, device=src.device)
             wp[:, 0, 0, :k.shape[1]] = k.to(src.device)
-            return ops.PackedConv(wp.to(torch.bfloat16), 1, w32=wp), f32(b, src.device)
+            pk = ops.PackedConv(wp.to(torch.bfloat16), 1, w32=wp)
+            if c.in_channels == 3:
+                pk.stem_u8 = ops.stem_u8_pack(wp, w.shape[0])            # uint8 sources: warp-MMA stem (csrc/stem_mma.cu)
+            return pk, f32(b, src.device)
 
         pw, b = self._packed("stem", torch.bfloat16, src.device, tensors, build)
         return ops.stem_conv(src, pw, b, c.out_channels, act_name(self.act), out=out)

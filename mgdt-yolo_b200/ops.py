@@ -126,6 +126,7 @@ class PackedConv:
         self.ohwi = ohwi
         self.umma = None
         self.f16 = False
+        self.stem_u8 = None     # mgdt_stem_u8_pack image (layer 0 only, see stem_u8_pack)
         self.shape = ohwi.shape
         self.dtype = ohwi.dtype
         cout, k, k2, cin = ohwi.shape
@@ -152,6 +153,7 @@ WEIGHT_F16 = False
 USE_UMMA = True  # tests flip this to compare the tcgen05 path with the CUDA-core path
 PER_IMAGE_WEIGHTS = os.environ.get('MGDT_PER_IMAGE_W', '1') != '0'  # per-(n,c) input scales folded into per-image weights
 FUSE_TOOD_SIBLINGS = os.environ.get('MGDT_FUSE_TOOD', '0') != '0'  # cls_decomp / reg_decomp / cls_prob_conv1 as one per-image-weight GEMM; measured SLOWER in an in-box A/B (19.5k -> 19.1k images/s: the DCN sampler then reads reg_feat as a slice of an 80-channel map, 108 -> 142 us), so off by default
+STEM_MMA = os.environ.get('MGDT_STEM_MMA', '1') != '0'  # uint8 stem on warp-level MMAs (stem_mma.cu); 0: the tcgen05 stem
 FUSE_MSPA_FRONT = True  # MSPA_C2f branch chain as one launch (bf16); tests flip this to compare with the unfused sequence
 
 
@@ -322,6 +324,19 @@ def mspa_front(x, w, bias, iw, act, ycat, ysp=None):
     return ysp
 
 
+def stem_u8_pack(w32, cout):
+    """B-fragment image of the stem's BN-folded fp32 weights (Cout, kp), k = (ky*3+kx)*3 + c, for mgdt_stem_u8; None if
+    the warp-MMA stem does not take this width."""
+    nbytes = lib().mgdt_stem_u8_packed_bytes(cout)
+    if not nbytes or not STEM_MMA:
+        return None
+    w32 = w32.reshape(cout, -1).contiguous()
+    out = torch.empty((nbytes,), dtype=torch.uint8, device=w32.device)
+    with torch.cuda.device(w32.device):
+        check(lib().mgdt_stem_u8_pack(w32.data_ptr(), w32.shape[1], cout, out.data_ptr(), stream_ptr()), "stem_u8_pack")
+    return out
+
+
 def stem_conv(src, w: "PackedConv", bias, cout, act, out=None):
     """Fused preprocess + 3x3/s2 stem conv from an NCHW uint8 (/255) or float32 image batch (bf16 out)."""
     require_cuda(src, "stem input")
@@ -336,6 +351,12 @@ def stem_conv(src, w: "PackedConv", bias, cout, act, out=None):
         raise ValueError("stem_conv: bad output shape")
     meta = dict(shape=f"stem {c}->{cout} k3s2 {n}x{h}x{wd}", flops=2.0 * n * ho * wo * cout * c * 9,
                 bytes=_nb(src, out), kernel="conv_umma2_kernel")
+    if (STEM_MMA and src.dtype == torch.uint8 and w.stem_u8 is not None and src.data_ptr() % 16 == 0
+            and lib().mgdt_stem_u8_supported(c, h, wd, cout, ycs)):
+        meta["kernel"] = "stem_mma_kernel"
+        _invoke("mgdt_stem_u8", meta, src.data_ptr(), w.stem_u8.data_ptr(), _p(bias), yp, ycs, n, h, wd, cout, ACTS[act],
+                stream_ptr())
+        return out
     _invoke("mgdt_stem_conv", meta, src.data_ptr(), 1 if src.dtype == torch.uint8 else 0, w.umma.data_ptr(),
             1 if w.f16 else 0, _p(bias),
             yp, ycs, n, c, h, wd, cout, ACTS[act], BF16, stream_ptr())

@@ -142,6 +142,43 @@ def test_fused_stem_matches_preprocess_plus_conv():
         assert parity.errs(fused_f, plain)[0] <= 2 ** -7
 
 
+@pytest.mark.parametrize("cout", [16, 32, 48, 80])
+def test_stem_u8_warp_mma_vs_fp32_conv(cout):
+    """uint8 stem on warp-level MMAs (csrc/stem_mma.cu, mgdt_stem_u8) against torch's fp32 conv2d on u / 255 with the
+    BN-folded fp32 weights: operands are exact bytes x fp16 weights, so only the weights' 2^-11 rounding and the bf16
+    output rounding remain (tolerance 2^-8 max-relative); odd heights, widths whose output is not a multiple of 16,
+    image borders, every supported width class; and against the tcgen05 stem it replaces."""
+    import torch.nn.functional as F
+    from mgdt_yolo_b200 import ops
+    from mgdt_yolo_b200.modules import Conv
+    from mgdt_yolo_b200.modules.conv import fold_conv_bn
+    from mgdt_yolo_b200.synth import synth_state_dict
+    c = Conv(3, cout, 3, 2)
+    c.load_state_dict(synth_state_dict(c.state_dict(), seed=5 + cout))
+    c = c.cuda().eval()
+    w, b = fold_conv_bn(c.conv, c.bn)
+    g = torch.Generator().manual_seed(3)
+    for shape in ((2, 3, 64, 96), (1, 3, 37, 48), (3, 3, 2, 16), (1, 3, 640, 640)):
+        u8 = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g).cuda()
+        u8[:, :, :, :2] = 255
+        u8[:, :, :, -2:] = 255          # the padding columns must contribute zeros, not neighbours
+        with torch.no_grad():
+            ops.PROFILE = []
+            got = c.forward_image(u8)
+            kern = [m["kernel"] for _, m, _, _ in ops.PROFILE]
+            ops.PROFILE = None
+            assert kern == ["stem_mma_kernel"], kern
+            ref = F.silu(F.conv2d(u8.float() / 255, w.cuda().float(), b.cuda().float(), stride=2, padding=1))
+            old, ops.STEM_MMA = ops.STEM_MMA, False
+            try:
+                umma = c.forward_image(u8)
+            finally:
+                ops.STEM_MMA = old
+        mx, l2 = parity.errs(got, ref)
+        assert got.shape == ref.shape and mx <= 2 ** -8, f"{shape} -> {cout}: max-rel {mx:.3e}, L2 {l2:.3e}"
+        assert parity.errs(got, umma)[0] <= 2 ** -7
+
+
 def test_full_size_properties():
     """BASELINE.json full size (640x640): size-independent properties instead of a CPU oracle run --
     batch-permutation equivariance of the whole pipeline and NMS idempotence."""
