@@ -61,7 +61,8 @@ void mgdt_set_pdl(int on);
  *                        experiment: measured no gain, tcgen05.mma accumulation chains are not the bound)
  *   "conv_tma_store" 1   TMA tensor stores of 1x1 epilogue units
  *   "conv_pair"      1   paired 16-column epilogue units (Cout <= 16)
- *   "conv_split"    -1   force the producer / epilogue warp split of the cp.async conv kernel (0 / 1 / 2) */
+ *   "conv_split"    -1   force the producer / epilogue warp split of the cp.async conv kernel (0 / 1 / 2)
+ *   "conv3x3_warp"   1   3x3 stride-1 layers with Cin = Cout in {8, 16, 32} on the warp-level MMA kernel (0: tcgen05) */
 int mgdt_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------- convolution
@@ -120,8 +121,9 @@ int mgdt_conv2d(const mgdt_conv_args* a, void* stream);
 /* Which kernel mgdt_conv2d would run for these arguments: 3 = conv_pointwise_kernel (narrow 1x1 layers, CUDA cores,
  * HBM-bound), 4 = conv1x1_tma_kernel (tcgen05, operand A fed by TMA: transform-free 1x1 layers), 5 = conv3x3_tma_kernel
  * (tcgen05, operand A fed by 4-D TMA boxes: transform-free 3x3 stride-1 layers with Cin <= 64), 2 = conv_umma2_kernel
- * (tcgen05, cp.async-fed: wide 3x3, stride 2, fused input transforms / statistics), 1 = conv_direct_kernel (CUDA cores).  Used by the bench to attribute
- * launches to kernels. */
+ * (tcgen05, cp.async-fed: wide 3x3, stride 2, fused input transforms / statistics), 6 = conv3x3_warp_kernel (warp-level
+ * mma.sync: transform-free 3x3 stride-1 layers with Cin = Cout in {8, 16, 32}, the Bottleneck pairs), 1 = conv_direct_kernel
+ * (CUDA cores).  Used by the bench to attribute launches to kernels. */
 int mgdt_conv2d_path(const mgdt_conv_args* a);
 
 /* tcgen05 path: K-major shared-memory image of the weights, [col split][16-byte K chunk][Nc][8].
@@ -159,6 +161,16 @@ size_t mgdt_stem_u8_packed_bytes(int Cout);
 int mgdt_stem_u8_pack(const float* w, int kp, int Cout, void* packed, void* stream);
 int mgdt_stem_u8(const void* src, const void* packed, const float* bias, void* y, int y_cs, int N, int H, int W, int Cout,
                  int act, void* stream);
+
+/* TOODHead classification tail in one launch (bf16): logits = cv3(cls_feat * sigmoid(cls_prob_conv2(prob))), nn/modules/
+ * head.py:519-521, 528.  prob (N,H,W,C1) is cls_prob_conv1's ReLU output, w2 the OHWI (1,3,3,C1) weights of
+ * cls_prob_conv2 (3x3, pad 1), feat (N,H,W,C2) the classification feature, w3 the (nc,C2) weights of cv3; out receives nc
+ * channels per pixel (a slice of the head's raw map, channel stride out_cs).  C1, C2 multiples of 8 (<= 64 / 256),
+ * nc <= 8 (mgdt_tood_cls_supported); otherwise run the two convolutions (mgdt_conv2d with pix_scale). */
+int mgdt_tood_cls_supported(int C1, int C2, int nc, int prob_cs, int feat_cs);
+int mgdt_tood_cls(const void* prob, int prob_cs, const void* w2, const float* b2, const void* feat, int feat_cs,
+                  const void* w3, const float* b3, void* out, int out_cs, int N, int H, int W, int C1, int C2, int nc,
+                  int dtype, void* stream);
 
 /* MSPA_C2f hierarchy front (nn/modules/block.py:248-262) in ONE launch (bf16): the chain of pointwise Conv+BN+act
  * branches  sp_0 = convs[0](spx[0]);  sp_i = convs[i](sp_{i-1} + spx[i]), i < nstage;  sp_in = sp_{nstage-1} + spx[nstage]

@@ -65,6 +65,8 @@ SIGNATURES = {
     "mgdt_stem_u8_packed_bytes": (sz, [i32]),
     "mgdt_stem_u8_pack": (C.c_int, [vp, i32, i32, vp, vp]),
     "mgdt_stem_u8": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "mgdt_tood_cls_supported": (C.c_int, [i32, i32, i32, i32, i32]),
+    "mgdt_tood_cls": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "mgdt_mspa_front_supported": (C.c_int, [i32, i32]),
     "mgdt_mspa_front_packed_bytes": (sz, [i32, i32]),
     "mgdt_mspa_front_pack": (C.c_int, [vp, i32, i32, vp, vp]),
@@ -115,7 +117,7 @@ def lib():
             raise RuntimeError("mgdt_yolo_b200: ABI version mismatch, rebuild the library")
         # the library reads no environment variables: forward the documented MGDT_* switches once, here
         for env, opt in (("MGDT_PDL", "pdl"), ("MGDT_CONV_TMA_LOAD", "conv_tma_load"), ("MGDT_CONV_TMA_STORE", "conv_tma_store"), ("MGDT_CONV_TMA_STATS", "conv_tma_stats"), ("MGDT_CONV_KSPLIT", "conv_ksplit"),
-                         ("MGDT_CONV_PAIR", "conv_pair"), ("MGDT_CONV_SPLIT", "conv_split"), ("MGDT_CONV_MB", "conv_mb"), ("MGDT_CONV_TMA3X3", "conv_tma3x3"), ("MGDT_CONV_TMA3X3_S2", "conv_tma3x3_s2"), ("MGDT_DW_PAIRS", "dw_pairs")):
+                         ("MGDT_CONV_PAIR", "conv_pair"), ("MGDT_CONV_SPLIT", "conv_split"), ("MGDT_CONV_MB", "conv_mb"), ("MGDT_CONV_TMA3X3", "conv_tma3x3"), ("MGDT_CONV_TMA3X3_S2", "conv_tma3x3_s2"), ("MGDT_DW_PAIRS", "dw_pairs"), ("MGDT_CONV3X3_WARP", "conv3x3_warp"), ("MGDT_CW_SPC", "conv3x3_warp_spc")):
             v = os.environ.get(env)
             if v is not None and v.lstrip("-").isdigit():
                 L.mgdt_set_option(opt.encode(), int(v))

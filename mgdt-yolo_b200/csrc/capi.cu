@@ -24,6 +24,9 @@ int blocks_set_option(const char* name, int value);
 int conv2d_direct(const mgdt_conv_args* a, cudaStream_t s);
 bool conv2d_pointwise_supported(const mgdt_conv_args* a);
 int conv2d_pointwise(const mgdt_conv_args* a, cudaStream_t s);
+extern int g_conv3x3_warp, g_conv3x3_warp_spc;
+bool conv3x3_warp_supported(const mgdt_conv_args* a);
+int conv3x3_warp(const mgdt_conv_args* a, cudaStream_t s);
 #ifdef MGDT_WITH_UMMA
 int conv_set_option(const char* name, int value);
 bool conv2d_umma_supported(const mgdt_conv_args* a);
@@ -42,6 +45,8 @@ extern "C" void mgdt_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 extern "C" int mgdt_set_option(const char* name, int value) {
     MGDT_CHECK(name, "set_option: null name");
     if (!strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "conv3x3_warp")) { g_conv3x3_warp = value; return 0; }
+    if (!strcmp(name, "conv3x3_warp_spc")) { g_conv3x3_warp_spc = value; return 0; }
     if (blocks_set_option(name, value)) return 0;
 #ifdef MGDT_WITH_UMMA
     if (conv_set_option(name, value)) return 0;
@@ -50,6 +55,7 @@ extern "C" int mgdt_set_option(const char* name, int value) {
 }
 extern "C" int mgdt_conv2d_path(const mgdt_conv_args* a) {
     if (a && a->impl == 0 && !a->stat_acc && !a->w_per_image && !a->act_cols && conv2d_pointwise_supported(a)) return 3;
+    if (a && conv3x3_warp_supported(a)) return 6;
 #ifdef MGDT_WITH_UMMA
     if (a && a->impl != 1 && conv2d_umma_supported(a)) return conv2d_umma_path(a);
 #endif
@@ -78,6 +84,7 @@ extern "C" int mgdt_conv2d(const mgdt_conv_args* a, void* stream) {
     MGDT_CHECK(!a->stat_acc || ((a->stat_q == 0 || a->stat_q == 1 || a->stat_q == 5) && a->stat_q + (a->stat_sq ? 1 : 0) > 0 &&
                                 ((uintptr_t)a->stat_acc & 7) == 0), "conv2d: bad fused-statistics request");
     if (a->impl == 0 && !a->stat_acc && !a->w_per_image && !a->act_cols && conv2d_pointwise_supported(a)) return conv2d_pointwise(a, s);   // narrow 1x1 layers: HBM-bound SIMT
+    if (conv3x3_warp_supported(a)) return conv3x3_warp(a, s);   // 3x3 s1 with 8 / 16 / 32 channels: warp-level MMAs, no per-launch set-up
 #ifdef MGDT_WITH_UMMA
     if (a->impl != 1 && conv2d_umma_supported(a)) return conv2d_umma(a, s);
 #endif

@@ -252,10 +252,12 @@ class TOODHead(_HeadBase):
             om = ops.conv2d(feat, p["off"][0], p["off"][1], 3)           # offsets 0..17, mask logits 18..26 (:514-517)
             reg = self.DyDCNV2(reg_feat, om[:, :self.offset_dim], om[:, self.offset_dim:], mask_is_logit=True,
                                act="relu")                               # GN, then the F.relu of :528
-            prob = ops.conv2d(prob, p["p2"][0], p["p2"][1], 3, act="sigmoid")
             raw = ops.new_act(n, self.no, h, w, xi.dtype, xi.device)
             ops.conv2d(reg, p["cv2"][0], p["cv2"][1], 1, out=raw[:, :rm4])
-            ops.conv2d(cls_feat, p["cv3"][0], p["cv3"][1], 1, pix_scale=prob, out=raw[:, rm4:])  # cv3(cls_feat * cls_prob)
+            # cv3(cls_feat * sigmoid(cls_prob_conv2(prob))): one launch, or the two convolutions
+            if ops.tood_cls(prob, p["p2"][0].ohwi, p["p2"][1], cls_feat, p["cv3"][0].ohwi, p["cv3"][1], raw[:, rm4:]) is None:
+                prob = ops.conv2d(prob, p["p2"][0], p["p2"][1], 3, act="sigmoid")
+                ops.conv2d(cls_feat, p["cv3"][0], p["cv3"][1], 1, pix_scale=prob, out=raw[:, rm4:])
             x[i] = raw
         return self._finish(x)
 

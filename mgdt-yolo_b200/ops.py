@@ -287,9 +287,29 @@ def conv2d(x, w, bias, k, s=1, p=None, act=None, out=None, pre_add=None, in_scal
             else:
                 a.stat_acc, a.stat_q, a.stat_sq, a.stat_copies = None, 0, 0, 0
     if PROFILE is not None:  # attribute the launch to the kernel the library will actually run
-        meta["kernel"] = {3: "conv_pointwise_kernel", 2: "conv_umma2_kernel", 4: "conv1x1_tma_kernel", 5: "conv3x3_tma_kernel"}.get(lib().mgdt_conv2d_path(C.byref(a)),
+        meta["kernel"] = {3: "conv_pointwise_kernel", 2: "conv_umma2_kernel", 4: "conv1x1_tma_kernel", 5: "conv3x3_tma_kernel", 6: "conv3x3_warp_kernel"}.get(lib().mgdt_conv2d_path(C.byref(a)),
                                                                                   "conv_direct_kernel")
     _invoke("mgdt_conv2d", meta, C.byref(a), stream_ptr())
+    return out
+
+
+FUSE_TOOD_CLS = os.environ.get('MGDT_TOOD_CLS', '1') != '0'  # cls_prob_conv2 + sigmoid + cv3(cls_feat * cls_prob) as one launch
+
+
+def tood_cls(prob, w2, b2, feat, w3, b3, out):
+    """out = cv3(feat * sigmoid(conv3x3(prob))) (TOODHead, head.py:519-521, 528) in one launch; returns None when the
+    fused kernel does not take the shape (the caller then runs the two convolutions)."""
+    pp, n, c1, h, w, pcs = view(prob)
+    fp, fn, c2, fh, fw, fcs = view(feat)
+    op, on, nc, oh, ow, ocs = view(out)
+    if (not FUSE_TOOD_CLS or prob.dtype != torch.bfloat16 or (fn, fh, fw) != (n, h, w) or (on, oh, ow) != (n, h, w)
+            or tuple(w2.shape) != (1, 3, 3, c1) or tuple(w3.shape[:1] + w3.shape[-1:]) != (nc, c2) or w3.numel() != nc * c2
+            or pp % 16 or fp % 16 or not lib().mgdt_tood_cls_supported(c1, c2, nc, pcs, fcs)):
+        return None
+    meta = dict(shape=f"tood_cls {c1}/{c2}->{nc} {n}x{h}x{w}", flops=2.0 * n * h * w * (9 * c1 + nc * c2),
+                bytes=2 * n * h * w * (c1 + c2 + nc), kernel="tood_cls_kernel")
+    _invoke("mgdt_tood_cls", meta, pp, pcs, w2.data_ptr(), _p(b2), fp, fcs, w3.data_ptr(), _p(b3), op, ocs, n, h, w, c1, c2, nc,
+            dtype_code(prob.dtype), stream_ptr())
     return out
 
 

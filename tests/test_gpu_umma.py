@@ -356,3 +356,73 @@ def test_tood_sibling_convs_as_one_gemm():
     for a, b in zip(outs[True], outs[False]):
         err = float((a - b).abs().max()) / float(b.abs().max())
         assert err <= 2 ** -7, f"fused sibling GEMM vs separate convs: {err:.3e}"
+
+
+@pytest.mark.parametrize("c,n,h,w", [(8, 2, 21, 19), (8, 3, 160, 160), (16, 2, 16, 24), (16, 4, 80, 80), (32, 2, 20, 20),
+                                     (32, 3, 40, 40), (32, 2, 80, 80), (16, 1, 3, 5), (8, 1, 1, 1), (32, 1, 7, 33)])
+@pytest.mark.parametrize("act", ["silu", "relu"])
+def test_conv3x3_warp_kernel(c, n, h, w, act):
+    """The warp-level MMA kernel for 3x3 stride-1 layers with Cin = Cout in {8, 16, 32} (csrc/conv3x3_warp.cu, the impl=0
+    dispatch of the Bottleneck pairs): against torch's fp32 conv2d on the identical bf16 operands (tolerance = bf16 output
+    rounding), against the tcgen05 path it replaces, with a residual and channel-slice input / output / residual (the
+    neighbouring channels of the buffers must stay untouched); ragged widths (tiles of 16 pixels), 1-pixel maps."""
+    from mgdt_yolo_b200 import ops
+    from mgdt_yolo_b200._lib import lib
+    lib().mgdt_set_option(b"conv3x3_warp", 2)      # 32 -> 32 is off by default (measured slower than the tcgen05 kernel)
+    g = torch.Generator().manual_seed(c + h)
+    xbuf = ops.as_act(torch.randn(n, 3 * c, h, w, generator=g).cuda().to(torch.bfloat16))
+    x = xbuf[:, c:2 * c]
+    wt = (torch.randn(c, 3, 3, c, generator=g) * (2.0 / (c * 9)) ** 0.5).cuda().to(torch.bfloat16)
+    bias = (torch.randn(c, generator=g) * 0.1).cuda()
+    pw = ops.PackedConv(wt, 1)
+    ops.PROFILE = []
+    try:
+        obuf = ops.new_act(n, 3 * c, h, w, torch.bfloat16, "cuda")
+        obuf.zero_()
+        ops.conv2d(x, pw, bias, 3, 1, act=act, out=obuf[:, 2 * c:], residual=xbuf[:, :c])
+        plain = ops.conv2d(x, pw, bias, 3, 1, act=act)
+        kern = [m["kernel"] for _, m, _, _ in ops.PROFILE]
+    finally:
+        ops.PROFILE = None
+        lib().mgdt_set_option(b"conv3x3_warp", 1)
+    assert kern == ["conv3x3_warp_kernel"] * 2, kern
+    try:
+        umma = ops.conv2d(x, pw, bias, 3, 1, act=act, impl=2)
+    except RuntimeError:
+        umma = None          # degenerate maps the tcgen05 path refuses
+    torch.cuda.synchronize()
+    fa = F.silu if act == "silu" else F.relu
+    ref = fa(F.conv2d(x.float(), wt.float().permute(0, 3, 1, 2), bias, padding=1))
+    scale = max(float(ref.abs().max()), 1e-3)
+    assert float(obuf[:, :2 * c].abs().max()) == 0
+    assert float((plain.float() - ref).abs().max()) / scale <= 2 ** -7
+    assert umma is None or float((plain.float() - umma.float()).abs().max()) / scale <= 2 ** -7
+    ref_r = ref + xbuf[:, :c].float()
+    assert float((obuf[:, 2 * c:].float() - ref_r).abs().max()) / max(float(ref_r.abs().max()), 1e-3) <= 2 ** -7
+
+
+@pytest.mark.parametrize("c1,c2,nc,n,h,w", [(16, 32, 2, 3, 80, 80), (8, 16, 1, 2, 13, 9), (32, 64, 5, 2, 20, 21), (16, 32, 8, 1, 1, 1)])
+def test_tood_cls_fused_tail(c1, c2, nc, n, h, w):
+    """cv3(cls_feat * sigmoid(cls_prob_conv2(prob))) in one launch (csrc/tood_cls.cu) against the two convolutions it
+    replaces (3x3 -> 1 channel + sigmoid, 1x1 with a per-pixel input scale) and against torch fp32 on the same bf16
+    operands; writes only its nc channels of the raw map."""
+    from mgdt_yolo_b200 import ops
+    g = torch.Generator().manual_seed(c1 + nc)
+    prob = ops.as_act(torch.rand(n, c1, h, w, generator=g).cuda().to(torch.bfloat16))
+    featb = ops.as_act(torch.randn(n, 2 * c2, h, w, generator=g).cuda().to(torch.bfloat16))
+    feat = featb[:, c2:]
+    w2 = (torch.randn(1, 3, 3, c1, generator=g) * 0.2).cuda().to(torch.bfloat16)
+    w3 = (torch.randn(nc, 1, 1, c2, generator=g) * 0.2).cuda().to(torch.bfloat16)
+    b2, b3 = torch.randn(1, generator=g).cuda(), torch.randn(nc, generator=g).cuda()
+    raw = ops.new_act(n, 64 + nc, h, w, torch.bfloat16, "cuda")
+    raw.zero_()
+    assert ops.tood_cls(prob, w2, b2, feat, w3, b3, raw[:, 64:]) is not None
+    pr = ops.conv2d(prob, ops.PackedConv(w2, 1), b2, 3, act="sigmoid")
+    two = ops.conv2d(feat, ops.PackedConv(w3, 1), b3, 1, pix_scale=pr)
+    torch.cuda.synchronize()
+    pr32 = torch.sigmoid(F.conv2d(prob.float(), w2.float().permute(0, 3, 1, 2), b2, padding=1)).to(torch.bfloat16).float()
+    ref = F.conv2d((feat.float() * pr32).to(torch.bfloat16).float(), w3.float().permute(0, 3, 1, 2), b3)
+    scale = max(float(ref.abs().max()), 1e-3)
+    assert float(raw[:, :64].abs().max()) == 0
+    assert float((raw[:, 64:].float() - ref).abs().max()) / scale <= 2 ** -6
+    assert float((raw[:, 64:].float() - two.float()).abs().max()) / scale <= 2 ** -6
