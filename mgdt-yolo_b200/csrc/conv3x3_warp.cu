@@ -16,6 +16,9 @@
 //   * output channels are permuted over the n-tiles so a thread owns 2 NT consecutive channels of its pixels: bias,
 //     activation, residual (requested before the MMA chain) and the NHWC store are 4 / 8 / 16-byte accesses; all
 //     per-tile addresses advance by pointer increments (no index arithmetic in the loop).
+// Tried and removed: the same scheme for the stride-2 layers 16 -> 32 @320^2 / 32 -> 64 @160^2 (input rows split by column
+// parity while staging): correct, but 72 / 54 us against 55 / 37 us on the TMA-fed tcgen05 kernel -- with 2 CTAs of 4 warps
+// per SM (85 KB of staged rows each) a load-then-compute CTA cannot hide its own staging latency.
 #include "common.cuh"
 
 #include <algorithm>

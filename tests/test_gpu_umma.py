@@ -426,3 +426,4 @@ def test_tood_cls_fused_tail(c1, c2, nc, n, h, w):
     assert float(raw[:, :64].abs().max()) == 0
     assert float((raw[:, 64:].float() - ref).abs().max()) / scale <= 2 ** -6
     assert float((raw[:, 64:].float() - two.float()).abs().max()) / scale <= 2 ** -6
+
