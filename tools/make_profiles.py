@@ -25,7 +25,7 @@ def short(name):
 # ---- (1) launch list
 rows = [r for r in csv.reader(open(os.path.join(G, f"launches_{R}.csv"))) if len(r) > 14 and r[0].isdigit()]
 names = [short(r[4]) for r in rows]
-stems = [i for i, n in enumerate(names) if n.startswith("conv_umma2_kernel<0, 3")]
+stems = [i for i, n in enumerate(names) if n.startswith("conv_umma2_kernel<0, 3") or n.startswith("stem_mma_kernel")]   # layer 0 = first launch of a step
 start = stems[-1]
 step = rows[start:start + PER_STEP]
 agg = {}
