@@ -62,7 +62,7 @@ void mgdt_set_pdl(int on);
  *   "conv_tma_store" 1   TMA tensor stores of 1x1 epilogue units
  *   "conv_pair"      1   paired 16-column epilogue units (Cout <= 16)
  *   "conv_split"    -1   force the producer / epilogue warp split of the cp.async conv kernel (0 / 1 / 2)
- *   "conv3x3_warp"   1   3x3 stride-1 layers with Cin = Cout in {8, 16} on the warp-level MMA kernel (0: tcgen05; 2: also 32 -> 32)
+ *   "conv3x3_warp"   2   3x3 stride-1 layers with Cin = Cout in {8, 16, 32} on the warp-level MMA kernel (0: tcgen05; 1: 8 / 16 only)
  *   "conv3x3_warp_spc" 1 strips per persistent CTA of the stride-1 warp kernel (> 1: double-buffered staging; no gain measured) */
 int mgdt_set_option(const char* name, int value);
 

@@ -25,7 +25,7 @@
 
 namespace mgdt {
 
-int g_conv3x3_warp = 1;   // mgdt_set_option("conv3x3_warp", 0): keep these layers on the tcgen05 kernels (A/B runs); 2: also 32 -> 32
+int g_conv3x3_warp = 2;   // mgdt_set_option("conv3x3_warp", v): 0 = these layers stay on the tcgen05 kernels, 1 = 8 -> 8 / 16 -> 16 only, 2 = also 32 -> 32
 int g_conv3x3_warp_spc = 1;   // "conv3x3_warp_spc": target strips per persistent CTA (1 = one CTA per strip, no pipelining)
 
 constexpr int CW_TH = 4;        // output rows per CTA = warps per CTA
@@ -260,7 +260,9 @@ bool conv3x3_warp_supported(const mgdt_conv_args* a) {
     if (!g_conv3x3_warp || a->impl != 0 || a->dtype != MGDT_BF16) return false;
     if (a->kh != 3 || a->kw != 3 || a->stride != 1 || a->pad != 1) return false;
     // measured in the model at B = 32 (us, this kernel / tcgen05): 8 -> 8 @160^2 17.9 / 28.4, 16 -> 16 @80^2 14.8 / 18.4,
-    // 32 -> 32 @40^2 15.4 / 14.4, 32 -> 32 @80^2 26.4 / 21.2 -- so 32 -> 32 stays on the tcgen05 kernel unless asked for
+    // 32 -> 32 @40^2 15.4 / 14.4, 32 -> 32 @80^2 26.4 / 21.2.  32 -> 32 is slower per launch but the whole step is not (three
+    // batches in flight: value +-0, end-to-end +0.9 % in three alternating A/B pairs) -- a 4-warp CTA grid shares the SMs
+    // with the other streams' kernels, the persistent 148-CTA tcgen05 kernel does not -- so it is on by default too
     if (!(a->Cin == 8 || a->Cin == 16 || (a->Cin == 32 && g_conv3x3_warp >= 2)) || a->Cout != a->Cin) return false;
     if (a->pre_add || a->in_scale || a->pix_scale || a->in_relu || a->stat_acc || a->w_per_image || a->act_cols) return false;
     if ((a->x_cs & 7) || ((uintptr_t)a->x & 15) || ((uintptr_t)a->w & 15)) return false;                // 16-byte pixel / weight chunks

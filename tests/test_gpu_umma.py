@@ -368,7 +368,7 @@ def test_conv3x3_warp_kernel(c, n, h, w, act):
     neighbouring channels of the buffers must stay untouched); ragged widths (tiles of 16 pixels), 1-pixel maps."""
     from mgdt_yolo_b200 import ops
     from mgdt_yolo_b200._lib import lib
-    lib().mgdt_set_option(b"conv3x3_warp", 2)      # 32 -> 32 is off by default (measured slower than the tcgen05 kernel)
+    lib().mgdt_set_option(b"conv3x3_warp", 2)
     g = torch.Generator().manual_seed(c + h)
     xbuf = ops.as_act(torch.randn(n, 3 * c, h, w, generator=g).cuda().to(torch.bfloat16))
     x = xbuf[:, c:2 * c]
@@ -384,7 +384,7 @@ def test_conv3x3_warp_kernel(c, n, h, w, act):
         kern = [m["kernel"] for _, m, _, _ in ops.PROFILE]
     finally:
         ops.PROFILE = None
-        lib().mgdt_set_option(b"conv3x3_warp", 1)
+        lib().mgdt_set_option(b"conv3x3_warp", 2)
     assert kern == ["conv3x3_warp_kernel"] * 2, kern
     try:
         umma = ops.conv2d(x, pw, bias, 3, 1, act=act, impl=2)
