@@ -27,7 +27,7 @@ __device__ __forceinline__ void tc_unpack8(const uint4& v, float* f) {
 
 template <int NC>
 __global__ void __launch_bounds__(128) tood_cls_kernel(const TcP p) {
-    extern __shared__ float sw[];                 // [9 * C1] conv2 weights (tap, channel), then [NC * C2] cv3 weights
+    extern __shared__ __align__(16) float sw[];   // [9 * C1] conv2 weights (tap, channel), then [NC * C2] cv3 weights (C1, C2 % 8 == 0: 16-byte rows)
     pdl_trigger();
     float* s3 = sw + 9 * p.C1;
     for (int i = threadIdx.x; i < 9 * p.C1; i += 128) sw[i] = __bfloat162float(p.w2[i]);          // OHWI with O = 1
@@ -51,8 +51,9 @@ __global__ void __launch_bounds__(128) tood_cls_kernel(const TcP p) {
             for (int c = 0; c < p.C1; c += 8) {
                 float f[8];
                 tc_unpack8(__ldg(reinterpret_cast<const uint4*>(src + c)), f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) a = fmaf(f[j], w[c + j], a);
+                const float4 wa = *reinterpret_cast<const float4*>(w + c), wb = *reinterpret_cast<const float4*>(w + c + 4);
+                a = fmaf(f[0], wa.x, a); a = fmaf(f[1], wa.y, a); a = fmaf(f[2], wa.z, a); a = fmaf(f[3], wa.w, a);
+                a = fmaf(f[4], wb.x, a); a = fmaf(f[5], wb.y, a); a = fmaf(f[6], wb.z, a); a = fmaf(f[7], wb.w, a);
             }
         }
     }
@@ -66,10 +67,14 @@ __global__ void __launch_bounds__(128) tood_cls_kernel(const TcP p) {
         float f[8];
         tc_unpack8(__ldg(reinterpret_cast<const uint4*>(fs + c)), f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float v = __bfloat162float(__float2bfloat16_rn(f[j] * pr));
+        for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(__float2bfloat16_rn(f[j] * pr));
 #pragma unroll
-            for (int k = 0; k < NC; ++k) acc[k] = fmaf(v, s3[k * p.C2 + c + j], acc[k]);
+        for (int k = 0; k < NC; ++k) {
+            const float4 wa = *reinterpret_cast<const float4*>(s3 + k * p.C2 + c), wb = *reinterpret_cast<const float4*>(s3 + k * p.C2 + c + 4);
+            float v = acc[k];
+            v = fmaf(f[0], wa.x, v); v = fmaf(f[1], wa.y, v); v = fmaf(f[2], wa.z, v); v = fmaf(f[3], wa.w, v);
+            v = fmaf(f[4], wb.x, v); v = fmaf(f[5], wb.y, v); v = fmaf(f[6], wb.z, v); v = fmaf(f[7], wb.w, v);
+            acc[k] = v;
         }
     }
     __nv_bfloat16* o = p.out + pix * p.out_cs;
