@@ -38,20 +38,27 @@ __global__ void __launch_bounds__(128) tood_cls_kernel(const TcP p) {
     if (q >= p.H * p.W) return;
     const int y = q / p.W, x = q - y * p.W;
     float a = p.b2 ? p.b2[0] : 0.f;
+    // taps outside the image read a clamped (valid) address and are zeroed afterwards: no branch between the loads, so
+    // the unrolled loop has all of a row's loads in flight before the first FMA
+    const __nv_bfloat16* pn = p.prob + (size_t)n * p.H * p.W * p.prob_cs;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-        const int iy = y + ky - 1;
-        if (iy < 0 || iy >= p.H) continue;
+        const int iy = y + ky - 1, iyc = min(max(iy, 0), p.H - 1);
+        const bool vy = iy == iyc;
+        for (int c = 0; c < p.C1; c += 8) {
+            uint4 v[3];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int ix = x + kx - 1;
-            if (ix < 0 || ix >= p.W) continue;
-            const __nv_bfloat16* src = p.prob + (((size_t)n * p.H + iy) * p.W + ix) * p.prob_cs;
-            const float* w = sw + (ky * 3 + kx) * p.C1;
-            for (int c = 0; c < p.C1; c += 8) {
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = x + kx - 1, ixc = min(max(ix, 0), p.W - 1);
+                v[kx] = __ldg(reinterpret_cast<const uint4*>(pn + ((size_t)iyc * p.W + ixc) * p.prob_cs + c));
+                if (!(vy && ix == ixc)) v[kx] = make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
                 float f[8];
-                tc_unpack8(__ldg(reinterpret_cast<const uint4*>(src + c)), f);
-                const float4 wa = *reinterpret_cast<const float4*>(w + c), wb = *reinterpret_cast<const float4*>(w + c + 4);
+                tc_unpack8(v[kx], f);
+                const float* w = sw + (ky * 3 + kx) * p.C1 + c;
+                const float4 wa = *reinterpret_cast<const float4*>(w), wb = *reinterpret_cast<const float4*>(w + 4);
                 a = fmaf(f[0], wa.x, a); a = fmaf(f[1], wa.y, a); a = fmaf(f[2], wa.z, a); a = fmaf(f[3], wa.w, a);
                 a = fmaf(f[4], wb.x, a); a = fmaf(f[5], wb.y, a); a = fmaf(f[6], wb.z, a); a = fmaf(f[7], wb.w, a);
             }
