@@ -8,4 +8,4 @@ print(f"eager step {d['eager_step_ms'] * 1e3:.0f} us, graph step {d['graph_step_
 for r in d["per_kernel"]:
     print(f"  {r['kernel']:28s} n={r['n']:2d} us/launch={r['us_per_launch']:6.1f} share={r['share']:.3f} hbm_frac={r['hbm_frac']:.2f}")
 for r in sorted(d["kernels"], key=lambda r: -r["ms"])[:top]:
-    print(f"{r['name']:22s} {r['shape']:40s} n={r['n']} us={1e3 * r['ms'] / r['n']:6.1f} tot={1e3 * r['ms']:6.1f} MB={r['bytes'] / 1e6 / r['n']:6.1f} hbm={r['hbm_frac']:.2f}")
+    print(f"{r['name']:22s} {r['shape']:40s} n={r['n']} us={1e3 * r['ms'] / r['n']:6.1f} tot={1e3 * r['ms']:6.1f} MB={r['bytes'] / 1e6:6.1f} hbm={r['hbm_frac']:.2f}")
