@@ -28,7 +28,10 @@ namespace mgdt {
 int g_conv3x3_warp = 2;   // mgdt_set_option("conv3x3_warp", v): 0 = these layers stay on the tcgen05 kernels, 1 = 8 -> 8 / 16 -> 16 only, 2 = also 32 -> 32
 int g_conv3x3_warp_spc = 1;   // "conv3x3_warp_spc": target strips per persistent CTA (1 = one CTA per strip, no pipelining)
 
-constexpr int CW_TH = 4;        // output rows per CTA = warps per CTA
+#ifndef MGDT_CW_TH
+#define MGDT_CW_TH 4
+#endif
+constexpr int CW_TH = MGDT_CW_TH;   // output rows per CTA = warps per CTA (variant build -DMGDT_CW_TH=8: -1 % images/s in an in-box A/B)
 
 struct CwP {
     const __nv_bfloat16 *x, *w, *res;
