@@ -427,3 +427,25 @@ def test_tood_cls_fused_tail(c1, c2, nc, n, h, w):
     assert float((raw[:, 64:].float() - ref).abs().max()) / scale <= 2 ** -6
     assert float((raw[:, 64:].float() - two.float()).abs().max()) / scale <= 2 ** -6
 
+
+
+def test_conv3x3_warp_kernel_persistent_option():
+    """`conv3x3_warp_spc` > 1: persistent CTAs walking several strips with double-buffered staging (off by default, no gain
+    measured) must give the same bytes as one CTA per strip."""
+    from mgdt_yolo_b200 import ops
+    from mgdt_yolo_b200._lib import lib
+    g = torch.Generator().manual_seed(21)
+    outs = {}
+    for c, n, h, w in ((8, 32, 160, 160), (16, 32, 80, 80), (32, 16, 40, 44)):
+        x = ops.as_act(torch.randn(n, c, h, w, generator=g).cuda().to(torch.bfloat16))
+        wt = (torch.randn(c, 3, 3, c, generator=g) * (2.0 / (c * 9)) ** 0.5).cuda().to(torch.bfloat16)
+        bias = (torch.randn(c, generator=g) * 0.1).cuda()
+        pw = ops.PackedConv(wt, 1)
+        for spc in (1, 3):
+            lib().mgdt_set_option(b"conv3x3_warp_spc", spc)
+            try:
+                outs[spc] = ops.conv2d(x, pw, bias, 3, 1, act="silu", residual=x)
+            finally:
+                lib().mgdt_set_option(b"conv3x3_warp_spc", 1)
+        torch.cuda.synchronize()
+        assert torch.equal(outs[1], outs[3]), f"persistent strips differ for C = {c}"
