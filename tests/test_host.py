@@ -123,3 +123,17 @@ def test_export_fused_round_trip(tmp_path):
     ref.fuse(verbose=False)
     a, b = ref.state_dict(), f.state_dict()
     assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_bench_clock_sampler_degrades_without_a_gpu():
+    """bench.py samples SM clocks through NVML (nvidia-smi as the fallback); with neither it must report None, not raise."""
+    import sys
+    import time
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(0)
+    s.start()
+    t0 = time.time()
+    time.sleep(0.05)
+    out = s.stop(t0, time.time())
+    assert out is None or {"sm_mhz", "sm_max_mhz", "reasons", "samples", "source"} <= set(out)
